@@ -1,0 +1,146 @@
+/*
+ * psb200.h -- C ABI of libpsb200.so, the B200 (sm_100a) replacement for pySpectrum's native layer.
+ *
+ * What it replaces (reference = changhoonhahn/pySpectrum):
+ *   - the f2py extension module `estimator` built from pyspectrum/estimator.f (setup.py:11-52,
+ *     imported at pyspectrum/pyspectrum.py:8), i.e. assign_quad, fcomb_periodic, fcomb_survey,
+ *     pk_pbox_rsd, bk_counts, ffting;
+ *   - the FFTW calls made through pyfftw (pyspectrum/pyspectrum.py:204-214, 389-399, 1000-1010,
+ *     1064-1075) and through sfftw_* (estimator.f:69-87, 275-280).
+ *
+ * Two families of entry points:
+ *   psb_host_*   same argument meaning as the f2py signatures (SURVEY 8b level 2): HOST pointers,
+ *                Fortran-ordered arrays, in/out semantics preserved; host<->device copies inside.
+ *                These are what a maintainer binds in place of `import estimator`.
+ *   psb_*        DEVICE pointers + a CUDA stream: the resident pipeline the Python API
+ *                (pyspectrum_b200.pyspectrum) drives; nothing is allocated behind the caller.
+ *
+ * Conventions: every function returns 0 on success or a negative PSB_ERR_* code and never throws;
+ * `stream` is a cudaStream_t passed as void*; complex arrays are interleaved (re,im) float pairs;
+ * "c64" = complex64.  There is no CPU fallback: without a CUDA device every compute call fails
+ * with PSB_ERR_CUDA.
+ */
+#ifndef PSB200_H
+#define PSB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSB_OK 0
+#define PSB_ERR_ARG (-1)            /* bad argument (odd grid, unsupported option, null pointer)        */
+#define PSB_ERR_UNSUPPORTED_N (-2)  /* grid size has a prime factor other than 2,3,5 or is too large    */
+#define PSB_ERR_CUDA (-3)           /* CUDA runtime error (no device, launch failure, out of memory)    */
+#define PSB_ERR_WORKSPACE (-4)      /* workspace smaller than the corresponding *_workspace_bytes()     */
+
+int psb_version(void);
+const char* psb_error_string(int code);
+
+/* ------------------------------------------------------------------------------------------------
+ * Host-side table builders (pure host code, no GPU needed).
+ * ---------------------------------------------------------------------------------------------- */
+/* tw[k] = exp(+2 pi i k/N), k = 0..N-1, evaluated in double; f32 or f64 interleaved output. */
+int psb_twiddles_f32(int ngrid, float* tw_c64);
+int psb_twiddles_f64(int ngrid, double* tw_c128);
+/* fcomb tables (estimator.f:615-645): rec[j] double-complex phase recurrence with single-rounded base,
+ * wk[j] single-precision sinc^4 window, j = 0..N/2. */
+int psb_fcomb_tables(int ngrid, double* rec_c128, float* wk);
+/* line-of-sight trig of estimator.f:172-181 with the host libm: trig4 = {cos th, sin th, cos ph, sin ph} */
+int psb_rsd_trig(int irsd, float* trig4);
+/* bin index imk = nint(Nbin*sqrt(m)/(N/2)) in single precision (estimator.f:206-207) for m = 0..mmax */
+int psb_rsd_bin_table(int ngrid, int nbin, int mmax, uint16_t* bin_of_m);
+/* shell index int(sqrt(m)/step + 0.5) in single precision (estimator.f:32-36) for m = 0..mmax */
+int psb_irk_table_f32(float step, int mmax, uint16_t* irk_of_m);
+
+/* ------------------------------------------------------------------------------------------------
+ * Device-pointer pipeline.
+ * ---------------------------------------------------------------------------------------------- */
+/* K1  estimator.f:284-512 (+ clip/cast of pyspectrum.py:938-941 when lbox_clip > 0).
+ *   pos      positions: float64 or float32; layout [3][np] (pos_aos=0) or [np][3] (pos_aos=1)
+ *   w        weights (float64/float32) or NULL (all ones)
+ *   mesh     float32 [N][N][N][2]: (A,B) interlaced = the reference's dtl(2*Ngrid,Ngrid,Ngrid)
+ *   zero_mesh  1: mesh is cleared first (FFT_periodic);  0: accumulate (f2py intent(inout))
+ *   sumw     device double: receives sum(w) in float64 (pyspectrum.py:957 np.sum(w)) */
+size_t psb_assign_workspace_bytes(int64_t np, int ngrid);
+int psb_assign_pcs_interlaced(const void* pos, int pos_f64, int pos_aos, const void* w, int w_f64,
+                              int64_t np, int ngrid, double lbox_clip, float kf_ks, float offset,
+                              float* mesh, int zero_mesh, void* ws, size_t ws_bytes, double* sumw, void* stream);
+
+/* K2+K3  pyspectrum.py:1060-1080 + estimator.f:605-675 + the [:N/2+1] slice (py:959).
+ *   mesh_c64  in: (A + iB) on [z][y][x]; destroyed (x and y passes run in place)
+ *   half_c64  out: delta(k) on [kz][ky][kx], kx = 0..N/2 (the reference's Fortran (N/2+1,N,N) array)
+ *   periodic  1: fcomb_periodic (divide by *sumw), 0: fcomb_survey */
+int psb_fft_mesh_to_delta(float* mesh_c64, float* half_c64, int ngrid, const float* tw_c64,
+                          const double* rec_c128, const float* wk, const double* sumw, int periodic, void* stream);
+/* plain in-place unnormalised 3-D c2c (dir=+1: FFTW_BACKWARD); estimator.f:266-282 */
+int psb_fft_c2c_3d(float* data_c64, int ngrid, int dir, const float* tw_c64, void* stream);
+/* fcomb alone on a transformed full grid -> half field */
+int psb_fcomb(const float* full_c64, float* half_c64, int ngrid, const double* rec_c128, const float* wk,
+              const double* sumw, int periodic, void* stream);
+
+/* K4  power spectra from the half field.
+ * psb_pk_monopole   : pyspectrum.py:690-716.  out (float64) = nk[nbin], sum|k|[nbin], sum|delta|^2[nbin]
+ * psb_pk_multipoles : estimator.f:196-244 (raw sums, before f:246-262).  out (float64) =
+ *                     nk,k,p0,p2,p4 [nbin] then nkm,km,mk,pkm [nmu][nbin] (= Fortran (nbin,nmu)) */
+int psb_pk_monopole(const float* half_c64, int ngrid, const uint16_t* bin_of_m, int nbin, double kf,
+                    double* out, void* stream);
+int psb_pk_multipoles(const float* half_c64, int ngrid, const uint16_t* bin_of_m, int nbin, int nmu,
+                      float kf32, const float* trig4_host, double* out, void* stream);
+
+/* K5  pyspectrum.py:373-404.  nk[j] = number of modes of the FULL grid in shell j (py:380). */
+int psb_shell_mode_counts(int ngrid, const uint16_t* irk_of_m, int nshell, uint64_t* nk, void* stream);
+/* One packed pair of shells (sa -> real part, sb -> imaginary part, sb<0: none), pruned to |k_i| <= R:
+ *   fa,fb   out: I_sa(x), I_sb(x) on [z][y][x] (fb may be NULL when sb < 0)
+ *   sumsq   device double[2]: += sum_x I_sa^2, sum_x I_sb^2   (py:404)
+ *   t1,t2   scratch of (2R+1)^2*N and (2R+1)*N^2 complex elements (clamped to N per axis)
+ *   half_c64 == NULL -> delta == 1 (triangle counts, py:977 / estimator.f:74-80) */
+int psb_bk_shell_pair_f32(const float* half_c64, const uint16_t* irk_of_m, int ngrid, int sa, int sb, int R,
+                          float* t1_c64, float* t2_c64, float* fa, float* fb, double* sumsq,
+                          const float* tw_c64, void* stream);
+int psb_bk_shell_pair_f64(const float* half_c64, const uint16_t* irk_of_m, int ngrid, int sa, int sb, int R,
+                          double* t1_c128, double* t2_c128, double* fa, double* fb, double* sumsq,
+                          const double* tw_c128, void* stream);
+
+/* K6  pyspectrum.py:415-430.  fields: device array of nfields device pointers (field slot = shell - s0),
+ * tiles: int32 [ntiles][68] = {i0,j0,l0,0, slot[64]} with slot[(a*4+b)*4+c] = index into sums[] of
+ * triangle (i0+a, j0+b, l0+c) or -1; i0+3, j0+3, l0+3 must be < nfields (pad the pointer array).
+ * sums (float64, device) receives sum_x I_i I_j I_l. */
+size_t psb_bk_triangle_workspace_bytes(int ntiles);
+int psb_bk_triangle_sums_f32(const float* const* fields, int nfields, int64_t ncell, const int32_t* tiles,
+                             int ntiles, double* sums, void* ws, size_t ws_bytes, void* stream);
+int psb_bk_triangle_sums_f64(const double* const* fields, int nfields, int64_t ncell, const int32_t* tiles,
+                             int ntiles, double* sums, void* ws, size_t ws_bytes, void* stream);
+
+/* host helper: triangle list [ntri][3] (shell indices i,j,l) -> tile descriptors; tiles == NULL only sizes */
+int psb_bk_build_tiles(const int32_t* tri_ijl, int ntri, int s0, int32_t* tiles, int* ntiles);
+
+/* ------------------------------------------------------------------------------------------------
+ * Host-buffer drop-ins: the f2py signatures of `estimator` (f2py -h, SURVEY 8b level 2).
+ * All arrays are HOST memory in Fortran order exactly as f2py would hand them to the Fortran.
+ * ---------------------------------------------------------------------------------------------- */
+/* assign_quad(r,w,dtl,kf_ks,offset,ia,ib,ic,id,[np,ngrid])   estimator.f:284
+ *   r (3,np) float32, w (np) float32, dtl (2*ngrid,ngrid,ngrid) float32 intent(inout).
+ *   Only ia=ib=ic=id=0 (the delta branch, the only one the periodic path uses) is implemented. */
+int psb_host_assign_quad(const float* r, const float* w, float* dtl, int64_t np, int ngrid,
+                         float kf_ks, float offset, int ia, int ib, int ic, int id);
+/* fcomb_periodic(dcl,n,[ngrid]) estimator.f:605; fcomb_survey(dcl,[ngrid]) estimator.f:677; in place,
+ * all 8 mirror images written as the Fortran does. */
+int psb_host_fcomb_periodic(float* dcl_c64, float n, int ngrid);
+int psb_host_fcomb_survey(float* dcl_c64, int ngrid);
+/* ffting(dtl,n,[ngrid]) estimator.f:266: in-place FFTW_BACKWARD c2c */
+int psb_host_ffting(float* dtl_c64, int ngrid);
+/* pk_pbox_rsd(dtl,irsd,lbox,nbin,nmu,[ngrid]) -> k,p0,p2,p4,nk,km,mk,pkm,nkm   estimator.f:155
+ *   dtl (ngrid/2+1,ngrid,ngrid) complex64; lbox INTEGER; outputs float64, (nbin) and (nbin,nmu) F-order */
+int psb_host_pk_pbox_rsd(const float* dtl_c64, double* k, double* p0, double* p2, double* p4, double* nk,
+                         double* km, double* mk, double* pkm, double* nkm,
+                         int irsd, int lbox, int nbin, int nmu, int ngrid);
+/* bk_counts(coun,nside,step,ncut,[nmax])  estimator.f:2: coun (nmax,nmax,nmax) float64 F-order, filled for
+ * ncut/step <= i <= j <= l with sum_x N_i N_j N_l = nside^3 * (exact integer; computed in float64). */
+int psb_host_bk_counts(double* coun, int nside, float step, int ncut, int nmax);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSB200_H */

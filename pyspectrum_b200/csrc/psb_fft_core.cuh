@@ -1,0 +1,177 @@
+// psb_fft_core.cuh -- radix planner, small in-register DFTs and the Stockham stage used by
+// every FFT pass (mesh -> delta(k): replaces the FFTW_BACKWARD call of pyspectrum.py:1073-1075;
+// shell fields: replaces the per-shell FFTW forward of pyspectrum.py:397-399).
+//
+// Line FFT = sequence of Stockham autosort stages executed in shared memory.  A stage with
+// radix R and Ns = product of the previous radices does, for butterfly j in [0, N/R):
+//     k  = j mod Ns
+//     v[q] = x[j + q*N/R] * W_N^{DIR * q*k*N/(Ns*R)}          q = 0..R-1
+//     v    = DFT_R(v)                                          (sign DIR)
+//     x'[(j/Ns)*Ns*R + k + q*Ns] = v[q]
+// After all stages x' holds the DFT in natural order.  W comes from a table
+// tw[i] = exp(+2*pi*i/N) computed in double on the host (pyspectrum_b200/plan.py).
+#pragma once
+#include "psb_common.cuh"
+
+namespace psb {
+
+constexpr int PSB_MAX_STAGES = 12;
+
+struct FftPlan {
+    int N;
+    int nstages;
+    int radix[PSB_MAX_STAGES];
+    int nb_max;      // max butterflies per line over the stages (= N / min radix)
+};
+
+// Factor N into radices from {8,9,5,4,3,2}; returns false if N has another prime factor.
+inline bool make_plan(int N, FftPlan* p)
+{
+    if (N < 2) return false;
+    int e2 = 0, e3 = 0, e5 = 0, n = N;
+    while (n % 2 == 0) { n /= 2; ++e2; }
+    while (n % 3 == 0) { n /= 3; ++e3; }
+    while (n % 5 == 0) { n /= 5; ++e5; }
+    if (n != 1) return false;
+    int ns = 0;
+    int r[64];
+    // powers of two: as many 8s as possible, never a lone radix-2 when a 4 can absorb it
+    int n8 = e2 / 3, rem = e2 % 3;
+    if (rem == 1 && n8 >= 1) { n8 -= 1; r[ns++] = 4; r[ns++] = 4; rem = 0; }
+    for (int i = 0; i < n8; ++i) r[ns++] = 8;
+    if (rem == 2) r[ns++] = 4;
+    if (rem == 1) r[ns++] = 2;
+    for (int i = 0; i < e3 / 2; ++i) r[ns++] = 9;
+    if (e3 % 2) r[ns++] = 3;
+    for (int i = 0; i < e5; ++i) r[ns++] = 5;
+    if (ns > PSB_MAX_STAGES) return false;
+    p->N = N;
+    p->nstages = ns;
+    int rmin = 1 << 30;
+    // largest radices first: the early stages (small Ns) have the worst smem write strides
+    for (int i = 0; i < ns; ++i)
+        for (int j = i + 1; j < ns; ++j)
+            if (r[j] > r[i]) { int t = r[i]; r[i] = r[j]; r[j] = t; }
+    for (int i = 0; i < PSB_MAX_STAGES; ++i) p->radix[i] = (i < ns) ? r[i] : 1;
+    for (int i = 0; i < ns; ++i) if (r[i] < rmin) rmin = r[i];
+    p->nb_max = N / rmin;
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------
+// small DFTs, out[p] = sum_q v[q] exp(DIR*2*pi*i*p*q/R), in place
+// ---------------------------------------------------------------------------------------
+template <int R, int DIR, typename T> struct Dft;
+
+template <int DIR, typename T> struct Dft<2, DIR, T> {
+    static PSB_HD void run(Cx<T>* v) { Cx<T> a = v[0], b = v[1]; v[0] = a + b; v[1] = a - b; }
+};
+
+template <int DIR, typename T> struct Dft<3, DIR, T> {
+    static PSB_HD void run(Cx<T>* v) {
+        const T h = (T)0.86602540378443864676;     // sqrt(3)/2
+        Cx<T> s = v[1] + v[2], d = v[1] - v[2];
+        Cx<T> t = mk<T>(v[0].x - (T)0.5 * s.x, v[0].y - (T)0.5 * s.y);
+        Cx<T> u = mul_i<DIR>(h * d);
+        v[0] = v[0] + s; v[1] = t + u; v[2] = t - u;
+    }
+};
+
+template <int DIR, typename T> struct Dft<4, DIR, T> {
+    static PSB_HD void run(Cx<T>* v) {
+        Cx<T> a = v[0] + v[2], b = v[0] - v[2], c = v[1] + v[3], d = mul_i<DIR>(v[1] - v[3]);
+        v[0] = a + c; v[1] = b + d; v[2] = a - c; v[3] = b - d;
+    }
+};
+
+template <int DIR, typename T> struct Dft<5, DIR, T> {
+    static PSB_HD void run(Cx<T>* v) {
+        const T c1 = (T)0.30901699437494742410, c2 = (T)-0.80901699437494742410;
+        const T s1 = (T)0.95105651629515357212, s2 = (T)0.58778525229247312917;
+        Cx<T> t1 = v[1] + v[4], t2 = v[2] + v[3], t3 = v[1] - v[4], t4 = v[2] - v[3];
+        Cx<T> m1 = mk<T>(v[0].x + c1 * t1.x + c2 * t2.x, v[0].y + c1 * t1.y + c2 * t2.y);
+        Cx<T> m2 = mk<T>(v[0].x + c2 * t1.x + c1 * t2.x, v[0].y + c2 * t1.y + c1 * t2.y);
+        Cx<T> n1 = mul_i<DIR>(mk<T>(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y));
+        Cx<T> n2 = mul_i<DIR>(mk<T>(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y));
+        v[0] = v[0] + t1 + t2;
+        v[1] = m1 + n1; v[4] = m1 - n1; v[2] = m2 + n2; v[3] = m2 - n2;
+    }
+};
+
+template <int DIR, typename T> struct Dft<8, DIR, T> {
+    static PSB_HD void run(Cx<T>* v) {
+        const T r = (T)0.70710678118654752440;
+        Cx<T> e[4] = { v[0], v[2], v[4], v[6] }, o[4] = { v[1], v[3], v[5], v[7] };
+        Dft<4, DIR, T>::run(e);
+        Dft<4, DIR, T>::run(o);
+        // W8^1 = r(1 + DIR i), W8^2 = DIR i, W8^3 = r(-1 + DIR i)
+        Cx<T> o1 = r * (o[1] + mul_i<DIR>(o[1]));
+        Cx<T> o2 = mul_i<DIR>(o[2]);
+        Cx<T> o3 = r * (mul_i<DIR>(o[3]) - o[3]);
+        v[0] = e[0] + o[0]; v[4] = e[0] - o[0];
+        v[1] = e[1] + o1;   v[5] = e[1] - o1;
+        v[2] = e[2] + o2;   v[6] = e[2] - o2;
+        v[3] = e[3] + o3;   v[7] = e[3] - o3;
+    }
+};
+
+template <int DIR, typename T> struct Dft<9, DIR, T> {
+    static PSB_HD void run(Cx<T>* v) {
+        // W9^1, W9^2, W9^4 = exp(DIR*2*pi*i*{1,2,4}/9)
+        const T c1 = (T)0.76604444311897803520, s1 = (T)0.64278760968653932632;
+        const T c2 = (T)0.17364817766693034885, s2 = (T)0.98480775301220805937;
+        const T c4 = (T)-0.93969262078590838405, s4 = (T)0.34202014332566873304;
+        Cx<T> a[3] = { v[0], v[3], v[6] }, b[3] = { v[1], v[4], v[7] }, c[3] = { v[2], v[5], v[8] };
+        Dft<3, DIR, T>::run(a); Dft<3, DIR, T>::run(b); Dft<3, DIR, T>::run(c);
+        const T sg = (T)DIR;
+        b[1] = b[1] * mk<T>(c1, sg * s1); b[2] = b[2] * mk<T>(c2, sg * s2);
+        c[1] = c[1] * mk<T>(c2, sg * s2); c[2] = c[2] * mk<T>(c4, sg * s4);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int p0 = 0; p0 < 3; ++p0) {
+            Cx<T> f[3] = { a[p0], b[p0], c[p0] };
+            Dft<3, DIR, T>::run(f);
+            v[p0] = f[0]; v[p0 + 3] = f[1]; v[p0 + 6] = f[2];
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------
+// one butterfly of a Stockham stage, split in its read and compute+write halves so that the
+// kernel can run all reads of a stage, barrier, then all writes (in-place in shared memory)
+// ---------------------------------------------------------------------------------------
+template <int R, typename T>
+PSB_HD void stage_read(const Cx<T>* s, int estride, int N, int j, Cx<T>* v)
+{
+    const int M = N / R;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int q = 0; q < R; ++q) v[q] = s[(size_t)(j + q * M) * estride];
+}
+
+template <int R, int DIR, typename T>
+PSB_HD void stage_write(Cx<T>* s, int estride, int N, int Ns, int j, const Cx<T>* tw, Cx<T>* v)
+{
+    const int k = j % Ns;
+    if (Ns > 1) {
+        const int tstep = k * (N / (Ns * R));            // q*tstep < N
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int q = 1; q < R; ++q) {
+            Cx<T> w = tw[q * tstep];
+            if (DIR < 0) w.y = -w.y;
+            v[q] = v[q] * w;
+        }
+    }
+    Dft<R, DIR, T>::run(v);
+    const int j0 = (j / Ns) * Ns * R + k;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int q = 0; q < R; ++q) s[(size_t)(j0 + q * Ns) * estride] = v[q];
+}
+
+}  // namespace psb

@@ -1,0 +1,35 @@
+// psb_fft_shell.cuh -- packed shell-pair transform: half field (or delta == 1) -> two real fields.
+// Replaces, per pair of shells, pyspectrum.py:387-404 (mask, complex64 FFTW forward, np.real, shell
+// power) and reflect_delta (py:1134-1157); with T = double and half == nullptr it is the counts cold
+// path (py:975-1011 / estimator.f:27-86).  All three passes are pruned to |k_i| <= R.
+#pragma once
+#include "psb_fft_lines.cuh"
+
+namespace psb {
+
+template <typename T>
+int fft_shell_pair(const Cx<float>* half, const unsigned short* irk, int N, int sa, int sb, int R,
+                   Cx<T>* t1, Cx<T>* t2, T* fa, T* fb, double* sumsq, const Cx<T>* tw, cudaStream_t st)
+{
+    FftPlan p;
+    if (N % 2 || !make_plan(N, &p)) return PSB_ERR_UNSUPPORTED_N;
+    const int Rp = R < N / 2 ? R : N / 2;
+    const int Rm = R < (N - 1) / 2 ? R : (N - 1) / 2;
+    const int W = Rm + Rp + 1;
+    return dispatch_plan(N, [&](auto cfg) -> int {
+        const int LPC = cfg_lpc(cfg, p);
+        if (LPC < 1) return (int)PSB_ERR_UNSUPPORTED_N;
+        IoShellX<T> io1{ half, irk, t1, sa, sb, Rm, Rp, W };
+        int rc = launch_any<T, -1>(cfg, p, LPC, dim3((W + LPC - 1) / LPC, W), tw, io1, st);
+        if (rc) return rc;
+        // pass 2 (y): batch = kz', T1[kz'][ky'][x] -> T2[kz'][y][x]
+        IoCols<T, true, false> io2{ t1, t2, nullptr, nullptr, nullptr, N, (long long)W * N, N, (long long)N * N, N, Rm, Rp };
+        rc = launch_any<T, -1>(cfg, p, LPC, dim3((N + LPC - 1) / LPC, W), tw, io2, st);
+        if (rc) return rc;
+        // pass 3 (z): batch = y, T2[kz'][y][x] -> real planes [z][y][x] (+ sums of squares)
+        IoCols<T, true, true> io3{ t2, nullptr, fa, fb, sumsq, N, N, (long long)N * N, N, (long long)N * N, Rm, Rp };
+        return launch_any<T, -1>(cfg, p, LPC, dim3((N + LPC - 1) / LPC, N), tw, io3, st);
+    });
+}
+
+}  // namespace psb

@@ -1,0 +1,56 @@
+// psb_kernels.h -- internal host-side entry points of the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include "psb_common.cuh"
+
+namespace psb {
+
+struct AssignIn {
+    const void* pos;      // positions
+    int pos_f64;          // 1: float64, 0: float32
+    int pos_aos;          // 1: [Np][3] (Fortran (3,Np)), 0: [3][Np] (numpy 3xN C order)
+    const void* w;        // weights or null
+    int w_f64;            // 1: float64, 0: float32
+    long long Np;
+    int N;
+    int do_clip;          // pyspectrum.py:938-941
+    double clip_hi;       // Lbox*(1-1e-6)
+    float kf_ks, offset;
+};
+
+size_t assign_workspace_bytes(long long Np, int N);
+int assign_pcs_interlaced(const AssignIn& in, float* mesh, int zero_mesh, void* ws, size_t ws_bytes, double* sumw, cudaStream_t st);
+
+int fft_mesh_to_delta(Cx<float>* mesh, Cx<float>* half, int N, const Cx<float>* tw,
+                      const Cx<double>* rec, const float* Wk, const double* sumw, int periodic, cudaStream_t st);
+int fft_c2c_3d(Cx<float>* data, int N, int dir, const Cx<float>* tw, cudaStream_t st);
+int fcomb_standalone(const Cx<float>* full, Cx<float>* half, int N, const Cx<double>* rec, const float* Wk,
+                     const double* sumw, int periodic, cudaStream_t st);
+template <typename T>
+int fft_shell_pair(const Cx<float>* half, const unsigned short* irk, int N, int sa, int sb, int R,
+                   Cx<T>* t1, Cx<T>* t2, T* fa, T* fb, double* sumsq, const Cx<T>* tw, cudaStream_t st);
+
+struct SpectraIn {
+    const Cx<float>* half;       // [kz][ky][kx]
+    int N;
+    const unsigned short* bin;   // bin index (1-based, 0 = none) of m = |k|^2, host table
+    int Nbin;
+    int mode;                    // 0: Pk_periodic (float64 |k|, realified self-conjugate points)
+                                 // 1: pk_pbox_rsd (float32 per-mode math of estimator.f:196-244)
+    double kf;                   // mode 0: 2*pi/Lbox (float64)
+    float kf32;                  // mode 1: tpi/Lbox in single (f:169)
+    int Nmu;
+    float costh, sinth, cosph, sinph;   // f:172-181 evaluated with the host libm
+};
+// out layout (all float64): mode 0: nk[Nbin], ksum[Nbin], psum[Nbin]
+//                           mode 1: nk,k,p0,p2,p4 [Nbin] then nkm,km,mk,pkm [Nmu][Nbin] (Fortran (Nbin,Nmu))
+int binned_spectra(const SpectraIn& in, double* out, cudaStream_t st);
+int shell_mode_counts(int N, const unsigned short* irk, int nshell_max, unsigned long long* nk, cudaStream_t st);
+
+// tiles: int32 [ntiles][68] = {i0,j0,l0,pad, slot[64]}; fields[] holds S device pointers (S padded so i0+3 < S)
+template <typename T>
+int triangle_sums_tiles(const T* const* fields, int S, long long ncell, const int* tiles, int ntiles,
+                        double* sums, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t triangle_workspace_bytes(int ntiles);
+
+}  // namespace psb

@@ -1,0 +1,112 @@
+// psb_spectra.cu -- K4: one pass over the half field -> binned power spectra.
+//   mode 0  replaces the Python bin loop of Pk_periodic (pyspectrum.py:690-716) on reflect_delta's field
+//   mode 1  replaces estimator.f:155-264 (pk_pbox_rsd): multipoles + (k,mu) table
+// A half-space mode with 0 < kx < N/2 stands for itself and its conjugate (weight 2); the kx = 0 and
+// kx = N/2 planes hold both partners explicitly (weight 1).  The reference visits all N^3 modes; under
+// k -> -k every float32 quantity of f:206-223 flips sign exactly, so |mu|, mu^2 and the bins agree.
+// Bin indices come from a host table indexed by m = kx^2+ky^2+kz^2 that evaluates the reference's own
+// expression (float64 int(x+0.5) for mode 0, float32 nint() for mode 1) -> mode counts are bit exact.
+// The mu bin needs IEEE float32 sqrt/div with no contraction: explicit _rn intrinsics.
+#include <cuda_runtime.h>
+#include "psb_kernels.h"
+
+namespace psb {
+
+__global__ void __launch_bounds__(256) k_spectra(SpectraIn in, double* out)
+{
+    const int N = in.N, h = N / 2, Nbin = in.Nbin;
+    const long long nmode = (long long)(h + 1) * N * N;
+    double* nk = out;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < nmode; e += (long long)gridDim.x * blockDim.x) {
+        const int ix = (int)(e % (h + 1));
+        const long long r = e / (h + 1);
+        const int iy = (int)(r % N), iz = (int)(r / N);
+        const int kx = ix, ky = kfreq(iy, N), kz = kfreq(iz, N);
+        const int m = kx * kx + ky * ky + kz * kz;
+        const int b = in.bin[m];
+        if (b == 0 || b > Nbin) continue;
+        const double wgt = (ix == 0 || ix == h) ? 1.0 : 2.0;
+        Cx<float> d = in.half[e];
+        if (in.mode == 0) {
+            // reflect_delta (py:1149-1156) makes the self-conjugate points real before |.|^2
+            if ((ix == 0 || ix == h) && (iy == 0 || iy == h) && (iz == 0 || iz == h)) d.y = 0.f;
+            const float p = d.x * d.x + d.y * d.y;
+            atomicAdd(&nk[b - 1], wgt);
+            atomicAdd(&out[Nbin + b - 1], wgt * (in.kf * sqrt((double)m)));
+            atomicAdd(&out[2 * Nbin + b - 1], wgt * (double)p);
+        } else {
+            const float rkx = (float)kx, rky = (float)ky, rkz = (float)kz;
+            const float rk = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(rkx, rkx), __fmul_rn(rky, rky)), __fmul_rn(rkz, rkz)));
+            const float cot1 = __fdiv_rn(rkz, rk);
+            const float sit1 = __fsqrt_rn(__fsub_rn(1.f, __fmul_rn(cot1, cot1)));
+            float cc = 0.f;
+            if (sit1 > 0.f) {
+                const float den = __fmul_rn(rk, sit1);
+                const float cp = __fdiv_rn(rkx, den), sp = __fdiv_rn(rky, den);
+                cc = __fadd_rn(__fmul_rn(in.sinph, sp), __fmul_rn(in.cosph, cp));
+            }
+            const double mu = (double)__fadd_rn(__fmul_rn(in.costh, cot1), __fmul_rn(__fmul_rn(in.sinth, sit1), cc));
+            const double mubin = (double)__fdiv_rn(1.f, (float)in.Nmu);
+            const double amu = fabs(mu);
+            const int imu = (int)__ddiv_rn(__dadd_rn(amu, mubin), mubin);
+            const double mu2 = mu * mu;
+            const double Le2 = -0.5 + 1.5 * mu2;
+            const double Le4 = 0.375 - 3.75 * mu2 + 4.375 * (mu2 * mu2);
+            const float ab = (float)sqrt((double)d.x * (double)d.x + (double)d.y * (double)d.y);    // cabs()
+            const double pk = (double)__fmul_rn(ab, ab);
+            const double kk = (double)__fmul_rn(in.kf32, rk);
+            atomicAdd(&nk[b - 1], wgt);
+            atomicAdd(&out[Nbin + b - 1], wgt * kk);
+            atomicAdd(&out[2 * Nbin + b - 1], wgt * pk);
+            atomicAdd(&out[3 * Nbin + b - 1], wgt * (pk * 5.0 * Le2));
+            atomicAdd(&out[4 * Nbin + b - 1], wgt * (pk * 9.0 * Le4));
+            if (imu <= in.Nmu && imu > 0) {
+                double* t = out + 5 * (long long)Nbin + (long long)(imu - 1) * Nbin + (b - 1);
+                const long long tb = (long long)Nbin * in.Nmu;
+                atomicAdd(t, wgt);
+                atomicAdd(t + tb, wgt * kk);
+                atomicAdd(t + 2 * tb, wgt * amu);
+                atomicAdd(t + 3 * tb, wgt * pk);
+            }
+        }
+    }
+}
+
+int binned_spectra(const SpectraIn& in, double* out, cudaStream_t st)
+{
+    if (in.N < 2 || in.N % 2 || in.Nbin < 1) return PSB_ERR_ARG;
+    const size_t nout = in.mode == 0 ? 3 * (size_t)in.Nbin : (5 + 4 * (size_t)in.Nmu) * in.Nbin;
+    if (cudaMemsetAsync(out, 0, nout * sizeof(double), st) != cudaSuccess) return PSB_ERR_CUDA;
+    k_spectra<<<148 * 8, 256, 0, st>>>(in, out);
+    return cudaGetLastError() == cudaSuccess ? PSB_OK : PSB_ERR_CUDA;
+}
+
+// Nk[j] = #{k on the full grid : irk(k) == j}, j = 0..nshell-1   (pyspectrum.py:380)
+__global__ void __launch_bounds__(256) k_shell_counts(int N, const unsigned short* irk, int nshell, unsigned long long* nk)
+{
+    extern __shared__ unsigned int hist[];
+    for (int i = threadIdx.x; i < nshell; i += blockDim.x) hist[i] = 0u;
+    __syncthreads();
+    const int h = N / 2;
+    const long long nmode = (long long)(h + 1) * N * N;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < nmode; e += (long long)gridDim.x * blockDim.x) {
+        const int ix = (int)(e % (h + 1));
+        const long long r = e / (h + 1);
+        const int ky = kfreq((int)(r % N), N), kz = kfreq((int)(r / N), N);
+        const int s = irk[ix * ix + ky * ky + kz * kz];
+        if (s < nshell) atomicAdd(&hist[s], (ix == 0 || ix == h) ? 1u : 2u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nshell; i += blockDim.x)
+        if (hist[i]) atomicAdd(&nk[i], (unsigned long long)hist[i]);
+}
+
+int shell_mode_counts(int N, const unsigned short* irk, int nshell, unsigned long long* nk, cudaStream_t st)
+{
+    if (N < 2 || N % 2 || nshell < 1 || nshell > 8192) return PSB_ERR_ARG;
+    if (cudaMemsetAsync(nk, 0, nshell * sizeof(unsigned long long), st) != cudaSuccess) return PSB_ERR_CUDA;
+    k_shell_counts<<<148 * 4, 256, nshell * sizeof(unsigned int), st>>>(N, irk, nshell, nk);
+    return cudaGetLastError() == cudaSuccess ? PSB_OK : PSB_ERR_CUDA;
+}
+
+}  // namespace psb

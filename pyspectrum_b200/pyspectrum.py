@@ -1,0 +1,542 @@
+"""pyspectrum_b200.pyspectrum -- drop-in for the periodic-box API of pySpectrum's pyspectrum/pyspectrum.py.
+
+Same public functions, arguments and output dictionaries as the reference:
+
+    Pk_periodic      (pyspectrum.py:644-728)
+    Pk_periodic_rsd  (pyspectrum.py:460-538, code='fortran' branch 628-641)
+    Bk_periodic      (pyspectrum.py:285-356 + _Bk_periodic 359-457)
+    FFT_periodic     (pyspectrum.py:909-959), reflect_delta (1134-1157), _counts_Bk123 (962-1030)
+
+Behind them the f2py module `estimator` and the pyfftw calls are replaced by hand-written sm_100a
+kernels reached through the C ABI of include/psb200.h (ctypes; torch tensors are only device buffers
+and the stream).  There is no CPU fallback: without libpsb200.so or a CUDA device the calls raise.
+
+Deliberate differences from the reference (all in DESIGN.md):
+  * `Ngrid == 360` assert of Bk_periodic (py:332) is relaxed to "even N = 2^a 3^b 5^c";
+  * Pk_periodic bins |delta_fft|^2 (py:713 indexes the wrong array and raises on numpy >= 1.13);
+  * `fft`, `nthreads`, `code` are accepted and ignored;
+  * triangle counts are exact integers computed in float64 on the GPU and cached (memory + a file in the
+    reference's own Fortran-record format) instead of the reference's pure-Python cold path.
+"""
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check
+
+__all__ = ['Pk_periodic', 'Pk_periodic_rsd', 'Bk_periodic', 'FFT_periodic', 'reflect_delta',
+           '_counts_Bk123', 'dat_dir', 'PeriodicPipeline']
+
+_DAT_DIR = os.environ.get('PYSPECTRUM_B200_DAT', os.path.join(os.path.dirname(os.path.realpath(__file__)), 'dat'))
+
+
+def dat_dir():
+    """Where triangle-count caches live (the reference's dat_dir(), pyspectrum/__init__.py:6)."""
+    return _DAT_DIR
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _np_ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _device():
+    if not torch.cuda.is_available():
+        raise RuntimeError('pyspectrum_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+def triangle_list(Nmax, Ncut, step):
+    """Shell-index triples (i,j,l) in the loop order of pyspectrum.py:415-417."""
+    s = Ncut // step
+    i = np.arange(s, Nmax + 1)
+    I, J, L = np.meshgrid(i, i, i, indexing='ij')
+    m = (J <= I) & (L <= J) & (L >= np.maximum(I - J, s))
+    return np.stack([I[m], J[m], L[m]], axis=1).astype(np.int32)      # C-order ravel == nested loop order
+
+
+class PeriodicPipeline(object):
+    """Device-resident pipeline for one (Ngrid) on the current CUDA device.  Holds the host-built tables
+    (twiddles, fcomb phase/window tables, shell / bin index tables) and caches per-configuration data
+    (mode counts, triangle tiles, exact triangle counts)."""
+
+    _cache = {}
+
+    @classmethod
+    def get(cls, Ngrid):
+        dev = _device()
+        key = (dev.index, int(Ngrid))
+        if key not in cls._cache:
+            cls._cache[key] = cls(int(Ngrid), dev)
+        return cls._cache[key]
+
+    def __init__(self, Ngrid, dev):
+        if Ngrid < 4 or Ngrid % 2:
+            raise ValueError('Ngrid must be even')
+        self.N, self.h, self.dev = Ngrid, Ngrid // 2, dev
+        self.L = _lib.lib()
+        N, h = self.N, self.h
+        tw = np.empty(2 * N, np.float32)
+        check(self.L.psb_twiddles_f32(N, _np_ptr(tw)), 'psb_twiddles_f32')
+        rec = np.empty(2 * (h + 1), np.float64)
+        wk = np.empty(h + 1, np.float32)
+        check(self.L.psb_fcomb_tables(N, _np_ptr(rec), _np_ptr(wk)), 'psb_fcomb_tables')
+        self.tw32 = torch.from_numpy(tw).to(dev)
+        self.rec = torch.from_numpy(rec).to(dev)
+        self.wk = torch.from_numpy(wk).to(dev)
+        self._tw64 = None
+        self.mmax = 3 * h * h
+        self._irk, self._bins, self._nk, self._tiles, self._counts = {}, {}, {}, {}, {}
+
+    # ------------------------------------------------------------------ tables
+    @property
+    def tw64(self):
+        if self._tw64 is None:
+            tw = np.empty(2 * self.N, np.float64)
+            check(self.L.psb_twiddles_f64(self.N, _np_ptr(tw)), 'psb_twiddles_f64')
+            self._tw64 = torch.from_numpy(tw).to(self.dev)
+        return self._tw64
+
+    def irk_table(self, step):
+        """irk = int(|k|/step + 0.5) as a function of m = |k|^2: the reference's float64 expression
+        (pyspectrum.py:376-378) evaluated on the host, so shell membership is bit-exact."""
+        if step not in self._irk:
+            m = np.arange(self.mmax + 1)
+            irk = (np.sqrt(m) / step + 0.5).astype(int)
+            self._irk[step] = torch.from_numpy(irk.astype(np.uint16)).to(self.dev)
+        return self._irk[step]
+
+    def pk_bin_table(self, Lbox):
+        """Pk_periodic's bin index (pyspectrum.py:696-703) as a function of m."""
+        key = ('pk', float(Lbox))
+        if key not in self._bins:
+            Nbins = self.N // 2
+            kf = 2 * np.pi / float(Lbox)
+            phys_nyq = kf * float(self.N) / 2.
+            rk = kf * np.sqrt(np.arange(self.mmax + 1))
+            irk = (Nbins * rk / phys_nyq + 0.5).astype(int)
+            self._bins[key] = torch.from_numpy(np.minimum(irk, 65535).astype(np.uint16)).to(self.dev)
+        return self._bins[key]
+
+    def rsd_bin_table(self, Nbins):
+        key = ('rsd', int(Nbins))
+        if key not in self._bins:
+            t = np.empty(self.mmax + 1, np.uint16)
+            check(self.L.psb_rsd_bin_table(self.N, int(Nbins), self.mmax, _np_ptr(t)), 'psb_rsd_bin_table')
+            self._bins[key] = torch.from_numpy(t).to(self.dev)
+        return self._bins[key]
+
+    # ------------------------------------------------------------------ K1..K3
+    def to_device(self, xyz, w=None):
+        """Positions (3xN, numpy or torch, float32/float64) and weights -> device tensors + layout flags."""
+        if isinstance(xyz, torch.Tensor):
+            pos = xyz
+            if pos.dtype not in (torch.float32, torch.float64):
+                pos = pos.double()
+            if pos.shape[0] != 3:
+                raise ValueError('xyz must be 3 x N')
+            aos = 0
+            if not pos.is_contiguous():
+                if pos.t().is_contiguous():
+                    aos = 1
+                else:
+                    pos = pos.contiguous()
+            pos = pos.to(self.dev, non_blocking=True)
+        else:
+            xyz = np.asarray(xyz)
+            if xyz.ndim != 2 or xyz.shape[0] != 3:
+                raise ValueError('xyz must be 3 x N')
+            if xyz.dtype not in (np.float32, np.float64):
+                xyz = xyz.astype(np.float64)
+            aos = 0
+            if xyz.flags.f_contiguous and not xyz.flags.c_contiguous:
+                aos = 1
+                pos = torch.from_numpy(xyz.T).to(self.dev, non_blocking=True)       # (N,3) contiguous
+            else:
+                pos = torch.from_numpy(np.ascontiguousarray(xyz)).to(self.dev, non_blocking=True)
+        wt = None
+        if w is not None:
+            if isinstance(w, torch.Tensor):
+                wt = w if w.dtype in (torch.float32, torch.float64) else w.double()
+                wt = wt.contiguous().to(self.dev, non_blocking=True)
+            else:
+                w = np.asarray(w)
+                if w.dtype not in (np.float32, np.float64):
+                    w = w.astype(np.float64)
+                wt = torch.from_numpy(np.ascontiguousarray(w)).to(self.dev, non_blocking=True)
+        return pos, aos, wt
+
+    def assign(self, pos, aos, wt, Lbox, offset=0., clip=True):
+        """K1: pyspectrum.py:931-951 + estimator.f:284-512.  Returns (mesh [N,N,N,2] float32, sumw tensor)."""
+        N = self.N
+        Np = pos.shape[0] if aos else pos.shape[1]
+        kf_ks = np.float32(float(N) / Lbox)
+        mesh = torch.empty((N, N, N, 2), dtype=torch.float32, device=self.dev)
+        wsb = self.L.psb_assign_workspace_bytes(Np, N)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=self.dev)
+        sumw = torch.empty(1, dtype=torch.float64, device=self.dev)
+        check(self.L.psb_assign_pcs_interlaced(_ptr(pos), int(pos.dtype == torch.float64), aos, _ptr(wt),
+                                               int(wt is not None and wt.dtype == torch.float64), Np, N,
+                                               float(Lbox) if clip else 0.0, kf_ks, np.float32(offset),
+                                               _ptr(mesh), 1, _ptr(ws), wsb, _ptr(sumw), _stream()),
+              'psb_assign_pcs_interlaced')
+        return mesh, sumw
+
+    def mesh_to_delta(self, mesh, sumw, periodic=1):
+        """K2+K3: pyspectrum.py:953-959.  Returns the half field as float32 [N,N,N/2+1,2] (kz,ky,kx)."""
+        N, h = self.N, self.h
+        half = torch.empty((N, N, h + 1, 2), dtype=torch.float32, device=self.dev)
+        check(self.L.psb_fft_mesh_to_delta(_ptr(mesh), _ptr(half), N, _ptr(self.tw32), _ptr(self.rec), _ptr(self.wk),
+                                           _ptr(sumw), periodic, _stream()), 'psb_fft_mesh_to_delta')
+        return half
+
+    def fft_periodic(self, xyz, w, Lbox):
+        pos, aos, wt = self.to_device(xyz, w)
+        mesh, sumw = self.assign(pos, aos, wt, Lbox)
+        half = self.mesh_to_delta(mesh, sumw)
+        return half, sumw
+
+    # ------------------------------------------------------------------ K4
+    def pk_monopole(self, half, Lbox):
+        Nbins = self.N // 2
+        out = torch.empty(3 * Nbins, dtype=torch.float64, device=self.dev)
+        kf = 2 * np.pi / float(Lbox)
+        check(self.L.psb_pk_monopole(_ptr(half), self.N, _ptr(self.pk_bin_table(Lbox)), Nbins, kf, _ptr(out), _stream()),
+              'psb_pk_monopole')
+        return out
+
+    def pk_multipoles(self, half, Lbox_int, rsd, Nmubin):
+        Nbins = self.N // 2
+        out = torch.empty((5 + 4 * Nmubin) * Nbins, dtype=torch.float64, device=self.dev)
+        trig = np.empty(4, np.float32)
+        check(self.L.psb_rsd_trig(int(rsd), _np_ptr(trig)), 'psb_rsd_trig')
+        pi = np.float32(3.141592654)
+        kf32 = np.float32(np.float32(2.) * pi) / np.float32(Lbox_int)              # estimator.f:164,169
+        check(self.L.psb_pk_multipoles(_ptr(half), self.N, _ptr(self.rsd_bin_table(Nbins)), Nbins, int(Nmubin),
+                                       kf32, _np_ptr(trig), _ptr(out), _stream()), 'psb_pk_multipoles')
+        return out, kf32
+
+    # ------------------------------------------------------------------ K5
+    def shell_mode_counts(self, step, Nmax):
+        key = (step, Nmax)
+        if key not in self._nk:
+            nk = torch.empty(Nmax + 1, dtype=torch.int64, device=self.dev)
+            check(self.L.psb_shell_mode_counts(self.N, _ptr(self.irk_table(step)), Nmax + 1, _ptr(nk), _stream()),
+                  'psb_shell_mode_counts')
+            self._nk[key] = nk.cpu().numpy()
+        return self._nk[key]
+
+    def shell_fields(self, half, step, s0, Nmax, dtype=torch.float32):
+        """K5: all shells s0..Nmax as real fields [S_alloc, N^3] + sum_x I_j^2 per shell.
+        half=None -> delta == 1 (counts).  Two shells ride on one complex transform."""
+        N = self.N
+        ncell = N * N * N
+        S = Nmax - s0 + 1
+        S_alloc = S + (S % 2)
+        f64 = dtype == torch.float64
+        fields = torch.empty((S_alloc, ncell), dtype=dtype, device=self.dev)
+        sumsq = torch.zeros(S_alloc, dtype=torch.float64, device=self.dev)
+        Rmax = int(np.floor(step * (Nmax + 0.5)))
+        W = min(2 * Rmax + 1, N)
+        cdt = torch.float64 if f64 else torch.float32
+        t1 = torch.empty(W * W * N * 2, dtype=cdt, device=self.dev)
+        t2 = torch.empty(W * N * N * 2, dtype=cdt, device=self.dev)
+        irk = self.irk_table(step)
+        fn = self.L.psb_bk_shell_pair_f64 if f64 else self.L.psb_bk_shell_pair_f32
+        tw = self.tw64 if f64 else self.tw32
+        st = _stream()
+        for s in range(0, S, 2):
+            sa = s0 + s
+            sb = sa + 1 if s + 1 < S else -1
+            R = int(np.floor(step * (max(sa, sb) + 0.5)))
+            check(fn(_ptr(half), _ptr(irk), N, sa, sb, R, _ptr(t1), _ptr(t2), _ptr(fields[s]), _ptr(fields[s + 1]),
+                     ctypes.c_void_p(sumsq.data_ptr() + 8 * s), _ptr(tw), st), 'psb_bk_shell_pair')
+        return fields, sumsq
+
+    # ------------------------------------------------------------------ K6
+    def triangle_tiles(self, Nmax, Ncut, step):
+        key = (Nmax, Ncut, step)
+        if key not in self._tiles:
+            tri = triangle_list(Nmax, Ncut, step)
+            s0 = Ncut // step
+            nt = ctypes.c_int(0)
+            tri_c = np.ascontiguousarray(tri)
+            check(self.L.psb_bk_build_tiles(_np_ptr(tri_c), len(tri_c), s0, None, ctypes.byref(nt)), 'psb_bk_build_tiles')
+            tiles = np.empty((nt.value, 68), np.int32)
+            check(self.L.psb_bk_build_tiles(_np_ptr(tri_c), len(tri_c), s0, _np_ptr(tiles), ctypes.byref(nt)), 'psb_bk_build_tiles')
+            self._tiles[key] = (tri, torch.from_numpy(tiles).to(self.dev), nt.value)
+        return self._tiles[key]
+
+    def triangle_sums(self, fields, Nmax, Ncut, step):
+        """K6: sum_x I_i I_j I_l for every triangle of the loop nest (float64 tensor, loop order)."""
+        tri, tiles, ntiles = self.triangle_tiles(Nmax, Ncut, step)
+        S = Nmax - Ncut // step + 1
+        nf = (S + 3) // 4 * 4
+        ptrs = [fields[min(f, S - 1)].data_ptr() for f in range(nf)]
+        dptr = torch.tensor(ptrs, dtype=torch.int64).to(self.dev)
+        sums = torch.zeros(len(tri), dtype=torch.float64, device=self.dev)
+        wsb = self.L.psb_bk_triangle_workspace_bytes(ntiles)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=self.dev)
+        fn = self.L.psb_bk_triangle_sums_f64 if fields.dtype == torch.float64 else self.L.psb_bk_triangle_sums_f32
+        check(fn(_ptr(dptr), nf, fields.shape[1], _ptr(tiles), ntiles, _ptr(sums), _ptr(ws), wsb, _stream()),
+              'psb_bk_triangle_sums')
+        return sums
+
+    # ------------------------------------------------------------------ counts
+    def counts(self, Nmax, Ncut, step, fft='pyfftw', silent=True):
+        """Raw triangle counts array (Nmax,Nmax,Nmax) float64 = N^3 * (#closed triangles), as the reference's
+        cache files hold (pyspectrum.py:962-1030).  Memory cache -> file in dat_dir() -> GPU float64 compute."""
+        key = (Nmax, Ncut, step)
+        if key in self._counts:
+            return self._counts[key]
+        N = self.N
+        fcnt = ''.join(['counts', '.Ngrid', str(N), '.Nmax', str(Nmax), '.Ncut', str(Ncut), '.step', str(step), '.', fft])
+        f_counts = os.path.join(dat_dir(), fcnt)
+        if os.path.isfile(f_counts):
+            counts = _read_fortran_record(f_counts, Nmax)
+        else:
+            if not silent:
+                print('--- calculating %s ---' % f_counts)
+            counts = self.compute_counts(Nmax, Ncut, step)
+            try:
+                os.makedirs(dat_dir(), exist_ok=True)
+                _write_fortran_record(f_counts, counts)
+            except OSError:
+                pass
+        self._counts[key] = counts
+        return counts
+
+    def compute_counts(self, Nmax, Ncut, step):
+        N = self.N
+        s0 = Ncut // step
+        fields, _ = self.shell_fields(None, step, s0, Nmax, dtype=torch.float64)
+        sums = self.triangle_sums(fields, Nmax, Ncut, step).cpu().numpy()
+        del fields
+        tri, _, _ = self.triangle_tiles(Nmax, Ncut, step)
+        n3 = float(N) ** 3
+        nint = np.rint(sums / n3)
+        if np.abs(sums / n3 - nint).max() > 1e-3:
+            raise RuntimeError('triangle counts did not come out as integers (max dev %g)' % np.abs(sums / n3 - nint).max())
+        counts = np.zeros((Nmax, Nmax, Nmax), dtype=np.float64)
+        counts[tri[:, 0] - 1, tri[:, 1] - 1, tri[:, 2] - 1] = nint * n3
+        return counts
+
+
+def _read_fortran_record(fname, Nmax):
+    """One Fortran sequential record of Nmax^3 float64 (scipy.io.FortranFile.read_reals, py:970-972)."""
+    raw = np.fromfile(fname, dtype=np.uint8)
+    n = int(np.frombuffer(raw[:4].tobytes(), '<i4')[0])
+    data = np.frombuffer(raw[4:4 + n].tobytes(), '<f8')
+    return data.reshape(Nmax, Nmax, Nmax).copy()
+
+
+def _write_fortran_record(fname, counts):
+    b = np.ascontiguousarray(counts, dtype='<f8').tobytes()
+    mark = np.array([len(b)], dtype='<i4').tobytes()
+    with open(fname, 'wb') as f:
+        f.write(mark + b + mark)
+
+
+# ----------------------------------------------------------------------------------------------
+# public API
+# ----------------------------------------------------------------------------------------------
+def _npart(xyz):
+    return int(xyz.shape[1])
+
+
+def _sum_w(w, N, sumw_dev):
+    """np.sum(w) of pyspectrum.py:323/679 (host value when the caller's weights live on the host)."""
+    if w is None:
+        return float(N)
+    if isinstance(w, torch.Tensor):
+        return float(sumw_dev.item())
+    return float(np.sum(w))
+
+
+def FFT_periodic(xyz, w=None, Lbox=2600., Ngrid=360, fft='pyfftw', silent=True):
+    """pyspectrum.py:909-959: returns delta(k) on the half grid, complex64, shape (Ngrid//2+1, Ngrid, Ngrid)
+    indexed [kx,ky,kz] (Fortran-contiguous view, exactly the reference's memory layout)."""
+    pipe = PeriodicPipeline.get(Ngrid)
+    half, _ = pipe.fft_periodic(xyz, w, Lbox)
+    if not silent:
+        print('position grid FFTed')
+        print('fcomb complete')
+    a = half.cpu().numpy().view(np.complex64)[..., 0]        # (kz,ky,kx) C-order
+    return a.transpose(2, 1, 0)
+
+
+def reflect_delta(delt, Ngrid=360, silent=True):
+    """pyspectrum.py:1134-1157: half field -> full Hermitian complex64 field (host utility; the GPU
+    kernels work from the half field and never materialise this)."""
+    if not silent:
+        print('reflecting the half field')
+    h = Ngrid // 2
+    idx = (-np.arange(Ngrid)) % Ngrid
+    delta = np.zeros((Ngrid, Ngrid, Ngrid), dtype=np.complex64)
+    delta[:h + 1] = delt
+    mirror = np.conj(delt[1:h])[:, idx][:, :, idx]            # value at (i,-j,-k) of rows 1..h-1
+    delta[Ngrid - 1:h:-1] = mirror
+    for p in [(h, 0, 0), (0, h, 0), (0, 0, h), (0, h, h), (h, 0, h), (h, h, 0), (h, h, h)]:
+        delta[p] = np.real(delt[p])
+    return delta
+
+
+def _counts_Bk123(Ngrid=360, Nmax=40, Ncut=3, step=3, fft='pyfftw', silent=True):
+    """pyspectrum.py:962-1030."""
+    return PeriodicPipeline.get(Ngrid).counts(Nmax, Ncut, step, fft=fft, silent=silent)
+
+
+def Pk_periodic(xyz, w=None, Lbox=2600, Ngrid=360, fft='pyfftw', silent=True):
+    """Power-spectrum monopole of a periodic box; see pyspectrum.py:644-728 for the contract."""
+    N = _npart(xyz)
+    pipe = PeriodicPipeline.get(Ngrid)
+    if not silent:
+        print('------------------')
+        print('%i positions in %i box' % (N, Lbox))
+        print('--- calculating the FFT ---')
+    half, sumw = pipe.fft_periodic(xyz, w, Lbox)
+    out = pipe.pk_monopole(half, Lbox).cpu().numpy()
+    nbar = _sum_w(w, N, sumw) / Lbox ** 3
+    kf = 2 * np.pi / float(Lbox)
+    Nbins = Ngrid // 2
+    nk, ksum, psum = out[:Nbins], out[Nbins:2 * Nbins], out[2 * Nbins:]
+    k = np.zeros(Nbins)
+    p0k = np.zeros(Nbins)
+    counts = np.zeros(Nbins)
+    ok = nk > 0
+    k[ok] = ksum[ok] / nk[ok]
+    p0k[ok] = psum[ok] / nk[ok] / kf ** 3
+    counts[ok] = nk[ok]
+    p0k *= (2. * np.pi) ** 3
+    if not silent:
+        print('--- correcting for shotnoise ---')
+    meta = {'Lbox': Lbox, 'Ngrid': Ngrid, 'N': N, 'nbar': nbar, 'kf': 2 * np.pi / Lbox}
+    return {'meta': meta, 'k': k, 'p0k': p0k - 1. / nbar, 'counts': counts, 'p0k_sn': 1. / nbar}
+
+
+def Pk_periodic_rsd(xyz, w=None, Lbox=2600, Ngrid=360, rsd=2, Nmubin=10, fft='pyfftw', code='fortran', silent=True):
+    """Power-spectrum multipoles + P(k,mu); see pyspectrum.py:460-538 for the contract."""
+    N = _npart(xyz)
+    nbar = float(N) / Lbox ** 3                      # py:510 (N, not sum w: SURVEY Q11)
+    kf = 2 * np.pi / Lbox
+    if rsd not in (0, 1, 2):
+        raise ValueError('rsd must be 0, 1 or 2')
+    pipe = PeriodicPipeline.get(Ngrid)
+    if not silent:
+        print('------------------')
+        print('%i positions in %i box' % (N, Lbox))
+        print('nbar = %f' % nbar)
+    half, _ = pipe.fft_periodic(xyz, w, Lbox)
+    Nbins = Ngrid // 2
+    raw, kf32 = pipe.pk_multipoles(half, int(Lbox), rsd, Nmubin)      # Lbox is an INTEGER dummy: estimator.f:158
+    raw = raw.cpu().numpy()
+    nk = raw[:Nbins].copy()
+    ks, p0k, p2k, p4k = [raw[(a + 1) * Nbins:(a + 2) * Nbins].copy() for a in range(4)]
+    tb = Nbins * Nmubin
+    o = 5 * Nbins
+    n_kmu, k_kmu, mu_kmu, p_kmu = [raw[o + a * tb:o + (a + 1) * tb].reshape(Nmubin, Nbins).T.copy(order='F') for a in range(4)]
+    kf3 = np.float64(np.float32(kf32 * kf32) * kf32)                 # dble(kf**3), f:249
+    ok = nk > 0
+    ks[ok] = ks[ok] / nk[ok]
+    for p in (p0k, p2k, p4k):
+        p[ok] = p[ok] / nk[ok] / kf3
+    okm = n_kmu > 0
+    k_kmu[okm] = k_kmu[okm] / n_kmu[okm]
+    mu_kmu[okm] = mu_kmu[okm] / n_kmu[okm]
+    p_kmu[okm] = p_kmu[okm] / n_kmu[okm] / kf3
+    pk_norm = (2. * np.pi) ** 3
+    p0k *= pk_norm
+    p2k *= pk_norm
+    p4k *= pk_norm
+    p_kmu *= pk_norm
+    if not silent:
+        print('--- correcting for shotnoise ---')
+    meta = {'Lbox': Lbox, 'Ngrid': Ngrid, 'N': N, 'nbar': nbar, 'kf': kf}
+    return {'meta': meta, 'k': ks, 'p0k': p0k - 1. / nbar, 'p2k': p2k, 'p4k': p4k,
+            'p_sn': np.repeat(1. / nbar, len(ks)), 'counts': nk, 'k_kmu': k_kmu, 'mu_kmu': mu_kmu,
+            'p_kmu': p_kmu - 1. / nbar, 'counts_kmu': n_kmu}
+
+
+def _bk_epilogue(Ngrid, tri, sums, sumsq, Nk, counts, step, Ncut, Nmax):
+    """pyspectrum.py:404 and 415-456 on the host (a few thousand float64 operations)."""
+    s0 = Ncut // step
+    p0k = np.zeros(Nmax)
+    for j in range(s0, Nmax + 1):
+        p0k[j - 1] = sumsq[j - s0] / Ngrid ** 3 / Nk[j]
+    i, j, l = tri[:, 0], tri[:, 1], tri[:, 2]
+    fac = np.ones(len(tri))
+    fac[(j == l) & (i == j)] = 6.
+    fac[(i == j) & (j != l)] = 2.
+    fac[(i == l) & (l != j)] = 2.
+    fac[(j == l) & (l != i)] = 2.
+    c = counts[i - 1, j - 1, l - 1]
+    pos = c > 0
+    cs = np.where(pos, c, 1.)
+    pi_, pj_, pl_ = p0k[i - 1], p0k[j - 1], p0k[l - 1]
+    b123 = np.where(pos, sums / cs, 0.)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        q123 = np.where(pos, sums / cs / (pi_ * pj_ + pj_ * pl_ + pl_ * pi_), 0.)
+    out = {}
+    out['i_k1'] = i[pos].astype(np.int64) * step       # index lists skip empty triangles, value lists do not (Q9)
+    out['i_k2'] = j[pos].astype(np.int64) * step
+    out['i_k3'] = l[pos].astype(np.int64) * step
+    out['p0k1'] = np.where(pos, pi_, 0.)
+    out['p0k2'] = np.where(pos, pj_, 0.)
+    out['p0k3'] = np.where(pos, pl_, 0.)
+    out['b123'] = b123
+    out['q123'] = q123
+    out['counts'] = np.where(pos, c / (fac * float(Ngrid ** 3)), 0.)
+    return out
+
+
+def Bk_periodic(xyz, w=None, Lbox=2600, Ngrid=360, step=3, Ncut=3, Nmax=40, fft='pyfftw', nthreads=1, silent=True):
+    """Bispectrum of a periodic box; see pyspectrum.py:285-356 for the contract."""
+    N = _npart(xyz)
+    kf = 2 * np.pi / Lbox
+    s0 = Ncut // step
+    if s0 < 1:
+        raise ValueError('Ncut//step must be >= 1 (the reference wraps p0k[-1] there, SURVEY Q9)')
+    pipe = PeriodicPipeline.get(Ngrid)
+    if not silent:
+        print('------------------')
+        print('%i positions in %i box' % (N, Lbox))
+        print('--- calculating the FFT ---')
+    half, sumw = pipe.fft_periodic(xyz, w, Lbox)
+    if not silent:
+        print('--- calculating the bispectrum ---')
+    Nk = pipe.shell_mode_counts(step, Nmax)
+    counts = pipe.counts(Nmax, Ncut, step, fft=fft, silent=silent)
+    fields, sumsq = pipe.shell_fields(half, step, s0, Nmax)
+    sums = pipe.triangle_sums(fields, Nmax, Ncut, step)
+    tri, _, _ = pipe.triangle_tiles(Nmax, Ncut, step)
+    host = torch.cat([sums, sumsq]).cpu().numpy()               # one device->host read
+    sums_h, sumsq_h = host[:len(tri)], host[len(tri):]
+    nbar = _sum_w(w, N, sumw) / Lbox ** 3
+    if not silent:
+        print('sum w_i = %f' % (nbar * Lbox ** 3))
+        print('nbar = %f' % nbar)
+    bispec = _bk_epilogue(Ngrid, tri, sums_h, sumsq_h, Nk, counts, step, Ncut, Nmax)
+    meta = {'Lbox': Lbox, 'Ngrid': Ngrid, 'step': step, 'Ncut': Ncut, 'Nmax': Nmax, 'N': N, 'nbar': nbar, 'kf': kf}
+    bispec['meta'] = meta
+    if not silent:
+        print('--- correcting for shotnoise ---')
+    bispec['p0k1'] = bispec['p0k1'] * (2 * np.pi) ** 3 / kf ** 3 - 1. / nbar
+    bispec['p0k2'] = bispec['p0k2'] * (2 * np.pi) ** 3 / kf ** 3 - 1. / nbar
+    bispec['p0k3'] = bispec['p0k3'] * (2 * np.pi) ** 3 / kf ** 3 - 1. / nbar
+    bispec['p0k_sn'] = 1. / nbar
+    b_shotnoise = (bispec['p0k1'] + bispec['p0k2'] + bispec['p0k3']) / nbar + 1. / nbar ** 2
+    bispec['b123'] = bispec['b123'] * (2 * np.pi) ** 6 / kf ** 6 - b_shotnoise
+    bispec['b123_sn'] = b_shotnoise
+    with np.errstate(divide='ignore', invalid='ignore'):
+        bispec['q123'] = bispec['b123'] / (bispec['p0k1'] * bispec['p0k2'] + bispec['p0k1'] * bispec['p0k3'] + bispec['p0k2'] * bispec['p0k3'])
+    return bispec

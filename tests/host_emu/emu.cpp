@@ -1,0 +1,70 @@
+// Host emulation harness (TEST ONLY): compiles the __host__ __device__ cores of the CUDA
+// kernels with g++ so their index math / butterflies / combine rules are checked on CPU.
+#include "../../pyspectrum_b200/csrc/psb_fft_core.cuh"
+#include <vector>
+#include <cmath>
+using namespace psb;
+
+template <typename T, int DIR>
+static int run_fft(T* data, int N, int estride)
+{
+    FftPlan p;
+    if (!make_plan(N, &p)) return -2;
+    std::vector<Cx<T>> tw(N);
+    for (int i = 0; i < N; ++i) { tw[i].x = (T)std::cos(2.0 * M_PI * i / N); tw[i].y = (T)std::sin(2.0 * M_PI * i / N); }
+    Cx<T>* s = reinterpret_cast<Cx<T>*>(data);
+    int Ns = 1;
+    for (int st = 0; st < p.nstages; ++st) {
+        const int R = p.radix[st];
+        const int M = N / R;
+        std::vector<Cx<T>> regs((size_t)M * R);
+        // phase 1: every butterfly reads; phase 2: every butterfly writes (as the kernel does around a barrier)
+        for (int j = 0; j < M; ++j) {
+            Cx<T>* v = &regs[(size_t)j * R];
+            switch (R) {
+                case 2: stage_read<2, T>(s, estride, N, j, v); break;
+                case 3: stage_read<3, T>(s, estride, N, j, v); break;
+                case 4: stage_read<4, T>(s, estride, N, j, v); break;
+                case 5: stage_read<5, T>(s, estride, N, j, v); break;
+                case 8: stage_read<8, T>(s, estride, N, j, v); break;
+                case 9: stage_read<9, T>(s, estride, N, j, v); break;
+                default: return -9;
+            }
+        }
+        for (int j = 0; j < M; ++j) {
+            Cx<T>* v = &regs[(size_t)j * R];
+            switch (R) {
+                case 2: stage_write<2, DIR, T>(s, estride, N, Ns, j, tw.data(), v); break;
+                case 3: stage_write<3, DIR, T>(s, estride, N, Ns, j, tw.data(), v); break;
+                case 4: stage_write<4, DIR, T>(s, estride, N, Ns, j, tw.data(), v); break;
+                case 5: stage_write<5, DIR, T>(s, estride, N, Ns, j, tw.data(), v); break;
+                case 8: stage_write<8, DIR, T>(s, estride, N, Ns, j, tw.data(), v); break;
+                case 9: stage_write<9, DIR, T>(s, estride, N, Ns, j, tw.data(), v); break;
+            }
+        }
+        Ns *= R;
+    }
+    return 0;
+}
+
+extern "C" int emu_fft_f32(float* data, int N, int dir, int estride) { return dir > 0 ? run_fft<float, 1>(data, N, estride) : run_fft<float, -1>(data, N, estride); }
+extern "C" int emu_fft_f64(double* data, int N, int dir, int estride) { return dir > 0 ? run_fft<double, 1>(data, N, estride) : run_fft<double, -1>(data, N, estride); }
+extern "C" int emu_plan(int N, int* radices) { FftPlan p; if (!make_plan(N, &p)) return -1; for (int i = 0; i < p.nstages; ++i) radices[i] = p.radix[i]; return p.nstages; }
+
+#include "../../pyspectrum_b200/csrc/psb_fcomb_core.cuh"
+// full: complex64 (N,N,N) Fortran order [ix + N*(iy + N*iz)] BEFORE fcomb; half: output (N/2+1,N,N) Fortran order
+extern "C" void emu_fcomb(const float* full_, float* half_, int N, float sumw, int periodic)
+{
+    const Cx<float>* F = reinterpret_cast<const Cx<float>*>(full_);
+    Cx<float>* H = reinterpret_cast<Cx<float>*>(half_);
+    const int h = N / 2;
+    std::vector<Cx<double>> rec(h + 1);
+    std::vector<float> Wk(h + 1);
+    fcomb_build_tables(N, rec.data(), Wk.data());
+    const float cf = periodic ? 1.f / (864.f * sumw) : 1.f / 864.f;
+    for (int iz = 0; iz < N; ++iz) for (int iy = 0; iy < N; ++iy) for (int ix = 0; ix <= h; ++ix) {
+        Cx<float> Fk = F[ix + (size_t)N * (iy + (size_t)N * iz)];
+        Cx<float> Fm = F[kneg(ix, N) + (size_t)N * (kneg(iy, N) + (size_t)N * kneg(iz, N))];
+        H[ix + (size_t)(h + 1) * (iy + (size_t)N * iz)] = fcomb_value(N, ix, iy, iz, Fk, Fm, rec.data(), Wk.data(), cf);
+    }
+}

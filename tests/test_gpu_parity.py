@@ -1,0 +1,272 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI of
+libpsb200.so -- either the f2py-shaped psb_host_* drop-ins (pyspectrum_b200.estimator) or the resident
+pipeline behind the reference's Python API (pyspectrum_b200.pyspectrum) -- and is compared with
+  * the CPU oracle (oracle/) on the same seeded inputs,
+  * golden outputs of the unmodified reference Python layer (tests/golden/small_*.npz, box360.npz),
+  * the reference's shipped triangle-count caches (tests/golden/counts_N360_*.npz).
+Tolerances: integer outputs (mode counts, triangle counts, i_k*) bit-exact; k 1e-12 (monopole) / 1e-6
+(rsd, float32 kf*rk); power spectra and bispectra rtol 1e-5 on the pre-shot-noise value.
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+@pytest.fixture(scope='module')
+def mods():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from pyspectrum_b200 import pyspectrum as pySpec, estimator
+    from oracle import pyspec_oracle as O
+    return pySpec, estimator, O
+
+
+def _g(golden_dir, name):
+    return dict(np.load(os.path.join(golden_dir, name)))
+
+
+def _cat(seed, Np, L):
+    rng = np.random.default_rng(seed)
+    npar = max(Np // 40, 1)
+    par = rng.uniform(0, L, (3, npar))
+    kids = par[:, rng.integers(0, npar, Np // 2)] + rng.normal(0, 0.03 * L, (3, Np // 2))
+    return np.ascontiguousarray(np.concatenate([kids, rng.uniform(0, L, (3, Np - Np // 2))], axis=1) % L)
+
+
+# ------------------------------------------------------------------------------ native drop-ins
+@pytest.mark.parametrize('N', [24, 32, 36, 40, 48, 64, 100, 128])       # 40, 100: runtime-plan fallback
+def test_ffting_matches_numpy(mods, N):
+    _, est, _ = mods
+    rng = np.random.default_rng(N)
+    x = (rng.normal(size=(N, N, N)) + 1j * rng.normal(size=(N, N, N))).astype(np.complex64)
+    d = np.asfortranarray(x)
+    est.ffting(d)
+    ref = np.fft.ifftn(x.astype(np.complex128)) * N ** 3          # FFTW_BACKWARD, unnormalised
+    assert np.abs(d - ref).max() / np.abs(ref).max() < 2e-6
+
+
+@pytest.mark.parametrize('N,Np', [(24, 1), (24, 3000), (36, 20000), (64, 200000)])
+def test_assign_quad_matches_oracle(mods, N, Np):
+    _, est, O = mods
+    rng = np.random.default_rng(Np)
+    L = 100.
+    r = np.asfortranarray(rng.uniform(0, L * (1 - 1e-6), (3, Np)).astype(np.float32))
+    r[:, 0] = [0., L * (1 - 1e-6), 0.5 * L]                       # faces: exercises the wrap of the stencil
+    w = rng.uniform(0.5, 2., Np).astype(np.float32)
+    kf_ks = np.float32(N / L)
+    a = np.zeros((2 * N, N, N), np.float32, order='F')
+    b = np.zeros((2 * N, N, N), np.float32, order='F')
+    est.assign_quad(r, w, a, kf_ks, 0, 0, 0, 0, 0)
+    O.assign_quad(r, w, b, kf_ks, 0, 0, 0, 0, 0)
+    assert abs(a[::2].sum(dtype=np.float64) / w.sum(dtype=np.float64) - 216.) < 1e-3
+    assert np.abs(a - b).max() <= 2e-6 * np.abs(b).max()            # summation order differs, nothing else
+    # intent(inout): a second call accumulates
+    est.assign_quad(r, w, a, kf_ks, 0, 0, 0, 0, 0)
+    assert np.abs(a - 2 * b).max() <= 4e-6 * np.abs(b).max()
+
+
+@pytest.mark.parametrize('N', [12, 24, 36])
+@pytest.mark.parametrize('periodic', [True, False])
+def test_fcomb_matches_oracle(mods, N, periodic):
+    _, est, O = mods
+    rng = np.random.default_rng(N)
+    F = np.asfortranarray((rng.normal(size=(N, N, N)) + 1j * rng.normal(size=(N, N, N))).astype(np.complex64))
+    a, b = F.copy(order='F'), F.copy(order='F')
+    if periodic:
+        est.fcomb_periodic(a, 321.5)
+        O.fcomb_periodic(b, 321.5)
+    else:
+        est.fcomb_survey(a)
+        O.fcomb_survey(b)
+    assert np.abs(a - b).max() <= 3e-7 * np.abs(b).max()            # same closed form; FMA contraction only
+
+
+@pytest.mark.parametrize('rsd', [0, 1, 2])
+@pytest.mark.parametrize('N,nmu', [(24, 5), (36, 10), (64, 120)])
+def test_pk_pbox_rsd_matches_oracle(mods, rsd, N, nmu):
+    _, est, O = mods
+    rng = np.random.default_rng(7 * N + rsd)
+    d = np.asfortranarray((rng.normal(size=(N // 2 + 1, N, N)) + 1j * rng.normal(size=(N // 2 + 1, N, N))).astype(np.complex64))
+    got = est.pk_pbox_rsd(d, rsd, 542, N // 2, nmu)
+    ref = O.pk_pbox_rsd(d, rsd, 542, N // 2, nmu)
+    names = ['k', 'p0', 'p2', 'p4', 'nk', 'km', 'mk', 'pkm', 'nkm']
+    for n, a, b in zip(names, got, ref):
+        if n in ('nk', 'nkm'):
+            assert np.array_equal(a, b), n                         # mode counts and (k,mu) counts: bit exact
+        else:
+            np.testing.assert_allclose(a, b, rtol=1e-6, atol=1e-6 * np.abs(b).max(), err_msg=n)
+
+
+def test_bk_counts_matches_bruteforce_definition(mods):
+    _, est, O = mods
+    N, nmax = 24, 3
+    c = np.zeros((nmax, nmax, nmax), np.float64, order='F')
+    est.bk_counts(c, N, 3., 3)
+    cb = O.counts_bruteforce(N, nmax, 3, 3)                         # indexed [i-1,j-1,l-1] with i>=j>=l
+    for (i, j, l) in O.triangle_list(nmax, 3, 3):
+        assert c[l - 1, j - 1, i - 1] == cb[i - 1, j - 1, l - 1] * N ** 3     # Fortran stores coun(i<=j<=l)
+
+
+# ------------------------------------------------------------------------------ Python API vs goldens
+@pytest.mark.parametrize('tag', ['A', 'B', 'C'])
+def test_api_matches_reference_goldens(mods, golden_dir, tag):
+    pySpec, _, _ = mods
+    g = _g(golden_dir, 'small_%s.npz' % tag)
+    N, L, w = int(g['Ngrid']), float(g['Lbox']), g.get('w')
+    d = pySpec.FFT_periodic(g['xyz'], w=w, Lbox=L, Ngrid=N)
+    assert d.shape == g['delta_half'].shape and d.dtype == np.complex64
+    assert np.abs(d - g['delta_half']).max() <= 3e-6 * np.abs(g['delta_half']).max()
+    pk = pySpec.Pk_periodic(g['xyz'], w=w, Lbox=L, Ngrid=N)
+    assert np.array_equal(pk['counts'], g['pk_counts'])
+    np.testing.assert_allclose(pk['k'], g['pk_k'], rtol=1e-12)
+    np.testing.assert_allclose(pk['p0k'] + pk['p0k_sn'], g['pk_p0k'] + g['pk_p0k_sn'], rtol=RTOL)
+    assert pk['p0k_sn'] == g['pk_p0k_sn']
+    for rsd in (0, 1, 2):
+        for nmu in (5, 10):
+            pr = pySpec.Pk_periodic_rsd(g['xyz'], w=w, Lbox=L, Ngrid=N, rsd=rsd, Nmubin=nmu)
+            pre = 'rsd%d_mu%d_' % (rsd, nmu)
+            assert np.array_equal(pr['counts'], g[pre + 'counts'])
+            assert np.array_equal(pr['counts_kmu'], g[pre + 'counts_kmu'])
+            np.testing.assert_allclose(pr['k'], g[pre + 'k'], rtol=1e-6)
+            sn = pr['p_sn'][0]
+            np.testing.assert_allclose(pr['p0k'] + sn, g[pre + 'p0k'] + sn, rtol=RTOL)
+            scale = np.abs(g[pre + 'p0k'] + sn)
+            assert np.all(np.abs(pr['p2k'] - g[pre + 'p2k']) <= 5 * RTOL * scale)
+            assert np.all(np.abs(pr['p4k'] - g[pre + 'p4k']) <= 9 * RTOL * scale)
+            m = g[pre + 'counts_kmu'] > 0
+            np.testing.assert_allclose((pr['p_kmu'] + sn)[m], (g[pre + 'p_kmu'] + sn)[m], rtol=RTOL)
+            np.testing.assert_allclose(pr['mu_kmu'], g[pre + 'mu_kmu'], rtol=1e-12, atol=1e-15)
+    for (step, Ncut, Nmax) in [(3, 3, 4), (2, 3, 6), (1, 1, 8)]:
+        pre = 'bk_s%d_c%d_m%d_' % (step, Ncut, Nmax)
+        if pre + 'b123' not in g:
+            continue
+        raw = pySpec._counts_Bk123(Ngrid=N, Nmax=Nmax, Ncut=Ncut, step=step)
+        assert np.array_equal(np.rint(raw / N ** 3).astype(np.int64), g[pre + 'rawcounts'])       # exact integers
+        bk = pySpec.Bk_periodic(g['xyz'], w=w, Lbox=L, Ngrid=N, step=step, Ncut=Ncut, Nmax=Nmax)
+        for key in ['i_k1', 'i_k2', 'i_k3']:
+            assert np.array_equal(bk[key], g[pre + key])
+        np.testing.assert_allclose(bk['counts'], g[pre + 'counts'], rtol=1e-13)
+        sn = bk['p0k_sn']
+        np.testing.assert_allclose(bk['p0k1'] + sn, g[pre + 'p0k1'] + sn, rtol=RTOL)
+        scale = np.abs(g[pre + 'b123'] + g[pre + 'b123_sn'])
+        assert np.all(np.abs(bk['b123'] - g[pre + 'b123']) <= RTOL * scale + 1e-7 * scale.max())
+
+
+def test_counts_match_shipped_reference_cache(mods, golden_dir):
+    """All 6350 entries of dat/counts.Ngrid360.Nmax40.Ncut3.step3.pyfftw as exact integers."""
+    pySpec, _, _ = mods
+    g = np.load(os.path.join(golden_dir, 'counts_N360_Nmax40_Ncut3_step3.npz'))
+    raw = pySpec.PeriodicPipeline.get(360).compute_counts(40, 3, 3)
+    ci = np.rint(raw / 360 ** 3).astype(np.int64)
+    ijl = g['ijl'].astype(int)
+    assert np.count_nonzero(ci) == len(g['n']) == 6350
+    assert np.array_equal(ci[ijl[:, 0] - 1, ijl[:, 1] - 1, ijl[:, 2] - 1], g['n'])
+
+
+def test_box360_matches_reference(mods, golden_dir):
+    """The reference's own fixture (dat/test_box.hdf5) at its default configuration, Ngrid=360."""
+    pySpec, _, _ = mods
+    g = _g(golden_dir, 'box360.npz')
+    xyz = g['xyz']
+    pk = pySpec.Pk_periodic(xyz, Lbox=2600., Ngrid=360)
+    assert np.array_equal(pk['counts'], g['pk_counts'])
+    np.testing.assert_allclose(pk['k'], g['pk_k'], rtol=1e-12)
+    np.testing.assert_allclose(pk['p0k'] + pk['p0k_sn'], g['pk_p0k'] + g['pk_p0k_sn'], rtol=RTOL)
+    pr = pySpec.Pk_periodic_rsd(xyz, Lbox=2600., Ngrid=360)
+    assert np.array_equal(pr['counts'], g['rsd2_mu10_counts'])
+    assert np.array_equal(pr['counts_kmu'], g['rsd2_mu10_counts_kmu'])
+    sn = pr['p_sn'][0]
+    np.testing.assert_allclose(pr['p0k'] + sn, g['rsd2_mu10_p0k'] + sn, rtol=RTOL)
+    bk = pySpec.Bk_periodic(xyz, Lbox=2600., Ngrid=360, step=3, Ncut=3, Nmax=40)
+    assert len(bk['b123']) == 6350
+    for key in ['i_k1', 'i_k2', 'i_k3']:
+        assert np.array_equal(bk[key], g['bk_' + key])
+    np.testing.assert_allclose(bk['counts'], g['bk_counts'], rtol=1e-13)
+    np.testing.assert_allclose(bk['p0k1'] + bk['p0k_sn'], g['bk_p0k1'] + bk['p0k_sn'], rtol=RTOL)
+    scale = np.abs(g['bk_b123'] + g['bk_b123_sn'])
+    assert np.all(np.abs(bk['b123'] - g['bk_b123']) <= RTOL * scale)
+    q = np.abs(bk['q123'] - g['bk_q123'])
+    assert np.median(q / np.abs(g['bk_q123'])) < 1e-3
+
+
+# ------------------------------------------------------------------------------ API vs oracle, seeded
+@pytest.mark.parametrize('N,Np,weighted', [(48, 30000, False), (64, 100000, True)])
+def test_api_matches_oracle_seeded(mods, N, Np, weighted):
+    pySpec, _, O = mods
+    L = 500.
+    xyz = _cat(N, Np, L)
+    w = np.random.default_rng(1).uniform(0.5, 2., Np) if weighted else None
+    pk, rk = pySpec.Pk_periodic(xyz, w=w, Lbox=L, Ngrid=N), O.Pk_periodic(xyz, w=w, Lbox=L, Ngrid=N)
+    assert np.array_equal(pk['counts'], rk['counts'])
+    np.testing.assert_allclose(pk['p0k'] + pk['p0k_sn'], rk['p0k'] + rk['p0k_sn'], rtol=RTOL)
+    bk = pySpec.Bk_periodic(xyz, w=w, Lbox=L, Ngrid=N, step=2, Ncut=3, Nmax=10)
+    rb = O.Bk_periodic(xyz, w=w, Lbox=L, Ngrid=N, step=2, Ncut=3, Nmax=10)
+    assert np.array_equal(bk['i_k1'], rb['i_k1']) and np.array_equal(bk['i_k2'], rb['i_k2'])
+    np.testing.assert_allclose(bk['counts'], rb['counts'], rtol=1e-12)
+    scale = np.abs(rb['b123'] + rb['b123_sn'])
+    assert np.all(np.abs(bk['b123'] - rb['b123']) <= RTOL * scale + 1e-7 * scale.max())
+
+
+def test_edge_cases(mods):
+    pySpec, _, O = mods
+    N, L = 24, 100.
+    # single particle, and particles outside the box (clipped, not wrapped: py:938-941)
+    x1 = np.array([[13.3], [47.7], [88.1]])
+    d = pySpec.FFT_periodic(x1, Lbox=L, Ngrid=N)
+    r = np.ascontiguousarray(O.FFT_periodic(x1, None, L, N))
+    assert abs(d[0, 0, 0] - 1.) < 1e-6 and np.abs(d - r).max() < 5e-6
+    out = np.array([[-5., 120., 50.], [0., 99.99999, 101.], [50., -1., 100.]])
+    d = pySpec.FFT_periodic(out, Lbox=L, Ngrid=N)
+    r = np.ascontiguousarray(O.FFT_periodic(out, None, L, N))
+    assert np.abs(d - r).max() < 5e-6
+    # float32 positions, Fortran-ordered input, torch CUDA input: same answer
+    import torch
+    xyz = _cat(3, 5000, L)
+    a = pySpec.Pk_periodic(xyz, Lbox=L, Ngrid=N)['p0k']
+    b = pySpec.Pk_periodic(np.asfortranarray(xyz), Lbox=L, Ngrid=N)['p0k']
+    c = pySpec.Pk_periodic(torch.from_numpy(xyz).cuda(), Lbox=L, Ngrid=N)['p0k']
+    np.testing.assert_allclose(a, b, rtol=1e-6)
+    np.testing.assert_allclose(a, c, rtol=1e-6)
+    with pytest.raises(Exception):
+        pySpec.Pk_periodic(xyz, Lbox=L, Ngrid=23)               # odd grid
+
+
+# ------------------------------------------------------------------------------ full-size properties
+def test_full_size_properties_c2(mods):
+    """BASELINE config 2 size (Ngrid=360, step=3, Ncut=3, Nmax=40, 1e7 particles): size-independent checks.
+    (a) sum_x I_j^2 / N^3 equals sum_{k in shell j} |delta|^2 (Parseval), through an independent torch path;
+    (b) rescaling all weights leaves every output unchanged; (c) the B(k1,k2,k3) triangle count is 6350."""
+    import torch
+    pySpec, _, _ = mods
+    N, L, Np = 360, 2600., 10 ** 7
+    rng = np.random.default_rng(2)
+    xyz = rng.uniform(0, L, (3, Np))
+    xyz[:, :Np // 4] = (xyz[:, :Np // 4] * 0.1 + 900.) % L
+    pipe = pySpec.PeriodicPipeline.get(N)
+    half, sumw = pipe.fft_periodic(xyz, None, L)
+    assert abs(float(sumw.item()) - Np) < 1e-3
+    fields, sumsq = pipe.shell_fields(half, 3, 1, 40)
+    hc = torch.view_as_complex(half)                               # [kz,ky,kx]
+    kk = torch.arange(N, device=hc.device)
+    kk = torch.where(kk <= N // 2, kk, kk - N)
+    m = (kk[:, None, None] ** 2 + kk[None, :, None] ** 2 + (kk[None, None, :N // 2 + 1]) ** 2)
+    irk = pipe.irk_table(3).long()[m]
+    wgt = torch.full((N // 2 + 1,), 2.0, device=hc.device, dtype=torch.float64)
+    wgt[0] = 1.0
+    wgt[N // 2] = 1.0
+    p = (hc.real.double() ** 2 + hc.imag.double() ** 2) * wgt[None, None, :]
+    for j in (1, 7, 20, 40):
+        direct = p[irk == j].sum().item()
+        assert abs(sumsq[j - 1].item() / N ** 3 - direct) <= 2e-5 * direct
+    bk1 = pySpec.Bk_periodic(xyz, Lbox=L, Ngrid=N)
+    bk2 = pySpec.Bk_periodic(xyz, w=np.full(Np, 3.0), Lbox=L, Ngrid=N)
+    assert len(bk1['b123']) == 6350
+    np.testing.assert_allclose(bk1['p0k1'] + bk1['p0k_sn'], bk2['p0k1'] + bk2['p0k_sn'], rtol=1e-5)
+    scale = np.abs(bk1['b123'] + bk1['b123_sn'])
+    assert np.all(np.abs((bk1['b123'] + bk1['b123_sn']) - (bk2['b123'] + bk2['b123_sn'])) <= 1e-5 * scale)
