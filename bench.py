@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: Bk_periodic seconds per catalogue on BASELINE config 2
+(~1e7-particle lognormal catalogue, Lbox=2600, Ngrid=360, step=3, Ncut=3, Nmax=40; 6350 triangles).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+b200 arm      one "step" = one full pass of the hot path over one catalogue:
+              PCS-interlaced assignment -> 3-D FFT + fcomb -> 40 shell fields -> 6350 triangle sums -> results.
+              `value`  : device-timed (CUDA events), catalogue already resident in HBM;
+              `e2e`    : the public API call pyspectrum_b200.pyspectrum.Bk_periodic on a pinned HOST catalogue,
+                         host->device copy, device->host read of the sums and the numpy epilogue inside the timer.
+              N > 1    : one process per GPU (torchrun), every rank works on its own catalogue, no data-path
+                         collective (catalogues are independent) -> weak scaling; time = max over ranks.
+reference arm the CPU oracle (oracle/: C restatement of estimator.f + pocketfft + the reference's Python
+              algorithm) on the host cores, every step a bounded sample of the same workload, extrapolated
+              linearly per shell / per triangle (the full reference run takes ~15 min and ~17 GB).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = dict(Lbox=2600., Ngrid=360, step=3, Ncut=3, Nmax=40, Np_target=10 ** 7)
+METRIC = 'Bk_periodic seconds per catalogue (Ngrid=360, step=3, Ncut=3, Nmax=40, ~1e7 particles)'
+
+
+# --------------------------------------------------------------------------------------------
+# synthetic catalogue: lognormal field + Poisson sampling
+# --------------------------------------------------------------------------------------------
+def lognormal_catalogue_torch(seed, dev, Np_target=10 ** 7, Lbox=2600., Ng=360):
+    """Gaussian field with P(k)=2e4 (k/0.02)/(1+(k/0.02)^2.6) on Ng^3 -> delta_LN -> Poisson sample -> jitter.
+    torch (cuFFT) is used for DATA GENERATION only; it is outside every timed region."""
+    import torch
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    kf = 2 * np.pi / Lbox
+    k1 = torch.fft.fftfreq(Ng, d=1. / Ng, device=dev) * kf
+    kz = torch.fft.rfftfreq(Ng, d=1. / Ng, device=dev) * kf
+    kk = torch.sqrt(k1[:, None, None] ** 2 + k1[None, :, None] ** 2 + kz[None, None, :] ** 2)
+    pk = 2e4 * (kk / 0.02) / (1 + (kk / 0.02) ** 2.6)
+    pk[0, 0, 0] = 0.
+    white = torch.randn((Ng, Ng, Ng), generator=g, device=dev, dtype=torch.float32)
+    wk = torch.fft.rfftn(white)
+    dk = wk * torch.sqrt(pk / Lbox ** 3 * Ng ** 3)          # <|d_k|^2> = P V / (cell volume)^2 ... normalised below
+    dg = torch.fft.irfftn(dk, s=(Ng, Ng, Ng))
+    del white, wk, dk, kk, pk
+    sig2 = dg.var()
+    dln = torch.exp(dg - sig2 / 2)                          # 1 + delta_LN
+    lam = dln * (Np_target / float(Ng ** 3))
+    n = torch.poisson(lam, generator=g).long()
+    idx = torch.repeat_interleave(torch.arange(Ng ** 3, device=dev), n.flatten())
+    Np = idx.numel()
+    cz = idx % Ng
+    cy = (idx // Ng) % Ng
+    cx = idx // (Ng * Ng)
+    jit = torch.rand((3, Np), generator=g, device=dev, dtype=torch.float64)
+    cell = Lbox / Ng
+    xyz = torch.stack([cx, cy, cz]).double()
+    xyz = (xyz + jit) * cell
+    return xyz.contiguous()                                 # (3, Np) float64 on device
+
+
+def lognormal_catalogue_numpy(seed, Np_target, Lbox=2600., Ng=180):
+    """Host version for the reference arm (smaller generating grid: the catalogue only has to be clustered)."""
+    import scipy.fft as sfft
+    rng = np.random.default_rng(seed)
+    kf = 2 * np.pi / Lbox
+    k1 = np.fft.fftfreq(Ng, d=1. / Ng) * kf
+    kz = np.fft.rfftfreq(Ng, d=1. / Ng) * kf
+    kk = np.sqrt(k1[:, None, None] ** 2 + k1[None, :, None] ** 2 + kz[None, None, :] ** 2)
+    pk = 2e4 * (kk / 0.02) / (1 + (kk / 0.02) ** 2.6)
+    pk[0, 0, 0] = 0.
+    wk = sfft.rfftn(rng.standard_normal((Ng, Ng, Ng)).astype(np.float32), workers=-1)
+    dg = sfft.irfftn(wk * np.sqrt(pk / Lbox ** 3 * Ng ** 3), s=(Ng, Ng, Ng), workers=-1)
+    dln = np.exp(dg - dg.var() / 2)
+    n = rng.poisson(dln * (Np_target / float(Ng ** 3)))
+    idx = np.repeat(np.arange(Ng ** 3), n.ravel())
+    cell = Lbox / Ng
+    xyz = np.stack([idx // (Ng * Ng), (idx // Ng) % Ng, idx % Ng]).astype(np.float64)
+    return np.ascontiguousarray((xyz + rng.random((3, idx.size))) * cell)
+
+
+# --------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for l in self.lines:
+            f = [x.strip() for x in l.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(nm)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': float(max(mx)) if mx else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------
+# b200 arm
+# --------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    from pyspectrum_b200 import pyspectrum as pySpec
+
+    L, N, step, Ncut, Nmax = CFG['Lbox'], CFG['Ngrid'], CFG['step'], CFG['Ncut'], CFG['Nmax']
+    s0 = Ncut // step
+    xyz_dev = lognormal_catalogue_torch(2 + rank, dev, CFG['Np_target'], L, N)
+    Np = xyz_dev.shape[1]
+    xyz_host = torch.empty((3, Np), dtype=torch.float64, pin_memory=True)
+    xyz_host.copy_(xyz_dev)
+    torch.cuda.synchronize()
+    pipe = pySpec.PeriodicPipeline.get(N)
+    pipe.counts(Nmax, Ncut, step)          # exact triangle counts: once per configuration, cached
+    Nk = pipe.shell_mode_counts(step, Nmax)
+    tri, _, ntiles = pipe.triangle_tiles(Nmax, Ncut, step)
+    S = Nmax - s0 + 1
+
+    engine = args.engine
+
+    def step_device():
+        mesh, sumw = pipe.assign(xyz_dev, 0, None, L)
+        half = pipe.mesh_to_delta(mesh, sumw)
+        fields, sumsq, scales, maxabs = pipe.shell_fields(half, step, s0, Nmax, scaled=True)
+        sums = pipe.triangle_sums(fields, Nmax, Ncut, step, engine=engine)
+        return torch.cat([sums, sumsq, scales.double()]).to('cpu', non_blocking=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    # per-stage device times (CUDA events on the launching stream), same timed loop
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for it in range(args.steps):
+        e = ev[it]
+        e[0].record()
+        mesh, sumw = pipe.assign(xyz_dev, 0, None, L)
+        e[1].record()
+        half = pipe.mesh_to_delta(mesh, sumw)
+        e[2].record()
+        fields, sumsq, scales, maxabs = pipe.shell_fields(half, step, s0, Nmax, scaled=True)
+        e[3].record()
+        sums = pipe.triangle_sums(fields, Nmax, Ncut, step, engine=engine)
+        e[4].record()
+        res = torch.cat([sums, sumsq, scales.double()]).to('cpu')
+        del mesh, half, fields
+    t_end.record()
+    barrier()
+    dev_ms = t_start.elapsed_time(t_end)
+    stage_ms = np.array([[e[i].elapsed_time(e[i + 1]) for i in range(4)] for e in ev]).mean(axis=0)
+
+    # end to end through the public API, host catalogue in pinned memory
+    for _ in range(max(1, args.warmup // 2)):
+        pySpec.Bk_periodic(xyz_host, Lbox=L, Ngrid=N, step=step, Ncut=Ncut, Nmax=Nmax)
+    barrier()
+    t0 = time.perf_counter()
+    for it in range(args.steps):
+        out = pySpec.Bk_periodic(xyz_host, Lbox=L, Ngrid=N, step=step, Ncut=Ncut, Nmax=Nmax)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    ck = clocks.stop()
+    assert len(out['b123']) == len(tri) == 6350 and np.all(np.isfinite(out['b123']))
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    ncat = args.steps * world
+    if rank == 0:
+        ncell = N ** 3
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+        peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else 'fallback 6.65 TB/s'
+        # dominant kernel: K6 triangle contraction (k_tri).  Algorithmic work: bytes 4*Nshell*N^3,
+        # flops (Npair + 2*Ntri)*N^3
+        tri_ms = float(stage_ms[3])
+        npair = S * (S + 1) // 2
+        alg_bytes = 4.0 * S * ncell
+        alg_flops = (npair + 2.0 * len(tri)) * ncell
+        ach_gbs = alg_bytes / (tri_ms * 1e-3) / 1e9
+        sm_clk = ck.get('sm_mhz') or 1965.0
+        fma_peak = 148 * 128 * 2 * sm_clk * 1e6 / 1e12
+        tf_peak = float(peaks.get('bf16_tflops', 1590.0))
+        ach_tf = alg_flops / (tri_ms * 1e-3) / 1e12
+        if engine in ('auto', 'tc'):
+            roof = {'kernel': 'k_tri_tc (K6 triangle sums: tcgen05 kind::f16, 3-term fp16 split, TMEM accumulators)',
+                    'bound': 'tensor', 'achieved': ach_tf, 'peak': tf_peak, 'unit': 'TFLOP/s', 'frac': ach_tf / tf_peak,
+                    'traffic': None, 'peak_source': peak_src.replace('hbm_gbs', 'bf16_tflops (fp16 = bf16 rate)'),
+                    'algorithmic_flops': alg_flops, 'algorithmic_bytes': alg_bytes, 'achieved_hbm_gbs': ach_gbs,
+                    'note': 'algorithmic flops = (Npair + 2 Ntri) N^3 (SURVEY 8d); the kernel issues 3 split MMAs on a '
+                            'dense 512 x 48 tile per 16 cells = 9.4x the algorithmic flops, and is co-limited by the CUDA-core '
+                            'formation of the fp16 pair-product operand'}
+        else:
+            roof = {'kernel': 'k_tri (K6 triangle sums, FFMA path)', 'bound': 'hbm', 'achieved': ach_gbs, 'peak': hbm_peak,
+                    'unit': 'GB/s', 'frac': ach_gbs / hbm_peak, 'traffic': None, 'peak_source': peak_src,
+                    'note': 'FMA-pipe bound (84 flop/B): see fma_* keys', 'fma_achieved_tflops': ach_tf,
+                    'fma_peak_tflops': fma_peak, 'fma_frac': ach_tf / fma_peak}
+        cpu = None if os.environ.get('PSB_BENCH_NO_CPU') else cpu_baseline_sample(threads=1)
+        line = {
+            'metric': METRIC, 'value': dev_ms * 1e-3 / ncat, 'unit': 's/catalog', 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dev_ms / args.steps,
+            'higher_is_better': False, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic lognormal catalogue (seeded, generated on device), %d particles per catalogue' % Np,
+            'config': {'workload': 'BASELINE configs[1]: Bk_periodic, Lbox=2600, Ngrid=360, step=3, Ncut=3, Nmax=40',
+                       'particles': Np, 'triangles': int(len(tri)), 'shells': S,
+                       'parallelism': 'one catalogue per GPU (independent catalogues, no data-path collective)',
+                       'l2': 'inputs larger than L2 (8 GB of shell fields, 240 MB of positions vs 126 MB): no flush needed',
+                       'counts': 'exact triangle counts cached per configuration (computed once in float64 before timing)'},
+            'e2e': {'value': e2e_ms * 1e-3 / ncat, 'unit': 's/catalog', 'h2d_bytes_per_step': int(3 * Np * 8),
+                    'd2h_bytes_per_step': int(8 * (len(tri) + S + (S % 2)))},
+            'gpu_launches': int(args.steps * (4 + 3 + 2 + 3 * ((S + 1) // 2) + 2)),
+            'stages_ms': {'assign': float(stage_ms[0]), 'fft_fcomb': float(stage_ms[1]), 'shell_fields': float(stage_ms[2]),
+                          'triangles': tri_ms},
+            'assign_mpart_per_s': Np / (float(stage_ms[0]) * 1e-3) / 1e6,
+            'roofline': roof,
+            'roofline_stages': {
+                'assign': {'bound': 'hbm', 'alg_bytes': 16.0 * Np + 8.0 * ncell,
+                           'achieved_gbs': (16.0 * Np + 8.0 * ncell) / (float(stage_ms[0]) * 1e-3) / 1e9},
+                'fft_fcomb': {'bound': 'hbm', 'alg_bytes': 44.0 * ncell, 'achieved_gbs': 44.0 * ncell / (float(stage_ms[1]) * 1e-3) / 1e9},
+                'shell_fields': {'bound': 'hbm', 'alg_bytes': 20.0 * ncell * S, 'achieved_gbs': 20.0 * ncell * S / (float(stage_ms[2]) * 1e-3) / 1e9}},
+            'cpu_baseline': cpu, 'clocks': ck,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------
+# CPU oracle, bounded sample (shared by the b200 arm's cpu_baseline and by --impl reference)
+# --------------------------------------------------------------------------------------------
+_CPU_CAT = {}
+
+
+def cpu_baseline_sample(threads=1, nshell_sample=4, ntri_sample=24, np_sample=2 * 10 ** 6):
+    """Time the oracle on a bounded sample of config C2 and extrapolate linearly:
+       assign on np_sample particles (scaled to 1e7), one 360^3 FFT + fcomb + reflect,
+       nshell_sample of the 40 shell FFTs, ntri_sample of the 6350 triangle sums."""
+    from oracle import pyspec_oracle as O
+    L, N, step, Ncut, Nmax = CFG['Lbox'], CFG['Ngrid'], CFG['step'], CFG['Ncut'], CFG['Nmax']
+    key = np_sample
+    if key not in _CPU_CAT:
+        _CPU_CAT[key] = lognormal_catalogue_numpy(2, np_sample, L)
+    xyz = _CPU_CAT[key]
+    tm = {}
+    t0 = time.perf_counter()
+    delta = O.FFT_periodic(xyz, None, L, N, workers=threads, timings=tm)
+    dfull = O.reflect_delta(delta, N)
+    t_front = time.perf_counter() - t0
+    shells = [5, 15, 25, 40][:nshell_sample]
+    tris = [(i, j, l) for i in shells for j in shells for l in shells if i >= j >= l and l >= max(i - j, 1)][:ntri_sample]
+    tm2 = {}
+    O._Bk_periodic(dfull, Nmax=Nmax, Ncut=Ncut, step=step, workers=threads, counts=np.ones((Nmax,) * 3),
+                   triangles=np.array(tris), timings=tm2, pool_threads=threads)
+    nsh = len(set(np.array(tris).ravel().tolist()))
+    t_assign = tm['assign'] * (CFG['Np_target'] / float(xyz.shape[1]))
+    t_other = t_front - tm['assign']
+    S = Nmax - Ncut // step + 1
+    t_shell = tm2['shells'] / nsh
+    t_tri = tm2['triangles'] / len(tris)
+    total = t_assign + t_other + t_shell * S + t_tri * 6350
+    return {'value': total, 'unit': 's/catalog', 'cores': threads, 'kind': 'port',
+            'sample': 'oracle (C restatement of estimator.f + pocketfft): assign on %d particles (x%.1f), 1 FFT+fcomb+reflect, '
+                      '%d of %d shell FFTs, %d of 6350 triangle sums; linear extrapolation' % (xyz.shape[1], CFG['Np_target'] / float(xyz.shape[1]), nsh, S, len(tris)),
+            'parts_s': {'assign': t_assign, 'fft_fcomb_reflect': t_other, 'shells': t_shell * S, 'triangles': t_tri * 6350}}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    for _ in range(min(args.warmup, 1)):
+        cpu_baseline_sample(threads=threads, nshell_sample=2, ntri_sample=4)
+    vals = []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        vals.append(cpu_baseline_sample(threads=threads))
+        if time.perf_counter() - t0 > 240:          # keep the whole arm within a few minutes
+            break
+    v = float(np.mean([x['value'] for x in vals]))
+    cb = dict(vals[-1]); cb['value'] = v
+    line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 's/catalog', 'n_gpus': int(os.environ.get('WORLD_SIZE', args.gpus)),
+            'steps': len(vals), 'warmup': min(args.warmup, 1), 'ms_per_step': v * 1e3, 'higher_is_better': False,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic lognormal catalogue (seeded, host)',
+            'config': {'workload': 'BASELINE configs[1]: Bk_periodic, Lbox=2600, Ngrid=360, step=3, Ncut=3, Nmax=40',
+                       'note': 'CPU oracle port of the reference on all host threads; each step is a bounded sample extrapolated linearly'},
+            'cpu_baseline': cb, 'e2e': {'value': v, 'unit': 's/catalog', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line))
+
+
+if __name__ == '__main__':
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--engine', default='auto', choices=['auto', 'tc', 'fma'], help='K6 kernel: tensor-core (default) or FFMA')
+    a = ap.parse_args()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -98,7 +98,15 @@ int psb_shell_mode_counts(int ngrid, const uint16_t* irk_of_m, int nshell, uint6
  *   half_c64 == NULL -> delta == 1 (triangle counts, py:977 / estimator.f:74-80) */
 int psb_bk_shell_pair_f32(const float* half_c64, const uint16_t* irk_of_m, int ngrid, int sa, int sb, int R,
                           float* t1_c64, float* t2_c64, float* fa, float* fb, double* sumsq,
-                          const float* tw_c64, void* stream);
+                          const float* scale2, uint32_t* maxabs2, const float* tw_c64, void* stream);
+/* Optional exact power-of-two normalisation of the stored shell fields (needed by the fp16-split tensor-core
+ * triangle kernel): scale2 = device float[2] multiplying (I_sa, I_sb) before the store and before sumsq;
+ * maxabs2 = device uint32[2] receiving max|stored value| as float bits (atomicMax; zero it first).
+ * psb_bk_shell_scales turns per-shell power sums (psb_pk_monopole with the shell table as bin table:
+ * psum[j] = sum_{k in shell j+1} |delta|^2) into scales[j] = 2^round(log2(target_rms / sqrt(psum[j]))). */
+/* psum[j] = sum_{k in shell j+1, full grid} |delta(k)|^2, j = 0..nshell-1 (Parseval: = sum_x I_{j+1}^2 / N^3) */
+int psb_bk_shell_power(const float* half_c64, int ngrid, const uint16_t* irk_of_m, int nshell, double* psum, void* stream);
+int psb_bk_shell_scales(const double* psum, int nshell, float target_rms, float* scales, void* stream);
 int psb_bk_shell_pair_f64(const float* half_c64, const uint16_t* irk_of_m, int ngrid, int sa, int sb, int R,
                           double* t1_c128, double* t2_c128, double* fa, double* fb, double* sumsq,
                           const double* tw_c128, void* stream);
@@ -112,6 +120,15 @@ int psb_bk_triangle_sums_f32(const float* const* fields, int nfields, int64_t nc
                              int ntiles, double* sums, void* ws, size_t ws_bytes, void* stream);
 int psb_bk_triangle_sums_f64(const double* const* fields, int nfields, int64_t ncell, const int32_t* tiles,
                              int ntiles, double* sums, void* ws, size_t ws_bytes, void* stream);
+
+/* K6 on the tensor cores (tcgen05, split fp16 hi/lo, float64 drain): one pass over `nrows` pair rows
+ * (padded to mt*128; pair_ij[r] = field slots (i,j) of row r) against all `nshell` fields (columns padded to
+ * nt, a multiple of 16, <= 128).  tri_rc[t] = (row, column) of triangle t in this pass or (-1,-1); sums[t]
+ * is written for the triangles of this pass.  Needs ncell % 64 == 0 and mt <= 4 (nt <= 64) or 2 (nt <= 128). */
+size_t psb_bk_triangle_tc_workspace_bytes(int mt, int nt);
+int psb_bk_triangle_sums_tc(const float* const* fields, int nshell, int64_t ncell, const int32_t* pair_ij, int nrows,
+                            int mt, int nt, const int32_t* tri_rc, int ntri, double* sums, void* ws, size_t ws_bytes,
+                            void* stream);
 
 /* host helper: triangle list [ntri][3] (shell indices i,j,l) -> tile descriptors; tiles == NULL only sizes */
 int psb_bk_build_tiles(const int32_t* tri_ijl, int ntri, int s0, int32_t* tiles, int* ntiles);

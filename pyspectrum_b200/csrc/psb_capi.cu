@@ -178,11 +178,11 @@ int psb_shell_mode_counts(int N, const uint16_t* irk, int nshell, uint64_t* nk, 
 }
 
 int psb_bk_shell_pair_f32(const float* half, const uint16_t* irk, int N, int sa, int sb, int R, float* t1, float* t2,
-                          float* fa, float* fb, double* sumsq, const float* tw, void* stream)
+                          float* fa, float* fb, double* sumsq, const float* scale2, uint32_t* maxabs2, const float* tw, void* stream)
 {
     if (!irk || !t1 || !t2 || !fa || !sumsq || !tw || R < 0 || (sb >= 0 && !fb)) return PSB_ERR_ARG;
     return fft_shell_pair<float>(reinterpret_cast<const Cx<float>*>(half), irk, N, sa, sb, R, reinterpret_cast<Cx<float>*>(t1),
-                                 reinterpret_cast<Cx<float>*>(t2), fa, fb, sumsq, reinterpret_cast<const Cx<float>*>(tw), S(stream));
+                                 reinterpret_cast<Cx<float>*>(t2), fa, fb, sumsq, scale2, maxabs2, reinterpret_cast<const Cx<float>*>(tw), S(stream));
 }
 
 int psb_bk_shell_pair_f64(const float* half, const uint16_t* irk, int N, int sa, int sb, int R, double* t1, double* t2,
@@ -190,7 +190,17 @@ int psb_bk_shell_pair_f64(const float* half, const uint16_t* irk, int N, int sa,
 {
     if (!irk || !t1 || !t2 || !fa || !sumsq || !tw || R < 0 || (sb >= 0 && !fb)) return PSB_ERR_ARG;
     return fft_shell_pair<double>(reinterpret_cast<const Cx<float>*>(half), irk, N, sa, sb, R, reinterpret_cast<Cx<double>*>(t1),
-                                  reinterpret_cast<Cx<double>*>(t2), fa, fb, sumsq, reinterpret_cast<const Cx<double>*>(tw), S(stream));
+                                  reinterpret_cast<Cx<double>*>(t2), fa, fb, sumsq, nullptr, nullptr, reinterpret_cast<const Cx<double>*>(tw), S(stream));
+}
+
+int psb_bk_shell_power(const float* half, int N, const uint16_t* irk, int nshell, double* psum, void* stream)
+{
+    return shell_power(reinterpret_cast<const Cx<float>*>(half), N, irk, nshell, psum, S(stream));
+}
+
+int psb_bk_shell_scales(const double* psum, int nshell, float target_rms, float* scales, void* stream)
+{
+    return shell_scales(psum, nshell, target_rms, scales, S(stream));
 }
 
 size_t psb_bk_triangle_workspace_bytes(int ntiles) { return triangle_workspace_bytes(ntiles); }
@@ -206,6 +216,15 @@ int psb_bk_triangle_sums_f64(const double* const* fields, int nfields, int64_t n
 {
     if (!fields || !tiles || !sums || !ws) return PSB_ERR_ARG;
     return triangle_sums_tiles<double>(fields, nfields, ncell, tiles, ntiles, sums, ws, ws_bytes, S(stream));
+}
+
+size_t psb_bk_triangle_tc_workspace_bytes(int mt, int nt) { return triangle_tc_workspace_bytes(mt, nt); }
+
+int psb_bk_triangle_sums_tc(const float* const* fields, int nshell, int64_t ncell, const int32_t* pair_ij, int nrows, int mt, int nt,
+                            const int32_t* tri_rc, int ntri, double* sums, void* ws, size_t ws_bytes, void* stream)
+{
+    if (!fields || !pair_ij || !tri_rc || !sums || !ws) return PSB_ERR_ARG;
+    return triangle_sums_tc_pass(fields, nshell, ncell, pair_ij, nrows, mt, nt, tri_rc, ntri, sums, ws, ws_bytes, S(stream));
 }
 
 /* host helper shared with the Python layer: tri [ntri][3] shell indices -> tiles; call with tiles == NULL to size */

