@@ -11,12 +11,15 @@
 // contiguous x range; tensor-core accumulation rounds toward zero, so TMEM is drained into float64
 // every p.flush_ksteps*16 cells (double-buffered accumulator sets: the drain overlaps the next MMAs).
 //
-// Warp roles (576 threads, 1 CTA/SM):
-//   warps 0..15  "formers": read the staged fp32 field chunk, form pair products, split to fp16 hi/lo and
-//                write them straight in the UMMA K-major / no-swizzle core-matrix layout; they also drain TMEM
-//   warp 16      MMA issuer (one elected lane): tcgen05.mma.cta_group::1.kind::f16, tcgen05.commit
-//   warp 17      TMA producer (one elected lane): cp.async.bulk (UBLKCP) of [S][64] fp32 field chunks
-// Pipelines: chunk ring (TMA -> formers), operand-stage ring (formers -> MMA), accumulator sets (MMA -> drain).
+// Warp roles (608 threads, 1 CTA/SM):
+//   warps 0..15  A formers, warp = 4*g + q: group g forms K-step g of every 64-cell chunk; a thread owns one TMEM lane in all
+//                M tiles (rows sharing the field i), forms the pair products, splits them to fp16 hi/lo and writes them
+//                straight into TMEM (tcgen05.st) as the A operand; group g also drains accumulator tile g
+//   warp 16      MMA issuer (one elected lane): tcgen05.mma.cta_group::1.kind::f16 with A from TMEM, B from smem; tcgen05.commit
+//   warp 17      TMA producer: cp.async.bulk (UBLKCP) of [S][64] fp32 field chunks, one row per lane
+//   warp 18      B former: fields -> fp16 hi/lo K-major core-matrix tiles in shared memory
+// Pipelines: chunk ring (TMA -> formers/B), four operand stages = the four K-steps of a chunk (formers/B -> MMA),
+// accumulators (MMA -> drain, one chunk late so nobody waits).
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <cstdlib>
@@ -29,11 +32,8 @@ namespace tc {
 constexpr int XCH = 64;              // cells per staged chunk (4 K-steps of 16)
 constexpr int ROWF = XCH + 4;        // padded fp32 row stride of a chunk (68 words: conflict-free LDS.128 across rows)
 constexpr int NCHUNKBUF = 3;
-constexpr int NSTAGE = 4;            // operand stages (one K-step = 16 cells each)
-constexpr int NFORM = 512;           // former threads
-constexpr int NTHREADS = NFORM + 64;
 constexpr int TMEM_COLS = 512;
-constexpr unsigned WATCHDOG = 1u << 27;
+constexpr unsigned WATCHDOG = 1u << 22;       // x 20 us suspend hint
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -49,15 +49,18 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// try_wait suspends the thread in hardware up to the hinted time, so waiting warps do not burn the issue
+// slots the MMA-issuing warp needs (polling formers made that warp the bottleneck: profiles/r1)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
     const uint32_t a = smem_u32(bar);
     uint32_t done = 0;
     unsigned spins = 0;
-    while (!done) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
-        if (!done && ++spins > WATCHDOG) asm volatile("trap;");      // a protocol bug must not hang the GPU
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(a), "r"(parity), "r"(20000u) : "memory");
+        if (done) break;
+        if (++spins > WATCHDOG) asm volatile("trap;");      // a protocol bug must not hang the GPU
     }
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -155,22 +158,61 @@ struct Params {
     int NT;                       // MMA N = shells padded to a multiple of 16 (<= 128)
     int MT;                       // M tiles (128 rows each) in this pass (<= 256 / tile_cols)
     int tile_cols;                // TMEM column spacing of one accumulator tile: 64 (NT <= 64) or 128
-    int nrows;                    // real pair rows in this pass (<= MT*128)
-    const int* pair_ij;           // [MT*128][2] field slots (i,j) of each row (padding rows: 0,0)
+    const int* lane_ij;           // [128][5]: field slot i of the lane and j of its row in tiles 0..3 (-1: padding row)
     long long nchunk;             // ncell / XCH
-    int flush_ksteps;             // TMEM accumulators are drained (fp32, round-to-nearest) every flush_ksteps K-steps
+    int flush_chunks;             // TMEM accumulators are drained (fp32, round-to-nearest) every flush_chunks chunks (x4 K-steps)
     int gflush_drains;            // the fp32 accumulators go to float64 global every gflush_drains drains
     double* partial;              // [gridDim.x][NT][MT*128] float64 partial sums (zeroed by the host)
 };
 
-// TMEM map (512 columns): [0,256) accumulator tiles (tile m at m*tile_cols);
-//                         [256,512) A-operand ring: stage s at 256 + s*64, tile m: hi at +m*16, lo at +m*16+8
-//                         (one K-step of one tile = 128 lanes x 16 fp16 = 8 columns of packed half2).
+constexpr int NFWARPS = 16;                      // A-operand formers: 4 groups (one per K-step of a chunk) x 4 lane quarters
+constexpr int W_MMA = 16, W_TMA = 17, W_B = 18;  // warp roles
+constexpr int NTHR = 19 * 32;
 constexpr int TMEM_A0 = 256;
 
+// TMEM map (512 columns): [0,256) accumulator tiles (tile m at m*tile_cols);
+//                         [256,512) A-operand stages: stage g (= K-step g of a chunk) at 256 + g*64, tile m: hi at +m*16,
+//                         lo at +m*16+8 (one K-step of one tile = 128 lanes x 16 fp16 = 8 columns of packed half2).
+
+// TMEM accumulators of tile `m` -> fp32 shared accumulators (round-to-nearest adds); every gflush_drains-th drain
+// (and the last one) moves them on to the float64 partial sums in global memory.
+__device__ __forceinline__ void drain_accumulators(const Params& p, uint64_t* acc_full, uint64_t* acc_empty, uint32_t& aph, int& ndrain,
+                                                   bool final_drain, bool live, uint32_t t_acc, float4* accs, int MR, int NT, int row, int lane)
+{
+    mbar_wait(acc_full, aph);
+    aph ^= 1;
+    tc_fence_after();
+    const bool to_global = (++ndrain == p.gflush_drains) || final_drain;
+    if (to_global) ndrain = 0;
+    if (live) {
+        double* dst = p.partial + (size_t)blockIdx.x * MR * NT + (size_t)row;     // [col][row]: coalesced
+        for (int c0 = 0; c0 < NT; c0 += 16) {
+            float v[16];
+            tmem_ld16(t_acc + (uint32_t)c0, v);
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+                float4* sp = &accs[(size_t)(c0 / 4 + q4) * MR + row];
+                float4 cur = *sp;
+                cur.x += v[4 * q4]; cur.y += v[4 * q4 + 1]; cur.z += v[4 * q4 + 2]; cur.w += v[4 * q4 + 3];
+                if (to_global) {
+                    dst[(size_t)(c0 + 4 * q4 + 0) * MR] += (double)cur.x;
+                    dst[(size_t)(c0 + 4 * q4 + 1) * MR] += (double)cur.y;
+                    dst[(size_t)(c0 + 4 * q4 + 2) * MR] += (double)cur.z;
+                    dst[(size_t)(c0 + 4 * q4 + 3) * MR] += (double)cur.w;
+                    cur = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                *sp = cur;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(acc_empty);
+}
+
 // shared memory carve-up (dynamic):
-//   chunk[NCHUNKBUF][S][ROWF] fp32 | B_hi[NSTAGE][2][NT][8] fp16 | B_lo[...] | accs[NT/4][MT*128][4] fp32 | barriers
-__global__ void __launch_bounds__(NTHREADS, 1) k_tri_tc(Params p)
+//   chunk[NCHUNKBUF][S][ROWF] fp32 | B_hi[4][2][NT][8] fp16 | B_lo[...] | accs[NT/4][MT*128][4] fp32 | barriers
+__global__ void __launch_bounds__(NTHR, 1) k_tri_tc(Params p)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
     const int S = p.S, NT = p.NT, MT = p.MT, MR = MT * 128;
@@ -179,34 +221,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tri_tc(Params p)
     unsigned char* bop = smem + ((NCHUNKBUF * chunk_bytes + 1023) / 1024) * 1024;
     const uint32_t b_stage_bytes = 2u * NT * 16u;
     unsigned char* b_hi = bop;
-    unsigned char* b_lo = b_hi + NSTAGE * b_stage_bytes;
-    float4* accs = reinterpret_cast<float4*>(b_lo + NSTAGE * b_stage_bytes);      // [NT/4][MR]
+    unsigned char* b_lo = b_hi + 4 * b_stage_bytes;
+    float4* accs = reinterpret_cast<float4*>(b_lo + 4 * b_stage_bytes);      // [NT/4][MR]
     uint64_t* bars = reinterpret_cast<uint64_t*>(accs + (size_t)(NT / 4) * MR);
-    uint64_t* chunk_full = bars;                  // [NCHUNKBUF]  TMA -> formers (tx bytes)
-    uint64_t* chunk_empty = bars + NCHUNKBUF;     // [NCHUNKBUF]  formers -> TMA (16 warps)
-    uint64_t* st_full = chunk_empty + NCHUNKBUF;  // [NSTAGE]     formers -> MMA (16 warps)
-    uint64_t* st_empty = st_full + NSTAGE;        // [NSTAGE]     MMA (commit) -> formers
-    uint64_t* acc_full = st_empty + NSTAGE;       // [1]          MMA (commit) -> drain
+    uint64_t* chunk_full = bars;                  // [NCHUNKBUF]  TMA -> formers + B warp (tx bytes)
+    uint64_t* chunk_empty = bars + NCHUNKBUF;     // [NCHUNKBUF]  16 former warps + B warp -> TMA
+    uint64_t* st_full = chunk_empty + NCHUNKBUF;  // [4]          4 former warps of the group + B warp -> MMA
+    uint64_t* st_empty = st_full + 4;             // [4]          MMA (commit) -> formers of the group, B warp
+    uint64_t* acc_full = st_empty + 4;            // [1]          MMA (commit) -> drain
     uint64_t* acc_empty = acc_full + 1;           // [1]          drain (16 warps) -> MMA
     uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(acc_empty + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
-        for (int i = 0; i < NCHUNKBUF; ++i) { mbar_init(&chunk_full[i], 1); mbar_init(&chunk_empty[i], NFORM / 32); }
-        for (int i = 0; i < NSTAGE; ++i) { mbar_init(&st_full[i], NFORM / 32); mbar_init(&st_empty[i], 1); }
+        for (int i = 0; i < NCHUNKBUF; ++i) { mbar_init(&chunk_full[i], 1); mbar_init(&chunk_empty[i], NFWARPS + 1); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&st_full[i], 5); mbar_init(&st_empty[i], 1); }
         mbar_init(acc_full, 1);
-        mbar_init(acc_empty, NFORM / 32);
+        mbar_init(acc_empty, NFWARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 16) {       // TMEM allocation by one full warp
+    if (warp == W_MMA) {       // TMEM allocation by one full warp
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_smem)), "r"((uint32_t)TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (tid < NFORM) {
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (tid < MR) for (int c4 = 0; c4 < NT / 4; ++c4) accs[(size_t)c4 * MR + tid] = z;
-    }
+    for (int e = tid; e < (NT / 4) * MR; e += NTHR) accs[e] = make_float4(0.f, 0.f, 0.f, 0.f);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -215,11 +254,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tri_tc(Params p)
     // contiguous chunk range of this CTA; everything below counts in 32 bits
     const long long c_begin = p.nchunk * blockIdx.x / gridDim.x, c_end = p.nchunk * (blockIdx.x + 1) / gridDim.x;
     const int nch = (int)(c_end - c_begin);
-    const int nks = nch * (XCH / 16);
-    const int F = p.flush_ksteps;
+    const int FC = p.flush_chunks;
 
-    if (warp == 17) {
-        // ------------------------------------------------------------------ TMA producer
+    if (warp == W_TMA) {
+        // ------------------------------------------------------------------ TMA producer (rows spread over the lanes)
         const float* src0 = lane < S ? p.fields[lane] : nullptr;
         const float* src1 = lane + 32 < S ? p.fields[lane + 32] : nullptr;
         int buf = 0;
@@ -237,139 +275,139 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_tri_tc(Params p)
             for (int f = lane + 64; f < S; f += 32) bulk_g2s(dst + (size_t)f * ROWF, p.fields[f] + x0, XCH * 4, &chunk_full[buf]);
             if (++buf == NCHUNKBUF) { buf = 0; ph ^= 1; }
         }
-    } else if (warp == 16) {
+    } else if (warp == W_MMA) {
         // ------------------------------------------------------------------ MMA issuer
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_f16(NT);
             const uint32_t b_lbo = (uint32_t)NT * 16u;
-            int st = 0, kf = 0;
-            uint32_t ph = 0, eph = 0;                      // stage phase, acc_empty phase
-            for (int ks = 0; ks < nks; ++ks) {
-                const bool first = kf == 0;
-                if (first && ks > 0) { mbar_wait(acc_empty, eph); eph ^= 1; }      // previous period drained
-                mbar_wait(&st_full[st], ph);
-                tc_fence_after();
-                const uint64_t dbh = umma_desc(smem_u32(b_hi + (size_t)st * b_stage_bytes), b_lbo, 128);
-                const uint64_t dbl = umma_desc(smem_u32(b_lo + (size_t)st * b_stage_bytes), b_lbo, 128);
-                const uint32_t a0 = tmem_base + (uint32_t)(TMEM_A0 + st * 64);
-                for (int m = 0; m < MT; ++m) {
-                    const uint32_t d = tmem_base + (uint32_t)(m * p.tile_cols);
-                    const uint32_t ah = a0 + (uint32_t)(m * 16), al = ah + 8u;
-                    umma_f16_ts(d, ah, dbh, idesc, first ? 0u : 1u);
-                    umma_f16_ts(d, ah, dbl, idesc, 1u);
-                    umma_f16_ts(d, al, dbh, idesc, 1u);
+            const uint64_t dbh0 = umma_desc(smem_u32(b_hi), b_lbo, 128), dbl0 = umma_desc(smem_u32(b_lo), b_lbo, 128);
+            const uint64_t dstep = (uint64_t)(b_stage_bytes >> 4);          // start-address field advances by one stage
+            const uint32_t tc_ = (uint32_t)p.tile_cols;
+            int cf = 0;
+            uint32_t eph = 0;
+            for (int c = 0; c < nch; ++c) {
+                const uint32_t ph = (uint32_t)(c & 1);
+                if (cf == 0 && c > 0) { mbar_wait(acc_empty, eph); eph ^= 1; }      // previous period drained
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const uint32_t acc = (cf == 0 && g == 0) ? 0u : 1u;
+                    mbar_wait(&st_full[g], ph);
+                    tc_fence_after();
+                    const uint64_t dbh = dbh0 + dstep * (uint64_t)g, dbl = dbl0 + dstep * (uint64_t)g;
+                    const uint32_t a0 = tmem_base + (uint32_t)(TMEM_A0 + g * 64);
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) {
+                        if (m < MT) {
+                            const uint32_t d = tmem_base + (uint32_t)m * tc_;
+                            const uint32_t ah = a0 + (uint32_t)(m * 16);
+                            umma_f16_ts(d, ah, dbh, idesc, acc);
+                            umma_f16_ts(d, ah, dbl, idesc, 1u);
+                            umma_f16_ts(d, ah + 8u, dbh, idesc, 1u);
+                        }
+                    }
+                    umma_commit(&st_empty[g]);                                   // operands of this stage consumed
                 }
-                umma_commit(&st_empty[st]);                                   // operands of this stage consumed
-                if (++kf == F || ks == nks - 1) { umma_commit(acc_full); kf = 0; }
-                if (++st == NSTAGE) { st = 0; ph ^= 1; }
+                if (++cf == FC || c == nch - 1) { umma_commit(acc_full); cf = 0; }
             }
         }
-    } else {
-        // ------------------------------------------------------------------ formers (+ TMEM drain)
-        const int row = tid;                                     // pair row owned by this thread == TMEM lane (row % 128)
-        const bool real = row < p.nrows;
-        const bool live = row < MR;                              // warp-uniform: MR is a multiple of 128
-        int fi = 0, fj = 0;
-        if (live) { fi = p.pair_ij[2 * row]; fj = p.pair_ij[2 * row + 1]; }
-        const int npad = NFORM - p.nrows;                        // threads without a real row convert B
+    } else if (warp == W_B) {
+        // ------------------------------------------------------------------ B-operand former: fields -> fp16 hi/lo tiles
+        int buf = 0;
+        uint32_t cph = 0;
         const int nbcell = 2 * NT;                               // (l, kchunk) cells of the B tile per K-step
-        const int bfirst = npad > 0 ? (real ? nbcell : tid - p.nrows) : tid;
-        const int bstride = npad > 0 ? npad : NFORM;
-        const uint32_t lane_quarter = (uint32_t)((warp & 3) * 32) << 16;
-        const int m = warp >> 2;                                 // M tile of this warp
-        const uint32_t t_acc = tmem_base + lane_quarter + (uint32_t)(m * p.tile_cols);
-        const uint32_t t_a = tmem_base + lane_quarter + (uint32_t)(TMEM_A0 + m * 16);
-        const uint32_t fio = (uint32_t)fi * ROWF, fjo = (uint32_t)fj * ROWF;
-        int buf = 0, st = 0, kf = 0, ndrain = 0, ks = 0;
-        uint32_t cph = 0, sph = 0, aph = 0;                      // chunk_full, st_empty, acc_full phases
         for (int c = 0; c < nch; ++c) {
             mbar_wait(&chunk_full[buf], cph);
             const float* ch = chunk + (size_t)buf * S * ROWF;
-#pragma unroll 1
-            for (int kk = 0; kk < XCH / 16; ++kk, ++ks) {
-                mbar_wait(&st_empty[st], sph ^ 1);
-                tc_fence_after();
-                if (live) {
-                    uint32_t hi[8], lo[8];
-                    if (real) {
-                        const float* pi = ch + fio + kk * 16;
-                        const float* pj = ch + fjo + kk * 16;
-#pragma unroll
-                        for (int q4 = 0; q4 < 4; ++q4) {
-                            const float4 a = *reinterpret_cast<const float4*>(pi + q4 * 4), b = *reinterpret_cast<const float4*>(pj + q4 * 4);
-                            split2(a.x * b.x, a.y * b.y, hi[2 * q4], lo[2 * q4]);
-                            split2(a.z * b.z, a.w * b.w, hi[2 * q4 + 1], lo[2 * q4 + 1]);
-                        }
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) { hi[q] = 0u; lo[q] = 0u; }       // padding rows of a real tile
-                    }
-                    tmem_st8(t_a + (uint32_t)(st * 64), hi);
-                    tmem_st8(t_a + (uint32_t)(st * 64 + 8), lo);
-                }
-                // B tile: cells (l, kchunk) shared among the threads without a real row (all threads if none)
-                for (int cell = bfirst; cell < nbcell; cell += bstride) {
+            for (int g = 0; g < 4; ++g) {
+                mbar_wait(&st_empty[g], (uint32_t)(c & 1) ^ 1);
+                for (int cell = lane; cell < nbcell; cell += 32) {
                     const int l = cell >> 1, kc = cell & 1;
                     uint4 h4 = make_uint4(0, 0, 0, 0), l4 = h4;
                     if (l < S) {
-                        const float* pl = ch + (size_t)l * ROWF + kk * 16 + kc * 8;
+                        const float* pl = ch + (size_t)l * ROWF + g * 16 + kc * 8;
                         const float4 a = *reinterpret_cast<const float4*>(pl), b = *reinterpret_cast<const float4*>(pl + 4);
                         split2(a.x, a.y, h4.x, l4.x); split2(a.z, a.w, h4.y, l4.y);
                         split2(b.x, b.y, h4.z, l4.z); split2(b.z, b.w, h4.w, l4.w);
                     }
-                    const size_t off = (size_t)st * b_stage_bytes + (size_t)kc * NT * 16 + (size_t)l * 16;
+                    const size_t off = (size_t)g * b_stage_bytes + (size_t)kc * NT * 16 + (size_t)l * 16;
                     *reinterpret_cast<uint4*>(b_hi + off) = h4;
                     *reinterpret_cast<uint4*>(b_lo + off) = l4;
                 }
-                if (live) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                fence_proxy_async();                  // generic-proxy smem writes (B) -> visible to the tensor core
-                tc_fence_before();
+                fence_proxy_async();                  // generic-proxy smem writes -> visible to the tensor core
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&st_full[st]);
-                if (++st == NSTAGE) { st = 0; sph ^= 1; }
-                // drain the accumulators when the period ends
-                if (++kf == F || ks == nks - 1) {
-                    kf = 0;
-                    mbar_wait(acc_full, aph);
-                    aph ^= 1;
-                    tc_fence_after();
-                    const bool to_global = (++ndrain == p.gflush_drains) || (ks == nks - 1);
-                    if (to_global) ndrain = 0;
-                    if (live) {
-                        double* dst = p.partial + (size_t)blockIdx.x * MR * NT + (size_t)row;     // [col][row]: coalesced
-                        for (int c0 = 0; c0 < NT; c0 += 16) {
-                            float v[16];
-                            tmem_ld16(t_acc + (uint32_t)c0, v);
-#pragma unroll
-                            for (int q4 = 0; q4 < 4; ++q4) {
-                                float4* sp = &accs[(size_t)(c0 / 4 + q4) * MR + row];
-                                float4 cur = *sp;
-                                cur.x += v[4 * q4]; cur.y += v[4 * q4 + 1]; cur.z += v[4 * q4 + 2]; cur.w += v[4 * q4 + 3];
-                                if (to_global) {
-                                    dst[(size_t)(c0 + 4 * q4 + 0) * MR] += (double)cur.x;
-                                    dst[(size_t)(c0 + 4 * q4 + 1) * MR] += (double)cur.y;
-                                    dst[(size_t)(c0 + 4 * q4 + 2) * MR] += (double)cur.z;
-                                    dst[(size_t)(c0 + 4 * q4 + 3) * MR] += (double)cur.w;
-                                    cur = make_float4(0.f, 0.f, 0.f, 0.f);
-                                }
-                                *sp = cur;
-                            }
-                        }
-                    }
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(acc_empty);
-                }
+                if (lane == 0) mbar_arrive(&st_full[g]);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&chunk_empty[buf]);
             if (++buf == NCHUNKBUF) { buf = 0; cph ^= 1; }
         }
+    } else {
+        // ------------------------------------------------------------------ A-operand formers (+ TMEM drain)
+        // warp = 4*g + q: group g forms K-step g of every chunk (== operand stage g); thread = TMEM lane 32*q + lane,
+        // which it owns in ALL tiles: rows (m*128 + lane) share the field i, so I_i is loaded once for MT products.
+        const int g = warp >> 2, q = warp & 3;
+        const int tl = q * 32 + lane;                            // TMEM lane
+        const int* lij = p.lane_ij + tl * 5;
+        const int fi = lij[0];
+        int fj[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) fj[m] = lij[1 + m];
+        const uint32_t lane_quarter = (uint32_t)(q * 32) << 16;
+        const uint32_t t_a = tmem_base + lane_quarter + (uint32_t)(TMEM_A0 + g * 64);
+        const bool drain_live = g < MT;                          // group g drains accumulator tile g
+        const uint32_t t_acc = tmem_base + lane_quarter + (uint32_t)(g * p.tile_cols);
+        const int drow = g * 128 + tl;
+        const uint32_t fio = (uint32_t)(fi < 0 ? 0 : fi) * ROWF + g * 16;
+        int buf = 0, cf = 0, ndrain = 0, pending = 0;
+        uint32_t cph = 0, aph = 0;
+        for (int c = 0; c < nch; ++c) {
+            mbar_wait(&chunk_full[buf], cph);
+            const float* ch = chunk + (size_t)buf * S * ROWF;
+            mbar_wait(&st_empty[g], (uint32_t)(c & 1) ^ 1);
+            tc_fence_after();
+            float4 vi[4];
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) vi[q4] = *reinterpret_cast<const float4*>(ch + fio + q4 * 4);
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                if (m < MT) {
+                    uint32_t hi[8], lo[8];
+                    if (fi >= 0 && fj[m] >= 0) {
+                        const float* pj = ch + (uint32_t)fj[m] * ROWF + g * 16;
+#pragma unroll
+                        for (int q4 = 0; q4 < 4; ++q4) {
+                            const float4 b = *reinterpret_cast<const float4*>(pj + q4 * 4);
+                            split2(vi[q4].x * b.x, vi[q4].y * b.y, hi[2 * q4], lo[2 * q4]);
+                            split2(vi[q4].z * b.z, vi[q4].w * b.w, hi[2 * q4 + 1], lo[2 * q4 + 1]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) { hi[k] = 0u; lo[k] = 0u; }       // padding rows
+                    }
+                    tmem_st8(t_a + (uint32_t)(m * 16), hi);
+                    tmem_st8(t_a + (uint32_t)(m * 16 + 8), lo);
+                }
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&st_full[g]); mbar_arrive(&chunk_empty[buf]); }
+            if (++buf == NCHUNKBUF) { buf = 0; cph ^= 1; }
+            // Drain the previous period one chunk late: its MMAs are done by now (no wait on acc_full) while the tensor
+            // core still has this chunk's four K-steps queued.  The last chunk also drains its own period.
+            const bool last = c == nch - 1;
+            if (pending) {
+                drain_accumulators(p, acc_full, acc_empty, aph, ndrain, false, drain_live, t_acc, accs, MR, NT, drow, lane);
+                pending = 0;
+            }
+            if (++cf == FC) { cf = 0; pending = 1; }
+            if (last) drain_accumulators(p, acc_full, acc_empty, aph, ndrain, true, drain_live, t_acc, accs, MR, NT, drow, lane);
+        }
     }
     // ---------------------------------------------------------------------- teardown
     tc_fence_before();
     __syncthreads();
-    if (warp == 16) {
+    if (warp == W_MMA) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
     }
 }
@@ -390,33 +428,33 @@ __global__ void k_tri_tc_fold(const double* __restrict__ partial, int ncta, int 
 
 size_t triangle_tc_workspace_bytes(int MT, int NT) { return (size_t)148 * MT * 128 * NT * sizeof(double); }
 
-// One pass: rows [pair_ij] (MT*128 padded) x all NT columns.  tri_rc[t] = (row, col) in this pass or (-1,-1).
-int triangle_sums_tc_pass(const float* const* fields, int S, long long ncell, const int* pair_ij, int nrows, int MT, int NT,
+// One pass: 128 lanes x MT tiles of pair rows (lane_ij) against all NT columns.  tri_rc[t] = (row, col) or (-1,-1).
+int triangle_sums_tc_pass(const float* const* fields, int S, long long ncell, const int* lane_ij, int MT, int NT,
                           const int* tri_rc, int ntri, double* sums, void* ws, size_t ws_bytes, cudaStream_t st)
 {
     using namespace tc;
     const int tile_cols = NT <= 64 ? 64 : 128;
-    if (S < 1 || S > NT || NT % 16 || NT > 128 || MT < 1 || MT > 256 / tile_cols || nrows < 1 || nrows > MT * 128 || ncell % XCH) return PSB_ERR_ARG;
+    if (S < 1 || S > NT || NT % 16 || NT > 128 || MT < 1 || MT > 256 / tile_cols || ncell % XCH) return PSB_ERR_ARG;
     if (ncell / XCH / 148 >= (1LL << 28)) return PSB_ERR_ARG;
     if (ws_bytes < triangle_tc_workspace_bytes(MT, NT)) return PSB_ERR_WORKSPACE;
     const int MR = MT * 128;
     const size_t chunk_bytes = (size_t)S * ROWF * 4;
     size_t smem = ((NCHUNKBUF * chunk_bytes + 1023) / 1024) * 1024;
-    smem += 2 * (size_t)NSTAGE * (2 * NT * 16);
+    smem += 2 * (size_t)4 * (2 * NT * 16);
     smem += (size_t)NT * MR * 4;
-    smem += (2 * NCHUNKBUF + 2 * NSTAGE + 2) * sizeof(uint64_t) + 16;
+    smem += (2 * NCHUNKBUF + 8 + 2) * sizeof(uint64_t) + 16;
     if (smem > 227 * 1024) return PSB_ERR_ARG;
     if (cudaFuncSetAttribute(k_tri_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PSB_ERR_CUDA;
     const int ncta = 148;
     if (cudaMemsetAsync(ws, 0, triangle_tc_workspace_bytes(MT, NT), st) != cudaSuccess) return PSB_ERR_CUDA;
     Params p;
-    p.fields = fields; p.S = S; p.NT = NT; p.MT = MT; p.tile_cols = tile_cols; p.nrows = nrows; p.pair_ij = pair_ij; p.nchunk = ncell / XCH;
+    p.fields = fields; p.S = S; p.NT = NT; p.MT = MT; p.tile_cols = tile_cols; p.lane_ij = lane_ij; p.nchunk = ncell / XCH;
     p.partial = static_cast<double*>(ws);
-    p.flush_ksteps = 16;
+    p.flush_chunks = 4;          // 16 K-steps = 48 accumulating MMAs per accumulator between round-to-nearest drains
     p.gflush_drains = 64;
-    if (const char* e = getenv("PSB_TC_FLUSH")) { int v = atoi(e); if (v >= 1 && v <= 4096) p.flush_ksteps = v; }
+    if (const char* e = getenv("PSB_TC_FLUSH")) { int v = atoi(e); if (v >= 1 && v <= 4096) p.flush_chunks = v; }
     if (const char* e = getenv("PSB_TC_GFLUSH")) { int v = atoi(e); if (v >= 1 && v <= 65536) p.gflush_drains = v; }
-    k_tri_tc<<<ncta, NTHREADS, smem, st>>>(p);
+    k_tri_tc<<<ncta, NTHR, smem, st>>>(p);
     k_tri_tc_fold<<<(ntri + 255) / 256, 256, 0, st>>>(p.partial, ncta, MR, NT, tri_rc, ntri, sums);
     return cudaGetLastError() == cudaSuccess ? PSB_OK : PSB_ERR_CUDA;
 }

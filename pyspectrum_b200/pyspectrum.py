@@ -320,32 +320,43 @@ class PeriodicPipeline(object):
         return sums
 
     def tc_passes(self, Nmax, Ncut, step):
-        """Host plan of the tensor-core kernel: pair rows (i,j) that own a triangle, sorted by (j,i), cut into
-        passes of at most (256 / tile_cols) * 128 rows; per pass the (row, column) of every triangle."""
+        """Host plan of the tensor-core kernel.  Pair rows (i,j) that own a triangle are grouped by i; a "lane" holds one
+        i and up to MT of its partners j (one per M tile), so a thread loads I_i once for MT rows.  Lanes are cut into
+        passes of 128; per pass the (row, column) of every triangle."""
         key = ('tc', Nmax, Ncut, step)
         if key not in self._tiles:
             tri = triangle_list(Nmax, Ncut, step)
             s0 = Ncut // step
             S = Nmax - s0 + 1
             NT = (S + 15) // 16 * 16
-            tile_cols = 64 if NT <= 64 else 128
-            rows_per_pass = (256 // tile_cols) * 128
-            pairs = sorted({(int(j), int(i)) for i, j, _ in tri})             # (j, i) order
-            row_of = {(i, j): r for r, (j, i) in enumerate(pairs)}
-            rows = np.array([row_of[(int(i), int(j))] for i, j, _ in tri])
+            MT = 4 if NT <= 64 else 2
+            partners = {}
+            for i, j, _ in tri:
+                partners.setdefault(int(i), set()).add(int(j))
+            lanes = []                                     # (i, [j_0..j_{MT-1}])
+            for i in sorted(partners):
+                js = sorted(partners[i])
+                nl = (len(js) + MT - 1) // MT
+                for k in range(nl):
+                    lanes.append((i, [js[k + m * nl] if k + m * nl < len(js) else -1 for m in range(MT)]))
             passes = []
-            for r0 in range(0, len(pairs), rows_per_pass):
-                nrows = min(rows_per_pass, len(pairs) - r0)
-                MT = (nrows + 127) // 128
-                pij = np.zeros((MT * 128, 2), np.int32)
-                for r in range(nrows):
-                    j, i = pairs[r0 + r]
-                    pij[r] = (i - s0, j - s0)
+            ti, tj, tl = tri[:, 0], tri[:, 1], tri[:, 2]
+            for l0 in range(0, len(lanes), 128):
+                sub = lanes[l0:l0 + 128]
+                lij = np.full((128, 5), -1, np.int32)
+                row_of = {}
+                for ln, (i, js) in enumerate(sub):
+                    lij[ln, 0] = i - s0
+                    for m, j in enumerate(js):
+                        if j >= 0:
+                            lij[ln, 1 + m] = j - s0
+                            row_of[(i, j)] = m * 128 + ln
                 rc = np.full((len(tri), 2), -1, np.int32)
-                m = (rows >= r0) & (rows < r0 + nrows)
-                rc[m, 0] = rows[m] - r0
-                rc[m, 1] = tri[m, 2] - s0
-                passes.append((torch.from_numpy(pij).to(self.dev), nrows, MT, torch.from_numpy(rc).to(self.dev)))
+                for t in range(len(tri)):
+                    r = row_of.get((int(ti[t]), int(tj[t])))
+                    if r is not None:
+                        rc[t] = (r, tl[t] - s0)
+                passes.append((torch.from_numpy(lij).to(self.dev), MT, torch.from_numpy(rc).to(self.dev)))
             self._tiles[key] = (tri, NT, passes)
         return self._tiles[key]
 
@@ -354,11 +365,11 @@ class PeriodicPipeline(object):
         S = Nmax - Ncut // step + 1
         dptr = torch.tensor([fields[f].data_ptr() for f in range(S)], dtype=torch.int64).to(self.dev)
         sums = torch.zeros(len(tri), dtype=torch.float64, device=self.dev)
-        MTmax = max(p[2] for p in passes)
-        wsb = self.L.psb_bk_triangle_tc_workspace_bytes(MTmax, NT)
+        MT = passes[0][1]
+        wsb = self.L.psb_bk_triangle_tc_workspace_bytes(MT, NT)
         ws = torch.empty(wsb, dtype=torch.uint8, device=self.dev)
-        for pij, nrows, MT, rc in passes:
-            check(self.L.psb_bk_triangle_sums_tc(_ptr(dptr), S, fields.shape[1], _ptr(pij), nrows, MT, NT, _ptr(rc), len(tri),
+        for lij, MT, rc in passes:
+            check(self.L.psb_bk_triangle_sums_tc(_ptr(dptr), S, fields.shape[1], _ptr(lij), MT, NT, _ptr(rc), len(tri),
                                                  _ptr(sums), _ptr(ws), wsb, _stream()), 'psb_bk_triangle_sums_tc')
         return sums
 
