@@ -11,13 +11,14 @@
 // contiguous x range; tensor-core accumulation rounds toward zero, so TMEM is drained into float64
 // every p.flush_ksteps*16 cells (double-buffered accumulator sets: the drain overlaps the next MMAs).
 //
-// Warp roles (608 threads, 1 CTA/SM):
-//   warps 0..15  A formers, warp = 4*g + q: group g forms K-step g of every 64-cell chunk; a thread owns one TMEM lane in all
-//                M tiles (rows sharing the field i), forms the pair products, splits them to fp16 hi/lo and writes them
-//                straight into TMEM (tcgen05.st) as the A operand; group g also drains accumulator tile g
+// Warp roles (704 threads, 1 CTA/SM):
+//   warps 0..15  A formers, warp = 4*g + q, g = 2*kp + tp: the group forms tiles {2tp,2tp+1} of K-steps kp and kp+2 of every
+//                64-cell chunk (two operand stages -> double buffered); a thread owns one TMEM lane in both tiles (rows
+//                sharing the field i), forms the pair products, splits them to fp16 hi/lo and writes them straight into
+//                TMEM (tcgen05.st) as the A operand; group g also drains accumulator tile g
 //   warp 16      MMA issuer (one elected lane): tcgen05.mma.cta_group::1.kind::f16 with A from TMEM, B from smem; tcgen05.commit
 //   warp 17      TMA producer: cp.async.bulk (UBLKCP) of [S][64] fp32 field chunks, one row per lane
-//   warp 18      B former: fields -> fp16 hi/lo K-major core-matrix tiles in shared memory
+//   warps 18..21 B formers (one per operand stage): fields -> fp16 hi/lo K-major core-matrix tiles in shared memory
 // Pipelines: chunk ring (TMA -> formers/B), four operand stages = the four K-steps of a chunk (formers/B -> MMA),
 // accumulators (MMA -> drain, one chunk late so nobody waits).
 #include <cuda_runtime.h>
@@ -29,9 +30,11 @@ namespace psb {
 
 namespace tc {
 
-constexpr int XCH = 64;              // cells per staged chunk (4 K-steps of 16)
-constexpr int ROWF = XCH + 4;        // padded fp32 row stride of a chunk (68 words: conflict-free LDS.128 across rows)
-constexpr int NCHUNKBUF = 3;
+constexpr int XCH = 256;             // cells per staged chunk: one 1 KB bulk copy per field row (256 B copies starve the TMA unit)
+constexpr int SUB = 64;              // cells per sub-chunk = 4 K-steps of 16 = one round of the four operand stages
+constexpr int NSUB = XCH / SUB;
+constexpr int ROWF = XCH + 4;        // padded fp32 row stride of a chunk (== 4 mod 32 words: conflict-free LDS.128 across rows)
+constexpr int NCHUNKBUF = 2;
 constexpr int TMEM_COLS = 512;
 constexpr unsigned WATCHDOG = 1u << 22;       // x 20 us suspend hint
 
@@ -51,14 +54,17 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 }
 // try_wait suspends the thread in hardware up to the hinted time, so waiting warps do not burn the issue
 // slots the MMA-issuing warp needs (polling formers made that warp the bottleneck: profiles/r1)
+__constant__ unsigned int c_wait_hint_ns = 20000u;
+
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
+    const uint32_t hint = c_wait_hint_ns;
     const uint32_t a = smem_u32(bar);
     uint32_t done = 0;
     unsigned spins = 0;
     while (true) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(a), "r"(parity), "r"(20000u) : "memory");
+                     : "=r"(done) : "r"(a), "r"(parity), "r"(hint) : "memory");
         if (done) break;
         if (++spins > WATCHDOG) asm volatile("trap;");      // a protocol bug must not hang the GPU
     }
@@ -160,14 +166,16 @@ struct Params {
     int tile_cols;                // TMEM column spacing of one accumulator tile: 64 (NT <= 64) or 128
     const int* lane_ij;           // [128][5]: field slot i of the lane and j of its row in tiles 0..3 (-1: padding row)
     long long nchunk;             // ncell / XCH
-    int flush_chunks;             // TMEM accumulators are drained (fp32, round-to-nearest) every flush_chunks chunks (x4 K-steps)
+    int flush_chunks;             // TMEM accumulators are drained (fp32, round-to-nearest) every flush_chunks 64-cell sub-chunks
     int gflush_drains;            // the fp32 accumulators go to float64 global every gflush_drains drains
     double* partial;              // [gridDim.x][NT][MT*128] float64 partial sums (zeroed by the host)
+    int debug;                    // ablation bits (profiling only): 1 no MMAs, 2 no forming math, 4 no tcgen05.st, 8 no drain body,
+                                  //                                  16 no TMA copies, 32 no B forming
 };
 
 constexpr int NFWARPS = 16;                      // A-operand formers: 4 groups (one per K-step of a chunk) x 4 lane quarters
-constexpr int W_MMA = 16, W_TMA = 17, W_B = 18;  // warp roles
-constexpr int NTHR = 19 * 32;
+constexpr int W_MMA = 16, W_TMA = 17, W_B = 18;  // warp roles; B formers are warps 18..21, one per operand stage
+constexpr int NTHR = 22 * 32;
 constexpr int TMEM_A0 = 256;
 
 // TMEM map (512 columns): [0,256) accumulator tiles (tile m at m*tile_cols);
@@ -184,7 +192,7 @@ __device__ __forceinline__ void drain_accumulators(const Params& p, uint64_t* ac
     tc_fence_after();
     const bool to_global = (++ndrain == p.gflush_drains) || final_drain;
     if (to_global) ndrain = 0;
-    if (live) {
+    if (live && !(p.debug & 8)) {
         double* dst = p.partial + (size_t)blockIdx.x * MR * NT + (size_t)row;     // [col][row]: coalesced
         for (int c0 = 0; c0 < NT; c0 += 16) {
             float v[16];
@@ -226,7 +234,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_tri_tc(Params p)
     uint64_t* bars = reinterpret_cast<uint64_t*>(accs + (size_t)(NT / 4) * MR);
     uint64_t* chunk_full = bars;                  // [NCHUNKBUF]  TMA -> formers + B warp (tx bytes)
     uint64_t* chunk_empty = bars + NCHUNKBUF;     // [NCHUNKBUF]  16 former warps + B warp -> TMA
-    uint64_t* st_full = chunk_empty + NCHUNKBUF;  // [4]          4 former warps of the group + B warp -> MMA
+    uint64_t* st_full = chunk_empty + NCHUNKBUF;  // [4]          8 former warps (two tile-pair groups) + B warp -> MMA
     uint64_t* st_empty = st_full + 4;             // [4]          MMA (commit) -> formers of the group, B warp
     uint64_t* acc_full = st_empty + 4;            // [1]          MMA (commit) -> drain
     uint64_t* acc_empty = acc_full + 1;           // [1]          drain (16 warps) -> MMA
@@ -235,8 +243,8 @@ __global__ void __launch_bounds__(NTHR, 1) k_tri_tc(Params p)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
-        for (int i = 0; i < NCHUNKBUF; ++i) { mbar_init(&chunk_full[i], 1); mbar_init(&chunk_empty[i], NFWARPS + 1); }
-        for (int i = 0; i < 4; ++i) { mbar_init(&st_full[i], 5); mbar_init(&st_empty[i], 1); }
+        for (int i = 0; i < NCHUNKBUF; ++i) { mbar_init(&chunk_full[i], 1); mbar_init(&chunk_empty[i], NFWARPS + 4); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&st_full[i], 9); mbar_init(&st_empty[i], 1); }
         mbar_init(acc_full, 1);
         mbar_init(acc_empty, NFWARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -265,9 +273,10 @@ __global__ void __launch_bounds__(NTHR, 1) k_tri_tc(Params p)
         for (int c = 0; c < nch; ++c) {
             if (lane == 0) {
                 mbar_wait(&chunk_empty[buf], ph ^ 1);
-                mbar_arrive_expect_tx(&chunk_full[buf], (uint32_t)(S * XCH * 4));
+                mbar_arrive_expect_tx(&chunk_full[buf], (p.debug & 16) ? 0u : (uint32_t)(S * XCH * 4));
             }
             __syncwarp();
+            if (p.debug & 16) { if (++buf == NCHUNKBUF) { buf = 0; ph ^= 1; } continue; }
             const long long x0 = (c_begin + c) * XCH;
             float* dst = chunk + (size_t)buf * S * ROWF;
             if (src0) bulk_g2s(dst + (size_t)lane * ROWF, src0 + x0, XCH * 4, &chunk_full[buf]);
@@ -285,19 +294,20 @@ __global__ void __launch_bounds__(NTHR, 1) k_tri_tc(Params p)
             const uint32_t tc_ = (uint32_t)p.tile_cols;
             int cf = 0;
             uint32_t eph = 0;
-            for (int c = 0; c < nch; ++c) {
+            const int nsub = nch * NSUB;
+            for (int c = 0; c < nsub; ++c) {                                       // c counts 64-cell sub-chunks here
                 const uint32_t ph = (uint32_t)(c & 1);
                 if (cf == 0 && c > 0) { mbar_wait(acc_empty, eph); eph ^= 1; }      // previous period drained
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     const uint32_t acc = (cf == 0 && g == 0) ? 0u : 1u;
                     mbar_wait(&st_full[g], ph);
-                    tc_fence_after();
+                    if (!(p.debug & 128)) tc_fence_after();
                     const uint64_t dbh = dbh0 + dstep * (uint64_t)g, dbl = dbl0 + dstep * (uint64_t)g;
                     const uint32_t a0 = tmem_base + (uint32_t)(TMEM_A0 + g * 64);
 #pragma unroll
                     for (int m = 0; m < 4; ++m) {
-                        if (m < MT) {
+                        if (m < MT && !(p.debug & 1)) {
                             const uint32_t d = tmem_base + (uint32_t)m * tc_;
                             const uint32_t ah = a0 + (uint32_t)(m * 16);
                             umma_f16_ts(d, ah, dbh, idesc, acc);
@@ -305,22 +315,26 @@ __global__ void __launch_bounds__(NTHR, 1) k_tri_tc(Params p)
                             umma_f16_ts(d, ah + 8u, dbh, idesc, 1u);
                         }
                     }
+                    if (p.debug & 64) mbar_arrive(&st_empty[g]); else
                     umma_commit(&st_empty[g]);                                   // operands of this stage consumed
                 }
-                if (++cf == FC || c == nch - 1) { umma_commit(acc_full); cf = 0; }
+                if (++cf == FC || c == nsub - 1) { if (p.debug & 64) mbar_arrive(acc_full); else umma_commit(acc_full); cf = 0; }
             }
         }
-    } else if (warp == W_B) {
+    } else if (warp >= W_B) {
         // ------------------------------------------------------------------ B-operand former: fields -> fp16 hi/lo tiles
         int buf = 0;
         uint32_t cph = 0;
         const int nbcell = 2 * NT;                               // (l, kchunk) cells of the B tile per K-step
         for (int c = 0; c < nch; ++c) {
             mbar_wait(&chunk_full[buf], cph);
-            const float* ch = chunk + (size_t)buf * S * ROWF;
-            for (int g = 0; g < 4; ++g) {
-                mbar_wait(&st_empty[g], (uint32_t)(c & 1) ^ 1);
-                for (int cell = lane; cell < nbcell; cell += 32) {
+            for (int sub = 0; sub < NSUB; ++sub) {
+            const float* ch = chunk + (size_t)buf * S * ROWF + sub * SUB;
+            const uint32_t sph = (uint32_t)((c * NSUB + sub) & 1);
+            {
+                const int g = warp - W_B;                         // this warp's operand stage (K-step g of every sub-chunk)
+                mbar_wait(&st_empty[g], sph ^ 1);
+                for (int cell = lane; cell < ((p.debug & 32) ? 0 : nbcell); cell += 32) {
                     const int l = cell >> 1, kc = cell & 1;
                     uint4 h4 = make_uint4(0, 0, 0, 0), l4 = h4;
                     if (l < S) {
@@ -337,71 +351,87 @@ __global__ void __launch_bounds__(NTHR, 1) k_tri_tc(Params p)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&st_full[g]);
             }
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(&chunk_empty[buf]);
             if (++buf == NCHUNKBUF) { buf = 0; cph ^= 1; }
         }
     } else {
         // ------------------------------------------------------------------ A-operand formers (+ TMEM drain)
-        // warp = 4*g + q: group g forms K-step g of every chunk (== operand stage g); thread = TMEM lane 32*q + lane,
-        // which it owns in ALL tiles: rows (m*128 + lane) share the field i, so I_i is loaded once for MT products.
-        const int g = warp >> 2, q = warp & 3;
+        // warp = 4*g + q, g = 2*kp + tp: the group forms tiles {2tp, 2tp+1} of the K-steps kp and kp+2 of every chunk,
+        // i.e. it alternates between two operand stages, so forming overlaps the MMAs of its other stage.  A thread is
+        // one TMEM lane (32*q + lane) in both tiles: the two rows share the field i, which is loaded once.
+        const int g = warp >> 2, q = warp & 3, tp = g & 1, kp = g >> 1;
         const int tl = q * 32 + lane;                            // TMEM lane
         const int* lij = p.lane_ij + tl * 5;
         const int fi = lij[0];
-        int fj[4];
-#pragma unroll
-        for (int m = 0; m < 4; ++m) fj[m] = lij[1 + m];
+        const int fj0 = lij[1 + 2 * tp], fj1 = lij[2 + 2 * tp];
+        const bool t0 = 2 * tp < MT, t1 = 2 * tp + 1 < MT;
+        const bool r0 = fi >= 0 && fj0 >= 0, r1 = fi >= 0 && fj1 >= 0;
         const uint32_t lane_quarter = (uint32_t)(q * 32) << 16;
-        const uint32_t t_a = tmem_base + lane_quarter + (uint32_t)(TMEM_A0 + g * 64);
+        const uint32_t t_a = tmem_base + lane_quarter + (uint32_t)(TMEM_A0 + 2 * tp * 16);
         const bool drain_live = g < MT;                          // group g drains accumulator tile g
         const uint32_t t_acc = tmem_base + lane_quarter + (uint32_t)(g * p.tile_cols);
         const int drow = g * 128 + tl;
-        const uint32_t fio = (uint32_t)(fi < 0 ? 0 : fi) * ROWF + g * 16;
+        const uint32_t fio = (uint32_t)(fi < 0 ? 0 : fi) * ROWF, fjo0 = (uint32_t)(fj0 < 0 ? 0 : fj0) * ROWF, fjo1 = (uint32_t)(fj1 < 0 ? 0 : fj1) * ROWF;
         int buf = 0, cf = 0, ndrain = 0, pending = 0;
         uint32_t cph = 0, aph = 0;
         for (int c = 0; c < nch; ++c) {
             mbar_wait(&chunk_full[buf], cph);
-            const float* ch = chunk + (size_t)buf * S * ROWF;
-            mbar_wait(&st_empty[g], (uint32_t)(c & 1) ^ 1);
-            tc_fence_after();
-            float4 vi[4];
+#pragma unroll 1
+            for (int sub = 0; sub < NSUB; ++sub) {
+            const float* ch = chunk + (size_t)buf * S * ROWF + sub * SUB;
+            const int t = c * NSUB + sub;                      // running sub-chunk index: stage phases flip once per sub-chunk
 #pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) vi[q4] = *reinterpret_cast<const float4*>(ch + fio + q4 * 4);
+            for (int h = 0; h < 2; ++h) {
+                const int kk = kp + 2 * h;
+                mbar_wait(&st_empty[kk], (uint32_t)(t & 1) ^ 1);
+                tc_fence_after();
+                float4 vi[4];
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
-                if (m < MT) {
-                    uint32_t hi[8], lo[8];
-                    if (fi >= 0 && fj[m] >= 0) {
-                        const float* pj = ch + (uint32_t)fj[m] * ROWF + g * 16;
+                for (int q4 = 0; q4 < 4; ++q4) vi[q4] = *reinterpret_cast<const float4*>(ch + fio + kk * 16 + q4 * 4);
 #pragma unroll
-                        for (int q4 = 0; q4 < 4; ++q4) {
-                            const float4 b = *reinterpret_cast<const float4*>(pj + q4 * 4);
-                            split2(vi[q4].x * b.x, vi[q4].y * b.y, hi[2 * q4], lo[2 * q4]);
-                            split2(vi[q4].z * b.z, vi[q4].w * b.w, hi[2 * q4 + 1], lo[2 * q4 + 1]);
+                for (int mm = 0; mm < 2; ++mm) {
+                    if (mm == 0 ? t0 : t1) {
+                        uint32_t hi[8], lo[8];
+                        if ((mm == 0 ? r0 : r1) && !(p.debug & 2)) {
+                            const float* pj = ch + (mm == 0 ? fjo0 : fjo1) + kk * 16;
+#pragma unroll
+                            for (int q4 = 0; q4 < 4; ++q4) {
+                                const float4 b = *reinterpret_cast<const float4*>(pj + q4 * 4);
+                                split2(vi[q4].x * b.x, vi[q4].y * b.y, hi[2 * q4], lo[2 * q4]);
+                                split2(vi[q4].z * b.z, vi[q4].w * b.w, hi[2 * q4 + 1], lo[2 * q4 + 1]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) { hi[k] = 0u; lo[k] = 0u; }       // padding rows
                         }
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) { hi[k] = 0u; lo[k] = 0u; }       // padding rows
+                        if (!(p.debug & 4)) {
+                            tmem_st8(t_a + (uint32_t)(kk * 64 + mm * 16), hi);
+                            tmem_st8(t_a + (uint32_t)(kk * 64 + mm * 16 + 8), lo);
+                        }
                     }
-                    tmem_st8(t_a + (uint32_t)(m * 16), hi);
-                    tmem_st8(t_a + (uint32_t)(m * 16 + 8), lo);
                 }
+                if (!(p.debug & 4)) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&st_full[kk]);
             }
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) { mbar_arrive(&st_full[g]); mbar_arrive(&chunk_empty[buf]); }
-            if (++buf == NCHUNKBUF) { buf = 0; cph ^= 1; }
-            // Drain the previous period one chunk late: its MMAs are done by now (no wait on acc_full) while the tensor
-            // core still has this chunk's four K-steps queued.  The last chunk also drains its own period.
-            const bool last = c == nch - 1;
+            if (sub == NSUB - 1) {                 // all reads of this chunk buffer are done
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&chunk_empty[buf]);
+            }
+            // Drain the previous period one sub-chunk late: its MMAs are done by now (no wait on acc_full) while the
+            // tensor core still has this sub-chunk's K-steps queued.  The last sub-chunk also drains its own period.
+            const bool last = (c == nch - 1) && (sub == NSUB - 1);
             if (pending) {
                 drain_accumulators(p, acc_full, acc_empty, aph, ndrain, false, drain_live, t_acc, accs, MR, NT, drow, lane);
                 pending = 0;
             }
             if (++cf == FC) { cf = 0; pending = 1; }
             if (last) drain_accumulators(p, acc_full, acc_empty, aph, ndrain, true, drain_live, t_acc, accs, MR, NT, drow, lane);
+            }
+            if (++buf == NCHUNKBUF) { buf = 0; cph ^= 1; }
         }
     }
     // ---------------------------------------------------------------------- teardown
@@ -450,6 +480,10 @@ int triangle_sums_tc_pass(const float* const* fields, int S, long long ncell, co
     Params p;
     p.fields = fields; p.S = S; p.NT = NT; p.MT = MT; p.tile_cols = tile_cols; p.lane_ij = lane_ij; p.nchunk = ncell / XCH;
     p.partial = static_cast<double*>(ws);
+    p.debug = 0;
+    { unsigned int hint = 20000u; if (const char* e = getenv("PSB_TC_HINT")) hint = (unsigned)atoi(e);
+      cudaMemcpyToSymbolAsync(c_wait_hint_ns, &hint, sizeof(hint), 0, cudaMemcpyHostToDevice, st); }
+    if (const char* e = getenv("PSB_TC_DEBUG")) p.debug = atoi(e);
     p.flush_chunks = 4;          // 16 K-steps = 48 accumulating MMAs per accumulator between round-to-nearest drains
     p.gflush_drains = 64;
     if (const char* e = getenv("PSB_TC_FLUSH")) { int v = atoi(e); if (v >= 1 && v <= 4096) p.flush_chunks = v; }
