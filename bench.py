@@ -142,18 +142,16 @@ class ClockSampler(object):
 def run_b200(args):
     import torch
     import torch.distributed as dist
-    rank = int(os.environ.get('RANK', 0))
-    world = int(os.environ.get('WORLD_SIZE', 1))
-    local = int(os.environ.get('LOCAL_RANK', 0))
+    from pyspectrum_b200 import dist as D
+    rank, world, local = D.rank_info()
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
+    D.init('nccl', dev)
     from pyspectrum_b200 import pyspectrum as pySpec
 
     L, N, step, Ncut, Nmax = CFG['Lbox'], CFG['Ngrid'], CFG['step'], CFG['Ncut'], CFG['Nmax']
     s0 = Ncut // step
-    xyz_dev = lognormal_catalogue_torch(2 + rank, dev, CFG['Np_target'], L, N)
+    xyz_dev = lognormal_catalogue_torch(D.catalogue_seed(2, rank), dev, CFG['Np_target'], L, N)
     Np = xyz_dev.shape[1]
     xyz_host = torch.empty((3, Np), dtype=torch.float64, pin_memory=True)
     xyz_host.copy_(xyz_dev)
@@ -173,10 +171,7 @@ def run_b200(args):
         sums = pipe.triangle_sums(fields, Nmax, Ncut, step, engine=engine)
         return torch.cat([sums, sumsq, scales.double()]).to('cpu', non_blocking=False)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    barrier = D.barrier
 
     for _ in range(args.warmup):
         step_device()
@@ -218,10 +213,7 @@ def run_b200(args):
     ck = clocks.stop()
     assert len(out['b123']) == len(tri) == 6350 and np.all(np.isfinite(out['b123']))
 
-    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    dev_ms, e2e_ms = D.max_over_ranks([dev_ms, e2e_s * 1e3], device=dev)
     ncat = args.steps * world
     if rank == 0:
         ncell = N ** 3
