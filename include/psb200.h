@@ -104,7 +104,8 @@ int psb_bk_shell_pair_f32(const float* half_c64, const uint16_t* irk_of_m, int n
  * maxabs2 = device uint32[2] receiving max|stored value| as float bits (atomicMax; zero it first).
  * psb_bk_shell_scales turns per-shell power sums (psb_pk_monopole with the shell table as bin table:
  * psum[j] = sum_{k in shell j+1} |delta|^2) into scales[j] = 2^round(log2(target_rms / sqrt(psum[j]))). */
-/* psum[j] = sum_{k in shell j+1, full grid} |delta(k)|^2, j = 0..nshell-1 (Parseval: = sum_x I_{j+1}^2 / N^3) */
+/* psum[j] ~ sum_{k in shell j+1, full grid} |delta(k)|^2, j = 0..nshell-1 (Parseval: = sum_x I_{j+1}^2 / N^3); exact for the first
+ * four shells, a 1-in-8 sampled estimate beyond -- it only feeds the power-of-two scale, the exact shell power comes from K5 */
 int psb_bk_shell_power(const float* half_c64, int ngrid, const uint16_t* irk_of_m, int nshell, double* psum, void* stream);
 int psb_bk_shell_scales(const double* psum, int nshell, float target_rms, float* scales, void* stream);
 int psb_bk_shell_pair_f64(const float* half_c64, const uint16_t* irk_of_m, int ngrid, int sa, int sb, int R,

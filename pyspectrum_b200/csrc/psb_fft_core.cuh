@@ -148,7 +148,7 @@ PSB_HD void stage_read(const Cx<T>* s, int estride, int N, int j, Cx<T>* v)
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int q = 0; q < R; ++q) v[q] = s[(size_t)(j + q * M) * estride];
+    for (int q = 0; q < R; ++q) v[q] = s[(j + q * M) * estride];
 }
 
 template <int R, int DIR, typename T>
@@ -171,7 +171,7 @@ PSB_HD void stage_write(Cx<T>* s, int estride, int N, int Ns, int j, const Cx<T>
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int q = 0; q < R; ++q) s[(size_t)(j0 + q * Ns) * estride] = v[q];
+    for (int q = 0; q < R; ++q) s[(j0 + q * Ns) * estride] = v[q];
 }
 
 }  // namespace psb

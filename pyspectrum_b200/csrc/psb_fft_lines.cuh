@@ -84,20 +84,21 @@ struct DynStages {
     }
 };
 
-template <typename T, int DIR, int MAXB, int NTHR, class STAGES, class IO>
-__global__ void __launch_bounds__(NTHR) fft_lines_kernel(FftPlan plan, int LPC, int TPL, const Cx<T>* __restrict__ tw_g, IO io)
+template <typename T, int DIR, int MAXB, int NTHR, int MINB, int LPC_T, class STAGES, class IO>
+__global__ void __launch_bounds__(NTHR, MINB) fft_lines_kernel(FftPlan plan, int lpc_rt, int TPL, const Cx<T>* __restrict__ tw_g, IO io)
 {
     extern __shared__ __align__(16) unsigned char psb_smem[];
     const int N = STAGES::IS_STATIC ? STAGES::N : plan.N;
-    const int LPCP = LPC + 1;
+    const int LPC = LPC_T > 0 ? LPC_T : lpc_rt;          // compile-time for the compiled plans: index math folds to shifts
+    const int LPCP = LPC + 2;                            // even row pitch: two adjacent lines form an aligned 16-byte pair
     Cx<T>* s = reinterpret_cast<Cx<T>*>(psb_smem);
     Cx<T>* tw = s + (size_t)N * LPCP;
     for (int i = threadIdx.x; i < N; i += blockDim.x) tw[i] = tw_g[i];
-    io.load(s, LPCP, LPC, N);
+    io.template load<LPC_T>(s, LPCP, LPC, N);
     __syncthreads();
     const int line = threadIdx.x % LPC, t = threadIdx.x / LPC;
     STAGES::template run<T, DIR, MAXB>(plan, s + line, LPCP, t, TPL, tw);
-    io.store(s, LPCP, LPC, N);
+    io.template store<LPC_T>(s, LPCP, LPC, N);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -106,26 +107,35 @@ __global__ void __launch_bounds__(NTHR) fft_lines_kernel(FftPlan plan, int LPC, 
 template <typename T> struct IoRows {
     Cx<T>* g;
     long long nrows;
-    __device__ void load(Cx<T>* s, int LPCP, int LPC, int N) const {
+    template <int LPC_T> __device__ void load(Cx<T>* s, int LPCP, int LPC, int N) const {
         const long long row0 = (long long)blockIdx.x * LPC;
+        const Cx<T>* base = g + row0 * N;
+        const int nvalid = (int)((nrows - row0 < LPC ? nrows - row0 : LPC)) * N;
         for (int e = threadIdx.x; e < LPC * N; e += blockDim.x) {
             const int line = e / N, idx = e - line * N;
-            const long long row = row0 + line;
-            s[(size_t)idx * LPCP + line] = row < nrows ? g[row * N + idx] : mk<T>(0, 0);
+            s[idx * LPCP + line] = e < nvalid ? base[e] : mk<T>(0, 0);
         }
     }
-    __device__ void store(const Cx<T>* s, int LPCP, int LPC, int N) const {
+    template <int LPC_T> __device__ void store(const Cx<T>* s, int LPCP, int LPC, int N) const {
         const long long row0 = (long long)blockIdx.x * LPC;
-        for (int e = threadIdx.x; e < LPC * N; e += blockDim.x) {
+        Cx<T>* base = g + row0 * N;
+        const int nvalid = (int)((nrows - row0 < LPC ? nrows - row0 : LPC)) * N;
+        for (int e = threadIdx.x; e < nvalid; e += blockDim.x) {
             const int line = e / N, idx = e - line * N;
-            const long long row = row0 + line;
-            if (row < nrows) g[row * N + idx] = s[(size_t)idx * LPCP + line];
+            base[e] = s[idx * LPCP + line];
         }
     }
 };
 
 // lines = `nlines` consecutive elements; line element idx lives at  base(b) + cidx*in_istride + line
 // where cidx = idx (dense) or the compact index of signed k in [-Rm, Rp] (pruned, zero outside).
+template <typename T> struct Pair;                     // two adjacent complex elements as one vector access
+template <> struct alignas(16) Pair<float> { Cx<float> a, b; };
+template <> struct alignas(32) Pair<double> { Cx<double> a, b; };
+template <typename T> struct Real2;
+template <> struct alignas(8) Real2<float> { float a, b; };
+template <> struct alignas(16) Real2<double> { double a, b; };
+
 template <typename T, bool PRUNED, bool REALOUT> struct IoCols {
     const Cx<T>* in;
     Cx<T>* out;            // complex output (REALOUT == false)
@@ -133,50 +143,53 @@ template <typename T, bool PRUNED, bool REALOUT> struct IoCols {
     double* sumsq;         // REALOUT: sumsq[0] += sum re^2, sumsq[1] += sum im^2 (of the stored, scaled values)
     const float* scale2;   // REALOUT: optional power-of-two scales for (re, im) applied before the store
     unsigned int* maxabs2; // REALOUT: optional running max |stored value| per plane (float bits, atomicMax)
-    int nlines;
+    int nlines;            // even; line strides and batch strides are even too (N is even) -> line pairs are 16-byte aligned
     long long in_bstride, in_istride, out_bstride, out_istride;
     int Rm, Rp;
-    __device__ void load(Cx<T>* s, int LPCP, int LPC, int N) const {
-        const int l0 = blockIdx.x * LPC;
-        const Cx<T>* base = in + (long long)blockIdx.y * in_bstride;
-        for (int e = threadIdx.x; e < LPC * N; e += blockDim.x) {
-            const int idx = e / LPC, line = e - idx * LPC;
-            Cx<T> v = mk<T>(0, 0);
+    template <int LPC_T> __device__ void load(Cx<T>* s, int LPCP, int LPC, int N) const {
+        const int l0 = blockIdx.x * LPC, HP = LPC / 2;
+        const Cx<T>* base = in + (long long)blockIdx.y * in_bstride + l0;
+        for (int e = threadIdx.x; e < HP * N; e += blockDim.x) {
+            const int idx = e / HP, line = 2 * (e - idx * HP);
+            Pair<T> v;
+            v.a = mk<T>(0, 0); v.b = v.a;
             if (l0 + line < nlines) {
                 if (PRUNED) {
                     const int k = kfreq(idx, N);
-                    if (k >= -Rm && k <= Rp) v = base[(long long)(k + Rm) * in_istride + l0 + line];
+                    if (k >= -Rm && k <= Rp) v = *reinterpret_cast<const Pair<T>*>(base + (long long)(k + Rm) * in_istride + line);
                 } else {
-                    v = base[(long long)idx * in_istride + l0 + line];
+                    v = *reinterpret_cast<const Pair<T>*>(base + (long long)idx * in_istride + line);
                 }
             }
-            s[(size_t)idx * LPCP + line] = v;
+            *reinterpret_cast<Pair<T>*>(s + idx * LPCP + line) = v;
         }
     }
-    __device__ void store(const Cx<T>* s, int LPCP, int LPC, int N) const {
-        const int l0 = blockIdx.x * LPC;
+    template <int LPC_T> __device__ void store(const Cx<T>* s, int LPCP, int LPC, int N) const {
+        const int l0 = blockIdx.x * LPC, HP = LPC / 2;
         if (!REALOUT) {
-            Cx<T>* base = out + (long long)blockIdx.y * out_bstride;
-            for (int e = threadIdx.x; e < LPC * N; e += blockDim.x) {
-                const int idx = e / LPC, line = e - idx * LPC;
-                if (l0 + line < nlines) base[(long long)idx * out_istride + l0 + line] = s[(size_t)idx * LPCP + line];
+            Cx<T>* base = out + (long long)blockIdx.y * out_bstride + l0;
+            for (int e = threadIdx.x; e < HP * N; e += blockDim.x) {
+                const int idx = e / HP, line = 2 * (e - idx * HP);
+                if (l0 + line < nlines)
+                    *reinterpret_cast<Pair<T>*>(base + (long long)idx * out_istride + line) = *reinterpret_cast<const Pair<T>*>(s + idx * LPCP + line);
             }
         } else {
-            const long long boff = (long long)blockIdx.y * out_bstride;
+            const long long boff = (long long)blockIdx.y * out_bstride + l0;
             double qa = 0.0, qb = 0.0;
             const T sa_ = scale2 ? (T)scale2[0] : (T)1, sb_ = scale2 ? (T)scale2[1] : (T)1;
             T ma = 0, mb = 0;
-            for (int e = threadIdx.x; e < LPC * N; e += blockDim.x) {
-                const int idx = e / LPC, line = e - idx * LPC;
+            for (int e = threadIdx.x; e < HP * N; e += blockDim.x) {
+                const int idx = e / HP, line = 2 * (e - idx * HP);
                 if (l0 + line < nlines) {
-                    Cx<T> v = s[(size_t)idx * LPCP + line];
-                    v.x *= sa_; v.y *= sb_;
-                    ma = fmax(ma, fabs(v.x)); mb = fmax(mb, fabs(v.y));
-                    const long long o = boff + (long long)idx * out_istride + l0 + line;
-                    outa[o] = v.x;
-                    if (outb) outb[o] = v.y;
-                    qa += (double)v.x * (double)v.x;
-                    qb += (double)v.y * (double)v.y;
+                    const Pair<T> v = *reinterpret_cast<const Pair<T>*>(s + idx * LPCP + line);
+                    Real2<T> ra, rb;
+                    ra.a = v.a.x * sa_; ra.b = v.b.x * sa_; rb.a = v.a.y * sb_; rb.b = v.b.y * sb_;
+                    ma = fmax(ma, fmax(fabs(ra.a), fabs(ra.b))); mb = fmax(mb, fmax(fabs(rb.a), fabs(rb.b)));
+                    const long long o = boff + (long long)idx * out_istride + line;
+                    *reinterpret_cast<Real2<T>*>(outa + o) = ra;
+                    if (outb) *reinterpret_cast<Real2<T>*>(outb + o) = rb;
+                    qa += (double)ra.a * (double)ra.a + (double)ra.b * (double)ra.b;
+                    qb += (double)rb.a * (double)rb.a + (double)rb.b * (double)rb.b;
                 }
             }
             if (maxabs2) {
@@ -207,7 +220,7 @@ struct IoZFcomb {
     const float* Wk;           // window table, N/2+1
     const double* sumw;        // device scalar: sum of weights (periodic) -- ignored if !periodic
     int periodic;
-    __device__ void load(Cx<float>* s, int LPCP, int LPC, int N) const {
+    template <int LPC_T> __device__ void load(Cx<float>* s, int LPCP, int LPC, int N) const {
         const int HW = LPC / 2, h = N / 2;
         const int kx0 = blockIdx.x * HW, ky = blockIdx.y;
         for (int e = threadIdx.x; e < LPC * N; e += blockDim.x) {
@@ -219,10 +232,10 @@ struct IoZFcomb {
                 const int x = line < HW ? kx : kneg(kx, N), y = line < HW ? ky : kneg(ky, N);
                 v = g[((long long)idx * N + y) * N + x];
             }
-            s[(size_t)idx * LPCP + line] = v;
+            s[idx * LPCP + line] = v;
         }
     }
-    __device__ void store(const Cx<float>* s, int LPCP, int LPC, int N) const {
+    template <int LPC_T> __device__ void store(const Cx<float>* s, int LPCP, int LPC, int N) const {
         const int HW = LPC / 2, h = N / 2;
         const int kx0 = blockIdx.x * HW, ky = blockIdx.y;
         const float cf = periodic ? 1.f / (864.f * (float)(*sumw)) : 1.f / 864.f;     // f:615 / f:686
@@ -230,8 +243,8 @@ struct IoZFcomb {
             const int kz = e / HW, l = e - kz * HW;
             const int kx = kx0 + l;
             if (kx <= h) {
-                const Cx<float> Fk = s[(size_t)kz * LPCP + l];
-                const Cx<float> Fm = s[(size_t)kneg(kz, N) * LPCP + HW + l];
+                const Cx<float> Fk = s[kz * LPCP + l];
+                const Cx<float> Fm = s[kneg(kz, N) * LPCP + HW + l];
                 half[((long long)kz * N + ky) * (h + 1) + kx] = fcomb_value(N, kx, ky, kz, Fk, Fm, rec, Wk, cf);
             }
         }
@@ -245,7 +258,7 @@ template <typename T> struct IoShellX {
     Cx<T>* out;                // T1 [kz'][ky'][x]
     int sa, sb;                // shell indices packed as real / imaginary part (sb < 0: none)
     int Rm, Rp, W;             // signed k range [-Rm,Rp], W = Rm+Rp+1
-    __device__ void load(Cx<T>* s, int LPCP, int LPC, int N) const {
+    template <int LPC_T> __device__ void load(Cx<T>* s, int LPCP, int LPC, int N) const {
         const int h = N / 2;
         const int kyp0 = blockIdx.x * LPC, kzp = blockIdx.y;
         const int kz = kzp - Rm;
@@ -274,15 +287,15 @@ template <typename T> struct IoShellX {
                     v = (sh == sa) ? mk<T>((T)d.x, (T)d.y) : mk<T>(-(T)d.y, (T)d.x);
                 }
             }
-            s[(size_t)idx * LPCP + line] = v;
+            s[idx * LPCP + line] = v;
         }
     }
-    __device__ void store(const Cx<T>* s, int LPCP, int LPC, int N) const {
+    template <int LPC_T> __device__ void store(const Cx<T>* s, int LPCP, int LPC, int N) const {
         const int kyp0 = blockIdx.x * LPC, kzp = blockIdx.y;
         for (int e = threadIdx.x; e < LPC * N; e += blockDim.x) {
             const int line = e / N, idx = e - line * N;
             const int kyp = kyp0 + line;
-            if (kyp < W) out[((long long)kzp * W + kyp) * N + idx] = s[(size_t)idx * LPCP + line];
+            if (kyp < W) out[((long long)kzp * W + kyp) * N + idx] = s[idx * LPCP + line];
         }
     }
 };
@@ -291,9 +304,9 @@ template <typename T> struct IoShellX {
 // launch: compiled plans for the production grids (BASELINE configs: 256, 360, 512, 1024) and the
 // small grids the parity tests use; any other N = 2^a 3^b 5^c takes the runtime-plan fallback.
 // ---------------------------------------------------------------------------------------
-template <class STAGES, int LPC_, int MAXB_> struct Cfg {
+template <class STAGES, int LPC_, int MAXB_, int MINB_ = 1> struct Cfg {
     using Stages = STAGES;
-    static constexpr int LPC = LPC_, MAXB = MAXB_;
+    static constexpr int LPC = LPC_, MAXB = MAXB_, MINB = MINB_;
     static constexpr int TPL = (STAGES::NB_MAX + MAXB_ - 1) / MAXB_;
     static constexpr int NTHR = LPC * TPL;
     static_assert(NTHR <= 1024, "too many threads");
@@ -304,9 +317,11 @@ template <typename T, int DIR, class CFG, class IO>
 static int launch_static(dim3 grid, const Cx<T>* tw, const IO& io, cudaStream_t st)
 {
     constexpr int N = CFG::Stages::N;
-    const size_t smem = ((size_t)N * (CFG::LPC + 1) + N) * sizeof(Cx<T>);
-    auto kern = fft_lines_kernel<T, DIR, CFG::MAXB, CFG::NTHR, typename CFG::Stages, IO>;
+    const size_t smem = ((size_t)N * (CFG::LPC + 2) + N) * sizeof(Cx<T>);
+    auto kern = fft_lines_kernel<T, DIR, CFG::MAXB, CFG::NTHR, (sizeof(T) == 4 ? CFG::MINB : 1), CFG::LPC, typename CFG::Stages, IO>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PSB_ERR_CUDA;
+    // ask for the largest shared-memory carveout so that several CTAs co-reside and overlap load / FFT / store
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     FftPlan p; p.N = N; p.nstages = 0; p.nb_max = 0;
     kern<<<grid, CFG::NTHR, smem, st>>>(p, CFG::LPC, CFG::TPL, tw, io);
     return cudaGetLastError() == cudaSuccess ? PSB_OK : PSB_ERR_CUDA;
@@ -317,9 +332,9 @@ static int launch_dyn(const FftPlan& p, int LPC, dim3 grid, const Cx<T>* tw, con
 {
     const int TPL = (p.nb_max + 1) / 2;
     if (LPC * TPL > 256) return PSB_ERR_UNSUPPORTED_N;
-    const size_t smem = ((size_t)p.N * (LPC + 1) + p.N) * sizeof(Cx<T>);
+    const size_t smem = ((size_t)p.N * (LPC + 2) + p.N) * sizeof(Cx<T>);
     if (smem > 200 * 1024) return PSB_ERR_UNSUPPORTED_N;
-    auto kern = fft_lines_kernel<T, DIR, 2, 256, DynStages, IO>;
+    auto kern = fft_lines_kernel<T, DIR, 2, 256, 1, 0, DynStages, IO>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PSB_ERR_CUDA;
     kern<<<grid, LPC * TPL, smem, st>>>(p, LPC, TPL, tw, io);
     return cudaGetLastError() == cudaSuccess ? PSB_OK : PSB_ERR_CUDA;
@@ -330,6 +345,7 @@ static inline int dyn_lpc(const FftPlan& p) { int tpl = (p.nb_max + 1) / 2; int 
 
 // F is a generic callable: f(cfg_tag) -> int, where cfg_tag is Cfg<...>{} or CfgDyn{}
 #define PSB_PLAN_CASE(N_, LPC_, MAXB_, ...) case N_: return f(Cfg<StaticStages<__VA_ARGS__>, LPC_, MAXB_>{});
+#define PSB_PLAN_CASE_OCC(N_, LPC_, MAXB_, MINB_, ...) case N_: return f(Cfg<StaticStages<__VA_ARGS__>, LPC_, MAXB_, MINB_>{});
 template <class F> static int dispatch_plan(int N, F&& f)
 {
     switch (N) {
@@ -339,9 +355,9 @@ template <class F> static int dispatch_plan(int N, F&& f)
         PSB_PLAN_CASE(48, 16, 1, 4, 4, 3)
         PSB_PLAN_CASE(64, 16, 1, 8, 8)
         PSB_PLAN_CASE(128, 16, 1, 8, 4, 4)
-        PSB_PLAN_CASE(256, 16, 2, 8, 8, 4)
-        PSB_PLAN_CASE(360, 16, 2, 9, 8, 5)
-        PSB_PLAN_CASE(512, 16, 2, 8, 8, 8)
+        PSB_PLAN_CASE_OCC(256, 16, 2, 2, 8, 8, 4)
+        PSB_PLAN_CASE_OCC(360, 16, 2, 2, 9, 8, 5)
+        PSB_PLAN_CASE_OCC(512, 16, 2, 2, 8, 8, 8)
         PSB_PLAN_CASE(1024, 8, 4, 8, 8, 4, 4)
         default: break;
     }
