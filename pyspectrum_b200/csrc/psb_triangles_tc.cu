@@ -36,7 +36,7 @@ constexpr int NSUB = XCH / SUB;
 constexpr int ROWF = XCH + 4;        // padded fp32 row stride of a chunk (== 4 mod 32 words: conflict-free LDS.128 across rows)
 constexpr int NCHUNKBUF = 2;
 constexpr int TMEM_COLS = 512;
-constexpr unsigned WATCHDOG = 1u << 22;       // x 20 us suspend hint
+constexpr unsigned WATCHDOG = 1u << 26;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -63,6 +63,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
     uint32_t done = 0;
     unsigned spins = 0;
     while (true) {
+        if (hint == 0xffffffffu)          // pure polling (profiling experiment)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(a), "r"(parity) : "memory");
+        else
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(done) : "r"(a), "r"(parity), "r"(hint) : "memory");
         if (done) break;
@@ -386,10 +390,10 @@ __global__ void __launch_bounds__(NTHR, 1) k_tri_tc(Params p)
             for (int h = 0; h < 2; ++h) {
                 const int kk = kp + 2 * h;
                 mbar_wait(&st_empty[kk], (uint32_t)(t & 1) ^ 1);
-                tc_fence_after();
+                if (!(p.debug & 256)) tc_fence_after();
                 float4 vi[4];
 #pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) vi[q4] = *reinterpret_cast<const float4*>(ch + fio + kk * 16 + q4 * 4);
+                for (int q4 = 0; q4 < 4; ++q4) vi[q4] = (p.debug & 512) ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(ch + fio + kk * 16 + q4 * 4);
 #pragma unroll
                 for (int mm = 0; mm < 2; ++mm) {
                     if (mm == 0 ? t0 : t1) {
@@ -413,7 +417,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_tri_tc(Params p)
                     }
                 }
                 if (!(p.debug & 4)) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                tc_fence_before();
+                if (!(p.debug & 256)) tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&st_full[kk]);
             }
@@ -481,7 +485,7 @@ int triangle_sums_tc_pass(const float* const* fields, int S, long long ncell, co
     p.fields = fields; p.S = S; p.NT = NT; p.MT = MT; p.tile_cols = tile_cols; p.lane_ij = lane_ij; p.nchunk = ncell / XCH;
     p.partial = static_cast<double*>(ws);
     p.debug = 0;
-    { unsigned int hint = 20000u; if (const char* e = getenv("PSB_TC_HINT")) hint = (unsigned)atoi(e);
+    { unsigned int hint = 20000u; if (const char* e = getenv("PSB_TC_HINT")) hint = (unsigned)strtoul(e, nullptr, 10);
       cudaMemcpyToSymbolAsync(c_wait_hint_ns, &hint, sizeof(hint), 0, cudaMemcpyHostToDevice, st); }
     if (const char* e = getenv("PSB_TC_DEBUG")) p.debug = atoi(e);
     p.flush_chunks = 4;          // 16 K-steps = 48 accumulating MMAs per accumulator between round-to-nearest drains
