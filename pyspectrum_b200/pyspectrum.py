@@ -445,8 +445,10 @@ def _read_fortran_record(fname, Nmax):
 def _write_fortran_record(fname, counts):
     b = np.ascontiguousarray(counts, dtype='<f8').tobytes()
     mark = np.array([len(b)], dtype='<i4').tobytes()
-    with open(fname, 'wb') as f:
+    tmp = '%s.tmp%d' % (fname, os.getpid())          # atomic: several ranks may fill the same cache concurrently
+    with open(tmp, 'wb') as f:
         f.write(mark + b + mark)
+    os.replace(tmp, fname)
 
 
 # ----------------------------------------------------------------------------------------------
