@@ -31,10 +31,8 @@ namespace psb {
 
 namespace tc {
 
-constexpr int XCH = 256;             // cells per staged chunk: one 1 KB bulk copy per field row (256 B copies starve the TMA unit)
+// XCH = cells per staged chunk (template parameter: 256 -> one 1 KB bulk copy per field row; 64 when many shells would not fit)
 constexpr int SUB = 64;              // cells per sub-chunk = 4 K-steps of 16 = one round of the four operand stages
-constexpr int NSUB = XCH / SUB;
-constexpr int ROWF = XCH + 4;        // padded fp32 row stride of a chunk (== 4 mod 32 words: conflict-free LDS.128 across rows)
 constexpr int NCHUNKBUF = 2;
 constexpr int TMEM_COLS = 512;
 constexpr unsigned WATCHDOG = 1u << 22;       // x 20 us suspend hint
@@ -175,7 +173,7 @@ struct Params {
     int MT;                       // M tiles (128 rows each) in this pass (<= 256 / tile_cols)
     int tile_cols;                // TMEM column spacing of one accumulator tile: 64 (NT <= 64) or 128
     const int* lane_ij;           // [128][5]: field slot i of the lane and j of its row in tiles 0..3 (-1: padding row)
-    long long nchunk;             // ncell / XCH
+    long long nchunk;             // ncell / XCH (chunk size of the launched instantiation)
     int flush_chunks;             // TMEM accumulators are drained (fp32, round-to-nearest) every flush_chunks 64-cell sub-chunks
     int gflush_drains;            // the fp32 accumulators go to float64 global every gflush_drains drains
     double* partial;              // [gridDim.x][NT][MT*128] float64 partial sums (zeroed by the host)
@@ -235,8 +233,11 @@ __device__ __forceinline__ void drain_accumulators(const Params& p, uint64_t* ac
 
 // shared memory carve-up (dynamic):
 //   chunk[NCHUNKBUF][S][ROWF] fp32 | B_hi[4][2][NT][8] fp16 | B_lo[...] | accs[NT/4][MT*128][4] fp32 | barriers
+template <int XCH>
 __global__ void __launch_bounds__(NTHR, 1) k_tri_tc(Params p)
 {
+    constexpr int NSUB = XCH / SUB;
+    constexpr int ROWF = XCH + 4;    // padded fp32 row stride (== 4 mod 32 words: conflict-free LDS.128 across rows)
     extern __shared__ __align__(1024) unsigned char smem[];
     const int S = p.S, NT = p.NT, MT = p.MT, MR = MT * 128;
     float* chunk = reinterpret_cast<float*>(smem);
@@ -492,21 +493,29 @@ int triangle_sums_tc_pass(const float* const* fields, int S, long long ncell, co
 {
     using namespace tc;
     const int tile_cols = NT <= 64 ? 64 : 128;
-    if (S < 1 || S > NT || NT % 16 || NT > 128 || MT < 1 || MT > 256 / tile_cols || ncell % XCH) return PSB_ERR_ARG;
-    if (ncell / XCH / 148 >= (1LL << 28)) return PSB_ERR_ARG;
+    if (S < 1 || S > NT || NT % 16 || NT > 128 || MT < 1 || MT > 256 / tile_cols || ncell % 64) return PSB_ERR_ARG;
+    if (ncell / 64 / 148 >= (1LL << 28)) return PSB_ERR_ARG;
     if (ws_bytes < triangle_tc_workspace_bytes(MT, NT)) return PSB_ERR_WORKSPACE;
     const int MR = MT * 128;
-    const size_t chunk_bytes = (size_t)S * ROWF * 4;
-    size_t smem = ((NCHUNKBUF * chunk_bytes + 1023) / 1024) * 1024;
-    smem += 2 * (size_t)4 * (2 * NT * 16);
-    smem += (size_t)NT * MR * 4;
-    smem += (2 * NCHUNKBUF + 8 + 2) * sizeof(uint64_t) + 16;
-    if (smem > 227 * 1024) return PSB_ERR_ARG;
-    if (cudaFuncSetAttribute(k_tri_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PSB_ERR_CUDA;
+    auto smem_for = [&](int xch) {
+        const size_t chunk_bytes = (size_t)S * (xch + 4) * 4;
+        size_t b = ((NCHUNKBUF * chunk_bytes + 1023) / 1024) * 1024;
+        b += 2 * (size_t)4 * (2 * NT * 16);
+        b += (size_t)NT * MR * 4;
+        b += (2 * NCHUNKBUF + 8 + 2) * sizeof(uint64_t) + 16;
+        return b;
+    };
+    int XCH = 256;
+    if (smem_for(256) > 227 * 1024 || ncell % 256) XCH = 64;
+    const size_t smem = smem_for(XCH);
+    if (smem > 227 * 1024 || ncell % XCH) return PSB_ERR_ARG;
+    auto kern = XCH == 256 ? k_tri_tc<256> : k_tri_tc<64>;
+    const long long nchunk_launch = ncell / XCH;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PSB_ERR_CUDA;
     const int ncta = 148;
     if (cudaMemsetAsync(ws, 0, triangle_tc_workspace_bytes(MT, NT), st) != cudaSuccess) return PSB_ERR_CUDA;
     Params p;
-    p.fields = fields; p.S = S; p.NT = NT; p.MT = MT; p.tile_cols = tile_cols; p.lane_ij = lane_ij; p.nchunk = ncell / XCH;
+    p.fields = fields; p.S = S; p.NT = NT; p.MT = MT; p.tile_cols = tile_cols; p.lane_ij = lane_ij; p.nchunk = nchunk_launch;
     p.partial = static_cast<double*>(ws);
     p.debug = 0;
     { unsigned int hint = 20000u; if (const char* e = getenv("PSB_TC_HINT")) hint = (unsigned)strtoul(e, nullptr, 10);
@@ -519,7 +528,7 @@ int triangle_sums_tc_pass(const float* const* fields, int S, long long ncell, co
     p.trace = nullptr;
     const char* trace_path = getenv("PSB_TC_TRACE");
     if (trace_path) { cudaMalloc(&p.trace, 4 * 8 * 64 * sizeof(long long)); cudaMemset(p.trace, 0, 4 * 8 * 64 * sizeof(long long)); }
-    k_tri_tc<<<ncta, NTHR, smem, st>>>(p);
+    kern<<<ncta, NTHR, smem, st>>>(p);
     if (trace_path) {
         static long long host_trace[4 * 8 * 64];
         cudaMemcpy(host_trace, p.trace, sizeof(host_trace), cudaMemcpyDeviceToHost);

@@ -302,9 +302,9 @@ class PeriodicPipeline(object):
         engine: 'tc' = tcgen05 split-fp16 kernel (float32 fields pre-scaled by shell_fields(scaled=True)),
                 'fma' = FFMA/DFMA register-tile kernel, 'auto' = tc when the shapes allow it."""
         S = Nmax - Ncut // step + 1
-        tc_ok = fields.dtype == torch.float32 and fields.shape[1] % 256 == 0 and S <= 128
+        tc_ok = fields.dtype == torch.float32 and fields.shape[1] % 64 == 0 and S <= 128
         if engine == 'tc' and not tc_ok:
-            raise ValueError('tensor-core triangle kernel needs float32 fields, N^3 % 256 == 0 and <= 128 shells')
+            raise ValueError('tensor-core triangle kernel needs float32 fields, N^3 % 64 == 0 and <= 128 shells')
         if engine == 'tc' or (engine == 'auto' and tc_ok):
             return self._triangle_sums_tc(fields, Nmax, Ncut, step)
         tri, tiles, ntiles = self.triangle_tiles(Nmax, Ncut, step)
@@ -381,7 +381,7 @@ class PeriodicPipeline(object):
         s0 = Ncut // step
         S = Nmax - s0 + 1
         fields, sumsq, scales, maxabs = self.shell_fields(half, step, s0, Nmax, scaled=True)
-        use_tc = engine in ('auto', 'tc') and fields.shape[1] % 256 == 0 and S <= 128
+        use_tc = engine in ('auto', 'tc') and fields.shape[1] % 64 == 0 and S <= 128
         sums = self.triangle_sums(fields, Nmax, Ncut, step, engine='tc' if use_tc else 'fma')
         host = torch.cat([sums, sumsq, scales.double(), maxabs.view(torch.float32).double()]).cpu().numpy()
         nt = sums.numel()
