@@ -1,0 +1,199 @@
+"""pyspectrum_b200.multigpu -- ONE catalogue sharded over the GPUs of a node (one process per GPU, torchrun + NCCL).
+
+Design ("alternative for grids that fit one GPU's memory", and what makes Ngrid=1024 fit at all):
+
+  1. particles are sharded arbitrarily over the ranks; every rank assigns its shard onto a FULL mesh (K1)
+     -> NCCL all-reduce (sum) of the mesh and of sum(w)                                   [exchange 1: 8 N^3 bytes]
+  2. every rank runs the FFT + fcomb (K2+K3) on the reduced mesh: identical delta(k) half field everywhere
+  3. the packed shell PAIRS are dealt round-robin to the ranks; each rank transforms only its pairs (K5)
+  4. NCCL all-to-all: every shell field is cut into G slabs of N^3/G cells, slab q goes to rank q
+     -> every rank holds all shells on its slab                                          [exchange 2: 4 S N^3 (G-1)/G bytes]
+  5. slab-local triangle sums (K6) and shell powers -> all-reduce of Ntri + S float64   [exchange 3: ~50-400 kB]
+  6. the float64 exact triangle counts use the same steps 3-5 with delta == 1
+
+Every kernel is the single-GPU one; only the orchestration differs.  The collectives are torch.distributed calls so the
+same code runs under NCCL (GPU) and gloo (the CPU tests of the host logic: tests/test_multigpu_host.py)."""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import pyspectrum as P
+
+
+def pair_assignment(npairs, world):
+    """Round-robin deal of packed shell pairs; every rank gets the same number (padding pairs = empty shells)."""
+    per = (npairs + world - 1) // world
+    return [[r + world * k for k in range(per)] for r in range(world)], per
+
+
+def slab_field_rows(S, world, per):
+    """After the all-to-all the slab buffer is laid out [k][owner rank][e] (k = local pair index, e = 0/1 within the pair);
+    returns for every shell slot f the row of that buffer which holds it."""
+    rows = []
+    for f in range(S):
+        p, e = divmod(f, 2)
+        owner, k = p % world, p // world
+        rows.append((k * world + owner) * 2 + e)
+    return rows
+
+
+def exchange_to_slabs(fields_local, world):
+    """fields_local: [2*per, ncell] on every rank (its shell pairs, full grid).  Returns [2*per*world, ncell/world]:
+    row ((k*world + owner)*2 + e) = slab of this rank of shell e of the k-th pair of rank `owner`."""
+    nrow, ncell = fields_local.shape
+    slab = ncell // world
+    per = nrow // 2
+    out = torch.empty((per, world, 2, slab), dtype=fields_local.dtype, device=fields_local.device)
+    if world == 1:
+        out.copy_(fields_local.view(per, 2, 1, slab).permute(0, 2, 1, 3))
+        return out.view(nrow, slab)
+    for k in range(per):
+        for e in range(2):
+            src = fields_local[2 * k + e].view(world, slab)                 # contiguous: slab q -> rank q
+            dst = torch.empty((world, slab), dtype=fields_local.dtype, device=fields_local.device)
+            dist.all_to_all_single(dst, src)
+            out[k, :, e, :] = dst                                            # dst[q'] = my slab of rank q''s row (k, e)
+    return out.view(nrow * world, slab)
+
+
+def _allreduce(t, op=dist.ReduceOp.SUM):
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=op)
+    return t
+
+
+def _world():
+    return dist.get_world_size() if dist.is_initialized() else 1
+
+
+def sharded_delta(pipe, xyz_local, w_local, Lbox):
+    """Steps 1-2: returns (half field, global sum of weights as a device tensor)."""
+    pos, aos, wt = pipe.to_device(xyz_local, w_local)
+    mesh, sumw = pipe.assign(pos, aos, wt, Lbox)
+    _allreduce(mesh)
+    _allreduce(sumw)
+    half = pipe.mesh_to_delta(mesh, sumw)
+    return half, sumw
+
+
+def sharded_triangle_sums(pipe, half, step, Ncut, Nmax, dtype=torch.float32):
+    """Steps 3-5.  Returns host arrays (sums per triangle, sum_x I_j^2 per shell) in the reference's units, identical
+    on every rank."""
+    world = _world()
+    rank = dist.get_rank() if world > 1 else 0
+    s0 = Ncut // step
+    S = Nmax - s0 + 1
+    npairs = (S + 1) // 2
+    assign, per = pair_assignment(npairs, world)
+    mine = assign[rank]
+    f64 = dtype == torch.float64
+    if f64:
+        fields, sumsq = pipe.shell_fields(half, step, s0, Nmax, dtype=torch.float64, pairs=mine)
+        sc_rows = None
+    else:
+        scales = pipe.shell_scales(half, step, s0, Nmax)
+        if world > 1:
+            dist.broadcast(scales, 0)                  # the sampled shell power uses unordered atomics: make ranks agree exactly
+        fields, sumsq, sc_rows, maxabs = pipe.shell_fields(half, step, s0, Nmax, scaled=True, pairs=mine, scales=scales)
+    slabs = exchange_to_slabs(fields, world)
+    del fields
+    rows = slab_field_rows(S, world, per)
+    engine = 'fma' if f64 else 'auto'
+    sums = pipe.triangle_sums(slabs, Nmax, Ncut, step, engine=engine, field_rows=rows)
+    _allreduce(sums)
+    # per-shell quantities live on the owner rank: scatter them into global shell order, then sum over ranks
+    glob_sq = torch.zeros(2 * npairs, dtype=torch.float64, device=pipe.dev)
+    glob_sc = torch.zeros(2 * npairs, dtype=torch.float64, device=pipe.dev)
+    glob_mx = torch.zeros(2 * npairs, dtype=torch.float64, device=pipe.dev)
+    for k, pidx in enumerate(mine):
+        if pidx < npairs:
+            glob_sq[2 * pidx:2 * pidx + 2] = sumsq[2 * k:2 * k + 2]
+            if not f64:
+                glob_sc[2 * pidx:2 * pidx + 2] = sc_rows[2 * k:2 * k + 2].double()
+                glob_mx[2 * pidx:2 * pidx + 2] = maxabs[2 * k:2 * k + 2].view(torch.float32).double()
+    _allreduce(glob_sq)
+    if f64:
+        return sums.cpu().numpy(), glob_sq.cpu().numpy()[:S]
+    _allreduce(glob_sc)
+    _allreduce(glob_mx)
+    host = torch.cat([sums, glob_sq, glob_sc, glob_mx]).cpu().numpy()
+    nt = sums.numel()
+    n2 = 2 * npairs
+    sums_h, sq, sc, mx = host[:nt], host[nt:nt + n2], host[nt + n2:nt + 2 * n2], host[nt + 2 * n2:]
+    if mx.max() ** 2 >= 4.0e4:                                           # fp16 range guard: redo with the FFMA kernel
+        sums = pipe.triangle_sums(slabs, Nmax, Ncut, step, engine='fma', field_rows=rows)
+        _allreduce(sums)
+        sums_h = sums.cpu().numpy()
+    tri = P.triangle_list(Nmax, Ncut, step)
+    sums_h = sums_h / (sc[tri[:, 0] - s0] * sc[tri[:, 1] - s0] * sc[tri[:, 2] - s0])
+    return sums_h, (sq / sc ** 2)[:S]
+
+
+def sharded_counts(pipe, step, Ncut, Nmax):
+    """Exact triangle counts with the float64 fields sharded over the ranks (at Ngrid=1024 they do not fit one GPU)."""
+    key = (Nmax, Ncut, step)
+    if key in pipe._counts:
+        return pipe._counts[key]
+    sums, _ = sharded_triangle_sums(pipe, None, step, Ncut, Nmax, dtype=torch.float64)
+    tri = P.triangle_list(Nmax, Ncut, step)
+    n3 = float(pipe.N) ** 3
+    nint = np.rint(sums / n3)
+    if np.abs(sums / n3 - nint).max() > 1e-3:
+        raise RuntimeError('triangle counts did not come out as integers')
+    counts = np.zeros((Nmax, Nmax, Nmax), dtype=np.float64)
+    counts[tri[:, 0] - 1, tri[:, 1] - 1, tri[:, 2] - 1] = nint * n3
+    pipe._counts[key] = counts
+    return counts
+
+
+def Bk_periodic_sharded(xyz_local, w_local=None, Lbox=2600, Ngrid=360, step=3, Ncut=3, Nmax=40, silent=True):
+    """Bk_periodic (pyspectrum.py:285-356) for ONE catalogue whose particles are spread over the ranks; every rank
+    passes its own shard and receives the full result dictionary."""
+    pipe = P.PeriodicPipeline.get(Ngrid)
+    s0 = Ncut // step
+    if s0 < 1:
+        raise ValueError('Ncut//step must be >= 1')
+    Nloc = torch.tensor([float(xyz_local.shape[1])], dtype=torch.float64, device=pipe.dev)
+    _allreduce(Nloc)
+    N = int(Nloc.item())
+    half, sumw = sharded_delta(pipe, xyz_local, w_local, Lbox)
+    Nk = pipe.shell_mode_counts(step, Nmax)
+    counts = sharded_counts(pipe, step, Ncut, Nmax)
+    sums_h, sumsq_h = sharded_triangle_sums(pipe, half, step, Ncut, Nmax)
+    tri = P.triangle_list(Nmax, Ncut, step)
+    nbar = (float(N) if w_local is None else float(sumw.item())) / Lbox ** 3
+    kf = 2 * np.pi / Lbox
+    bispec = P._bk_epilogue(Ngrid, tri, sums_h, sumsq_h, Nk, counts, step, Ncut, Nmax)
+    bispec['meta'] = {'Lbox': Lbox, 'Ngrid': Ngrid, 'step': step, 'Ncut': Ncut, 'Nmax': Nmax, 'N': N, 'nbar': nbar, 'kf': kf}
+    for k in ('p0k1', 'p0k2', 'p0k3'):
+        bispec[k] = bispec[k] * (2 * np.pi) ** 3 / kf ** 3 - 1. / nbar
+    bispec['p0k_sn'] = 1. / nbar
+    b_sn = (bispec['p0k1'] + bispec['p0k2'] + bispec['p0k3']) / nbar + 1. / nbar ** 2
+    bispec['b123'] = bispec['b123'] * (2 * np.pi) ** 6 / kf ** 6 - b_sn
+    bispec['b123_sn'] = b_sn
+    with np.errstate(divide='ignore', invalid='ignore'):
+        bispec['q123'] = bispec['b123'] / (bispec['p0k1'] * bispec['p0k2'] + bispec['p0k1'] * bispec['p0k3'] + bispec['p0k2'] * bispec['p0k3'])
+    return bispec
+
+
+def Pk_periodic_sharded(xyz_local, w_local=None, Lbox=2600, Ngrid=360, silent=True):
+    """Pk_periodic (pyspectrum.py:644-728) for one catalogue sharded over the ranks (binning is done redundantly: it is
+    one pass over the half field)."""
+    pipe = P.PeriodicPipeline.get(Ngrid)
+    Nloc = torch.tensor([float(xyz_local.shape[1])], dtype=torch.float64, device=pipe.dev)
+    _allreduce(Nloc)
+    N = int(Nloc.item())
+    half, sumw = sharded_delta(pipe, xyz_local, w_local, Lbox)
+    out = pipe.pk_monopole(half, Lbox).cpu().numpy()
+    nbar = (float(N) if w_local is None else float(sumw.item())) / Lbox ** 3
+    kf = 2 * np.pi / float(Lbox)
+    Nbins = Ngrid // 2
+    nk, ksum, psum = out[:Nbins], out[Nbins:2 * Nbins], out[2 * Nbins:]
+    k = np.zeros(Nbins); p0k = np.zeros(Nbins); cnt = np.zeros(Nbins)
+    ok = nk > 0
+    k[ok] = ksum[ok] / nk[ok]
+    p0k[ok] = psum[ok] / nk[ok] / kf ** 3
+    cnt[ok] = nk[ok]
+    p0k *= (2. * np.pi) ** 3
+    meta = {'Lbox': Lbox, 'Ngrid': Ngrid, 'N': N, 'nbar': nbar, 'kf': 2 * np.pi / Lbox}
+    return {'meta': meta, 'k': k, 'p0k': p0k - 1. / nbar, 'counts': cnt, 'p0k_sn': 1. / nbar}

@@ -236,51 +236,75 @@ class PeriodicPipeline(object):
             self._nk[key] = nk.cpu().numpy()
         return self._nk[key]
 
-    def shell_fields(self, half, step, s0, Nmax, dtype=torch.float32, scaled=False):
-        """K5: all shells s0..Nmax as real fields [S_alloc, N^3] + sum_x I_j^2 per shell.
+    def shell_scales(self, half, step, s0, Nmax):
+        """Exact power-of-two normalisation per shell (rms of the stored field ~ 2) from the Parseval shell power."""
+        S = Nmax - s0 + 1
+        S_alloc = S + (S % 2)
+        st = _stream()
+        pw = torch.empty(Nmax, dtype=torch.float64, device=self.dev)
+        check(self.L.psb_bk_shell_power(_ptr(half), self.N, _ptr(self.irk_table(step)), Nmax, _ptr(pw), st), 'psb_bk_shell_power')
+        scales = torch.ones(S_alloc, dtype=torch.float32, device=self.dev)
+        check(self.L.psb_bk_shell_scales(ctypes.c_void_p(pw.data_ptr() + 8 * (s0 - 1)), S, np.float32(2.0), _ptr(scales), st),
+              'psb_bk_shell_scales')
+        return scales
+
+    def shell_fields(self, half, step, s0, Nmax, dtype=torch.float32, scaled=False, pairs=None, scales=None):
+        """K5: shells s0..Nmax as real fields [S_alloc, N^3] + sum_x I_j^2 per shell.
         half=None -> delta == 1 (counts).  Two shells ride on one complex transform.
         scaled=True stores I_j * scale_j with scale_j an exact power of two putting the rms near 2 (from the
-        Parseval shell power), which the fp16-split tensor-core triangle kernel needs; returns
-        (fields, sumsq, scales, maxabs) -- sumsq and maxabs refer to the stored (scaled) values."""
+        Parseval shell power, or the `scales` tensor if given), which the fp16-split tensor-core triangle kernel needs;
+        returns (fields, sumsq, scales, maxabs) -- sumsq and maxabs refer to the stored (scaled) values.
+        pairs: optional list of pair indices p (shells s0+2p, s0+2p+1) to compute -- the multi-GPU path shards shells this way;
+        the returned fields then hold only those pairs, in the given order (2 rows per pair), sumsq/maxabs likewise."""
         N = self.N
         ncell = N * N * N
         S = Nmax - s0 + 1
         S_alloc = S + (S % 2)
         f64 = dtype == torch.float64
-        fields = torch.empty((S_alloc, ncell), dtype=dtype, device=self.dev)
-        sumsq = torch.zeros(S_alloc, dtype=torch.float64, device=self.dev)
-        scales = maxabs = None
+        plist = list(range(S_alloc // 2)) if pairs is None else list(pairs)
+        nrow = 2 * len(plist)
+        fields = torch.empty((nrow, ncell), dtype=dtype, device=self.dev)
+        sumsq = torch.zeros(nrow, dtype=torch.float64, device=self.dev)
+        maxabs = None
         st = _stream()
         irk = self.irk_table(step)
         if scaled:
             assert not f64 and half is not None
-            pw = torch.empty(Nmax, dtype=torch.float64, device=self.dev)
-            check(self.L.psb_bk_shell_power(_ptr(half), N, _ptr(irk), Nmax, _ptr(pw), st), 'psb_bk_shell_power')
-            scales = torch.ones(S_alloc, dtype=torch.float32, device=self.dev)
-            check(self.L.psb_bk_shell_scales(ctypes.c_void_p(pw.data_ptr() + 8 * (s0 - 1)), S, np.float32(2.0),
-                                             _ptr(scales), st), 'psb_bk_shell_scales')
-            maxabs = torch.zeros(S_alloc, dtype=torch.int32, device=self.dev)
+            if scales is None:
+                scales = self.shell_scales(half, step, s0, Nmax)
+            maxabs = torch.zeros(nrow, dtype=torch.int32, device=self.dev)
+            if pairs is None:
+                sc_local = scales
+            else:                                        # one gather: rows of this rank's pairs (padding pairs -> scale 1)
+                rows = [min(2 * q + e, S_alloc - 1) for q in plist for e in (0, 1)]
+                sc_local = scales[torch.tensor(rows, dtype=torch.long, device=self.dev)].contiguous()
         Rmax = int(np.floor(step * (Nmax + 0.5)))
         W = min(2 * Rmax + 1, N)
         cdt = torch.float64 if f64 else torch.float32
         t1 = torch.empty(W * W * N * 2, dtype=cdt, device=self.dev)
         t2 = torch.empty(W * N * N * 2, dtype=cdt, device=self.dev)
         tw = self.tw64 if f64 else self.tw32
-        for s in range(0, S, 2):
+        for r, pidx in enumerate(plist):
+            s = 2 * pidx
+            if s >= S:                                   # padding pair (shard equalisation): empty shells -> zero fields
+                fields[2 * r:2 * r + 2].zero_()
+                continue
             sa = s0 + s
             sb = sa + 1 if s + 1 < S else -1
             R = int(np.floor(step * (max(sa, sb) + 0.5)))
-            sq = ctypes.c_void_p(sumsq.data_ptr() + 8 * s)
+            sq = ctypes.c_void_p(sumsq.data_ptr() + 8 * 2 * r)
             if f64:
-                check(self.L.psb_bk_shell_pair_f64(_ptr(half), _ptr(irk), N, sa, sb, R, _ptr(t1), _ptr(t2), _ptr(fields[s]),
-                                                   _ptr(fields[s + 1]), sq, _ptr(tw), st), 'psb_bk_shell_pair_f64')
+                check(self.L.psb_bk_shell_pair_f64(_ptr(half), _ptr(irk), N, sa, sb, R, _ptr(t1), _ptr(t2), _ptr(fields[2 * r]),
+                                                   _ptr(fields[2 * r + 1]), sq, _ptr(tw), st), 'psb_bk_shell_pair_f64')
             else:
-                sc = ctypes.c_void_p(scales.data_ptr() + 4 * s) if scaled else None
-                mx = ctypes.c_void_p(maxabs.data_ptr() + 4 * s) if scaled else None
-                check(self.L.psb_bk_shell_pair_f32(_ptr(half), _ptr(irk), N, sa, sb, R, _ptr(t1), _ptr(t2), _ptr(fields[s]),
-                                                   _ptr(fields[s + 1]), sq, sc, mx, _ptr(tw), st), 'psb_bk_shell_pair_f32')
+                sc = mx = None
+                if scaled:
+                    sc = ctypes.c_void_p(sc_local.data_ptr() + 4 * 2 * r)
+                    mx = ctypes.c_void_p(maxabs.data_ptr() + 4 * 2 * r)
+                check(self.L.psb_bk_shell_pair_f32(_ptr(half), _ptr(irk), N, sa, sb, R, _ptr(t1), _ptr(t2), _ptr(fields[2 * r]),
+                                                   _ptr(fields[2 * r + 1]), sq, sc, mx, _ptr(tw), st), 'psb_bk_shell_pair_f32')
         if scaled:
-            return fields, sumsq, scales, maxabs
+            return fields, sumsq, sc_local, maxabs
         return fields, sumsq
 
     # ------------------------------------------------------------------ K6
@@ -297,11 +321,12 @@ class PeriodicPipeline(object):
             self._tiles[key] = (tri, torch.from_numpy(tiles).to(self.dev), nt.value)
         return self._tiles[key]
 
-    def triangle_sums(self, fields, Nmax, Ncut, step, engine='auto'):
+    def triangle_sums(self, fields, Nmax, Ncut, step, engine='auto', field_rows=None):
         """K6: sum_x I_i I_j I_l for every triangle of the loop nest (float64 tensor, loop order).
         engine: 'tc' = tcgen05 split-fp16 kernel (float32 fields pre-scaled by shell_fields(scaled=True)),
                 'fma' = FFMA/DFMA register-tile kernel, 'auto' = tc when the shapes allow it."""
         S = Nmax - Ncut // step + 1
+        self._field_rows = list(range(S)) if field_rows is None else list(field_rows)      # row of `fields` holding shell slot f
         tc_ok = fields.dtype == torch.float32 and fields.shape[1] % 64 == 0 and S <= 128
         if engine == 'tc' and not tc_ok:
             raise ValueError('tensor-core triangle kernel needs float32 fields, N^3 % 64 == 0 and <= 128 shells')
@@ -309,7 +334,7 @@ class PeriodicPipeline(object):
             return self._triangle_sums_tc(fields, Nmax, Ncut, step)
         tri, tiles, ntiles = self.triangle_tiles(Nmax, Ncut, step)
         nf = (S + 3) // 4 * 4
-        ptrs = [fields[min(f, S - 1)].data_ptr() for f in range(nf)]
+        ptrs = [fields[self._field_rows[min(f, S - 1)]].data_ptr() for f in range(nf)]
         dptr = torch.tensor(ptrs, dtype=torch.int64).to(self.dev)
         sums = torch.zeros(len(tri), dtype=torch.float64, device=self.dev)
         wsb = self.L.psb_bk_triangle_workspace_bytes(ntiles)
@@ -363,7 +388,7 @@ class PeriodicPipeline(object):
     def _triangle_sums_tc(self, fields, Nmax, Ncut, step):
         tri, NT, passes = self.tc_passes(Nmax, Ncut, step)
         S = Nmax - Ncut // step + 1
-        dptr = torch.tensor([fields[f].data_ptr() for f in range(S)], dtype=torch.int64).to(self.dev)
+        dptr = torch.tensor([fields[self._field_rows[f]].data_ptr() for f in range(S)], dtype=torch.int64).to(self.dev)
         sums = torch.zeros(len(tri), dtype=torch.float64, device=self.dev)
         MT = passes[0][1]
         wsb = self.L.psb_bk_triangle_tc_workspace_bytes(MT, NT)

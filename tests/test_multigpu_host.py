@@ -1,0 +1,71 @@
+"""CPU: host logic of the single-catalogue multi-GPU path (pyspectrum_b200/multigpu.py) on world_size-2 gloo:
+pair dealing, the all-to-all to slabs and the row bookkeeping that K6 relies on."""
+import os
+
+import numpy as np
+import torch
+
+
+def test_pair_assignment_and_rows():
+    from pyspectrum_b200.multigpu import pair_assignment, slab_field_rows
+    for S, world in [(40, 1), (40, 2), (40, 8), (7, 2), (80, 4), (5, 4)]:
+        npairs = (S + 1) // 2
+        assign, per = pair_assignment(npairs, world)
+        assert all(len(a) == per for a in assign)
+        got = sorted(p for a in assign for p in a if p < npairs)
+        assert got == list(range(npairs))
+        rows = slab_field_rows(S, world, per)
+        assert len(set(rows)) == S and max(rows) < 2 * per * world
+        for f, r in enumerate(rows):                       # row -> (k, owner, e) -> shell slot
+            k, rem = divmod(r, 2 * world)
+            owner, e = divmod(rem, 2)
+            assert 2 * (owner + world * k) + e == f
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    import torch.distributed as dist
+    dist.init_process_group('gloo')
+    from pyspectrum_b200.multigpu import pair_assignment, slab_field_rows, exchange_to_slabs
+    S, ncell = 7, 24
+    npairs = (S + 1) // 2
+    assign, per = pair_assignment(npairs, world)
+    # field of shell slot f at cell x has the value 100*f + x  (padding pairs: -1)
+    rows = []
+    for p in assign[rank]:
+        for e in (0, 1):
+            f = 2 * p + e
+            rows.append(100. * f + torch.arange(ncell, dtype=torch.float32) if p < npairs else torch.full((ncell,), -1.))
+    local = torch.stack(rows)
+    slabs = exchange_to_slabs(local, world)
+    slab = ncell // world
+    fr = slab_field_rows(S, world, per)
+    ok = True
+    for f in range(S):
+        expect = 100. * f + torch.arange(rank * slab, (rank + 1) * slab, dtype=torch.float32)
+        ok &= bool(torch.equal(slabs[fr[f]], expect))
+    out.put((rank, ok, tuple(slabs.shape)))
+    dist.destroy_process_group()
+
+
+def test_exchange_to_slabs_two_ranks_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29700 + os.getpid() % 2000
+    ps = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in ps]
+    res = sorted(q.get(timeout=120) for _ in ps)
+    [p.join(60) for p in ps]
+    assert all(p.exitcode == 0 for p in ps)
+    for rank, ok, shape in res:
+        assert ok and shape == (8, 12)
+
+
+def test_exchange_single_rank_is_a_reshape():
+    from pyspectrum_b200.multigpu import exchange_to_slabs, slab_field_rows
+    local = torch.arange(4 * 10, dtype=torch.float32).view(4, 10)
+    slabs = exchange_to_slabs(local, 1)
+    rows = slab_field_rows(4, 1, 2)
+    for f in range(4):
+        assert torch.equal(slabs[rows[f]], local[f])
