@@ -98,14 +98,17 @@ int psb_shell_mode_counts(int ngrid, const uint16_t* irk_of_m, int nshell, uint6
  *   half_c64 == NULL -> delta == 1 (triangle counts, py:977 / estimator.f:74-80) */
 int psb_bk_shell_pair_f32(const float* half_c64, const uint16_t* irk_of_m, int ngrid, int sa, int sb, int R,
                           float* t1_c64, float* t2_c64, float* fa, float* fb, double* sumsq,
-                          const float* scale2, uint32_t* maxabs2, const float* tw_c64, void* stream);
-/* Optional exact power-of-two normalisation of the stored shell fields (needed by the fp16-split tensor-core
+                          const float* scale2, uint32_t* maxabs2, int pack_half, const float* tw_c64, void* stream);
+/* pack_half != 0: each aligned pair of cells (x, x+1) of fa/fb is stored as the two 32-bit words
+ * {half2 hi(x,x+1), half2 lo(x,x+1)} with hi = fp16(v), lo = fp16(v - hi) (same 4 bytes per cell; the layout the
+ * tensor-core triangle kernel consumes; requires scale2 so that the values sit in fp16 range).
+ * Optional exact power-of-two normalisation of the stored shell fields (needed by the fp16-split tensor-core
  * triangle kernel): scale2 = device float[2] multiplying (I_sa, I_sb) before the store and before sumsq;
  * maxabs2 = device uint32[2] receiving max|stored value| as float bits (atomicMax; zero it first).
  * psb_bk_shell_scales turns per-shell power sums (psb_pk_monopole with the shell table as bin table:
  * psum[j] = sum_{k in shell j+1} |delta|^2) into scales[j] = 2^round(log2(target_rms / sqrt(psum[j]))). */
-/* psum[j] ~ sum_{k in shell j+1, full grid} |delta(k)|^2, j = 0..nshell-1 (Parseval: = sum_x I_{j+1}^2 / N^3); exact for the first
- * four shells, a 1-in-8 sampled estimate beyond -- it only feeds the power-of-two scale, the exact shell power comes from K5 */
+/* psum[j] = sum_{k in shell j+1, full grid} |delta(k)|^2, j = 0..nshell-1 (Parseval: = sum_x I_{j+1}^2 / N^3), float64 atomics
+ * (last-bit order dependent) -- it only feeds the power-of-two scale, the shell power that is reported comes from K5; nshell <= 1024 */
 int psb_bk_shell_power(const float* half_c64, int ngrid, const uint16_t* irk_of_m, int nshell, double* psum, void* stream);
 int psb_bk_shell_scales(const double* psum, int nshell, float target_rms, float* scales, void* stream);
 int psb_bk_shell_pair_f64(const float* half_c64, const uint16_t* irk_of_m, int ngrid, int sa, int sb, int R,
@@ -115,10 +118,11 @@ int psb_bk_shell_pair_f64(const float* half_c64, const uint16_t* irk_of_m, int n
 /* K6  pyspectrum.py:415-430.  fields: device array of nfields device pointers (field slot = shell - s0),
  * tiles: int32 [ntiles][68] = {i0,j0,l0,0, slot[64]} with slot[(a*4+b)*4+c] = index into sums[] of
  * triangle (i0+a, j0+b, l0+c) or -1; i0+3, j0+3, l0+3 must be < nfields (pad the pointer array).
- * sums (float64, device) receives sum_x I_i I_j I_l. */
+ * sums (float64, device) receives sum_x I_i I_j I_l.  packed_half != 0 (f32 only): the fields are in the packed hi/lo layout
+ * of psb_bk_shell_pair_f32(pack_half=1) and are decoded on load. */
 size_t psb_bk_triangle_workspace_bytes(int ntiles);
 int psb_bk_triangle_sums_f32(const float* const* fields, int nfields, int64_t ncell, const int32_t* tiles,
-                             int ntiles, double* sums, void* ws, size_t ws_bytes, void* stream);
+                             int ntiles, double* sums, void* ws, size_t ws_bytes, int packed_half, void* stream);
 int psb_bk_triangle_sums_f64(const double* const* fields, int nfields, int64_t ncell, const int32_t* tiles,
                              int ntiles, double* sums, void* ws, size_t ws_bytes, void* stream);
 
@@ -127,7 +131,8 @@ int psb_bk_triangle_sums_f64(const double* const* fields, int nfields, int64_t n
  * of 16, <= 128):  lane_ij = int32 [128][5] = {field slot i of the lane, field slot j of its row in tile 0..3}
  * (-1 = padding).  Row (m*128 + lane) is the pair (i, j_m).  tri_rc[t] = (row, column) of triangle t in this pass or
  * (-1,-1); sums[t] is written for the triangles of this pass.  Needs ncell % 64 == 0, mt <= 4 (nt <= 64) or 2.
- * Fields must be pre-scaled so that |I_i I_j| stays inside the fp16 range (psb_bk_shell_scales). */
+ * Fields: the packed hi/lo halves written by psb_bk_shell_pair_f32(pack_half=1), pre-scaled so that |I_i I_j| stays inside
+ * the fp16 range (psb_bk_shell_scales). */
 size_t psb_bk_triangle_tc_workspace_bytes(int mt, int nt);
 int psb_bk_triangle_sums_tc(const float* const* fields, int nshell, int64_t ncell, const int32_t* lane_ij,
                             int mt, int nt, const int32_t* tri_rc, int ntri, double* sums, void* ws, size_t ws_bytes,

@@ -178,11 +178,11 @@ int psb_shell_mode_counts(int N, const uint16_t* irk, int nshell, uint64_t* nk, 
 }
 
 int psb_bk_shell_pair_f32(const float* half, const uint16_t* irk, int N, int sa, int sb, int R, float* t1, float* t2,
-                          float* fa, float* fb, double* sumsq, const float* scale2, uint32_t* maxabs2, const float* tw, void* stream)
+                          float* fa, float* fb, double* sumsq, const float* scale2, uint32_t* maxabs2, int pack_half, const float* tw, void* stream)
 {
     if (!irk || !t1 || !t2 || !fa || !sumsq || !tw || R < 0 || (sb >= 0 && !fb)) return PSB_ERR_ARG;
     return fft_shell_pair<float>(reinterpret_cast<const Cx<float>*>(half), irk, N, sa, sb, R, reinterpret_cast<Cx<float>*>(t1),
-                                 reinterpret_cast<Cx<float>*>(t2), fa, fb, sumsq, scale2, maxabs2, reinterpret_cast<const Cx<float>*>(tw), S(stream));
+                                 reinterpret_cast<Cx<float>*>(t2), fa, fb, sumsq, scale2, maxabs2, pack_half, reinterpret_cast<const Cx<float>*>(tw), S(stream));
 }
 
 int psb_bk_shell_pair_f64(const float* half, const uint16_t* irk, int N, int sa, int sb, int R, double* t1, double* t2,
@@ -190,7 +190,7 @@ int psb_bk_shell_pair_f64(const float* half, const uint16_t* irk, int N, int sa,
 {
     if (!irk || !t1 || !t2 || !fa || !sumsq || !tw || R < 0 || (sb >= 0 && !fb)) return PSB_ERR_ARG;
     return fft_shell_pair<double>(reinterpret_cast<const Cx<float>*>(half), irk, N, sa, sb, R, reinterpret_cast<Cx<double>*>(t1),
-                                  reinterpret_cast<Cx<double>*>(t2), fa, fb, sumsq, nullptr, nullptr, reinterpret_cast<const Cx<double>*>(tw), S(stream));
+                                  reinterpret_cast<Cx<double>*>(t2), fa, fb, sumsq, nullptr, nullptr, 0, reinterpret_cast<const Cx<double>*>(tw), S(stream));
 }
 
 int psb_bk_shell_power(const float* half, int N, const uint16_t* irk, int nshell, double* psum, void* stream)
@@ -206,16 +206,16 @@ int psb_bk_shell_scales(const double* psum, int nshell, float target_rms, float*
 size_t psb_bk_triangle_workspace_bytes(int ntiles) { return triangle_workspace_bytes(ntiles); }
 
 int psb_bk_triangle_sums_f32(const float* const* fields, int nfields, int64_t ncell, const int32_t* tiles, int ntiles,
-                             double* sums, void* ws, size_t ws_bytes, void* stream)
+                             double* sums, void* ws, size_t ws_bytes, int packed_half, void* stream)
 {
     if (!fields || !tiles || !sums || !ws) return PSB_ERR_ARG;
-    return triangle_sums_tiles<float>(fields, nfields, ncell, tiles, ntiles, sums, ws, ws_bytes, S(stream));
+    return triangle_sums_tiles<float>(fields, nfields, ncell, tiles, ntiles, sums, ws, ws_bytes, packed_half, S(stream));
 }
 int psb_bk_triangle_sums_f64(const double* const* fields, int nfields, int64_t ncell, const int32_t* tiles, int ntiles,
                              double* sums, void* ws, size_t ws_bytes, void* stream)
 {
     if (!fields || !tiles || !sums || !ws) return PSB_ERR_ARG;
-    return triangle_sums_tiles<double>(fields, nfields, ncell, tiles, ntiles, sums, ws, ws_bytes, S(stream));
+    return triangle_sums_tiles<double>(fields, nfields, ncell, tiles, ntiles, sums, ws, ws_bytes, 0, S(stream));
 }
 
 size_t psb_bk_triangle_tc_workspace_bytes(int mt, int nt) { return triangle_tc_workspace_bytes(mt, nt); }

@@ -22,6 +22,7 @@
 #include <cuda_runtime.h>
 #include "psb_fft_core.cuh"
 #include "psb_fcomb_core.cuh"
+#include <cuda_fp16.h>
 #include "psb_kernels.h"
 
 namespace psb {
@@ -136,6 +137,19 @@ template <typename T> struct Real2;
 template <> struct alignas(8) Real2<float> { float a, b; };
 template <> struct alignas(16) Real2<double> { double a, b; };
 
+// (a,b) = values of two adjacent cells -> {half2 hi(a,b), half2 lo(a,b)} with hi + lo = value to ~2^-22 (bit patterns in a Real2)
+__device__ __forceinline__ Real2<float> pack_hilo(Real2<float> v)
+{
+    const __half2 hh = __floats2half2_rn(v.a, v.b);
+    const float2 back = __half22float2(hh);
+    const __half2 ll = __floats2half2_rn(v.a - back.x, v.b - back.y);
+    Real2<float> r;
+    r.a = __uint_as_float(*reinterpret_cast<const unsigned int*>(&hh));
+    r.b = __uint_as_float(*reinterpret_cast<const unsigned int*>(&ll));
+    return r;
+}
+__device__ __forceinline__ Real2<double> pack_hilo(Real2<double> v) { return v; }       // float64 path is never packed
+
 template <typename T, bool PRUNED, bool REALOUT> struct IoCols {
     const Cx<T>* in;
     Cx<T>* out;            // complex output (REALOUT == false)
@@ -143,6 +157,7 @@ template <typename T, bool PRUNED, bool REALOUT> struct IoCols {
     double* sumsq;         // REALOUT: sumsq[0] += sum re^2, sumsq[1] += sum im^2 (of the stored, scaled values)
     const float* scale2;   // REALOUT: optional power-of-two scales for (re, im) applied before the store
     unsigned int* maxabs2; // REALOUT: optional running max |stored value| per plane (float bits, atomicMax)
+    int halfpack;          // REALOUT, float only: store each aligned cell pair (x, x+1) as {half2 hi(x,x+1), half2 lo(x,x+1)} (same 4 B/cell)
     int nlines;            // even; line strides and batch strides are even too (N is even) -> line pairs are 16-byte aligned
     long long in_bstride, in_istride, out_bstride, out_istride;
     int Rm, Rp;
@@ -185,11 +200,12 @@ template <typename T, bool PRUNED, bool REALOUT> struct IoCols {
                     Real2<T> ra, rb;
                     ra.a = v.a.x * sa_; ra.b = v.b.x * sa_; rb.a = v.a.y * sb_; rb.b = v.b.y * sb_;
                     ma = fmax(ma, fmax(fabs(ra.a), fabs(ra.b))); mb = fmax(mb, fmax(fabs(rb.a), fabs(rb.b)));
-                    const long long o = boff + (long long)idx * out_istride + line;
-                    *reinterpret_cast<Real2<T>*>(outa + o) = ra;
-                    if (outb) *reinterpret_cast<Real2<T>*>(outb + o) = rb;
                     qa += (double)ra.a * (double)ra.a + (double)ra.b * (double)ra.b;
                     qb += (double)rb.a * (double)rb.a + (double)rb.b * (double)rb.b;
+                    const long long o = boff + (long long)idx * out_istride + line;
+                    if (halfpack) { ra = pack_hilo(ra); rb = pack_hilo(rb); }
+                    *reinterpret_cast<Real2<T>*>(outa + o) = ra;
+                    if (outb) *reinterpret_cast<Real2<T>*>(outb + o) = rb;
                 }
             }
             if (maxabs2) {

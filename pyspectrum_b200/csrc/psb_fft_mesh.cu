@@ -17,7 +17,7 @@ int fft_mesh_to_delta(Cx<float>* mesh, Cx<float>* half, int N, const Cx<float>* 
         IoRows<float> io1{ mesh, nrows };
         int rc = launch_any<float, +1>(cfg, p, LPC, dim3((unsigned)((nrows + LPC - 1) / LPC)), tw, io1, st);
         if (rc) return rc;
-        IoCols<float, false, false> io2{ mesh, mesh, nullptr, nullptr, nullptr, nullptr, nullptr, N, (long long)N * N, N, (long long)N * N, N, 0, 0 };
+        IoCols<float, false, false> io2{ mesh, mesh, nullptr, nullptr, nullptr, nullptr, nullptr, 0, N, (long long)N * N, N, (long long)N * N, N, 0, 0 };
         rc = launch_any<float, +1>(cfg, p, LPC, dim3((N + LPC - 1) / LPC, N), tw, io2, st);
         if (rc) return rc;
         IoZFcomb io3{ mesh, half, rec, Wk, sumw, periodic };
@@ -37,8 +37,8 @@ int fft_c2c_3d(Cx<float>* data, int N, int dir, const Cx<float>* tw, cudaStream_
         if (LPC < 1) return (int)PSB_ERR_UNSUPPORTED_N;
         const long long nrows = (long long)N * N;
         IoRows<float> io1{ data, nrows };
-        IoCols<float, false, false> io2{ data, data, nullptr, nullptr, nullptr, nullptr, nullptr, N, (long long)N * N, N, (long long)N * N, N, 0, 0 };
-        IoCols<float, false, false> io3{ data, data, nullptr, nullptr, nullptr, nullptr, nullptr, N, N, (long long)N * N, N, (long long)N * N, 0, 0 };
+        IoCols<float, false, false> io2{ data, data, nullptr, nullptr, nullptr, nullptr, nullptr, 0, N, (long long)N * N, N, (long long)N * N, N, 0, 0 };
+        IoCols<float, false, false> io3{ data, data, nullptr, nullptr, nullptr, nullptr, nullptr, 0, N, N, (long long)N * N, N, (long long)N * N, 0, 0 };
         dim3 g1((unsigned)((nrows + LPC - 1) / LPC)), g2((N + LPC - 1) / LPC, N);
         int rc;
         if (dir > 0) {

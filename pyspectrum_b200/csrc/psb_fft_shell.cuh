@@ -9,7 +9,7 @@ namespace psb {
 
 template <typename T>
 int fft_shell_pair(const Cx<float>* half, const unsigned short* irk, int N, int sa, int sb, int R,
-                   Cx<T>* t1, Cx<T>* t2, T* fa, T* fb, double* sumsq, const float* scale2, unsigned int* maxabs2,
+                   Cx<T>* t1, Cx<T>* t2, T* fa, T* fb, double* sumsq, const float* scale2, unsigned int* maxabs2, int halfpack,
                    const Cx<T>* tw, cudaStream_t st)
 {
     FftPlan p;
@@ -24,11 +24,11 @@ int fft_shell_pair(const Cx<float>* half, const unsigned short* irk, int N, int 
         int rc = launch_any<T, -1>(cfg, p, LPC, dim3((W + LPC - 1) / LPC, W), tw, io1, st);
         if (rc) return rc;
         // pass 2 (y): batch = kz', T1[kz'][ky'][x] -> T2[kz'][y][x]
-        IoCols<T, true, false> io2{ t1, t2, nullptr, nullptr, nullptr, nullptr, nullptr, N, (long long)W * N, N, (long long)N * N, N, Rm, Rp };
+        IoCols<T, true, false> io2{ t1, t2, nullptr, nullptr, nullptr, nullptr, nullptr, 0, N, (long long)W * N, N, (long long)N * N, N, Rm, Rp };
         rc = launch_any<T, -1>(cfg, p, LPC, dim3((N + LPC - 1) / LPC, W), tw, io2, st);
         if (rc) return rc;
         // pass 3 (z): batch = y, T2[kz'][y][x] -> real planes [z][y][x] (+ sums of squares)
-        IoCols<T, true, true> io3{ t2, nullptr, fa, fb, sumsq, scale2, maxabs2, N, N, (long long)N * N, N, (long long)N * N, Rm, Rp };
+        IoCols<T, true, true> io3{ t2, nullptr, fa, fb, sumsq, scale2, maxabs2, halfpack, N, N, (long long)N * N, N, (long long)N * N, Rm, Rp };
         return launch_any<T, -1>(cfg, p, LPC, dim3((N + LPC - 1) / LPC, N), tw, io3, st);
     });
 }

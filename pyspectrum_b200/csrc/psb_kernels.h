@@ -28,7 +28,7 @@ int fcomb_standalone(const Cx<float>* full, Cx<float>* half, int N, const Cx<dou
                      const double* sumw, int periodic, cudaStream_t st);
 template <typename T>
 int fft_shell_pair(const Cx<float>* half, const unsigned short* irk, int N, int sa, int sb, int R,
-                   Cx<T>* t1, Cx<T>* t2, T* fa, T* fb, double* sumsq, const float* scale2, unsigned int* maxabs2,
+                   Cx<T>* t1, Cx<T>* t2, T* fa, T* fb, double* sumsq, const float* scale2, unsigned int* maxabs2, int halfpack,
                    const Cx<T>* tw, cudaStream_t st);
 
 struct SpectraIn {
@@ -53,7 +53,7 @@ int shell_mode_counts(int N, const unsigned short* irk, int nshell_max, unsigned
 // tiles: int32 [ntiles][68] = {i0,j0,l0,pad, slot[64]}; fields[] holds S device pointers (S padded so i0+3 < S)
 template <typename T>
 int triangle_sums_tiles(const T* const* fields, int S, long long ncell, const int* tiles, int ntiles,
-                        double* sums, void* ws, size_t ws_bytes, cudaStream_t st);
+                        double* sums, void* ws, size_t ws_bytes, int packed_half, cudaStream_t st);
 size_t triangle_workspace_bytes(int ntiles);
 
 // tensor-core K6 (psb_triangles_tc.cu): one pass over MT*128 pair rows x NT shell columns

@@ -124,36 +124,62 @@ int shell_mode_counts(int N, const unsigned short* irk, int nshell, unsigned lon
     return cudaGetLastError() == cudaSuccess ? PSB_OK : PSB_ERR_CUDA;
 }
 
-// psum[j] ~ sum over the FULL grid of |delta(k)|^2 for modes in shell j+1 (exact for shells 1..4, a 1-in-8 sample estimate beyond;
-// the self-conjugate points are made real first, as reflect_delta does)
+// psum[j] = sum over the FULL grid of |delta(k)|^2 for modes in shell j+1 (the self-conjugate points are made real first, as
+// reflect_delta does).  One warp per (kz,ky) row of the half field; rows whose smallest |k| already lies beyond the last shell
+// are skipped without a load.  Along a row the shell index is non-decreasing in kx, so a 5-step segmented shuffle reduction
+// leaves one shared-memory atomic per (warp iteration, shell); blocks flush their bins with one global atomic per shell.
+constexpr int SHELL_POWER_MAXBINS = 1024;
 __global__ void __launch_bounds__(256) k_shell_power(const Cx<float>* __restrict__ half, int N, const unsigned short* __restrict__ irk,
                                                     int nshell, double* psum)
 {
-    const int h = N / 2;
-    const long long nmode = (long long)(h + 1) * N * N;
-    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < nmode; e += (long long)gridDim.x * blockDim.x) {
-        const int ix = (int)(e % (h + 1));
-        const long long r = e / (h + 1);
-        const int iy = (int)(r % N), iz = (int)(r / N);
+    __shared__ double bins[SHELL_POWER_MAXBINS];
+    for (int i = threadIdx.x; i < nshell; i += blockDim.x) bins[i] = 0.0;
+    __syncthreads();
+    const int h = N / 2, lane = threadIdx.x & 31;
+    const int nrow = N * N, nwarp = gridDim.x * (blockDim.x >> 5);
+    for (int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < nrow; r += nwarp) {
+        const int iz = r / N, iy = r - iz * N;
         const int ky = kfreq(iy, N), kz = kfreq(iz, N);
-        const int s = irk[ix * ix + ky * ky + kz * kz];
-        if (s < 1 || s > nshell) continue;
-        // only the power-of-two field scale depends on this sum: shells beyond the first few are sampled 1-in-8
-        // (unbiased in direction) to keep the same-address float64 atomics off the critical path
-        const bool sampled = s > 4;
-        if (sampled && ((iy + 3 * iz + 5 * ix) & 7)) continue;
-        Cx<float> d = half[e];
-        if ((ix == 0 || ix == h) && (iy == 0 || iy == h) && (iz == 0 || iz == h)) d.y = 0.f;
-        const double w = ((ix == 0 || ix == h) ? 1.0 : 2.0) * (sampled ? 8.0 : 1.0);
-        atomicAdd(&psum[s - 1], w * ((double)d.x * d.x + (double)d.y * d.y));
+        const int m0 = ky * ky + kz * kz;
+        if (irk[m0] > nshell) continue;                          // irk is non-decreasing in m: the whole row is outside
+        const bool selfyz = (iy == 0 || iy == h) && (iz == 0 || iz == h);
+        const Cx<float>* row = half + (long long)r * (h + 1);
+        for (int x0 = 0; x0 <= h; x0 += 32) {
+            const int ix = x0 + lane;
+            int sh = 0;
+            double v = 0.0;
+            if (ix <= h) {
+                sh = irk[m0 + ix * ix];
+                if (sh >= 1 && sh <= nshell) {
+                    Cx<float> d = row[ix];
+                    const bool edge = ix == 0 || ix == h;
+                    if (edge && selfyz) d.y = 0.f;
+                    v = (edge ? 1.0 : 2.0) * ((double)d.x * d.x + (double)d.y * d.y);
+                } else {
+                    sh = 0;
+                }
+            }
+            if (__ballot_sync(0xffffffffu, sh != 0) == 0u) { if (irk[m0 + x0 * x0] > nshell) break; else continue; }
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double tv = __shfl_down_sync(0xffffffffu, v, o);
+                const int ts = __shfl_down_sync(0xffffffffu, sh, o);
+                if (lane + o < 32 && ts == sh) v += tv;
+            }
+            const int prev = __shfl_up_sync(0xffffffffu, sh, 1);
+            if (sh != 0 && (lane == 0 || prev != sh)) atomicAdd(&bins[sh - 1], v);
+        }
     }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nshell; i += blockDim.x)
+        if (bins[i] != 0.0) atomicAdd(&psum[i], bins[i]);
 }
 
 int shell_power(const Cx<float>* half, int N, const unsigned short* irk, int nshell, double* psum, cudaStream_t st)
 {
-    if (!half || !irk || !psum || N < 2 || N % 2 || nshell < 1) return PSB_ERR_ARG;
+    if (!half || !irk || !psum || N < 2 || N % 2 || nshell < 1 || nshell > SHELL_POWER_MAXBINS) return PSB_ERR_ARG;
     if (cudaMemsetAsync(psum, 0, nshell * sizeof(double), st) != cudaSuccess) return PSB_ERR_CUDA;
-    k_shell_power<<<148 * 8, 256, 0, st>>>(half, N, irk, nshell, psum);
+    k_shell_power<<<148 * 4, 256, 0, st>>>(half, N, irk, nshell, psum);
     return cudaGetLastError() == cudaSuccess ? PSB_OK : PSB_ERR_CUDA;
 }
 

@@ -9,15 +9,27 @@
 // A second kernel folds the per-CTA partials into the output.  Cross-chunk accumulation is float64;
 // within a chunk a lane adds XC/32 float32 products (float64 throughout for the counts path).
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include "psb_kernels.h"
 
 namespace psb {
 
 constexpr int TILE_INTS = 4 + 64;     // i0, j0, l0, pad, slot[64] (output index or -1); i0.. are 0-based field slots
 
+// cell x of a field row; packed rows hold, per aligned cell pair (x, x+1), the words {half2 hi(x,x+1), half2 lo(x,x+1)}
+__device__ __forceinline__ float load_cell(const float* src, int x, int packed_half)
+{
+    if (!packed_half) return src[x];
+    const unsigned int hw = __float_as_uint(src[x & ~1]), lw = __float_as_uint(src[x | 1]);
+    const unsigned short h = (x & 1) ? (unsigned short)(hw >> 16) : (unsigned short)(hw & 0xffffu);
+    const unsigned short l = (x & 1) ? (unsigned short)(lw >> 16) : (unsigned short)(lw & 0xffffu);
+    return __half2float(__ushort_as_half(h)) + __half2float(__ushort_as_half(l));
+}
+__device__ __forceinline__ double load_cell(const double* src, int x, int) { return src[x]; }
+
 template <typename T, int NT>
 __global__ void __launch_bounds__(NT, 1) k_tri(const T* const* __restrict__ fields, int S, long long ncell, int XC,
-                                             const int* __restrict__ tiles, int ntiles, double* __restrict__ partial)
+                                             const int* __restrict__ tiles, int ntiles, double* __restrict__ partial, int packed_half)
 {
     extern __shared__ __align__(16) unsigned char tri_smem[];
     T* fs = reinterpret_cast<T*>(tri_smem);                    // [S][XC]
@@ -29,7 +41,7 @@ __global__ void __launch_bounds__(NT, 1) k_tri(const T* const* __restrict__ fiel
         __syncthreads();
         for (int f = 0; f < S; ++f) {
             const T* src = fields[f] + x0;
-            for (int x = threadIdx.x; x < XC; x += NT) fs[f * XC + x] = (x0 + x < ncell) ? src[x] : (T)0;
+            for (int x = threadIdx.x; x < XC; x += NT) fs[f * XC + x] = (x0 + x < ncell) ? load_cell(src, x, packed_half) : (T)0;
         }
         __syncthreads();
         for (int tile = warp; tile < ntiles; tile += nwarp) {
@@ -94,7 +106,7 @@ size_t triangle_workspace_bytes(int ntiles)
 
 template <typename T>
 int triangle_sums_tiles(const T* const* fields, int S, long long ncell, const int* tiles, int ntiles,
-                        double* sums, void* ws, size_t ws_bytes, cudaStream_t st)
+                        double* sums, void* ws, size_t ws_bytes, int packed_half, cudaStream_t st)
 {
     if (S < 4 || ntiles < 1 || ncell < 1) return PSB_ERR_ARG;
     if (ws_bytes < triangle_workspace_bytes(ntiles)) return PSB_ERR_WORKSPACE;
@@ -107,12 +119,12 @@ int triangle_sums_tiles(const T* const* fields, int S, long long ncell, const in
     double* partial = static_cast<double*>(ws);
     if (cudaMemsetAsync(partial, 0, triangle_workspace_bytes(ntiles), st) != cudaSuccess) return PSB_ERR_CUDA;
     const int ncta = tri_ctas();
-    kern<<<ncta, NT, smem, st>>>(fields, S, ncell, XC, tiles, ntiles, partial);
+    kern<<<ncta, NT, smem, st>>>(fields, S, ncell, XC, tiles, ntiles, partial, packed_half);
     k_tri_fold<<<(ntiles * 64 + 255) / 256, 256, 0, st>>>(partial, ncta, tiles, ntiles, sums);
     return cudaGetLastError() == cudaSuccess ? PSB_OK : PSB_ERR_CUDA;
 }
 
-template int triangle_sums_tiles<float>(const float* const*, int, long long, const int*, int, double*, void*, size_t, cudaStream_t);
-template int triangle_sums_tiles<double>(const double* const*, int, long long, const int*, int, double*, void*, size_t, cudaStream_t);
+template int triangle_sums_tiles<float>(const float* const*, int, long long, const int*, int, double*, void*, size_t, int, cudaStream_t);
+template int triangle_sums_tiles<double>(const double* const*, int, long long, const int*, int, double*, void*, size_t, int, cudaStream_t);
 
 }  // namespace psb

@@ -7,15 +7,19 @@
 // B[x,l] = I_l(x).  Operands are split into fp16 hi + fp16 lo (A = Ah+Al, B = Bh+Bl, each 11 significant
 // bits) and three MMAs  Ah.Bh + Ah.Bl + Al.Bh  recover ~2^-21 relative accuracy per product -- the
 // "3x split" scheme north_star allows, with fp16 rather than TF32 pieces (kind::f16 runs at twice the
-// kind::tf32 rate).  Every CTA keeps the whole C (MT x 128 rows x NT columns) resident in TMEM and owns a
+// kind::tf32 rate).  The shell fields arrive already split (K5's epilogue stores {half2 hi, half2 lo} per cell
+// pair, 4 bytes per cell as before), so B needs no arithmetic and the A products are formed and re-split in
+// packed half2 FMAs (prod_split: 2 instructions per product).  Every CTA keeps the whole C (MT x 128 rows x NT columns) resident in TMEM and owns a
 // contiguous x range; tensor-core accumulation rounds toward zero, so TMEM is drained into float64
 // every p.flush_ksteps*16 cells (double-buffered accumulator sets: the drain overlaps the next MMAs).
 //
 // Warp roles (704 threads, 1 CTA/SM):
 //   warps 0..15  A formers, warp = 4*g + q, g = 2*kp + tp: the group forms tiles {2tp,2tp+1} of K-steps kp and kp+2 of every
-//                64-cell chunk (two operand stages -> double buffered); a thread owns one TMEM lane in both tiles (rows
-//                sharing the field i), forms the pair products, splits them to fp16 hi/lo and writes them straight into
-//                TMEM (tcgen05.st) as the A operand; group g also drains accumulator tile g
+//                64-cell sub-chunk (two operand stages -> double buffered); a thread owns one TMEM lane in both tiles (rows
+//                sharing the field i), forms the pair products in packed half2 (already hi/lo split) and writes them straight
+//                into TMEM (tcgen05.st) as the A operand; group g also drains accumulator tile g.
+//                (A 2x2-block variant -- four rows from four field vectors, 1/3 less shared-memory traffic -- measured slower:
+//                the kernel is bound by the per-stage handshake/latency chain, not by shared-memory throughput; profiles/.)
 //   warp 19      MMA issuer (one elected lane): tcgen05.mma.cta_group::1.kind::f16 with A from TMEM, B from smem; tcgen05.commit
 //   warp 18      TMA producer: cp.async.bulk (UBLKCP) of [S][64] fp32 field chunks, one row per lane
 //   warps 16,17,20,21 B formers (one per operand stage): fields -> fp16 hi/lo K-major core-matrix tiles in shared memory
@@ -67,6 +71,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
         if (done) break;
         if (++spins > WATCHDOG) asm volatile("trap;");      // a protocol bug must not hang the GPU
     }
+}
+// non-blocking probe (issued early, consumed later: hides the ~150-cycle barrier read behind useful work)
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return done != 0;
 }
 // one lane of a converged warp (the CUTLASS elect_one_sync idiom): keeps the warp's control flow uniform so that the
 // uniform-datapath instructions (UTCHMMA, UTCBAR, UBLKCP) are issued directly instead of through a per-lane waterfall loop
@@ -123,15 +135,24 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r)
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
                  ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
 }
-// (a,b) -> packed fp16 hi (round to nearest) and packed fp16 lo = fp16(v - hi).  (A mantissa-mask hi saves the HADD2.F32
-// back-conversion but is not faster here and makes the dropped lo*lo term systematically signed: bias -1.5e-6 instead of -8e-7.)
-__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo)
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t* r)
 {
-    const __half2 hh = __floats2half2_rn(a, b);
-    const float2 back = __half22float2(hh);
-    const __half2 ll = __floats2half2_rn(a - back.x, b - back.y);
-    hi = *reinterpret_cast<const uint32_t*>(&hh);
-    lo = *reinterpret_cast<const uint32_t*>(&ll);
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
+// Pair product of two hi/lo-split values, itself hi/lo split, entirely in packed half2 arithmetic (two cells per instruction):
+//   hi = fp16(ih*jh);  lo = fp16(il*jh + fp16(ih*jl + (ih*jh - hi)))      -- the inner residual ih*jh - hi is exact (one FMA),
+// so hi + lo = (ih+il)(jh+jl) - il*jl to ~2^-22 relative: 4 FMA-pipe instructions per two products, no conversions.
+__device__ __forceinline__ void prod_split(uint32_t ih, uint32_t il, uint32_t jh, uint32_t jl, uint32_t& hi, uint32_t& lo)
+{
+    const __half2 a = *reinterpret_cast<const __half2*>(&ih), al = *reinterpret_cast<const __half2*>(&il);
+    const __half2 b = *reinterpret_cast<const __half2*>(&jh), bl = *reinterpret_cast<const __half2*>(&jl);
+    const __half2 h = __hmul2(a, b);
+    __half2 r = __hfma2(a, b, __hneg2(h));
+    r = __hfma2(a, bl, r);
+    r = __hfma2(al, b, r);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&r);
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar)
 {
@@ -150,24 +171,8 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v)
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// split 8 fp32 values into fp16 hi (round to nearest) and fp16 lo = fp16(v - hi); 16 bytes each
-__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo)
-{
-    uint32_t h[4], l[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const __half2 hh = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
-        const float2 back = __half22float2(hh);
-        const __half2 ll = __floats2half2_rn(v[2 * q] - back.x, v[2 * q + 1] - back.y);
-        h[q] = *reinterpret_cast<const uint32_t*>(&hh);
-        l[q] = *reinterpret_cast<const uint32_t*>(&ll);
-    }
-    hi = make_uint4(h[0], h[1], h[2], h[3]);
-    lo = make_uint4(l[0], l[1], l[2], l[3]);
-}
-
 struct Params {
-    const float* const* fields;   // S device pointers, each ncell floats (16-byte aligned)
+    const float* const* fields;   // S device pointers, each ncell 32-bit words of packed hi/lo halves (16-byte aligned)
     int S;                        // real shells (rows of a chunk)
     int NT;                       // MMA N = shells padded to a multiple of 16 (<= 128)
     int MT;                       // M tiles (128 rows each) in this pass (<= 256 / tile_cols)
@@ -240,7 +245,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_tri_tc(Params p)
     constexpr int ROWF = XCH + 4;    // padded fp32 row stride (== 4 mod 32 words: conflict-free LDS.128 across rows)
     extern __shared__ __align__(1024) unsigned char smem[];
     const int S = p.S, NT = p.NT, MT = p.MT, MR = MT * 128;
-    float* chunk = reinterpret_cast<float*>(smem);
+    uint32_t* chunk = reinterpret_cast<uint32_t*>(smem);      // one 32-bit word per cell (packed hi/lo pairs, see psb_fft_lines.cuh pack_hilo)
     const size_t chunk_bytes = (size_t)S * ROWF * 4;
     unsigned char* bop = smem + ((NCHUNKBUF * chunk_bytes + 1023) / 1024) * 1024;
     const uint32_t b_stage_bytes = 2u * NT * 16u;
@@ -292,7 +297,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_tri_tc(Params p)
             __syncwarp();
             if (p.debug & 16) { if (++buf == NCHUNKBUF) { buf = 0; ph ^= 1; } continue; }
             const long long x0 = (c_begin + c) * XCH;
-            float* dst = chunk + (size_t)buf * S * ROWF;
+            uint32_t* dst = chunk + (size_t)buf * S * ROWF;
             if (src0) bulk_g2s(dst + (size_t)lane * ROWF, src0 + x0, XCH * 4, &chunk_full[buf]);
             if (src1) bulk_g2s(dst + (size_t)(lane + 32) * ROWF, src1 + x0, XCH * 4, &chunk_full[buf]);
             for (int f = lane + 64; f < S; f += 32) bulk_g2s(dst + (size_t)f * ROWF, p.fields[f] + x0, XCH * 4, &chunk_full[buf]);
@@ -309,6 +314,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_tri_tc(Params p)
             const uint32_t tc_ = (uint32_t)p.tile_cols;
             int cf = 0;
             uint32_t eph = 0;
+            bool ready = false;
             const int nsub = nch * NSUB;
             for (int c = 0; c < nsub; ++c) {                                       // c counts 64-cell sub-chunks here
                 const uint32_t ph = (uint32_t)(c & 1);
@@ -317,9 +323,11 @@ __global__ void __launch_bounds__(NTHR, 1) k_tri_tc(Params p)
                 for (int g = 0; g < 4; ++g) {
                     const uint32_t acc = (cf == 0 && g == 0) ? 0u : 1u;
                     if (p.trace && blockIdx.x == 0 && c < 64 && lane == 0) p.trace[(0 * 8 + 4 + g) * 64 + c] = clock64();
-                    mbar_wait(&st_full[g], ph);
+                    if (!ready) mbar_wait(&st_full[g], ph);
                     if (p.trace && blockIdx.x == 0 && c < 64 && lane == 0) p.trace[(0 * 8 + g) * 64 + c] = clock64();
                     tc_fence_after();
+                    // probe the next stage now, look at the answer after this stage's MMAs are issued
+                    ready = mbar_test(&st_full[(g + 1) & 3], g == 3 ? (ph ^ 1u) : ph);
                     const uint64_t dbh = dbh0 + dstep * (uint64_t)g, dbl = dbl0 + dstep * (uint64_t)g;
                     const uint32_t a0 = tmem_base + (uint32_t)(TMEM_A0 + g * 64);
                     if (elect_one()) {
@@ -349,7 +357,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_tri_tc(Params p)
         for (int c = 0; c < nch; ++c) {
             mbar_wait(&chunk_full[buf], cph);
             for (int sub = 0; sub < NSUB; ++sub) {
-            const float* ch = chunk + (size_t)buf * S * ROWF + sub * SUB;
+            const uint32_t* ch = chunk + (size_t)buf * S * ROWF + sub * SUB;
             const uint32_t sph = (uint32_t)((c * NSUB + sub) & 1);
             {
                 const int g = b_stage_of_warp(warp);              // this warp's operand stage (K-step g of every sub-chunk)
@@ -357,14 +365,15 @@ __global__ void __launch_bounds__(NTHR, 1) k_tri_tc(Params p)
                 if (p.trace && blockIdx.x == 0 && tt < 64 && lane == 0 && g == 0) p.trace[(2 * 8 + 0) * 64 + tt] = clock64();
                 mbar_wait(&st_empty[g], sph ^ 1);
                 if (p.trace && blockIdx.x == 0 && tt < 64 && lane == 0 && g == 0) p.trace[(2 * 8 + 1) * 64 + tt] = clock64();
+                // lane <-> field: rows are 260 words apart (== 4 mod 32), so 8 consecutive fields hit 8 distinct bank groups
                 for (int cell = lane; cell < ((p.debug & 32) ? 0 : nbcell); cell += 32) {
-                    const int l = cell >> 1, kc = cell & 1;
+                    const int kc = cell >= NT ? 1 : 0, l = cell - kc * NT;
                     uint4 h4 = make_uint4(0, 0, 0, 0), l4 = h4;
-                    if (l < S) {
-                        const float* pl = ch + (size_t)l * ROWF + g * 16 + kc * 8;
-                        const float4 a = *reinterpret_cast<const float4*>(pl), b = *reinterpret_cast<const float4*>(pl + 4);
-                        split2(a.x, a.y, h4.x, l4.x); split2(a.z, a.w, h4.y, l4.y);
-                        split2(b.x, b.y, h4.z, l4.z); split2(b.z, b.w, h4.w, l4.w);
+                    if (l < S) {                       // 8 cells = 4 x {hi2, lo2}: pure data movement, K5 already split the fields
+                        const uint32_t* pl = ch + (size_t)l * ROWF + g * 16 + kc * 8;
+                        const uint4 a = *reinterpret_cast<const uint4*>(pl), b = *reinterpret_cast<const uint4*>(pl + 4);
+                        h4 = make_uint4(a.x, a.z, b.x, b.z);
+                        l4 = make_uint4(a.y, a.w, b.y, b.w);
                     }
                     const size_t off = (size_t)g * b_stage_bytes + (size_t)kc * NT * 16 + (size_t)l * 16;
                     *reinterpret_cast<uint4*>(b_hi + off) = h4;
@@ -405,7 +414,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_tri_tc(Params p)
             mbar_wait(&chunk_full[buf], cph);
 #pragma unroll 1
             for (int sub = 0; sub < NSUB; ++sub) {
-            const float* ch = chunk + (size_t)buf * S * ROWF + sub * SUB;
+            const uint32_t* ch = chunk + (size_t)buf * S * ROWF + sub * SUB;
             const int t = c * NSUB + sub;                      // running sub-chunk index: stage phases flip once per sub-chunk
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -413,21 +422,21 @@ __global__ void __launch_bounds__(NTHR, 1) k_tri_tc(Params p)
                 if (p.trace && blockIdx.x == 0 && t < 64 && lane == 0 && (warp == 0 || warp == 12)) p.trace[((warp == 0 ? 1 : 3) * 8 + 4 * h) * 64 + t] = clock64();
                 mbar_wait(&st_empty[kk], (uint32_t)(t & 1) ^ 1);
                 if (p.trace && blockIdx.x == 0 && t < 64 && lane == 0 && (warp == 0 || warp == 12)) p.trace[((warp == 0 ? 1 : 3) * 8 + 4 * h + 1) * 64 + t] = clock64();
-                if (!(p.debug & 256)) tc_fence_after();
-                float4 vi[4];
+                tc_fence_after();
+                uint4 vi[4];                       // 16 cells of I_i: per 4 cells {hi2(0,1), lo2(0,1), hi2(2,3), lo2(2,3)}
 #pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) vi[q4] = (p.debug & 512) ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(ch + fio + kk * 16 + q4 * 4);
+                for (int q4 = 0; q4 < 4; ++q4) vi[q4] = (p.debug & 512) ? make_uint4(0, 0, 0, 0) : *reinterpret_cast<const uint4*>(ch + fio + kk * 16 + q4 * 4);
 #pragma unroll
                 for (int mm = 0; mm < 2; ++mm) {
                     if (mm == 0 ? t0 : t1) {
                         uint32_t hi[8], lo[8];
                         if ((mm == 0 ? r0 : r1) && !(p.debug & 2)) {
-                            const float* pj = ch + (mm == 0 ? fjo0 : fjo1) + kk * 16;
+                            const uint32_t* pj = ch + (mm == 0 ? fjo0 : fjo1) + kk * 16;
 #pragma unroll
                             for (int q4 = 0; q4 < 4; ++q4) {
-                                const float4 b = *reinterpret_cast<const float4*>(pj + q4 * 4);
-                                split2(vi[q4].x * b.x, vi[q4].y * b.y, hi[2 * q4], lo[2 * q4]);
-                                split2(vi[q4].z * b.z, vi[q4].w * b.w, hi[2 * q4 + 1], lo[2 * q4 + 1]);
+                                const uint4 b = *reinterpret_cast<const uint4*>(pj + q4 * 4);
+                                prod_split(vi[q4].x, vi[q4].y, b.x, b.y, hi[2 * q4], lo[2 * q4]);
+                                prod_split(vi[q4].z, vi[q4].w, b.z, b.w, hi[2 * q4 + 1], lo[2 * q4 + 1]);
                             }
                         } else {
 #pragma unroll
@@ -441,7 +450,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_tri_tc(Params p)
                 }
                 if (p.trace && blockIdx.x == 0 && t < 64 && lane == 0 && (warp == 0 || warp == 12)) p.trace[((warp == 0 ? 1 : 3) * 8 + 4 * h + 3) * 64 + t] = clock64();
                 if (!(p.debug & 4)) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                if (!(p.debug & 256)) tc_fence_before();
+                tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&st_full[kk]);
                 if (p.trace && blockIdx.x == 0 && t < 64 && lane == 0 && (warp == 0 || warp == 12)) p.trace[((warp == 0 ? 1 : 3) * 8 + 4 * h + 2) * 64 + t] = clock64();

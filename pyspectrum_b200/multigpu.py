@@ -99,7 +99,7 @@ def sharded_triangle_sums(pipe, half, step, Ncut, Nmax, dtype=torch.float32):
     del fields
     rows = slab_field_rows(S, world, per)
     engine = 'fma' if f64 else 'auto'
-    sums = pipe.triangle_sums(slabs, Nmax, Ncut, step, engine=engine, field_rows=rows)
+    sums = pipe.triangle_sums(slabs, Nmax, Ncut, step, engine=engine, field_rows=rows, packed=not f64)
     _allreduce(sums)
     # per-shell quantities live on the owner rank: scatter them into global shell order, then sum over ranks
     glob_sq = torch.zeros(2 * npairs, dtype=torch.float64, device=pipe.dev)
@@ -121,7 +121,7 @@ def sharded_triangle_sums(pipe, half, step, Ncut, Nmax, dtype=torch.float32):
     n2 = 2 * npairs
     sums_h, sq, sc, mx = host[:nt], host[nt:nt + n2], host[nt + n2:nt + 2 * n2], host[nt + 2 * n2:]
     if mx.max() ** 2 >= 4.0e4:                                           # fp16 range guard: redo with the FFMA kernel
-        sums = pipe.triangle_sums(slabs, Nmax, Ncut, step, engine='fma', field_rows=rows)
+        sums = pipe.triangle_sums(slabs, Nmax, Ncut, step, engine='fma', field_rows=rows, packed=True)
         _allreduce(sums)
         sums_h = sums.cpu().numpy()
     tri = P.triangle_list(Nmax, Ncut, step)

@@ -149,6 +149,7 @@ class PeriodicPipeline(object):
             if not pos.is_contiguous():
                 if pos.t().is_contiguous():
                     aos = 1
+                    pos = pos.t()                        # (N,3) contiguous, like the numpy branch
                 else:
                     pos = pos.contiguous()
             pos = pos.to(self.dev, non_blocking=True)
@@ -252,8 +253,10 @@ class PeriodicPipeline(object):
         """K5: shells s0..Nmax as real fields [S_alloc, N^3] + sum_x I_j^2 per shell.
         half=None -> delta == 1 (counts).  Two shells ride on one complex transform.
         scaled=True stores I_j * scale_j with scale_j an exact power of two putting the rms near 2 (from the
-        Parseval shell power, or the `scales` tensor if given), which the fp16-split tensor-core triangle kernel needs;
-        returns (fields, sumsq, scales, maxabs) -- sumsq and maxabs refer to the stored (scaled) values.
+        Parseval shell power, or the `scales` tensor if given) and stored pre-split for the tensor-core triangle kernel:
+        each aligned cell pair (x, x+1) holds the words {half2 hi(x,x+1), half2 lo(x,x+1)}, hi = fp16(v), lo = fp16(v - hi)
+        (still 4 bytes per cell; `unpack_fields` gives the float32 values back).
+        returns (fields, sumsq, scales, maxabs) -- sumsq and maxabs refer to the scaled values before the split.
         pairs: optional list of pair indices p (shells s0+2p, s0+2p+1) to compute -- the multi-GPU path shards shells this way;
         the returned fields then hold only those pairs, in the given order (2 rows per pair), sumsq/maxabs likewise."""
         N = self.N
@@ -302,10 +305,19 @@ class PeriodicPipeline(object):
                     sc = ctypes.c_void_p(sc_local.data_ptr() + 4 * 2 * r)
                     mx = ctypes.c_void_p(maxabs.data_ptr() + 4 * 2 * r)
                 check(self.L.psb_bk_shell_pair_f32(_ptr(half), _ptr(irk), N, sa, sb, R, _ptr(t1), _ptr(t2), _ptr(fields[2 * r]),
-                                                   _ptr(fields[2 * r + 1]), sq, sc, mx, _ptr(tw), st), 'psb_bk_shell_pair_f32')
+                                                   _ptr(fields[2 * r + 1]), sq, sc, mx, 1 if scaled else 0, _ptr(tw), st),
+                      'psb_bk_shell_pair_f32')
         if scaled:
+            fields.psb_packed = True                     # rows hold {half2 hi, half2 lo} per cell pair (see unpack_fields)
             return fields, sumsq, sc_local, maxabs
         return fields, sumsq
+
+    @staticmethod
+    def unpack_fields(fields):
+        """float32 values of packed shell fields (shell_fields(scaled=True)): value = hi + lo per cell."""
+        nrow, ncell = fields.shape
+        h = fields.view(torch.float16).view(nrow, ncell // 2, 2, 2)        # [pair][hi word | lo word][cell parity]
+        return (h[:, :, 0, :].float() + h[:, :, 1, :].float()).reshape(nrow, ncell)
 
     # ------------------------------------------------------------------ K6
     def triangle_tiles(self, Nmax, Ncut, step):
@@ -321,15 +333,19 @@ class PeriodicPipeline(object):
             self._tiles[key] = (tri, torch.from_numpy(tiles).to(self.dev), nt.value)
         return self._tiles[key]
 
-    def triangle_sums(self, fields, Nmax, Ncut, step, engine='auto', field_rows=None):
+    def triangle_sums(self, fields, Nmax, Ncut, step, engine='auto', field_rows=None, packed=None):
         """K6: sum_x I_i I_j I_l for every triangle of the loop nest (float64 tensor, loop order).
-        engine: 'tc' = tcgen05 split-fp16 kernel (float32 fields pre-scaled by shell_fields(scaled=True)),
-                'fma' = FFMA/DFMA register-tile kernel, 'auto' = tc when the shapes allow it."""
+        engine: 'tc' = tcgen05 split-fp16 kernel (needs the scaled + packed fields of shell_fields(scaled=True)),
+                'fma' = FFMA/DFMA register-tile kernel (plain float32/float64 fields, or packed ones which it decodes),
+                'auto' = tc when the fields are packed and the shapes allow it.
+        packed: whether `fields` holds packed hi/lo halves (default: the tag shell_fields put on the tensor)."""
         S = Nmax - Ncut // step + 1
         self._field_rows = list(range(S)) if field_rows is None else list(field_rows)      # row of `fields` holding shell slot f
-        tc_ok = fields.dtype == torch.float32 and fields.shape[1] % 64 == 0 and S <= 128
+        if packed is None:
+            packed = bool(getattr(fields, 'psb_packed', False))
+        tc_ok = packed and fields.dtype == torch.float32 and fields.shape[1] % 64 == 0 and S <= 128
         if engine == 'tc' and not tc_ok:
-            raise ValueError('tensor-core triangle kernel needs float32 fields, N^3 % 64 == 0 and <= 128 shells')
+            raise ValueError('tensor-core triangle kernel needs packed float32 fields, N^3 % 64 == 0 and <= 128 shells')
         if engine == 'tc' or (engine == 'auto' and tc_ok):
             return self._triangle_sums_tc(fields, Nmax, Ncut, step)
         tri, tiles, ntiles = self.triangle_tiles(Nmax, Ncut, step)
@@ -339,9 +355,12 @@ class PeriodicPipeline(object):
         sums = torch.zeros(len(tri), dtype=torch.float64, device=self.dev)
         wsb = self.L.psb_bk_triangle_workspace_bytes(ntiles)
         ws = torch.empty(wsb, dtype=torch.uint8, device=self.dev)
-        fn = self.L.psb_bk_triangle_sums_f64 if fields.dtype == torch.float64 else self.L.psb_bk_triangle_sums_f32
-        check(fn(_ptr(dptr), nf, fields.shape[1], _ptr(tiles), ntiles, _ptr(sums), _ptr(ws), wsb, _stream()),
-              'psb_bk_triangle_sums')
+        if fields.dtype == torch.float64:
+            rc = self.L.psb_bk_triangle_sums_f64(_ptr(dptr), nf, fields.shape[1], _ptr(tiles), ntiles, _ptr(sums), _ptr(ws), wsb, _stream())
+        else:
+            rc = self.L.psb_bk_triangle_sums_f32(_ptr(dptr), nf, fields.shape[1], _ptr(tiles), ntiles, _ptr(sums), _ptr(ws), wsb,
+                                                 1 if packed else 0, _stream())
+        check(rc, 'psb_bk_triangle_sums')
         return sums
 
     def tc_passes(self, Nmax, Ncut, step):
@@ -626,6 +645,62 @@ def _bk_epilogue(Ngrid, tri, sums, sumsq, Nk, counts, step, Ncut, Nmax):
     out['q123'] = q123
     out['counts'] = np.where(pos, c / (fac * float(Ngrid ** 3)), 0.)
     return out
+
+
+def _prefetched(catalogues, Ngrid):
+    """Yield (xyz_dev, w_dev) for every catalogue of the iterable, uploading catalogue n+1 on a copy stream while the
+    caller works on catalogue n (host->device copies overlap the kernels when the host arrays are pinned torch tensors;
+    pageable numpy arrays work too, the copy then just does not overlap).  Items are `xyz` or `(xyz, w)`."""
+    pipe = PeriodicPipeline.get(Ngrid)
+    if getattr(pipe, '_copy_stream', None) is None:
+        pipe._copy_stream = torch.cuda.Stream(device=pipe.dev)      # kept: its allocator pool then recycles the upload buffers
+    copy_stream = pipe._copy_stream
+
+    def stage(item):
+        xyz, w = item if isinstance(item, (tuple, list)) else (item, None)
+        with torch.cuda.stream(copy_stream):
+            pos, aos, wt = pipe.to_device(xyz, w)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return (pos.t() if aos else pos), wt, ev
+
+    it = iter(catalogues)
+    nxt = None
+    for item in it:
+        nxt = stage(item)
+        break
+    while nxt is not None:
+        cur, nxt = nxt, None
+        for item in it:                                  # enqueue the next upload BEFORE this catalogue's blocking result read
+            nxt = stage(item)
+            break
+        main = torch.cuda.current_stream(pipe.dev)
+        main.wait_event(cur[2])
+        for t in cur[:2]:
+            if t is not None and t.is_cuda:
+                t.record_stream(main)                    # allocated on the copy stream, consumed on the main stream
+        yield cur[0], cur[1]
+
+
+def Bk_periodic_many(catalogues, Lbox=2600, Ngrid=360, step=3, Ncut=3, Nmax=40, fft='pyfftw', nthreads=1, silent=True):
+    """Generator: Bk_periodic (pyspectrum.py:285-356) for every catalogue of an iterable -- the thousands-of-mocks use of the
+    reference -- with the upload of catalogue n+1 overlapped with the computation of catalogue n.  Yields the same
+    dictionaries as Bk_periodic, in order."""
+    for xyz_d, w_d in _prefetched(catalogues, Ngrid):
+        yield Bk_periodic(xyz_d, w=w_d, Lbox=Lbox, Ngrid=Ngrid, step=step, Ncut=Ncut, Nmax=Nmax, fft=fft, nthreads=nthreads,
+                          silent=silent)
+
+
+def Pk_periodic_many(catalogues, Lbox=2600, Ngrid=360, fft='pyfftw', silent=True):
+    """Generator: Pk_periodic (pyspectrum.py:644-728) over many catalogues with overlapped uploads."""
+    for xyz_d, w_d in _prefetched(catalogues, Ngrid):
+        yield Pk_periodic(xyz_d, w=w_d, Lbox=Lbox, Ngrid=Ngrid, fft=fft, silent=silent)
+
+
+def Pk_periodic_rsd_many(catalogues, Lbox=2600, Ngrid=360, rsd=2, Nmubin=10, fft='pyfftw', code='fortran', silent=True):
+    """Generator: Pk_periodic_rsd (pyspectrum.py:460-538) over many catalogues with overlapped uploads."""
+    for xyz_d, w_d in _prefetched(catalogues, Ngrid):
+        yield Pk_periodic_rsd(xyz_d, w=w_d, Lbox=Lbox, Ngrid=Ngrid, rsd=rsd, Nmubin=Nmubin, fft=fft, code=code, silent=silent)
 
 
 def Bk_periodic(xyz, w=None, Lbox=2600, Ngrid=360, step=3, Ncut=3, Nmax=40, fft='pyfftw', nthreads=1, silent=True):

@@ -254,7 +254,7 @@ def test_triangle_engines_vs_float64(mods, N, Np, step, Ncut, Nmax):
     s0 = Ncut // step
     fields, sumsq, scales, maxabs = pipe.shell_fields(half, step, s0, Nmax, scaled=True)
     tri = pySpec.triangle_list(Nmax, Ncut, step)
-    f64 = fields.double()
+    f64 = pipe.unpack_fields(fields).double()                # the stored fields are fp16 hi/lo packed
     ti = torch.from_numpy(tri.astype(np.int64) - s0).to(fields.device)
     ref = torch.empty(len(tri), dtype=torch.float64, device=fields.device)
     nrm = torch.empty_like(ref)
@@ -273,7 +273,35 @@ def test_triangle_engines_vs_float64(mods, N, Np, step, Ncut, Nmax):
     sc = scales.cpu().numpy()
     assert np.all(np.log2(sc) == np.rint(np.log2(sc)))
     S = Nmax - s0 + 1
-    assert np.allclose(maxabs.view(torch.float32).cpu().numpy()[:S], fields[:S].abs().max(dim=1).values.cpu().numpy())
+    assert np.allclose(maxabs.view(torch.float32).cpu().numpy()[:S], pipe.unpack_fields(fields)[:S].abs().max(dim=1).values.cpu().numpy(), rtol=1e-6)
+
+
+def test_many_generators_match_single_calls(mods):
+    """Bk/Pk/Pk_rsd *_many (upload of catalogue n+1 overlapped with the kernels of n) give the single-call results, in order,
+    for pinned torch tensors, numpy arrays (C and Fortran order) and (xyz, w) items."""
+    import torch
+    pySpec, _, _ = mods
+    L, N = 200., 48
+    cats = [_cat(70 + k, 30000 + 1000 * k, L) for k in range(4)]
+    w3 = np.random.default_rng(5).uniform(0.5, 1.5, cats[3].shape[1])
+    pinned = torch.from_numpy(cats[0]).pin_memory()
+    items = [pinned, cats[1], np.asfortranarray(cats[2]), (cats[3], w3)]
+    kw = dict(Lbox=L, Ngrid=N, step=3, Ncut=3, Nmax=7)
+    outs = list(pySpec.Bk_periodic_many(items, **kw))
+    assert len(outs) == 4
+    for k, o in enumerate(outs):
+        ref = pySpec.Bk_periodic(cats[k], w=(w3 if k == 3 else None), **kw)
+        assert np.array_equal(o['counts'], ref['counts'])
+        assert np.allclose(o['b123'] + o['b123_sn'], ref['b123'] + ref['b123_sn'], rtol=2e-5)
+        assert np.allclose(o['p0k1'], ref['p0k1'], rtol=1e-5)
+    pk = list(pySpec.Pk_periodic_many(items, Lbox=L, Ngrid=N))
+    pr = list(pySpec.Pk_periodic_rsd_many(items, Lbox=L, Ngrid=N, rsd=2, Nmubin=5))
+    for k in range(4):
+        ref = pySpec.Pk_periodic(cats[k], w=(w3 if k == 3 else None), Lbox=L, Ngrid=N)
+        assert np.array_equal(pk[k]['counts'], ref['counts']) and np.allclose(pk[k]['p0k'], ref['p0k'], rtol=1e-5, atol=1e-3)
+        ref = pySpec.Pk_periodic_rsd(cats[k], w=(w3 if k == 3 else None), Lbox=L, Ngrid=N, rsd=2, Nmubin=5)
+        assert np.array_equal(pr[k]['counts'], ref['counts']) and np.allclose(pr[k]['p2k'], ref['p2k'], rtol=1e-4, atol=1e-2)
+    assert list(pySpec.Bk_periodic_many([], **kw)) == []
 
 
 # ------------------------------------------------------------------------------ full-size properties

@@ -18,7 +18,7 @@ for (N, Np, step, Ncut, Nmax) in [(32, 20000, 1, 1, 12), (64, 100000, 1, 3, 30),
     s0 = Ncut // step
     fields, sumsq, scales, maxabs = pipe.shell_fields(half, step, s0, Nmax, scaled=True)
     tri = pySpec.triangle_list(Nmax, Ncut, step)
-    f64 = fields.double()
+    f64 = pipe.unpack_fields(fields).double()                # the stored fields are fp16 hi/lo packed
     ti = torch.from_numpy(tri.astype(np.int64) - s0).to(fields.device)
     ref = torch.empty(len(tri), dtype=torch.float64, device=fields.device); nrm = torch.empty_like(ref)
     B = max(1, (1 << 26) // fields.shape[1])
