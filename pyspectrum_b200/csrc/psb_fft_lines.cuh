@@ -20,6 +20,8 @@
 //           per-shell pyfftw fftn + np.real (pyspectrum.py:387-400), reflect_delta (py:1134-1157).
 #pragma once
 #include <cuda_runtime.h>
+#include <utility>
+#include <type_traits>
 #include "psb_fft_core.cuh"
 #include "psb_fcomb_core.cuh"
 #include <cuda_fp16.h>
@@ -46,6 +48,61 @@ __device__ __forceinline__ void run_stage(Cx<T>* sl, int estride, int N, int Ns,
     __syncthreads();
 }
 
+// Fused edge stages: the first stage takes its inputs straight from the IO functor (global memory -> registers: no staging
+// pass through shared memory, and all loads of a thread are in flight together), the last one hands its outputs to the
+// functor's epilogue from registers.  Only the exchanges between stages go through shared memory.
+template <typename T, int R, int DIR, int MAXB, int LPC, class IO>
+__device__ __forceinline__ void first_stage_fused(Cx<T>* sl, int estride, int N, int t, int TPL, const IO& io, int line)
+{
+    Cx<T> v[MAXB][R];
+    const int M = N / R;
+#pragma unroll
+    for (int b = 0; b < MAXB; ++b) {
+        const int j = t + b * TPL;
+        if (j < M) {
+#pragma unroll
+            for (int q = 0; q < R; ++q) v[b][q] = io.template fetch<LPC>(j + q * M, line, N);
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < MAXB; ++b) {
+        const int j = t + b * TPL;
+        if (j < M) {
+            Dft<R, DIR, T>::run(v[b]);                     // Ns = 1: no twiddles, outputs at j*R + q
+#pragma unroll
+            for (int q = 0; q < R; ++q) sl[(j * R + q) * estride] = v[b][q];
+        }
+    }
+}
+
+template <typename T, int R, int DIR, int MAXB, int LPC, class IO>
+__device__ __forceinline__ void last_stage_fused(const Cx<T>* sl, int estride, int N, int t, int TPL, const Cx<T>* tw, const IO& io,
+                                                 int line, typename IO::Acc& acc)
+{
+    const int M = N / R;                                   // == Ns of the last stage
+#pragma unroll
+    for (int b = 0; b < MAXB; ++b) {
+        const int j = t + b * TPL;
+        const bool act = j < M;
+        Cx<T> v[R];
+        if (act) {
+            stage_read<R, T>(sl, estride, N, j, v);
+#pragma unroll
+            for (int q = 1; q < R; ++q) {
+                Cx<T> w = tw[q * j];
+                if (DIR < 0) w.y = -w.y;
+                v[q] = v[q] * w;
+            }
+            Dft<R, DIR, T>::run(v);
+        } else {
+#pragma unroll
+            for (int q = 0; q < R; ++q) v[q] = mk<T>(0, 0);
+        }
+#pragma unroll
+        for (int q = 0; q < R; ++q) io.template emit<LPC>(j + q * M, line, v[q], act, acc);     // every lane calls (warp shuffles inside)
+    }
+}
+
 // Stage policies: StaticStages<RS...> expands the radix sequence at compile time (straight-line
 // stages, N a compile-time constant); DynStages walks a runtime plan with a switch.  The switch form
 // makes ptxas speculate the shared-memory reads of every case (245 registers unconstrained), so it is
@@ -60,6 +117,32 @@ template <int... RS> struct StaticStages {
     static __device__ __forceinline__ void run(const FftPlan&, Cx<T>* sl, int estride, int t, int TPL, const Cx<T>* tw) {
         int Ns = 1;
         ((run_stage<T, RS, DIR, MAXB>(sl, estride, N, Ns, t, TPL, tw), Ns *= RS), ...);
+    }
+    // fused variant: stage 0 reads through io.fetch, the last stage writes through io.emit
+    template <typename T, int DIR, int MAXB, int LPC, class IO, int I, int R>
+    static __device__ __forceinline__ void fused_stage(Cx<T>* sl, int estride, int& Ns, int t, int TPL, const Cx<T>* tw, const IO& io,
+                                                       int line, typename IO::Acc& acc) {
+        if constexpr (I == 0) {
+            first_stage_fused<T, R, DIR, MAXB, LPC, IO>(sl, estride, N, t, TPL, io, line);
+            __syncthreads();
+        } else if constexpr (I == NSTAGES - 1) {
+            last_stage_fused<T, R, DIR, MAXB, LPC, IO>(sl, estride, N, t, TPL, tw, io, line, acc);
+        } else {
+            run_stage<T, R, DIR, MAXB>(sl, estride, N, Ns, t, TPL, tw);
+        }
+        Ns *= R;
+    }
+    template <typename T, int DIR, int MAXB, int LPC, class IO, int... I>
+    static __device__ __forceinline__ void run_fused_impl(Cx<T>* sl, int estride, int t, int TPL, const Cx<T>* tw, const IO& io, int line,
+                                                          typename IO::Acc& acc, std::integer_sequence<int, I...>) {
+        int Ns = 1;
+        (fused_stage<T, DIR, MAXB, LPC, IO, I, RS>(sl, estride, Ns, t, TPL, tw, io, line, acc), ...);
+    }
+    template <typename T, int DIR, int MAXB, int LPC, class IO>
+    static __device__ __forceinline__ void run_fused(Cx<T>* sl, int estride, int t, int TPL, const Cx<T>* tw, const IO& io, int line,
+                                                     typename IO::Acc& acc) {
+        static_assert(NSTAGES >= 2, "fused edge stages need at least two stages");
+        run_fused_impl<T, DIR, MAXB, LPC, IO>(sl, estride, t, TPL, tw, io, line, acc, std::make_integer_sequence<int, NSTAGES>{});
     }
 };
 
@@ -100,6 +183,22 @@ __global__ void __launch_bounds__(NTHR, MINB) fft_lines_kernel(FftPlan plan, int
     const int line = threadIdx.x % LPC, t = threadIdx.x / LPC;
     STAGES::template run<T, DIR, MAXB>(plan, s + line, LPCP, t, TPL, tw);
     io.template store<LPC_T>(s, LPCP, LPC, N);
+}
+
+template <typename T, int DIR, int MAXB, int NTHR, int MINB, int LPC, class STAGES, class IO>
+__global__ void __launch_bounds__(NTHR, MINB) fft_lines_fused_kernel(int TPL, const Cx<T>* __restrict__ tw_g, IO io)
+{
+    extern __shared__ __align__(16) unsigned char psb_smem[];
+    constexpr int N = STAGES::N;
+    constexpr int LPCP = LPC + 2;
+    Cx<T>* s = reinterpret_cast<Cx<T>*>(psb_smem);
+    Cx<T>* tw = s + (size_t)N * LPCP;
+    for (int i = threadIdx.x; i < N; i += NTHR) tw[i] = tw_g[i];           // first used after the stage-0 barrier
+    const int line = threadIdx.x % LPC, t = threadIdx.x / LPC;
+    typename IO::Acc acc;
+    io.acc_init(acc);
+    STAGES::template run_fused<T, DIR, MAXB, LPC, IO>(s + line, LPCP, t, TPL, tw, io, line, acc);
+    io.finish(acc);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -161,6 +260,67 @@ template <typename T, bool PRUNED, bool REALOUT> struct IoCols {
     int nlines;            // even; line strides and batch strides are even too (N is even) -> line pairs are 16-byte aligned
     long long in_bstride, in_istride, out_bstride, out_istride;
     int Rm, Rp;
+    // ---- fused edge stages (fft_lines_fused_kernel): element-wise access from registers
+    static constexpr bool FUSED = true;
+    struct Acc { T m; T q; };                              // running max |value| and sum of squares of this thread's plane
+    __device__ __forceinline__ void acc_init(Acc& a) const { a.m = (T)0; a.q = (T)0; }
+    template <int LPC> __device__ __forceinline__ Cx<T> fetch(int idx, int line, int N) const {
+        const int l = blockIdx.x * LPC + line;
+        if (l >= nlines) return mk<T>(0, 0);
+        const Cx<T>* base = in + (long long)blockIdx.y * in_bstride + l;
+        if (PRUNED) {
+            const int k = kfreq(idx, N);
+            if (k < -Rm || k > Rp) return mk<T>(0, 0);
+            return base[(long long)(k + Rm) * in_istride];
+        }
+        return base[(long long)idx * in_istride];
+    }
+    template <int LPC> __device__ __forceinline__ void emit(int idx, int line, Cx<T> v, bool act, Acc& acc) const {
+        const int l = blockIdx.x * LPC + line;
+        const bool ok = act && l < nlines;
+        if (!REALOUT) {
+            if (ok) out[(long long)blockIdx.y * out_bstride + (long long)idx * out_istride + l] = v;
+        } else {
+            // lanes (line, line^1) are neighbours: the even one takes the pair of real parts (plane a), the odd one the pair of
+            // imaginary parts (plane b), so every thread packs and stores one aligned cell pair
+            const T sa_ = scale2 ? (T)scale2[0] : (T)1, sb_ = scale2 ? (T)scale2[1] : (T)1;
+            const T ra = v.x * sa_, rb = v.y * sb_;
+            const bool even = (line & 1) == 0;
+            const T recv = __shfl_xor_sync(0xffffffffu, even ? rb : ra, 1);
+            Real2<T> r;
+            r.a = even ? ra : recv;
+            r.b = even ? recv : rb;
+            T* outp = even ? outa : outb;
+            if (ok) {
+                acc.m = fmax(acc.m, fmax(fabs(r.a), fabs(r.b)));
+                acc.q += r.a * r.a + r.b * r.b;
+                if (outp) {
+                    if (halfpack) r = pack_hilo(r);
+                    *reinterpret_cast<Real2<T>*>(outp + (long long)blockIdx.y * out_bstride + (long long)idx * out_istride + (l & ~1)) = r;
+                }
+            }
+        }
+    }
+    __device__ __forceinline__ void finish(Acc& acc) const {
+        if (!REALOUT) return;
+        T m = acc.m;
+        double q = (double)acc.q;
+        for (int o = 2; o < 32; o <<= 1) {                 // keeps the lane parity: lane 0 ends with plane a, lane 1 with plane b
+            m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+            q += __shfl_xor_sync(0xffffffffu, q, o);
+        }
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+        if (maxabs2 && lane < 2) atomicMax(&maxabs2[lane], __float_as_uint((float)m));
+        __shared__ double red[2][32];
+        if (lane < 2) red[lane][w] = q;
+        __syncthreads();
+        if (threadIdx.x < 64) {
+            const int pl = threadIdx.x >> 5;
+            q = lane < nw ? red[pl][lane] : 0.0;
+            for (int o = 16; o > 0; o >>= 1) q += __shfl_down_sync(0xffffffffu, q, o);
+            if (lane == 0) atomicAdd(&sumsq[pl], q);
+        }
+    }
     template <int LPC_T> __device__ void load(Cx<T>* s, int LPCP, int LPC, int N) const {
         const int l0 = blockIdx.x * LPC, HP = LPC / 2;
         const Cx<T>* base = in + (long long)blockIdx.y * in_bstride + l0;
@@ -329,11 +489,22 @@ template <class STAGES, int LPC_, int MAXB_, int MINB_ = 1> struct Cfg {
 };
 struct CfgDyn { using Stages = DynStages; static constexpr int MAXB = 2, NTHR = 256; };
 
+template <class IO, class = void> struct io_is_fused : std::false_type {};
+template <class IO> struct io_is_fused<IO, std::enable_if_t<IO::FUSED>> : std::true_type {};
+
 template <typename T, int DIR, class CFG, class IO>
 static int launch_static(dim3 grid, const Cx<T>* tw, const IO& io, cudaStream_t st)
 {
     constexpr int N = CFG::Stages::N;
     const size_t smem = ((size_t)N * (CFG::LPC + 2) + N) * sizeof(Cx<T>);
+    if constexpr (io_is_fused<IO>::value && CFG::Stages::NSTAGES >= 2) {
+        static_assert(CFG::LPC % 2 == 0 && 32 % CFG::LPC == 0, "line pairs must sit in one warp");
+        auto kf = fft_lines_fused_kernel<T, DIR, CFG::MAXB, CFG::NTHR, (sizeof(T) == 4 ? CFG::MINB : 1), CFG::LPC, typename CFG::Stages, IO>;
+        if (cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PSB_ERR_CUDA;
+        cudaFuncSetAttribute(kf, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        kf<<<grid, CFG::NTHR, smem, st>>>(CFG::TPL, tw, io);
+        return cudaGetLastError() == cudaSuccess ? PSB_OK : PSB_ERR_CUDA;
+    }
     auto kern = fft_lines_kernel<T, DIR, CFG::MAXB, CFG::NTHR, (sizeof(T) == 4 ? CFG::MINB : 1), CFG::LPC, typename CFG::Stages, IO>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PSB_ERR_CUDA;
     // ask for the largest shared-memory carveout so that several CTAs co-reside and overlap load / FFT / store
