@@ -52,7 +52,7 @@ __device__ __forceinline__ void run_stage(Cx<T>* sl, int estride, int N, int Ns,
 // pass through shared memory, and all loads of a thread are in flight together), the last one hands its outputs to the
 // functor's epilogue from registers.  Only the exchanges between stages go through shared memory.
 template <typename T, int R, int DIR, int MAXB, int LPC, class IO>
-__device__ __forceinline__ void first_stage_fused(Cx<T>* sl, int estride, int N, int t, int TPL, const IO& io, int line)
+__device__ __forceinline__ void first_stage_fused(Cx<T>* sl, int estride, int N, int t, int TPL, const IO& io, const typename IO::Acc& acc)
 {
     Cx<T> v[MAXB][R];
     const int M = N / R;
@@ -61,7 +61,7 @@ __device__ __forceinline__ void first_stage_fused(Cx<T>* sl, int estride, int N,
         const int j = t + b * TPL;
         if (j < M) {
 #pragma unroll
-            for (int q = 0; q < R; ++q) v[b][q] = io.template fetch<LPC>(j + q * M, line, N);
+            for (int q = 0; q < R; ++q) v[b][q] = io.fetch(j + q * M, N, acc);
         }
     }
 #pragma unroll
@@ -99,7 +99,7 @@ __device__ __forceinline__ void last_stage_fused(const Cx<T>* sl, int estride, i
             for (int q = 0; q < R; ++q) v[q] = mk<T>(0, 0);
         }
 #pragma unroll
-        for (int q = 0; q < R; ++q) io.template emit<LPC>(j + q * M, line, v[q], act, acc);     // every lane calls (warp shuffles inside)
+        for (int q = 0; q < R; ++q) io.emit(j + q * M, line, v[q], act, acc);     // every lane calls (warp shuffles inside)
     }
 }
 
@@ -123,7 +123,7 @@ template <int... RS> struct StaticStages {
     static __device__ __forceinline__ void fused_stage(Cx<T>* sl, int estride, int& Ns, int t, int TPL, const Cx<T>* tw, const IO& io,
                                                        int line, typename IO::Acc& acc) {
         if constexpr (I == 0) {
-            first_stage_fused<T, R, DIR, MAXB, LPC, IO>(sl, estride, N, t, TPL, io, line);
+            first_stage_fused<T, R, DIR, MAXB, LPC, IO>(sl, estride, N, t, TPL, io, acc);
             __syncthreads();
         } else if constexpr (I == NSTAGES - 1) {
             last_stage_fused<T, R, DIR, MAXB, LPC, IO>(sl, estride, N, t, TPL, tw, io, line, acc);
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(NTHR, MINB) fft_lines_fused_kernel(int TPL, co
     for (int i = threadIdx.x; i < N; i += NTHR) tw[i] = tw_g[i];           // first used after the stage-0 barrier
     const int line = threadIdx.x % LPC, t = threadIdx.x / LPC;
     typename IO::Acc acc;
-    io.acc_init(acc);
+    io.template acc_init_t<LPC>(acc, line);
     STAGES::template run_fused<T, DIR, MAXB, LPC, IO>(s + line, LPCP, t, TPL, tw, io, line, acc);
     io.finish(acc);
 }
@@ -262,41 +262,56 @@ template <typename T, bool PRUNED, bool REALOUT> struct IoCols {
     int Rm, Rp;
     // ---- fused edge stages (fft_lines_fused_kernel): element-wise access from registers
     static constexpr bool FUSED = true;
-    struct Acc { T m; T q; };                              // running max |value| and sum of squares of this thread's plane
-    __device__ __forceinline__ void acc_init(Acc& a) const { a.m = (T)0; a.q = (T)0; }
-    template <int LPC> __device__ __forceinline__ Cx<T> fetch(int idx, int line, int N) const {
+    struct Acc {
+        T m, q;                                            // running max |value| and sum of squares of this thread's plane
+        T sa, sb;                                          // plane scales (loaded once)
+        T* outp;                                           // this thread's output plane (even line: a, odd line: b), offset to its cell pair
+        const Cx<T>* inp;                                  // this thread's input column
+        bool live;                                         // line inside the grid
+    };
+    template <int LPC> __device__ __forceinline__ void acc_init_t(Acc& a, int line) const {
+        a.m = (T)0; a.q = (T)0;
         const int l = blockIdx.x * LPC + line;
-        if (l >= nlines) return mk<T>(0, 0);
-        const Cx<T>* base = in + (long long)blockIdx.y * in_bstride + l;
+        a.live = l < nlines;
+        a.inp = in + (long long)blockIdx.y * in_bstride + l;
+        if (REALOUT) {
+            a.sa = scale2 ? (T)scale2[0] : (T)1;
+            a.sb = scale2 ? (T)scale2[1] : (T)1;
+            T* pl = (line & 1) ? outb : outa;
+            a.outp = pl ? pl + (long long)blockIdx.y * out_bstride + (l & ~1) : nullptr;
+        } else {
+            a.sa = a.sb = (T)1;
+            a.outp = reinterpret_cast<T*>(out + (long long)blockIdx.y * out_bstride + l);
+        }
+    }
+    __device__ __forceinline__ Cx<T> fetch(int idx, int N, const Acc& a) const {
         if (PRUNED) {
             const int k = kfreq(idx, N);
-            if (k < -Rm || k > Rp) return mk<T>(0, 0);
-            return base[(long long)(k + Rm) * in_istride];
+            if (!a.live || k < -Rm || k > Rp) return mk<T>(0, 0);
+            return a.inp[(long long)(k + Rm) * in_istride];
         }
-        return base[(long long)idx * in_istride];
+        if (!a.live) return mk<T>(0, 0);
+        return a.inp[(long long)idx * in_istride];
     }
-    template <int LPC> __device__ __forceinline__ void emit(int idx, int line, Cx<T> v, bool act, Acc& acc) const {
-        const int l = blockIdx.x * LPC + line;
-        const bool ok = act && l < nlines;
+    __device__ __forceinline__ void emit(int idx, int line, Cx<T> v, bool act, Acc& acc) const {
+        const bool ok = act && acc.live;
         if (!REALOUT) {
-            if (ok) out[(long long)blockIdx.y * out_bstride + (long long)idx * out_istride + l] = v;
+            if (ok) reinterpret_cast<Cx<T>*>(acc.outp)[(long long)idx * out_istride] = v;
         } else {
             // lanes (line, line^1) are neighbours: the even one takes the pair of real parts (plane a), the odd one the pair of
             // imaginary parts (plane b), so every thread packs and stores one aligned cell pair
-            const T sa_ = scale2 ? (T)scale2[0] : (T)1, sb_ = scale2 ? (T)scale2[1] : (T)1;
-            const T ra = v.x * sa_, rb = v.y * sb_;
+            const T ra = v.x * acc.sa, rb = v.y * acc.sb;
             const bool even = (line & 1) == 0;
             const T recv = __shfl_xor_sync(0xffffffffu, even ? rb : ra, 1);
             Real2<T> r;
             r.a = even ? ra : recv;
             r.b = even ? recv : rb;
-            T* outp = even ? outa : outb;
             if (ok) {
                 acc.m = fmax(acc.m, fmax(fabs(r.a), fabs(r.b)));
                 acc.q += r.a * r.a + r.b * r.b;
-                if (outp) {
+                if (acc.outp) {
                     if (halfpack) r = pack_hilo(r);
-                    *reinterpret_cast<Real2<T>*>(outp + (long long)blockIdx.y * out_bstride + (long long)idx * out_istride + (l & ~1)) = r;
+                    *reinterpret_cast<Real2<T>*>(acc.outp + (long long)idx * out_istride) = r;
                 }
             }
         }
