@@ -137,6 +137,70 @@ template <int DIR, typename T> struct Dft<9, DIR, T> {
     }
 };
 
+
+// ---------------------------------------------------------------------------------------
+// composite in-register DFTs (R = RA*RB, natural order in and out), built from the small ones above:
+//   X[c + RA d] = sum_b W_RB^{bd} W_R^{bc} sum_a W_RA^{ac} v[RB a + b]        (all indices compile-time)
+// Used for the two-stage plans (360 = 20 x 18, 256 = 16 x 16): one shared-memory exchange per line FFT.
+// ---------------------------------------------------------------------------------------
+template <int R> struct RootTable;
+template <> struct RootTable<16> {
+    static PSB_HD double c(int m) { constexpr double t[16] = { 1.00000000000000000000, 0.92387953251128673848, 0.70710678118654757274, 0.38268343236508983729, 0.00000000000000006123, -0.38268343236508972627, -0.70710678118654746172, -0.92387953251128673848, -1.00000000000000000000, -0.92387953251128684951, -0.70710678118654768376, -0.38268343236509033689, -0.00000000000000018370, 0.38268343236509000382, 0.70710678118654735069, 0.92387953251128651644 }; return t[m]; }
+    static PSB_HD double s(int m) { constexpr double t[16] = { 0.00000000000000000000, 0.38268343236508978178, 0.70710678118654746172, 0.92387953251128673848, 1.00000000000000000000, 0.92387953251128673848, 0.70710678118654757274, 0.38268343236508989280, 0.00000000000000012246, -0.38268343236508967076, -0.70710678118654746172, -0.92387953251128651644, -1.00000000000000000000, -0.92387953251128662746, -0.70710678118654768376, -0.38268343236509039240 }; return t[m]; }
+};
+template <> struct RootTable<18> {
+    static PSB_HD double c(int m) { constexpr double t[18] = { 1.00000000000000000000, 0.93969262078590842791, 0.76604444311897801345, 0.50000000000000011102, 0.17364817766693041445, -0.17364817766693030343, -0.49999999999999977796, -0.76604444311897790243, -0.93969262078590831688, -1.00000000000000000000, -0.93969262078590842791, -0.76604444311897834652, -0.50000000000000044409, -0.17364817766693033119, 0.17364817766692997036, 0.49999999999999933387, 0.76604444311897779141, 0.93969262078590842791 }; return t[m]; }
+    static PSB_HD double s(int m) { constexpr double t[18] = { 0.00000000000000000000, 0.34202014332566871291, 0.64278760968653925190, 0.86602540378443859659, 0.98480775301220802032, 0.98480775301220802032, 0.86602540378443870761, 0.64278760968653947394, 0.34202014332566887944, 0.00000000000000012246, -0.34202014332566865740, -0.64278760968653891883, -0.86602540378443837454, -0.98480775301220802032, -0.98480775301220813134, -0.86602540378443904068, -0.64278760968653958496, -0.34202014332566860189 }; return t[m]; }
+};
+template <> struct RootTable<20> {
+    static PSB_HD double c(int m) { constexpr double t[20] = { 1.00000000000000000000, 0.95105651629515353118, 0.80901699437494745126, 0.58778525229247313710, 0.30901699437494745126, 0.00000000000000006123, -0.30901699437494734024, -0.58778525229247302608, -0.80901699437494734024, -0.95105651629515353118, -1.00000000000000000000, -0.95105651629515375323, -0.80901699437494756229, -0.58778525229247324813, -0.30901699437494756229, -0.00000000000000018370, 0.30901699437494722922, 0.58778525229247291506, 0.80901699437494734024, 0.95105651629515353118 }; return t[m]; }
+    static PSB_HD double s(int m) { constexpr double t[20] = { 0.00000000000000000000, 0.30901699437494739575, 0.58778525229247313710, 0.80901699437494745126, 0.95105651629515353118, 1.00000000000000000000, 0.95105651629515364220, 0.80901699437494745126, 0.58778525229247324813, 0.30901699437494750677, 0.00000000000000012246, -0.30901699437494689615, -0.58778525229247302608, -0.80901699437494734024, -0.95105651629515353118, -1.00000000000000000000, -0.95105651629515364220, -0.80901699437494756229, -0.58778525229247335915, -0.30901699437494761780 }; return t[m]; }
+};
+
+template <int RA, int RB, int DIR, typename T> struct DftComposite {
+    static constexpr int R = RA * RB;
+    static PSB_HD void run(Cx<T>* v) {
+        Cx<T> y[RB][RA];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int b = 0; b < RB; ++b) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int a = 0; a < RA; ++a) y[b][a] = v[RB * a + b];
+            Dft<RA, DIR, T>::run(y[b]);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int c = 1; c < RA; ++c) {
+                if (b > 0) {
+                    const int m = (b * c) % R;
+                    y[b][c] = y[b][c] * mk<T>((T)RootTable<R>::c(m), (T)((double)DIR * RootTable<R>::s(m)));
+                }
+            }
+        }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int c = 0; c < RA; ++c) {
+            Cx<T> w[RB];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int b = 0; b < RB; ++b) w[b] = y[b][c];
+            Dft<RB, DIR, T>::run(w);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int d = 0; d < RB; ++d) v[c + RA * d] = w[d];
+        }
+    }
+};
+template <int DIR, typename T> struct Dft<16, DIR, T> { static PSB_HD void run(Cx<T>* v) { DftComposite<4, 4, DIR, T>::run(v); } };
+template <int DIR, typename T> struct Dft<18, DIR, T> { static PSB_HD void run(Cx<T>* v) { DftComposite<9, 2, DIR, T>::run(v); } };
+template <int DIR, typename T> struct Dft<20, DIR, T> { static PSB_HD void run(Cx<T>* v) { DftComposite<5, 4, DIR, T>::run(v); } };
+
 // ---------------------------------------------------------------------------------------
 // one butterfly of a Stockham stage, split in its read and compute+write halves so that the
 // kernel can run all reads of a stage, barrier, then all writes (in-place in shared memory)
