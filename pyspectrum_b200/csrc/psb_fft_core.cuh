@@ -156,6 +156,10 @@ template <> struct RootTable<20> {
     static PSB_HD double c(int m) { constexpr double t[20] = { 1.00000000000000000000, 0.95105651629515353118, 0.80901699437494745126, 0.58778525229247313710, 0.30901699437494745126, 0.00000000000000006123, -0.30901699437494734024, -0.58778525229247302608, -0.80901699437494734024, -0.95105651629515353118, -1.00000000000000000000, -0.95105651629515375323, -0.80901699437494756229, -0.58778525229247324813, -0.30901699437494756229, -0.00000000000000018370, 0.30901699437494722922, 0.58778525229247291506, 0.80901699437494734024, 0.95105651629515353118 }; return t[m]; }
     static PSB_HD double s(int m) { constexpr double t[20] = { 0.00000000000000000000, 0.30901699437494739575, 0.58778525229247313710, 0.80901699437494745126, 0.95105651629515353118, 1.00000000000000000000, 0.95105651629515364220, 0.80901699437494745126, 0.58778525229247324813, 0.30901699437494750677, 0.00000000000000012246, -0.30901699437494689615, -0.58778525229247302608, -0.80901699437494734024, -0.95105651629515353118, -1.00000000000000000000, -0.95105651629515364220, -0.80901699437494756229, -0.58778525229247335915, -0.30901699437494761780 }; return t[m]; }
 };
+template <> struct RootTable<32> {
+    static PSB_HD double c(int m) { constexpr double t[32] = { 1.00000000000000000000, 0.98078528040323043058, 0.92387953251128673848, 0.83146961230254523567, 0.70710678118654757274, 0.55557023301960228867, 0.38268343236508983729, 0.19509032201612833135, 0.00000000000000006123, -0.19509032201612819257, -0.38268343236508972627, -0.55557023301960195560, -0.70710678118654746172, -0.83146961230254534669, -0.92387953251128673848, -0.98078528040323043058, -1.00000000000000000000, -0.98078528040323043058, -0.92387953251128684951, -0.83146961230254545772, -0.70710678118654768376, -0.55557023301960217765, -0.38268343236509033689, -0.19509032201612866442, -0.00000000000000018370, 0.19509032201612830359, 0.38268343236509000382, 0.55557023301960184458, 0.70710678118654735069, 0.83146961230254523567, 0.92387953251128651644, 0.98078528040323031956 }; return t[m]; }
+    static PSB_HD double s(int m) { constexpr double t[32] = { 0.00000000000000000000, 0.19509032201612824808, 0.38268343236508978178, 0.55557023301960217765, 0.70710678118654746172, 0.83146961230254523567, 0.92387953251128673848, 0.98078528040323043058, 1.00000000000000000000, 0.98078528040323043058, 0.92387953251128673848, 0.83146961230254545772, 0.70710678118654757274, 0.55557023301960217765, 0.38268343236508989280, 0.19509032201612860891, 0.00000000000000012246, -0.19509032201612835911, -0.38268343236508967076, -0.55557023301960195560, -0.70710678118654746172, -0.83146961230254523567, -0.92387953251128651644, -0.98078528040323031956, -1.00000000000000000000, -0.98078528040323043058, -0.92387953251128662746, -0.83146961230254545772, -0.70710678118654768376, -0.55557023301960217765, -0.38268343236509039240, -0.19509032201612871993 }; return t[m]; }
+};
 
 template <int RA, int RB, int DIR, typename T> struct DftComposite {
     static constexpr int R = RA * RB;
@@ -198,6 +202,7 @@ template <int RA, int RB, int DIR, typename T> struct DftComposite {
     }
 };
 template <int DIR, typename T> struct Dft<16, DIR, T> { static PSB_HD void run(Cx<T>* v) { DftComposite<4, 4, DIR, T>::run(v); } };
+template <int DIR, typename T> struct Dft<32, DIR, T> { static PSB_HD void run(Cx<T>* v) { DftComposite<8, 4, DIR, T>::run(v); } };
 template <int DIR, typename T> struct Dft<18, DIR, T> { static PSB_HD void run(Cx<T>* v) { DftComposite<9, 2, DIR, T>::run(v); } };
 template <int DIR, typename T> struct Dft<20, DIR, T> { static PSB_HD void run(Cx<T>* v) { DftComposite<5, 4, DIR, T>::run(v); } };
 
