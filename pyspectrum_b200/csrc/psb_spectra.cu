@@ -12,8 +12,9 @@
 
 namespace psb {
 
-// one mode of the estimator.f:196-244 loop body with signed integer wave numbers (rkx,rky,rkz)
-__device__ __forceinline__ void rsd_mode(const SpectraIn& in, double* out, int b, float rkx, float rky, float rkz, double pk, double wgt)
+// one mode of the estimator.f:196-244 loop body with signed integer wave numbers (rkx,rky,rkz): adds the five per-k-bin
+// contributions to acc[0..4] and the four (k,mu)-table contributions straight into `tab` (shared or global memory)
+__device__ __forceinline__ void rsd_mode(const SpectraIn& in, double* acc, double* tab, int b, float rkx, float rky, float rkz, double pk, double wgt)
 {
     const int Nbin = in.Nbin;
     const float rk = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(rkx, rkx), __fmul_rn(rky, rky)), __fmul_rn(rkz, rkz)));
@@ -33,13 +34,13 @@ __device__ __forceinline__ void rsd_mode(const SpectraIn& in, double* out, int b
     const double Le2 = -0.5 + 1.5 * mu2;
     const double Le4 = 0.375 - 3.75 * mu2 + 4.375 * (mu2 * mu2);
     const double kk = (double)__fmul_rn(in.kf32, rk);
-    atomicAdd(&out[b - 1], wgt);
-    atomicAdd(&out[Nbin + b - 1], wgt * kk);
-    atomicAdd(&out[2 * Nbin + b - 1], wgt * pk);
-    atomicAdd(&out[3 * Nbin + b - 1], wgt * (pk * 5.0 * Le2));
-    atomicAdd(&out[4 * Nbin + b - 1], wgt * (pk * 9.0 * Le4));
+    acc[0] += wgt;
+    acc[1] += wgt * kk;
+    acc[2] += wgt * pk;
+    acc[3] += wgt * (pk * 5.0 * Le2);
+    acc[4] += wgt * (pk * 9.0 * Le4);
     if (imu <= in.Nmu && imu > 0) {
-        double* t = out + 5 * (long long)Nbin + (long long)(imu - 1) * Nbin + (b - 1);
+        double* t = tab + (long long)(imu - 1) * Nbin + (b - 1);
         const long long tb = (long long)Nbin * in.Nmu;
         atomicAdd(t, wgt);
         atomicAdd(t + tb, wgt * kk);
@@ -48,43 +49,80 @@ __device__ __forceinline__ void rsd_mode(const SpectraIn& in, double* out, int b
     }
 }
 
-__global__ void __launch_bounds__(256) k_spectra(SpectraIn in, double* out)
+// One warp per (kz,ky) row of the half field.  Along a row the k-bin is non-decreasing in kx, so the per-bin sums are first
+// reduced inside the warp (segmented shuffle reduction), then added to the CTA's bins in shared memory; one global float64
+// atomic per CTA and bin at the end.  Rows that start beyond the last bin (the corners of the cube) are skipped without a load.
+template <int MODE>
+__global__ void __launch_bounds__(256) k_spectra(SpectraIn in, double* out, int table_in_smem)
 {
-    const int N = in.N, h = N / 2, Nbin = in.Nbin;
-    const long long nmode = (long long)(h + 1) * N * N;
-    double* nk = out;
-    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < nmode; e += (long long)gridDim.x * blockDim.x) {
-        const int ix = (int)(e % (h + 1));
-        const long long r = e / (h + 1);
-        const int iy = (int)(r % N), iz = (int)(r / N);
-        const int kx = ix, ky = kfreq(iy, N), kz = kfreq(iz, N);
-        const int m = kx * kx + ky * ky + kz * kz;
-        const int b = in.bin[m];
-        if (b == 0 || b > Nbin) continue;
-        const double wgt = (ix == 0 || ix == h) ? 1.0 : 2.0;
-        Cx<float> d = in.half[e];
-        if (in.mode == 0) {
-            // reflect_delta (py:1149-1156) makes the self-conjugate points real before |.|^2
-            if ((ix == 0 || ix == h) && (iy == 0 || iy == h) && (iz == 0 || iz == h)) d.y = 0.f;
-            const float p = d.x * d.x + d.y * d.y;
-            atomicAdd(&nk[b - 1], wgt);
-            atomicAdd(&out[Nbin + b - 1], wgt * (in.kf * sqrt((double)m)));
-            atomicAdd(&out[2 * Nbin + b - 1], wgt * (double)p);
-        } else {
-            const float ab = (float)sqrt((double)d.x * (double)d.x + (double)d.y * (double)d.y);    // cabs()
-            const double pk = (double)__fmul_rn(ab, ab);
-            if (ix == 0 || ix == h) {
-                rsd_mode(in, out, b, (float)kx, (float)ky, (float)kz, pk, 1.0);
-            } else if (iy != h && iz != h) {
-                rsd_mode(in, out, b, (float)kx, (float)ky, (float)kz, pk, 2.0);      // partner is exactly -k
-            } else {
-                // the conjugate partner visited by the Fortran loop is (-kx, -ky, -kz) with a Nyquist
-                // component folded back to +N/2 (f:198-204), so it is not the exact negation: do both
-                rsd_mode(in, out, b, (float)kx, (float)ky, (float)kz, pk, 1.0);
-                rsd_mode(in, out, b, (float)(-kx), (float)(iy == h ? h : -ky), (float)(iz == h ? h : -kz), pk, 1.0);
+    extern __shared__ double sbin[];
+    constexpr int NV = MODE == 0 ? 3 : 5;
+    const int N = in.N, h = N / 2, Nbin = in.Nbin, lane = threadIdx.x & 31;
+    const int nsm = NV * Nbin + ((MODE == 1 && table_in_smem) ? 4 * in.Nmu * Nbin : 0);
+    for (int i = threadIdx.x; i < nsm; i += blockDim.x) sbin[i] = 0.0;
+    __syncthreads();
+    double* tab = (MODE == 1 && table_in_smem) ? sbin + NV * Nbin : out + 5 * (long long)Nbin;
+    const int nrow = N * N, nwarp = gridDim.x * (blockDim.x >> 5);
+    for (int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < nrow; r += nwarp) {
+        const int iz = r / N, iy = r - iz * N;
+        const int ky = kfreq(iy, N), kz = kfreq(iz, N);
+        const int m0 = ky * ky + kz * kz;
+        if (in.bin[m0] > Nbin) continue;                         // bins are non-decreasing in m
+        const Cx<float>* row = in.half + (long long)r * (h + 1);
+        for (int x0 = 0; x0 <= h; x0 += 32) {
+            const int ix = x0 + lane;
+            int b = 0;
+            if (ix <= h) { b = in.bin[m0 + ix * ix]; if (b > Nbin) b = 0; }
+            if (__ballot_sync(0xffffffffu, b != 0) == 0u) { if (in.bin[m0 + x0 * x0] > Nbin) break; else continue; }
+            double v[NV];
+#pragma unroll
+            for (int i = 0; i < NV; ++i) v[i] = 0.0;
+            if (b) {
+                Cx<float> d = row[ix];
+                const bool edge = ix == 0 || ix == h;
+                if (MODE == 0) {
+                    // reflect_delta (py:1149-1156) makes the self-conjugate points real before |.|^2
+                    if (edge && (iy == 0 || iy == h) && (iz == 0 || iz == h)) d.y = 0.f;
+                    const float pw = d.x * d.x + d.y * d.y;
+                    const double wgt = edge ? 1.0 : 2.0;
+                    v[0] = wgt;
+                    v[1] = wgt * (in.kf * sqrt((double)(m0 + ix * ix)));
+                    v[2] = wgt * (double)pw;
+                } else {
+                    const float ab = (float)sqrt((double)d.x * (double)d.x + (double)d.y * (double)d.y);    // cabs()
+                    const double pk = (double)__fmul_rn(ab, ab);
+                    if (edge) {
+                        rsd_mode(in, v, tab, b, (float)ix, (float)ky, (float)kz, pk, 1.0);
+                    } else if (iy != h && iz != h) {
+                        rsd_mode(in, v, tab, b, (float)ix, (float)ky, (float)kz, pk, 2.0);      // partner is exactly -k
+                    } else {
+                        // the conjugate partner visited by the Fortran loop is (-kx, -ky, -kz) with a Nyquist
+                        // component folded back to +N/2 (f:198-204), so it is not the exact negation: do both
+                        rsd_mode(in, v, tab, b, (float)ix, (float)ky, (float)kz, pk, 1.0);
+                        rsd_mode(in, v, tab, b, (float)(-ix), (float)(iy == h ? h : -ky), (float)(iz == h ? h : -kz), pk, 1.0);
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int tb = __shfl_down_sync(0xffffffffu, b, o);
+                const bool take = lane + o < 32 && tb == b;
+#pragma unroll
+                for (int i = 0; i < NV; ++i) {
+                    const double tv = __shfl_down_sync(0xffffffffu, v[i], o);
+                    if (take) v[i] += tv;
+                }
+            }
+            const int prev = __shfl_up_sync(0xffffffffu, b, 1);
+            if (b != 0 && (lane == 0 || prev != b)) {
+#pragma unroll
+                for (int i = 0; i < NV; ++i) atomicAdd(&sbin[i * Nbin + b - 1], v[i]);
             }
         }
     }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nsm; i += blockDim.x)
+        if (sbin[i] != 0.0) atomicAdd(&out[i], sbin[i]);
 }
 
 int binned_spectra(const SpectraIn& in, double* out, cudaStream_t st)
@@ -92,7 +130,19 @@ int binned_spectra(const SpectraIn& in, double* out, cudaStream_t st)
     if (in.N < 2 || in.N % 2 || in.Nbin < 1) return PSB_ERR_ARG;
     const size_t nout = in.mode == 0 ? 3 * (size_t)in.Nbin : (5 + 4 * (size_t)in.Nmu) * in.Nbin;
     if (cudaMemsetAsync(out, 0, nout * sizeof(double), st) != cudaSuccess) return PSB_ERR_CUDA;
-    k_spectra<<<148 * 8, 256, 0, st>>>(in, out);
+    if (in.mode == 0) {
+        const size_t smem = 3 * (size_t)in.Nbin * sizeof(double);
+        if (smem > 200 * 1024) return PSB_ERR_ARG;
+        if (cudaFuncSetAttribute(k_spectra<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PSB_ERR_CUDA;
+        k_spectra<0><<<148 * 4, 256, smem, st>>>(in, out, 0);
+    } else {
+        size_t smem = nout * sizeof(double);
+        int tab_smem = 1;
+        if (smem > 96 * 1024) { smem = 5 * (size_t)in.Nbin * sizeof(double); tab_smem = 0; }       // big (k,mu) tables stay in global memory
+        if (smem > 200 * 1024) return PSB_ERR_ARG;
+        if (cudaFuncSetAttribute(k_spectra<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PSB_ERR_CUDA;
+        k_spectra<1><<<148 * 2, 256, smem, st>>>(in, out, tab_smem);
+    }
     return cudaGetLastError() == cudaSuccess ? PSB_OK : PSB_ERR_CUDA;
 }
 

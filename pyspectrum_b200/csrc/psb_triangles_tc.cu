@@ -59,7 +59,9 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 // slots the MMA-issuing warp needs (polling formers made that warp the bottleneck: profiles/r1)
 __constant__ unsigned int c_wait_hint_ns = 20000u;
 
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+// backoff_ns > 0: roles with slack (B formers, TMA producer) sleep between probes -- the hardware try_wait returns every ~85 cycles,
+// and eight spinning warps were issuing a third of all instructions of the SM (profiles/r1_summary.md)
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsigned backoff_ns = 0)
 {
     const uint32_t hint = c_wait_hint_ns;
     const uint32_t a = smem_u32(bar);
@@ -69,6 +71,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(done) : "r"(a), "r"(parity), "r"(hint) : "memory");
         if (done) break;
+        if (backoff_ns) __nanosleep(backoff_ns);
         if (++spins > WATCHDOG) asm volatile("trap;");      // a protocol bug must not hang the GPU
     }
 }
@@ -182,7 +185,8 @@ struct Params {
     int flush_chunks;             // TMEM accumulators are drained (fp32, round-to-nearest) every flush_chunks 64-cell sub-chunks
     int gflush_drains;            // the fp32 accumulators go to float64 global every gflush_drains drains
     double* partial;              // [gridDim.x][NT][MT*128] float64 partial sums (zeroed by the host)
-    long long* trace;             // optional clock64 timeline of CTA 0 (profiling only): [role][event][sub-chunk]
+    long long* trace;             // optional clock64 timeline of CTA 0 (profiling only): [role 0..4][event][sub-chunk]
+    unsigned backoff_ns;          // sleep between barrier probes of the roles with slack (B formers; x5 for the TMA producer)
     int debug;                    // ablation bits (profiling only): 1 no MMAs, 2 no forming math, 4 no tcgen05.st, 8 no drain body,
                                   //                                  16 no TMA copies, 32 no B forming
 };
@@ -292,7 +296,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_tri_tc(Params p)
         int buf = 0;
         uint32_t ph = 0;
         for (int c = 0; c < nch; ++c) {
-            mbar_wait(&chunk_empty[buf], ph ^ 1);          // whole warp waits: uniform control flow
+            mbar_wait(&chunk_empty[buf], ph ^ 1, 5u * p.backoff_ns);    // whole warp waits: uniform control flow; a chunk lasts ~8 us
             if (elect_one()) mbar_arrive_expect_tx(&chunk_full[buf], (p.debug & 16) ? 0u : (uint32_t)(S * XCH * 4));
             __syncwarp();
             if (p.debug & 16) { if (++buf == NCHUNKBUF) { buf = 0; ph ^= 1; } continue; }
@@ -355,7 +359,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_tri_tc(Params p)
         uint32_t cph = 0;
         const int nbcell = 2 * NT;                               // (l, kchunk) cells of the B tile per K-step
         for (int c = 0; c < nch; ++c) {
-            mbar_wait(&chunk_full[buf], cph);
+            mbar_wait(&chunk_full[buf], cph, p.backoff_ns);
             for (int sub = 0; sub < NSUB; ++sub) {
             const uint32_t* ch = chunk + (size_t)buf * S * ROWF + sub * SUB;
             const uint32_t sph = (uint32_t)((c * NSUB + sub) & 1);
@@ -363,7 +367,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_tri_tc(Params p)
                 const int g = b_stage_of_warp(warp);              // this warp's operand stage (K-step g of every sub-chunk)
                 const int tt = c * NSUB + sub;
                 if (p.trace && blockIdx.x == 0 && tt < 64 && lane == 0 && g == 0) p.trace[(2 * 8 + 0) * 64 + tt] = clock64();
-                mbar_wait(&st_empty[g], sph ^ 1);
+                mbar_wait(&st_empty[g], sph ^ 1, p.backoff_ns);     // ~2600 cycles of slack per stage
                 if (p.trace && blockIdx.x == 0 && tt < 64 && lane == 0 && g == 0) p.trace[(2 * 8 + 1) * 64 + tt] = clock64();
                 // lane <-> field: rows are 260 words apart (== 4 mod 32), so 8 consecutive fields hit 8 distinct bank groups
                 for (int cell = lane; cell < ((p.debug & 32) ? 0 : nbcell); cell += 32) {
@@ -423,9 +427,13 @@ __global__ void __launch_bounds__(NTHR, 1) k_tri_tc(Params p)
                 mbar_wait(&st_empty[kk], (uint32_t)(t & 1) ^ 1);
                 if (p.trace && blockIdx.x == 0 && t < 64 && lane == 0 && (warp == 0 || warp == 12)) p.trace[((warp == 0 ? 1 : 3) * 8 + 4 * h + 1) * 64 + t] = clock64();
                 tc_fence_after();
+                // (Issuing the operand loads before the barrier wait shortens this warp's K-step -- by 20% with all twelve loads
+                // hoisted -- but slows the whole kernel by 5-20%: measured twice, profiles/r1_summary.md.)
                 uint4 vi[4];                       // 16 cells of I_i: per 4 cells {hi2(0,1), lo2(0,1), hi2(2,3), lo2(2,3)}
 #pragma unroll
                 for (int q4 = 0; q4 < 4; ++q4) vi[q4] = (p.debug & 512) ? make_uint4(0, 0, 0, 0) : *reinterpret_cast<const uint4*>(ch + fio + kk * 16 + q4 * 4);
+                const bool ftr = p.trace && blockIdx.x == 0 && t < 64 && warp == 0 && h == 0;      // fine-grained timeline of one former warp
+                if (ftr) { asm volatile("" ::"r"(vi[3].w)); if (lane == 0) p.trace[(4 * 8 + 1) * 64 + t] = clock64(); }
 #pragma unroll
                 for (int mm = 0; mm < 2; ++mm) {
                     if (mm == 0 ? t0 : t1) {
@@ -442,14 +450,17 @@ __global__ void __launch_bounds__(NTHR, 1) k_tri_tc(Params p)
 #pragma unroll
                             for (int k = 0; k < 8; ++k) { hi[k] = 0u; lo[k] = 0u; }       // padding rows
                         }
+                        if (ftr) { asm volatile("" ::"r"(lo[7]), "r"(hi[7])); if (lane == 0) p.trace[(4 * 8 + 2 + 2 * mm) * 64 + t] = clock64(); }
                         if (!(p.debug & 4)) {
                             tmem_st8(t_a + (uint32_t)(kk * 64 + mm * 16), hi);
                             tmem_st8(t_a + (uint32_t)(kk * 64 + mm * 16 + 8), lo);
                         }
+                        if (ftr && lane == 0) p.trace[(4 * 8 + 3 + 2 * mm) * 64 + t] = clock64();
                     }
                 }
                 if (p.trace && blockIdx.x == 0 && t < 64 && lane == 0 && (warp == 0 || warp == 12)) p.trace[((warp == 0 ? 1 : 3) * 8 + 4 * h + 3) * 64 + t] = clock64();
                 if (!(p.debug & 4)) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                if (ftr && lane == 0) p.trace[(4 * 8 + 6) * 64 + t] = clock64();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&st_full[kk]);
@@ -527,6 +538,8 @@ int triangle_sums_tc_pass(const float* const* fields, int S, long long ncell, co
     p.fields = fields; p.S = S; p.NT = NT; p.MT = MT; p.tile_cols = tile_cols; p.lane_ij = lane_ij; p.nchunk = nchunk_launch;
     p.partial = static_cast<double*>(ws);
     p.debug = 0;
+    p.backoff_ns = 0;
+    if (const char* e = getenv("PSB_TC_BACKOFF")) p.backoff_ns = (unsigned)strtoul(e, nullptr, 10);
     { unsigned int hint = 20000u; if (const char* e = getenv("PSB_TC_HINT")) hint = (unsigned)strtoul(e, nullptr, 10);
       cudaMemcpyToSymbolAsync(c_wait_hint_ns, &hint, sizeof(hint), 0, cudaMemcpyHostToDevice, st); }
     if (const char* e = getenv("PSB_TC_DEBUG")) p.debug = atoi(e);
@@ -536,10 +549,10 @@ int triangle_sums_tc_pass(const float* const* fields, int S, long long ncell, co
     if (const char* e = getenv("PSB_TC_GFLUSH")) { int v = atoi(e); if (v >= 1 && v <= 65536) p.gflush_drains = v; }
     p.trace = nullptr;
     const char* trace_path = getenv("PSB_TC_TRACE");
-    if (trace_path) { cudaMalloc(&p.trace, 4 * 8 * 64 * sizeof(long long)); cudaMemset(p.trace, 0, 4 * 8 * 64 * sizeof(long long)); }
+    if (trace_path) { cudaMalloc(&p.trace, 5 * 8 * 64 * sizeof(long long)); cudaMemset(p.trace, 0, 5 * 8 * 64 * sizeof(long long)); }
     kern<<<ncta, NTHR, smem, st>>>(p);
     if (trace_path) {
-        static long long host_trace[4 * 8 * 64];
+        static long long host_trace[5 * 8 * 64];
         cudaMemcpy(host_trace, p.trace, sizeof(host_trace), cudaMemcpyDeviceToHost);
         if (FILE* f = fopen(trace_path, "wb")) { fwrite(host_trace, 1, sizeof(host_trace), f); fclose(f); }
         cudaFree(p.trace);
