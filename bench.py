@@ -246,13 +246,26 @@ def run_b200(args):
         tf_peak = float(peaks.get('bf16_tflops', 1590.0))
         ach_tf = alg_flops / (tri_ms * 1e-3) / 1e12
         if engine in ('auto', 'tc'):
-            roof = {'kernel': 'k_tri_tc (K6 triangle sums: tcgen05 kind::f16, 3-term fp16 split, TMEM accumulators)',
-                    'bound': 'tensor', 'achieved': ach_tf, 'peak': tf_peak, 'unit': 'TFLOP/s', 'frac': ach_tf / tf_peak,
-                    'traffic': None, 'peak_source': peak_src.replace('hbm_gbs', 'bf16_tflops (fp16 = bf16 rate)'),
-                    'algorithmic_flops': alg_flops, 'algorithmic_bytes': alg_bytes, 'achieved_hbm_gbs': ach_gbs,
-                    'note': 'algorithmic flops = (Npair + 2 Ntri) N^3 (SURVEY 8d); the kernel issues 3 split MMAs on a '
-                            'dense 512 x 48 tile per 16 cells = 9.4x the algorithmic flops, and is co-limited by the CUDA-core '
-                            'formation of the fp16 pair-product operand'}
+            # the algorithm's arithmetic intensity (84.5 flop/B) is below the machine balance (bf16 peak / HBM peak = 256 flop/B):
+            # the HBM roof is the one that applies; the tensor-pipe view is reported next to it
+            traffic = None
+            try:                                         # dram read+write of one k_tri_tc launch at this shape (ncu --set full, profiles/)
+                prof = json.load(open(os.path.join(ROOT, 'profiles', 'r1_k_tri_tc_ncu_full.json')))['metrics']
+                if S == 40 and N == 360:
+                    traffic = (float(prof['dram__bytes_read.sum']['value']) * {'Gbyte': 1e9, 'Mbyte': 1e6}[prof['dram__bytes_read.sum']['unit']]
+                               + float(prof['dram__bytes_write.sum']['value']) * {'Gbyte': 1e9, 'Mbyte': 1e6}[prof['dram__bytes_write.sum']['unit']])
+            except Exception:
+                traffic = None
+            roof = {'kernel': 'k_tri_tc (K6 triangle sums: tcgen05 kind::f16, 3-term fp16 split, A operand formed into TMEM)',
+                    'bound': 'hbm', 'achieved': ach_gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach_gbs / hbm_peak,
+                    'traffic': traffic, 'peak_source': peak_src,
+                    'algorithmic_bytes': alg_bytes, 'algorithmic_flops': alg_flops,
+                    'tensor_view': {'achieved_tflops_algorithmic': ach_tf, 'issued_tflops': 9.4 * ach_tf, 'peak_tflops': tf_peak,
+                                    'frac_algorithmic': ach_tf / tf_peak, 'frac_issued': 9.4 * ach_tf / tf_peak},
+                    'note': 'algorithmic bytes = 4 Nshell N^3 (every field read once), algorithmic flops = (Npair + 2 Ntri) N^3 '
+                            '(SURVEY 8d); as a GEMM the kernel issues 3 split MMAs on a dense 512 x 48 tile per 16 cells = 9.4x '
+                            'the algorithmic flops; it is limited by the CUDA-core formation of the fp16 pair-product operand '
+                            '(handshake/latency chain, profiles/r1_summary.md), not by HBM or the tensor pipe'}
         else:
             roof = {'kernel': 'k_tri (K6 triangle sums, FFMA path)', 'bound': 'hbm', 'achieved': ach_gbs, 'peak': hbm_peak,
                     'unit': 'GB/s', 'frac': ach_gbs / hbm_peak, 'traffic': None, 'peak_source': peak_src,
