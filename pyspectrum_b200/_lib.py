@@ -6,7 +6,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, 'csrc')
-_SO = os.path.join(_CSRC, 'libpsb200.so')
+_SO = os.environ.get('PSB200_LIB') or os.path.join(_CSRC, 'libpsb200.so')      # PSB200_LIB: A/B runs of two builds in one session
 _LIB = None
 
 ERRORS = {0: 'PSB_OK', -1: 'PSB_ERR_ARG', -2: 'PSB_ERR_UNSUPPORTED_N', -3: 'PSB_ERR_CUDA', -4: 'PSB_ERR_WORKSPACE'}

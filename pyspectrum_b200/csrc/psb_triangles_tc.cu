@@ -162,24 +162,21 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar)
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v)
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* r)
 {
-    uint32_t r[16];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
                    "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                  : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 struct Params {
     const float* const* fields;   // S device pointers, each ncell 32-bit words of packed hi/lo halves (16-byte aligned)
     int S;                        // real shells (rows of a chunk)
     int NT;                       // MMA N = shells padded to a multiple of 16 (<= 128)
     int MT;                       // M tiles (128 rows each) in this pass (<= 256 / tile_cols)
-    int tile_cols;                // TMEM column spacing of one accumulator tile: 64 (NT <= 64) or 128
+    int tile_cols;                // TMEM column spacing of one accumulator tile: 64 (NT <= 64) or NT
     const int* lane_ij;           // [128][5]: field slot i of the lane and j of its row in tiles 0..3 (-1: padding row)
     long long nchunk;             // ncell / XCH (chunk size of the launched instantiation)
     int flush_chunks;             // TMEM accumulators are drained (fp32, round-to-nearest) every flush_chunks 64-cell sub-chunks
@@ -216,14 +213,18 @@ __device__ __forceinline__ void drain_accumulators(const Params& p, uint64_t* ac
     if (to_global) ndrain = 0;
     if (live && !(p.debug & 8)) {
         double* dst = p.partial + (size_t)blockIdx.x * MR * NT + (size_t)row;     // [col][row]: coalesced
+        // one 16-column TMEM load per round trip: keeping two or three in flight needs 32-48 more live registers and spills at the
+        // 80-register cap of this 704-thread CTA (measured: 11.7 -> 15.6 ms)
         for (int c0 = 0; c0 < NT; c0 += 16) {
-            float v[16];
-            tmem_ld16(t_acc + (uint32_t)c0, v);
+            uint32_t r[16];
+            tmem_ld16_issue(t_acc + (uint32_t)c0, r);
+            tmem_ld_wait();
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4) {
                 float4* sp = &accs[(size_t)(c0 / 4 + q4) * MR + row];
                 float4 cur = *sp;
-                cur.x += v[4 * q4]; cur.y += v[4 * q4 + 1]; cur.z += v[4 * q4 + 2]; cur.w += v[4 * q4 + 3];
+                cur.x += __uint_as_float(r[4 * q4]); cur.y += __uint_as_float(r[4 * q4 + 1]);
+                cur.z += __uint_as_float(r[4 * q4 + 2]); cur.w += __uint_as_float(r[4 * q4 + 3]);
                 if (to_global) {
                     dst[(size_t)(c0 + 4 * q4 + 0) * MR] += (double)cur.x;
                     dst[(size_t)(c0 + 4 * q4 + 1) * MR] += (double)cur.y;
@@ -512,7 +513,7 @@ int triangle_sums_tc_pass(const float* const* fields, int S, long long ncell, co
                           const int* tri_rc, int ntri, double* sums, void* ws, size_t ws_bytes, cudaStream_t st)
 {
     using namespace tc;
-    const int tile_cols = NT <= 64 ? 64 : 128;
+    const int tile_cols = NT <= 64 ? 64 : NT;           // accumulator tiles packed at NT columns: 3 tiles for 65..80 shells, 2 above
     if (S < 1 || S > NT || NT % 16 || NT > 128 || MT < 1 || MT > 256 / tile_cols || ncell % 64) return PSB_ERR_ARG;
     if (ncell / 64 / 148 >= (1LL << 28)) return PSB_ERR_ARG;
     if (ws_bytes < triangle_tc_workspace_bytes(MT, NT)) return PSB_ERR_WORKSPACE;

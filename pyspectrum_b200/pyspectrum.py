@@ -373,7 +373,7 @@ class PeriodicPipeline(object):
             s0 = Ncut // step
             S = Nmax - s0 + 1
             NT = (S + 15) // 16 * 16
-            MT = 4 if NT <= 64 else 2
+            MT = 4 if NT <= 64 else 256 // NT          # accumulator tiles that fit in 256 TMEM columns
             partners = {}
             for i, j, _ in tri:
                 partners.setdefault(int(i), set()).add(int(j))

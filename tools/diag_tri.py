@@ -11,7 +11,10 @@ def cat(seed, Np, L):
     kids = par[:, rng.integers(0, npar, Np // 2)] + rng.normal(0, 0.03 * L, (3, Np // 2))
     return np.ascontiguousarray(np.concatenate([kids, rng.uniform(0, L, (3, Np - Np // 2))], axis=1) % L)
 
-for (N, Np, step, Ncut, Nmax) in [(32, 20000, 1, 1, 12), (64, 100000, 1, 3, 30), (128, 2000000, 3, 3, 20)]:
+CASES = [(32, 20000, 1, 1, 12), (64, 100000, 1, 3, 30), (128, 2000000, 3, 3, 20)]
+if len(sys.argv) > 1 and sys.argv[1] == 'big':
+    CASES = [(192, 400000, 1, 3, 72), (192, 4000000, 1, 3, 72)]
+for (N, Np, step, Ncut, Nmax) in CASES:
     L = 300.
     pipe = pySpec.PeriodicPipeline.get(N)
     half, _ = pipe.fft_periodic(cat(N + Nmax, Np, L), None, L)
