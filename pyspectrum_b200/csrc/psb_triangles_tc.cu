@@ -185,7 +185,7 @@ struct Params {
     long long* trace;             // optional clock64 timeline of CTA 0 (profiling only): [role 0..4][event][sub-chunk]
     unsigned backoff_ns;          // sleep between barrier probes of the roles with slack (B formers; x5 for the TMA producer)
     int debug;                    // ablation bits (profiling only): 1 no MMAs, 2 no forming math, 4 no tcgen05.st, 8 no drain body,
-                                  //                                  16 no TMA copies, 32 no B forming
+                                  //                                  16 no TMA copies, 32 no B forming, 256 no tcgen05 fences in the formers, 512 no I_i loads
 };
 
 constexpr int NFWARPS = 16;                      // A-operand formers: 4 groups (one per K-step of a chunk) x 4 lane quarters
@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_tri_tc(Params p)
                 if (p.trace && blockIdx.x == 0 && t < 64 && lane == 0 && (warp == 0 || warp == 12)) p.trace[((warp == 0 ? 1 : 3) * 8 + 4 * h) * 64 + t] = clock64();
                 mbar_wait(&st_empty[kk], (uint32_t)(t & 1) ^ 1);
                 if (p.trace && blockIdx.x == 0 && t < 64 && lane == 0 && (warp == 0 || warp == 12)) p.trace[((warp == 0 ? 1 : 3) * 8 + 4 * h + 1) * 64 + t] = clock64();
-                tc_fence_after();
+                if (!(p.debug & 256)) tc_fence_after();
                 // (Issuing the operand loads before the barrier wait shortens this warp's K-step -- by 20% with all twelve loads
                 // hoisted -- but slows the whole kernel by 5-20%: measured twice, profiles/r1_summary.md.)
                 uint4 vi[4];                       // 16 cells of I_i: per 4 cells {hi2(0,1), lo2(0,1), hi2(2,3), lo2(2,3)}
@@ -462,7 +462,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_tri_tc(Params p)
                 if (p.trace && blockIdx.x == 0 && t < 64 && lane == 0 && (warp == 0 || warp == 12)) p.trace[((warp == 0 ? 1 : 3) * 8 + 4 * h + 3) * 64 + t] = clock64();
                 if (!(p.debug & 4)) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 if (ftr && lane == 0) p.trace[(4 * 8 + 6) * 64 + t] = clock64();
-                tc_fence_before();
+                if (!(p.debug & 256)) tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&st_full[kk]);
                 if (p.trace && blockIdx.x == 0 && t < 64 && lane == 0 && (warp == 0 || warp == 12)) p.trace[((warp == 0 ? 1 : 3) * 8 + 4 * h + 2) * 64 + t] = clock64();
