@@ -417,25 +417,53 @@ class PeriodicPipeline(object):
                                                  _ptr(sums), _ptr(ws), wsb, _stream()), 'psb_bk_triangle_sums_tc')
         return sums
 
-    def bispectrum_sums(self, half, step, Ncut, Nmax, engine='auto'):
-        """K5 + K6 for one catalogue: returns host arrays (sum_x I_i I_j I_l per triangle, sum_x I_j^2 per shell)
-        in the reference's units, with one device->host read.  The tensor-core path works on power-of-two
-        scaled fields; if a pair product could leave the fp16 range (max|I_i| max|I_j| >= 4e4 after scaling --
-        only for pathologically concentrated catalogues) the triangle sums are redone by the FFMA kernel."""
+    def _pinned(self, n):
+        """float64 pinned host buffer of n elements from a small free list (cudaHostAlloc per call would cost more than K4)."""
+        pool = self.__dict__.setdefault('_pin_pool', {})
+        free = pool.setdefault(n, [])
+        return free.pop() if free else torch.empty(n, dtype=torch.float64, pin_memory=True)
+
+    def bispectrum_launch(self, half, step, Ncut, Nmax, engine='auto', sumw=None):
+        """Enqueue K5 + K6 for one catalogue and the device->host copy of everything the host epilogue needs (triangle sums,
+        shell powers, scales, max|I|, sum of weights) into pinned memory.  Returns a handle for `bispectrum_finish`; nothing
+        here waits for the GPU, so the caller can enqueue the next catalogue before collecting this one."""
         s0 = Ncut // step
         S = Nmax - s0 + 1
         fields, sumsq, scales, maxabs = self.shell_fields(half, step, s0, Nmax, scaled=True)
         use_tc = engine in ('auto', 'tc') and fields.shape[1] % 64 == 0 and S <= 128
         sums = self.triangle_sums(fields, Nmax, Ncut, step, engine='tc' if use_tc else 'fma')
-        host = torch.cat([sums, sumsq, scales.double(), maxabs.view(torch.float32).double()]).cpu().numpy()
-        nt = sums.numel()
-        SA = sumsq.numel()
-        sums_h, sumsq_h, sc, mx = host[:nt], host[nt:nt + SA], host[nt + SA:nt + 2 * SA], host[nt + 2 * SA:]
-        if use_tc and mx.max() ** 2 >= 4.0e4:
-            sums_h = self.triangle_sums(fields, Nmax, Ncut, step, engine='fma').cpu().numpy()
+        sw = sumw.double().reshape(1) if sumw is not None else torch.zeros(1, dtype=torch.float64, device=self.dev)
+        dev = torch.cat([sums, sumsq, scales.double(), maxabs.view(torch.float32).double(), sw])
+        host = self._pinned(dev.numel())
+        host.copy_(dev, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return {'host': host, 'ev': ev, 'fields': fields, 'nt': sums.numel(), 'SA': sumsq.numel(), 'use_tc': use_tc,
+                'args': (Nmax, Ncut, step)}
+
+    def bispectrum_finish(self, h):
+        """Wait for a `bispectrum_launch` and return host arrays (sum_x I_i I_j I_l per triangle, sum_x I_j^2 per shell,
+        sum of weights) in the reference's units.  The tensor-core path works on power-of-two scaled fields; if a pair
+        product could leave the fp16 range (max|I_i| max|I_j| >= 4e4 after scaling -- only for pathologically concentrated
+        catalogues) the triangle sums are redone by the FFMA kernel."""
+        h['ev'].synchronize()
+        host = h['host'].numpy().copy()
+        self._pin_pool[h['host'].numel()].append(h['host'])
+        Nmax, Ncut, step = h['args']
+        s0 = Ncut // step
+        nt, SA = h['nt'], h['SA']
+        sums_h, sumsq_h, sc, mx = host[:nt], host[nt:nt + SA], host[nt + SA:nt + 2 * SA], host[nt + 2 * SA:nt + 3 * SA]
+        if h['use_tc'] and mx.max() ** 2 >= 4.0e4:
+            sums_h = self.triangle_sums(h['fields'], Nmax, Ncut, step, engine='fma').cpu().numpy()
+        h['fields'] = None
         tri = triangle_list(Nmax, Ncut, step)
         sums_h = sums_h / (sc[tri[:, 0] - s0] * sc[tri[:, 1] - s0] * sc[tri[:, 2] - s0])
         sumsq_h = sumsq_h / sc ** 2
+        return sums_h, sumsq_h, float(host[-1])
+
+    def bispectrum_sums(self, half, step, Ncut, Nmax, engine='auto'):
+        """K5 + K6 for one catalogue with one device->host read: (triangle sums, shell powers) as host arrays."""
+        sums_h, sumsq_h, _ = self.bispectrum_finish(self.bispectrum_launch(half, step, Ncut, Nmax, engine))
         return sums_h, sumsq_h
 
     # ------------------------------------------------------------------ counts
@@ -684,11 +712,17 @@ def _prefetched(catalogues, Ngrid):
 
 def Bk_periodic_many(catalogues, Lbox=2600, Ngrid=360, step=3, Ncut=3, Nmax=40, fft='pyfftw', nthreads=1, silent=True):
     """Generator: Bk_periodic (pyspectrum.py:285-356) for every catalogue of an iterable -- the thousands-of-mocks use of the
-    reference -- with the upload of catalogue n+1 overlapped with the computation of catalogue n.  Yields the same
-    dictionaries as Bk_periodic, in order."""
+    reference -- as a software pipeline: the upload of catalogue n+1 runs on a copy stream and the kernels of catalogue n are
+    queued while the host still waits for / post-processes catalogue n-1.  Yields the same dictionaries as Bk_periodic, in order
+    (each one after the following catalogue has been queued).  Two catalogues' shell fields are alive at a time."""
+    pending = None
     for xyz_d, w_d in _prefetched(catalogues, Ngrid):
-        yield Bk_periodic(xyz_d, w=w_d, Lbox=Lbox, Ngrid=Ngrid, step=step, Ncut=Ncut, Nmax=Nmax, fft=fft, nthreads=nthreads,
-                          silent=silent)
+        h = _bk_launch(xyz_d, w_d, Lbox, Ngrid, step, Ncut, Nmax, fft, silent)     # kernels of catalogue n are queued ...
+        if pending is not None:
+            yield _bk_finish(pending)                                              # ... before the host waits for catalogue n-1
+        pending = h
+    if pending is not None:
+        yield _bk_finish(pending)
 
 
 def Pk_periodic_many(catalogues, Lbox=2600, Ngrid=360, fft='pyfftw', silent=True):
@@ -703,10 +737,10 @@ def Pk_periodic_rsd_many(catalogues, Lbox=2600, Ngrid=360, rsd=2, Nmubin=10, fft
         yield Pk_periodic_rsd(xyz_d, w=w_d, Lbox=Lbox, Ngrid=Ngrid, rsd=rsd, Nmubin=Nmubin, fft=fft, code=code, silent=silent)
 
 
-def Bk_periodic(xyz, w=None, Lbox=2600, Ngrid=360, step=3, Ncut=3, Nmax=40, fft='pyfftw', nthreads=1, silent=True):
-    """Bispectrum of a periodic box; see pyspectrum.py:285-356 for the contract."""
+def _bk_launch(xyz, w, Lbox, Ngrid, step, Ncut, Nmax, fft, silent):
+    """First half of Bk_periodic: everything that only enqueues GPU work (assignment, FFT, shell fields, triangle sums, result
+    copy).  The exact triangle counts and shell mode counts are cached per configuration."""
     N = _npart(xyz)
-    kf = 2 * np.pi / Lbox
     s0 = Ncut // step
     if s0 < 1:
         raise ValueError('Ncut//step must be >= 1 (the reference wraps p0k[-1] there, SURVEY Q9)')
@@ -715,18 +749,32 @@ def Bk_periodic(xyz, w=None, Lbox=2600, Ngrid=360, step=3, Ncut=3, Nmax=40, fft=
         print('------------------')
         print('%i positions in %i box' % (N, Lbox))
         print('--- calculating the FFT ---')
+    Nk = pipe.shell_mode_counts(step, Nmax)
+    counts = pipe.counts(Nmax, Ncut, step, fft=fft, silent=silent)
     half, sumw = pipe.fft_periodic(xyz, w, Lbox)
     if not silent:
         print('--- calculating the bispectrum ---')
-    Nk = pipe.shell_mode_counts(step, Nmax)
-    counts = pipe.counts(Nmax, Ncut, step, fft=fft, silent=silent)
-    sums_h, sumsq_h = pipe.bispectrum_sums(half, step, Ncut, Nmax)
+    h = pipe.bispectrum_launch(half, step, Ncut, Nmax, sumw=sumw)
+    h.update(N=N, w=None if (w is None or isinstance(w, torch.Tensor)) else w, w_is_dev=isinstance(w, torch.Tensor), Nk=Nk, counts=counts,
+             cfg=(Lbox, Ngrid, step, Ncut, Nmax), silent=silent)
+    return h
+
+
+def _bk_finish(h):
+    """Second half of Bk_periodic: wait for the results and run the float64 host epilogue (pyspectrum.py:321-356)."""
+    Lbox, Ngrid, step, Ncut, Nmax = h['cfg']
+    silent, N = h['silent'], h['N']
+    pipe = PeriodicPipeline.get(Ngrid)
+    kf = 2 * np.pi / Lbox
+    sums_h, sumsq_h, sumw_dev = pipe.bispectrum_finish(h)
     tri = triangle_list(Nmax, Ncut, step)
-    nbar = _sum_w(w, N, sumw) / Lbox ** 3
+    # np.sum(w) of pyspectrum.py:323 (host value when the caller's weights live on the host)
+    sum_w = float(np.sum(h['w'])) if h['w'] is not None else (sumw_dev if h['w_is_dev'] else float(N))
+    nbar = sum_w / Lbox ** 3
     if not silent:
         print('sum w_i = %f' % (nbar * Lbox ** 3))
         print('nbar = %f' % nbar)
-    bispec = _bk_epilogue(Ngrid, tri, sums_h, sumsq_h, Nk, counts, step, Ncut, Nmax)
+    bispec = _bk_epilogue(Ngrid, tri, sums_h, sumsq_h, h['Nk'], h['counts'], step, Ncut, Nmax)
     meta = {'Lbox': Lbox, 'Ngrid': Ngrid, 'step': step, 'Ncut': Ncut, 'Nmax': Nmax, 'N': N, 'nbar': nbar, 'kf': kf}
     bispec['meta'] = meta
     if not silent:
@@ -741,3 +789,8 @@ def Bk_periodic(xyz, w=None, Lbox=2600, Ngrid=360, step=3, Ncut=3, Nmax=40, fft=
     with np.errstate(divide='ignore', invalid='ignore'):
         bispec['q123'] = bispec['b123'] / (bispec['p0k1'] * bispec['p0k2'] + bispec['p0k1'] * bispec['p0k3'] + bispec['p0k2'] * bispec['p0k3'])
     return bispec
+
+
+def Bk_periodic(xyz, w=None, Lbox=2600, Ngrid=360, step=3, Ncut=3, Nmax=40, fft='pyfftw', nthreads=1, silent=True):
+    """Bispectrum of a periodic box; see pyspectrum.py:285-356 for the contract."""
+    return _bk_finish(_bk_launch(xyz, w, Lbox, Ngrid, step, Ncut, Nmax, fft, silent))
