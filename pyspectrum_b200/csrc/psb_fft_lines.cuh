@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(NTHR, MINB) fft_lines_fused_kernel(int TPL, co
     for (int i = threadIdx.x; i < N; i += NTHR) tw[i] = tw_g[i];           // first used after the stage-0 barrier
     const int line = threadIdx.x % LPC, t = threadIdx.x / LPC;
     typename IO::Acc acc;
-    io.template acc_init_t<LPC>(acc, line);
+    io.template acc_init_t<LPC>(acc, line, N);
     STAGES::template run_fused<T, DIR, MAXB, LPC, IO>(s + line, LPCP, t, TPL, tw, io, line, acc);
     io.finish(acc);
 }
@@ -267,51 +267,62 @@ template <typename T, bool PRUNED, bool REALOUT> struct IoCols {
         T sa, sb;                                          // plane scales (loaded once)
         T* outp;                                           // this thread's output plane (even line: a, odd line: b), offset to its cell pair
         const Cx<T>* inp;                                  // this thread's input column
-        bool live;                                         // line inside the grid
+        unsigned istr, ostr;                               // element strides between line indices (32-bit: every offset is < N^3 <= 2^30)
+        int lo_max, hi_min, hi_sub;                        // pruned input: idx <= lo_max -> row idx + Rm; idx >= hi_min -> row idx - hi_sub
+        bool live, st, even, pack;                         // line inside the grid; this thread stores; line parity; packed-half output
     };
-    template <int LPC> __device__ __forceinline__ void acc_init_t(Acc& a, int line) const {
+    template <int LPC> __device__ __forceinline__ void acc_init_t(Acc& a, int line, int N) const {
         a.m = (T)0; a.q = (T)0;
         const int l = blockIdx.x * LPC + line;
         a.live = l < nlines;
         a.inp = in + (long long)blockIdx.y * in_bstride + l;
+        a.istr = (unsigned)in_istride; a.ostr = (unsigned)out_istride;
+        a.lo_max = a.live ? Rp : -1;                       // dead lines: no index passes the range tests
+        a.hi_min = a.live ? N - Rm : (1 << 30);
+        a.hi_sub = N - Rm;
+        a.even = (line & 1) == 0;
+        a.pack = halfpack != 0;
         if (REALOUT) {
             a.sa = scale2 ? (T)scale2[0] : (T)1;
             a.sb = scale2 ? (T)scale2[1] : (T)1;
             T* pl = (line & 1) ? outb : outa;
-            a.outp = pl ? pl + (long long)blockIdx.y * out_bstride + (l & ~1) : nullptr;
+            a.st = a.live && pl != nullptr;
+            a.outp = (pl ? pl : outa) + (long long)blockIdx.y * out_bstride + (l & ~1);
         } else {
             a.sa = a.sb = (T)1;
+            a.st = a.live;
             a.outp = reinterpret_cast<T*>(out + (long long)blockIdx.y * out_bstride + l);
         }
     }
     __device__ __forceinline__ Cx<T> fetch(int idx, int N, const Acc& a) const {
         if (PRUNED) {
-            const int k = kfreq(idx, N);
-            if (!a.live || k < -Rm || k > Rp) return mk<T>(0, 0);
-            return a.inp[(long long)(k + Rm) * in_istride];
+            // signed frequency k of idx lies in [-Rm, Rp]  <=>  idx <= Rp  or  idx >= N - Rm; compact row = k + Rm
+            const bool lo = idx <= a.lo_max, hi = idx >= a.hi_min;
+            if (!(lo || hi)) return mk<T>(0, 0);
+            const unsigned row = (unsigned)(lo ? idx + Rm : idx - a.hi_sub);
+            return a.inp[row * a.istr];
         }
         if (!a.live) return mk<T>(0, 0);
-        return a.inp[(long long)idx * in_istride];
+        return a.inp[(unsigned)idx * a.istr];
     }
     __device__ __forceinline__ void emit(int idx, int line, Cx<T> v, bool act, Acc& acc) const {
         const bool ok = act && acc.live;
         if (!REALOUT) {
-            if (ok) reinterpret_cast<Cx<T>*>(acc.outp)[(long long)idx * out_istride] = v;
+            if (ok) reinterpret_cast<Cx<T>*>(acc.outp)[(unsigned)idx * acc.ostr] = v;
         } else {
             // lanes (line, line^1) are neighbours: the even one takes the pair of real parts (plane a), the odd one the pair of
             // imaginary parts (plane b), so every thread packs and stores one aligned cell pair
             const T ra = v.x * acc.sa, rb = v.y * acc.sb;
-            const bool even = (line & 1) == 0;
-            const T recv = __shfl_xor_sync(0xffffffffu, even ? rb : ra, 1);
+            const T recv = __shfl_xor_sync(0xffffffffu, acc.even ? rb : ra, 1);
             Real2<T> r;
-            r.a = even ? ra : recv;
-            r.b = even ? recv : rb;
+            r.a = acc.even ? ra : recv;
+            r.b = acc.even ? recv : rb;
             if (ok) {
                 acc.m = fmax(acc.m, fmax(fabs(r.a), fabs(r.b)));
                 acc.q += r.a * r.a + r.b * r.b;
-                if (acc.outp) {
+                if (acc.st) {
                     if (halfpack) r = pack_hilo(r);
-                    *reinterpret_cast<Real2<T>*>(acc.outp + (long long)idx * out_istride) = r;
+                    *reinterpret_cast<Real2<T>*>(acc.outp + (unsigned)idx * acc.ostr) = r;
                 }
             }
         }
