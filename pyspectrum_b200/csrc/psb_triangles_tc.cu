@@ -14,10 +14,11 @@
 // every p.flush_ksteps*16 cells (double-buffered accumulator sets: the drain overlaps the next MMAs).
 //
 // Warp roles (704 threads, 1 CTA/SM):
-//   warps 0..15  A formers, warp = 4*g + q, g = 2*kp + tp: the group forms tiles {2tp,2tp+1} of K-steps kp and kp+2 of every
-//                64-cell sub-chunk (two operand stages -> double buffered); a thread owns one TMEM lane in both tiles (rows
-//                sharing the field i), forms the pair products in packed half2 (already hi/lo split) and writes them straight
-//                into TMEM (tcgen05.st) as the A operand; group g also drains accumulator tile g.
+//   warps 0..15  A formers, warp = 4*g + q.  Work unit n = (sub-chunk, K-step k, tile pair tp); group g takes n = g (mod 4), i.e.
+//                tiles {2tp,2tp+1} of K-steps kp and kp+2 of every 64-cell sub-chunk (two operand stages -> double buffered); a
+//                thread owns one TMEM lane in both tiles (rows sharing the field i), forms the pair products in packed half2
+//                (already hi/lo split) and writes them straight into TMEM (one tcgen05.st.x16 per tile) as the A operand; the
+//                groups take turns draining the accumulator tiles.  (PSB_TC_GROUPS=6 runs 24 former warps: same speed.)
 //                (A 2x2-block variant -- four rows from four field vectors, 1/3 less shared-memory traffic -- measured slower:
 //                the kernel is bound by the per-stage handshake/latency chain, not by shared-memory throughput; profiles/.)
 //   warp 19      MMA issuer (one elected lane): tcgen05.mma.cta_group::1.kind::f16 with A from TMEM, B from smem; tcgen05.commit
@@ -138,6 +139,13 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r)
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
                  ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
 }
+// hi (8 columns) and lo (8 columns) of one tile and K-step are adjacent in TMEM: one 16-column store instead of two 8-column ones
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* a, const uint32_t* b)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 ::"r"(taddr), "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+                   "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]) : "memory");
+}
 __device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t* r)
 {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};"
@@ -188,13 +196,17 @@ struct Params {
                                   //                                  16 no TMA copies, 32 no B forming, 256 no tcgen05 fences in the formers, 512 no I_i loads
 };
 
-constexpr int NFWARPS = 16;                      // A-operand formers: 4 groups (one per K-step of a chunk) x 4 lane quarters
-// Warp roles.  The SM sub-partition arbiter favours the highest warp id, and the single MMA-issuing thread sits on every stage's
-// critical path (timeline in profiles/): it gets the highest id of the least loaded sub-partition (warp 19 on SMSP 3), the TMA
-// warp the highest id of SMSP 2; the four B formers (one per operand stage) are warps 16, 17, 20, 21.
-constexpr int W_MMA = 19, W_TMA = 18;
-__device__ __forceinline__ int b_stage_of_warp(int w) { return w == 16 ? 0 : (w == 17 ? 1 : (w == 20 ? 2 : 3)); }
-constexpr int NTHR = 22 * 32;
+// Warp roles for NG former groups (NG*4 former warps: warp = 4*group + lane quarter).
+//   NG = 4 (704 threads, <= 80 registers): the SM sub-partition arbiter favours the highest warp id, and the single MMA-issuing
+//           thread sits on every stage's critical path: it is warp 19 (SMSP 3), the TMA warp 18, the B formers 16, 17, 20, 21.
+//   NG = 6 (960 threads, 64 registers): formers 0..23, B formers 24..27, TMA 28, MMA 29.
+template <int NG> struct Roles {
+    static constexpr int NFW = NG * 4;
+    static constexpr int NTHR = (NFW + 6) * 32;
+    static constexpr int W_MMA = NG == 4 ? 19 : NFW + 5;
+    static constexpr int W_TMA = NG == 4 ? 18 : NFW + 4;
+    static __device__ __forceinline__ int b_stage(int w) { return NG == 4 ? (w == 16 ? 0 : (w == 17 ? 1 : (w == 20 ? 2 : 3))) : w - NFW; }
+};
 constexpr int TMEM_A0 = 256;
 
 // TMEM map (512 columns): [0,256) accumulator tiles (tile m at m*tile_cols);
@@ -203,14 +215,12 @@ constexpr int TMEM_A0 = 256;
 
 // TMEM accumulators of tile `m` -> fp32 shared accumulators (round-to-nearest adds); every gflush_drains-th drain
 // (and the last one) moves them on to the float64 partial sums in global memory.
-__device__ __forceinline__ void drain_accumulators(const Params& p, uint64_t* acc_full, uint64_t* acc_empty, uint32_t& aph, int& ndrain,
-                                                   bool final_drain, bool live, uint32_t t_acc, float4* accs, int MR, int NT, int row, int lane)
+__device__ __forceinline__ void drain_accumulators(const Params& p, uint64_t* acc_full, uint64_t* acc_empty, int period, bool final_drain,
+                                                   bool live, uint32_t t_acc, float4* accs, int MR, int NT, int row, int lane)
 {
-    mbar_wait(acc_full, aph);
-    aph ^= 1;
+    mbar_wait(acc_full, (uint32_t)(period & 1));
     tc_fence_after();
-    const bool to_global = (++ndrain == p.gflush_drains) || final_drain;
-    if (to_global) ndrain = 0;
+    const bool to_global = ((period + 1) % p.gflush_drains == 0) || final_drain;
     if (live && !(p.debug & 8)) {
         double* dst = p.partial + (size_t)blockIdx.x * MR * NT + (size_t)row;     // [col][row]: coalesced
         // one 16-column TMEM load per round trip: keeping two or three in flight needs 32-48 more live registers and spills at the
@@ -243,9 +253,11 @@ __device__ __forceinline__ void drain_accumulators(const Params& p, uint64_t* ac
 
 // shared memory carve-up (dynamic):
 //   chunk[NCHUNKBUF][S][ROWF] fp32 | B_hi[4][2][NT][8] fp16 | B_lo[...] | accs[NT/4][MT*128][4] fp32 | barriers
-template <int XCH>
-__global__ void __launch_bounds__(NTHR, 1) k_tri_tc(Params p)
+template <int XCH, int NG>
+__global__ void __launch_bounds__(Roles<NG>::NTHR, 1) k_tri_tc(Params p)
 {
+    using R = Roles<NG>;
+    constexpr int NTHR = R::NTHR, NFWARPS = R::NFW, W_MMA = R::W_MMA, W_TMA = R::W_TMA;
     constexpr int NSUB = XCH / SUB;
     constexpr int ROWF = XCH + 4;    // padded fp32 row stride (== 4 mod 32 words: conflict-free LDS.128 across rows)
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -272,7 +284,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_tri_tc(Params p)
         for (int i = 0; i < NCHUNKBUF; ++i) { mbar_init(&chunk_full[i], 1); mbar_init(&chunk_empty[i], NFWARPS + 4); }
         for (int i = 0; i < 4; ++i) { mbar_init(&st_full[i], 9); mbar_init(&st_empty[i], 1); }
         mbar_init(acc_full, 1);
-        mbar_init(acc_empty, NFWARPS);
+        mbar_init(acc_empty, 16);                  // the four groups on drain duty
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == W_MMA) {       // TMEM allocation by one full warp
@@ -365,7 +377,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_tri_tc(Params p)
             const uint32_t* ch = chunk + (size_t)buf * S * ROWF + sub * SUB;
             const uint32_t sph = (uint32_t)((c * NSUB + sub) & 1);
             {
-                const int g = b_stage_of_warp(warp);              // this warp's operand stage (K-step g of every sub-chunk)
+                const int g = R::b_stage(warp);                   // this warp's operand stage (K-step g of every sub-chunk)
                 const int tt = c * NSUB + sub;
                 if (p.trace && blockIdx.x == 0 && tt < 64 && lane == 0 && g == 0) p.trace[(2 * 8 + 0) * 64 + tt] = clock64();
                 mbar_wait(&st_empty[g], sph ^ 1, p.backoff_ns);     // ~2600 cycles of slack per stage
@@ -397,92 +409,91 @@ __global__ void __launch_bounds__(NTHR, 1) k_tri_tc(Params p)
         }
     } else {
         // ------------------------------------------------------------------ A-operand formers (+ TMEM drain)
-        // warp = 4*g + q, g = 2*kp + tp: the group forms tiles {2tp, 2tp+1} of the K-steps kp and kp+2 of every chunk,
-        // i.e. it alternates between two operand stages, so forming overlaps the MMAs of its other stage.  A thread is
-        // one TMEM lane (32*q + lane) in both tiles: the two rows share the field i, which is loaded once.
-        const int g = warp >> 2, q = warp & 3, tp = g & 1, kp = g >> 1;
+        // Work unit n = (sub-chunk t = n >> 3, K-step k = (n >> 1) & 3, tile pair tp = n & 1): tiles {2tp, 2tp+1} of operand stage k.
+        // Group g = warp >> 2 takes the units n = g (mod NG).  With NG = 4 that is the fixed pairing (k, k+2; tp) of one tile pair
+        // with two alternating stages; with NG = 6 the 24 former warps rotate through all (stage, tile pair) combinations.
+        // A thread is one TMEM lane (32*q + lane) in every tile: the rows of a lane share the field i, which is loaded once per unit.
+        const int g = warp >> 2, q = warp & 3;
         const int tl = q * 32 + lane;                            // TMEM lane
         const int* lij = p.lane_ij + tl * 5;
         const int fi = lij[0];
-        const int fj0 = lij[1 + 2 * tp], fj1 = lij[2 + 2 * tp];
-        const bool t0 = 2 * tp < MT, t1 = 2 * tp + 1 < MT;
-        const bool r0 = fi >= 0 && fj0 >= 0, r1 = fi >= 0 && fj1 >= 0;
+        const uint32_t fio = (uint32_t)(fi < 0 ? 0 : fi) * ROWF;
+        uint32_t fjo[4];
+        bool rv[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) { const int fj = lij[1 + m]; rv[m] = fi >= 0 && fj >= 0 && m < MT; fjo[m] = (uint32_t)(fj < 0 ? 0 : fj) * ROWF; }
         const uint32_t lane_quarter = (uint32_t)(q * 32) << 16;
-        const uint32_t t_a = tmem_base + lane_quarter + (uint32_t)(TMEM_A0 + 2 * tp * 16);
-        const bool drain_live = g < MT;                          // group g drains accumulator tile g
-        const uint32_t t_acc = tmem_base + lane_quarter + (uint32_t)(g * p.tile_cols);
-        const int drow = g * 128 + tl;
-        const uint32_t fio = (uint32_t)(fi < 0 ? 0 : fi) * ROWF, fjo0 = (uint32_t)(fj0 < 0 ? 0 : fj0) * ROWF, fjo1 = (uint32_t)(fj1 < 0 ? 0 : fj1) * ROWF;
-        int buf = 0, cf = 0, ndrain = 0, pending = 0;
-        uint32_t cph = 0, aph = 0;
-        for (int c = 0; c < nch; ++c) {
-            mbar_wait(&chunk_full[buf], cph);
-#pragma unroll 1
-            for (int sub = 0; sub < NSUB; ++sub) {
+        const uint32_t t_a = tmem_base + lane_quarter + (uint32_t)TMEM_A0;
+        const int nsub = nch * NSUB;
+        const int nperiods = (nsub + FC - 1) / FC;
+        int cur_chunk = -1, buf = 0, dP = 0;                     // dP = periods this warp has passed (drained or skipped)
+        // drain duty of period P: tile m is drained by group (m + P) % NG (all four groups for NG = 4: tile g)
+        auto drain_period = [&](int P, bool fin) {
+            int m = g - P % NG; if (m < 0) m += NG;
+            if (m < 4) drain_accumulators(p, acc_full, acc_empty, P, fin, m < MT, tmem_base + lane_quarter + (uint32_t)(m * p.tile_cols),
+                                          accs, MR, NT, m * 128 + tl, lane);
+        };
+        for (int n = g; n < nsub * 8; n += NG) {
+            const int t = n >> 3, kk = (n >> 1) & 3, tp = n & 1;
+            const int c = t / NSUB, sub = t - c * NSUB;
+            if (c != cur_chunk) {
+                if (cur_chunk >= 0) { __syncwarp(); if (lane == 0) mbar_arrive(&chunk_empty[buf]); }     // all reads of the old buffer are done
+                cur_chunk = c;
+                buf = c % NCHUNKBUF;
+                mbar_wait(&chunk_full[buf], (uint32_t)((c / NCHUNKBUF) & 1));
+            }
             const uint32_t* ch = chunk + (size_t)buf * S * ROWF + sub * SUB;
-            const int t = c * NSUB + sub;                      // running sub-chunk index: stage phases flip once per sub-chunk
+            const bool tr = p.trace && blockIdx.x == 0 && t < 64 && lane == 0 && (warp == 0 || warp == 12);
+            const int tre = ((warp == 0 ? 1 : 3) * 8 + 4 * (kk >> 1)) * 64 + t;
+            if (tr) p.trace[tre] = clock64();
+            mbar_wait(&st_empty[kk], (uint32_t)(t & 1) ^ 1);
+            if (tr) p.trace[tre + 64] = clock64();
+            if (!(p.debug & 256)) tc_fence_after();
+            // (Issuing the operand loads before the barrier wait, or in longer bursts, shortens this warp's K-step but slows the
+            // whole kernel by 3-20%: measured several ways, profiles/r1_summary.md.)
+            uint4 vi[4];                       // 16 cells of I_i: per 4 cells {hi2(0,1), lo2(0,1), hi2(2,3), lo2(2,3)}
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int kk = kp + 2 * h;
-                if (p.trace && blockIdx.x == 0 && t < 64 && lane == 0 && (warp == 0 || warp == 12)) p.trace[((warp == 0 ? 1 : 3) * 8 + 4 * h) * 64 + t] = clock64();
-                mbar_wait(&st_empty[kk], (uint32_t)(t & 1) ^ 1);
-                if (p.trace && blockIdx.x == 0 && t < 64 && lane == 0 && (warp == 0 || warp == 12)) p.trace[((warp == 0 ? 1 : 3) * 8 + 4 * h + 1) * 64 + t] = clock64();
-                if (!(p.debug & 256)) tc_fence_after();
-                // (Issuing the operand loads before the barrier wait shortens this warp's K-step -- by 20% with all twelve loads
-                // hoisted -- but slows the whole kernel by 5-20%: measured twice, profiles/r1_summary.md.)
-                uint4 vi[4];                       // 16 cells of I_i: per 4 cells {hi2(0,1), lo2(0,1), hi2(2,3), lo2(2,3)}
+            for (int q4 = 0; q4 < 4; ++q4) vi[q4] = (p.debug & 512) ? make_uint4(0, 0, 0, 0) : *reinterpret_cast<const uint4*>(ch + fio + kk * 16 + q4 * 4);
 #pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) vi[q4] = (p.debug & 512) ? make_uint4(0, 0, 0, 0) : *reinterpret_cast<const uint4*>(ch + fio + kk * 16 + q4 * 4);
-                const bool ftr = p.trace && blockIdx.x == 0 && t < 64 && warp == 0 && h == 0;      // fine-grained timeline of one former warp
-                if (ftr) { asm volatile("" ::"r"(vi[3].w)); if (lane == 0) p.trace[(4 * 8 + 1) * 64 + t] = clock64(); }
+            for (int mm = 0; mm < 2; ++mm) {
+                const int m = 2 * tp + mm;
+                if (m < MT) {
+                    uint32_t hi[8], lo[8];
+                    const bool rvm = tp ? (mm ? rv[3] : rv[2]) : (mm ? rv[1] : rv[0]);
+                    if (rvm && !(p.debug & 2)) {
+                        const uint32_t* pj = ch + (tp ? (mm ? fjo[3] : fjo[2]) : (mm ? fjo[1] : fjo[0])) + kk * 16;
 #pragma unroll
-                for (int mm = 0; mm < 2; ++mm) {
-                    if (mm == 0 ? t0 : t1) {
-                        uint32_t hi[8], lo[8];
-                        if ((mm == 0 ? r0 : r1) && !(p.debug & 2)) {
-                            const uint32_t* pj = ch + (mm == 0 ? fjo0 : fjo1) + kk * 16;
+                        for (int q4 = 0; q4 < 4; ++q4) {
+                            const uint4 b = *reinterpret_cast<const uint4*>(pj + q4 * 4);
+                            prod_split(vi[q4].x, vi[q4].y, b.x, b.y, hi[2 * q4], lo[2 * q4]);
+                            prod_split(vi[q4].z, vi[q4].w, b.z, b.w, hi[2 * q4 + 1], lo[2 * q4 + 1]);
+                        }
+                    } else {
 #pragma unroll
-                            for (int q4 = 0; q4 < 4; ++q4) {
-                                const uint4 b = *reinterpret_cast<const uint4*>(pj + q4 * 4);
-                                prod_split(vi[q4].x, vi[q4].y, b.x, b.y, hi[2 * q4], lo[2 * q4]);
-                                prod_split(vi[q4].z, vi[q4].w, b.z, b.w, hi[2 * q4 + 1], lo[2 * q4 + 1]);
-                            }
+                        for (int k = 0; k < 8; ++k) { hi[k] = 0u; lo[k] = 0u; }       // padding rows
+                    }
+                    if (!(p.debug & 4)) {
+                        if (p.debug & 1024) {
+                            tmem_st8(t_a + (uint32_t)(kk * 64 + m * 16), hi);
+                            tmem_st8(t_a + (uint32_t)(kk * 64 + m * 16 + 8), lo);
                         } else {
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) { hi[k] = 0u; lo[k] = 0u; }       // padding rows
+                            tmem_st16(t_a + (uint32_t)(kk * 64 + m * 16), hi, lo);
                         }
-                        if (ftr) { asm volatile("" ::"r"(lo[7]), "r"(hi[7])); if (lane == 0) p.trace[(4 * 8 + 2 + 2 * mm) * 64 + t] = clock64(); }
-                        if (!(p.debug & 4)) {
-                            tmem_st8(t_a + (uint32_t)(kk * 64 + mm * 16), hi);
-                            tmem_st8(t_a + (uint32_t)(kk * 64 + mm * 16 + 8), lo);
-                        }
-                        if (ftr && lane == 0) p.trace[(4 * 8 + 3 + 2 * mm) * 64 + t] = clock64();
                     }
                 }
-                if (p.trace && blockIdx.x == 0 && t < 64 && lane == 0 && (warp == 0 || warp == 12)) p.trace[((warp == 0 ? 1 : 3) * 8 + 4 * h + 3) * 64 + t] = clock64();
-                if (!(p.debug & 4)) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                if (ftr && lane == 0) p.trace[(4 * 8 + 6) * 64 + t] = clock64();
-                if (!(p.debug & 256)) tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&st_full[kk]);
-                if (p.trace && blockIdx.x == 0 && t < 64 && lane == 0 && (warp == 0 || warp == 12)) p.trace[((warp == 0 ? 1 : 3) * 8 + 4 * h + 2) * 64 + t] = clock64();
             }
-            if (sub == NSUB - 1) {                 // all reads of this chunk buffer are done
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&chunk_empty[buf]);
-            }
-            // Drain the previous period one sub-chunk late: its MMAs are done by now (no wait on acc_full) while the
-            // tensor core still has this sub-chunk's K-steps queued.  The last sub-chunk also drains its own period.
-            const bool last = (c == nch - 1) && (sub == NSUB - 1);
-            if (pending) {
-                drain_accumulators(p, acc_full, acc_empty, aph, ndrain, false, drain_live, t_acc, accs, MR, NT, drow, lane);
-                pending = 0;
-            }
-            if (++cf == FC) { cf = 0; pending = 1; }
-            if (last) drain_accumulators(p, acc_full, acc_empty, aph, ndrain, true, drain_live, t_acc, accs, MR, NT, drow, lane);
-            }
-            if (++buf == NCHUNKBUF) { buf = 0; cph ^= 1; }
+            if (tr) p.trace[tre + 3 * 64] = clock64();
+            if (!(p.debug & 4)) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            if (!(p.debug & 256)) tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&st_full[kk]);
+            if (tr) p.trace[tre + 2 * 64] = clock64();
+            // Drain the previous period once this warp has formed a unit of the next one: its MMAs are done by now (no wait on
+            // acc_full) while the tensor core still has this sub-chunk's K-steps queued.  Every group owns a unit of every sub-chunk.
+            if (dP < t / FC) { drain_period(dP, false); ++dP; }
         }
+        if (cur_chunk >= 0) { __syncwarp(); if (lane == 0) mbar_arrive(&chunk_empty[buf]); }
+        while (dP < nperiods) { drain_period(dP, dP == nperiods - 1); ++dP; }
     }
     // ---------------------------------------------------------------------- teardown
     tc_fence_before();
@@ -530,7 +541,10 @@ int triangle_sums_tc_pass(const float* const* fields, int S, long long ncell, co
     if (smem_for(256) > 227 * 1024 || ncell % 256) XCH = 64;
     const size_t smem = smem_for(XCH);
     if (smem > 227 * 1024 || ncell % XCH) return PSB_ERR_ARG;
-    auto kern = XCH == 256 ? k_tri_tc<256> : k_tri_tc<64>;
+    int NG = 4;                                            // former groups: 4 (704 threads) or 6 (960 threads, 64 registers)
+    if (const char* e = getenv("PSB_TC_GROUPS")) { if (atoi(e) == 6) NG = 6; }
+    auto kern = NG == 6 ? (XCH == 256 ? k_tri_tc<256, 6> : k_tri_tc<64, 6>) : (XCH == 256 ? k_tri_tc<256, 4> : k_tri_tc<64, 4>);
+    const int NTHR = NG == 6 ? Roles<6>::NTHR : Roles<4>::NTHR;
     const long long nchunk_launch = ncell / XCH;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PSB_ERR_CUDA;
     const int ncta = 148;

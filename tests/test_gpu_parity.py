@@ -240,7 +240,7 @@ def test_edge_cases(mods):
         pySpec.Pk_periodic(xyz, Lbox=L, Ngrid=23)               # odd grid
 
 
-@pytest.mark.parametrize('N,Np,step,Ncut,Nmax', [(32, 20000, 1, 1, 12), (48, 60000, 2, 3, 10), (64, 100000, 1, 3, 30),
+@pytest.mark.parametrize('N,Np,step,Ncut,Nmax', [(32, 20000, 1, 1, 12), (48, 60000, 2, 3, 10), (48, 60000, 2, 3, 11), (64, 100000, 1, 3, 30),     # 11: odd shell count
                                                  (192, 400000, 1, 3, 72)])      # 70 shells: three accumulator tiles of 80 columns
 def test_triangle_engines_vs_float64(mods, N, Np, step, Ncut, Nmax):
     """K6 alone: the tcgen05 split-fp16 kernel and the FFMA kernel against a float64 torch evaluation of
