@@ -129,12 +129,13 @@ int psb_bk_triangle_sums_f64(const double* const* fields, int nfields, int64_t n
 /* K6 on the tensor cores (tcgen05: fp16 hi/lo split operands, A operand in TMEM, fp32/float64 drains).
  * One pass covers 128 "lanes" x mt tiles of pair rows against all `nshell` fields (columns padded to nt, a multiple
  * of 16, <= 128):  lane_ij = int32 [128][5] = {field slot i of the lane, field slot j of its row in tile 0..3}
- * (-1 = padding).  Row (m*128 + lane) is the pair (i, j_m).  tri_rc[t] = (row, column) of triangle t in this pass or
+ * (-1 = padding).  Row (m*128 + lane) is the pair (i, j_m).  lane_layout = 1 (needs mt == 4): 2x2 row blocks,
+ * lane_ij = {i0, i1, j0, j1, -}, rows (i0,j0), (i0,j1), (i1,j0), (i1,j1) in tiles 0..3.  tri_rc[t] = (row, column) of triangle t in this pass or
  * (-1,-1); sums[t] is written for the triangles of this pass.  Needs ncell % 64 == 0, mt <= 4 (nt <= 64) or 2.
  * Fields: the packed hi/lo halves written by psb_bk_shell_pair_f32(pack_half=1), pre-scaled so that |I_i I_j| stays inside
  * the fp16 range (psb_bk_shell_scales). */
 size_t psb_bk_triangle_tc_workspace_bytes(int mt, int nt);
-int psb_bk_triangle_sums_tc(const float* const* fields, int nshell, int64_t ncell, const int32_t* lane_ij,
+int psb_bk_triangle_sums_tc(const float* const* fields, int nshell, int64_t ncell, const int32_t* lane_ij, int lane_layout,
                             int mt, int nt, const int32_t* tri_rc, int ntri, double* sums, void* ws, size_t ws_bytes,
                             void* stream);
 

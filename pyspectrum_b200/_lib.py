@@ -61,7 +61,7 @@ PROTOTYPES = {
     'psb_bk_triangle_sums_f32': (_i, [_vp, _i, _i64, _vp, _i, _vp, _vp, _sz, _i, _vp]),
     'psb_bk_triangle_sums_f64': (_i, [_vp, _i, _i64, _vp, _i, _vp, _vp, _sz, _vp]),
     'psb_bk_triangle_tc_workspace_bytes': (_sz, [_i, _i]),
-    'psb_bk_triangle_sums_tc': (_i, [_vp, _i, _i64, _vp, _i, _i, _vp, _i, _vp, _vp, _sz, _vp]),
+    'psb_bk_triangle_sums_tc': (_i, [_vp, _i, _i64, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _sz, _vp]),
     'psb_bk_build_tiles': (_i, [_vp, _i, _i, _vp, _vp]),
     'psb_host_assign_quad': (_i, [_vp, _vp, _vp, _i64, _i, _f, _f, _i, _i, _i, _i]),
     'psb_host_fcomb_periodic': (_i, [_vp, _f, _i]),

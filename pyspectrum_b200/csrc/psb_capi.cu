@@ -220,11 +220,11 @@ int psb_bk_triangle_sums_f64(const double* const* fields, int nfields, int64_t n
 
 size_t psb_bk_triangle_tc_workspace_bytes(int mt, int nt) { return triangle_tc_workspace_bytes(mt, nt); }
 
-int psb_bk_triangle_sums_tc(const float* const* fields, int nshell, int64_t ncell, const int32_t* lane_ij, int mt, int nt,
+int psb_bk_triangle_sums_tc(const float* const* fields, int nshell, int64_t ncell, const int32_t* lane_ij, int lane_layout, int mt, int nt,
                             const int32_t* tri_rc, int ntri, double* sums, void* ws, size_t ws_bytes, void* stream)
 {
     if (!fields || !lane_ij || !tri_rc || !sums || !ws) return PSB_ERR_ARG;
-    return triangle_sums_tc_pass(fields, nshell, ncell, lane_ij, mt, nt, tri_rc, ntri, sums, ws, ws_bytes, S(stream));
+    return triangle_sums_tc_pass(fields, nshell, ncell, lane_ij, lane_layout, mt, nt, tri_rc, ntri, sums, ws, ws_bytes, S(stream));
 }
 
 /* host helper shared with the Python layer: tri [ntri][3] shell indices -> tiles; call with tiles == NULL to size */

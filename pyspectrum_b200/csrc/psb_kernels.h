@@ -58,7 +58,7 @@ size_t triangle_workspace_bytes(int ntiles);
 
 // tensor-core K6 (psb_triangles_tc.cu): one pass over MT*128 pair rows x NT shell columns
 size_t triangle_tc_workspace_bytes(int MT, int NT);
-int triangle_sums_tc_pass(const float* const* fields, int S, long long ncell, const int* lane_ij, int MT, int NT,
+int triangle_sums_tc_pass(const float* const* fields, int S, long long ncell, const int* lane_ij, int lane_layout, int MT, int NT,
                           const int* tri_rc, int ntri, double* sums, void* ws, size_t ws_bytes, cudaStream_t st);
 
 }  // namespace psb

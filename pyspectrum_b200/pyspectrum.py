@@ -363,37 +363,54 @@ class PeriodicPipeline(object):
         check(rc, 'psb_bk_triangle_sums')
         return sums
 
-    def tc_passes(self, Nmax, Ncut, step):
-        """Host plan of the tensor-core kernel.  Pair rows (i,j) that own a triangle are grouped by i; a "lane" holds one
-        i and up to MT of its partners j (one per M tile), so a thread loads I_i once for MT rows.  Lanes are cut into
-        passes of 128; per pass the (row, column) of every triangle."""
-        key = ('tc', Nmax, Ncut, step)
+    def tc_passes(self, Nmax, Ncut, step, layout=None):
+        """Host plan of the tensor-core kernel: which pair row (i,j) sits in which TMEM lane and M tile.
+        layout 0: a lane holds one i and up to MT of its partners j (one per M tile): a thread loads I_i once for MT rows.
+        layout 1 (MT == 4): a lane holds a 2x2 block (i0,i1) x (j0,j1), rows (i0,j0), (i0,j1), (i1,j0), (i1,j1) in tiles 0..3:
+                 four field vectors give four rows of products.
+        Lanes are cut into passes of 128; per pass the (row, column) of every triangle."""
+        if layout is None:
+            layout = int(os.environ.get('PSB_TC_LAYOUT', '1'))       # 2x2 blocks: 17 % faster (profiles/r1_summary.md)
+        tri = triangle_list(Nmax, Ncut, step)
+        s0 = Ncut // step
+        S = Nmax - s0 + 1
+        NT = (S + 15) // 16 * 16
+        MT = 4 if NT <= 64 else 256 // NT          # accumulator tiles that fit in 256 TMEM columns
+        if MT != 4:
+            layout = 0
+        key = ('tc', Nmax, Ncut, step, layout)
         if key not in self._tiles:
-            tri = triangle_list(Nmax, Ncut, step)
-            s0 = Ncut // step
-            S = Nmax - s0 + 1
-            NT = (S + 15) // 16 * 16
-            MT = 4 if NT <= 64 else 256 // NT          # accumulator tiles that fit in 256 TMEM columns
             partners = {}
             for i, j, _ in tri:
                 partners.setdefault(int(i), set()).add(int(j))
-            lanes = []                                     # (i, [j_0..j_{MT-1}])
-            for i in sorted(partners):
-                js = sorted(partners[i])
-                nl = (len(js) + MT - 1) // MT
-                for k in range(nl):
-                    lanes.append((i, [js[k + m * nl] if k + m * nl < len(js) else -1 for m in range(MT)]))
+            lanes = []                                     # 5 field slots per lane (shell indices, -1 = unused) + its rows
+            if layout == 0:
+                for i in sorted(partners):
+                    js = sorted(partners[i])
+                    nl = (len(js) + MT - 1) // MT
+                    for k in range(nl):
+                        jl = [js[k + m * nl] if k + m * nl < len(js) else -1 for m in range(MT)]
+                        lanes.append(([i] + jl + [-1] * (4 - MT), [(i, j) for j in jl]))
+            else:
+                ivals = sorted(partners)
+                for a in range(0, len(ivals), 2):
+                    grp = ivals[a:a + 2]
+                    i0, i1 = grp[0], (grp[1] if len(grp) > 1 else -1)
+                    js = sorted(set().union(*[partners[i] for i in grp]))
+                    nl = (len(js) + 1) // 2               # consecutive lanes take consecutive j: rows one apart -> conflict-free LDS.128
+                    for k in range(nl):
+                        j0, j1 = js[k], (js[k + nl] if k + nl < len(js) else -1)
+                        lanes.append(([i0, i1, j0, j1, -1], [(i0, j0), (i0, j1), (i1, j0), (i1, j1)]))
             passes = []
             ti, tj, tl = tri[:, 0], tri[:, 1], tri[:, 2]
             for l0 in range(0, len(lanes), 128):
                 sub = lanes[l0:l0 + 128]
                 lij = np.full((128, 5), -1, np.int32)
                 row_of = {}
-                for ln, (i, js) in enumerate(sub):
-                    lij[ln, 0] = i - s0
-                    for m, j in enumerate(js):
-                        if j >= 0:
-                            lij[ln, 1 + m] = j - s0
+                for ln, (slots, rows) in enumerate(sub):
+                    lij[ln] = [v - s0 if v >= 0 else -1 for v in slots]
+                    for m, (i, j) in enumerate(rows):
+                        if i >= 0 and j >= 0:
                             row_of[(i, j)] = m * 128 + ln
                 rc = np.full((len(tri), 2), -1, np.int32)
                 for t in range(len(tri)):
@@ -401,11 +418,11 @@ class PeriodicPipeline(object):
                     if r is not None:
                         rc[t] = (r, tl[t] - s0)
                 passes.append((torch.from_numpy(lij).to(self.dev), MT, torch.from_numpy(rc).to(self.dev)))
-            self._tiles[key] = (tri, NT, passes)
+            self._tiles[key] = (tri, NT, passes, layout)
         return self._tiles[key]
 
     def _triangle_sums_tc(self, fields, Nmax, Ncut, step):
-        tri, NT, passes = self.tc_passes(Nmax, Ncut, step)
+        tri, NT, passes, layout = self.tc_passes(Nmax, Ncut, step)
         S = Nmax - Ncut // step + 1
         dptr = torch.tensor([fields[self._field_rows[f]].data_ptr() for f in range(S)], dtype=torch.int64).to(self.dev)
         sums = torch.zeros(len(tri), dtype=torch.float64, device=self.dev)
@@ -413,7 +430,7 @@ class PeriodicPipeline(object):
         wsb = self.L.psb_bk_triangle_tc_workspace_bytes(MT, NT)
         ws = torch.empty(wsb, dtype=torch.uint8, device=self.dev)
         for lij, MT, rc in passes:
-            check(self.L.psb_bk_triangle_sums_tc(_ptr(dptr), S, fields.shape[1], _ptr(lij), MT, NT, _ptr(rc), len(tri),
+            check(self.L.psb_bk_triangle_sums_tc(_ptr(dptr), S, fields.shape[1], _ptr(lij), layout, MT, NT, _ptr(rc), len(tri),
                                                  _ptr(sums), _ptr(ws), wsb, _stream()), 'psb_bk_triangle_sums_tc')
         return sums
 
