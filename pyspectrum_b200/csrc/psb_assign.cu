@@ -9,6 +9,7 @@
 // (z,y) row so that concurrently running warps hit a few-MB window of the mesh that stays L2 resident;
 // HBM then sees the mesh once (zero fill + final write-back) plus 16 B per sorted particle.
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include "psb_kernels.h"
 
 namespace psb {
@@ -174,6 +175,48 @@ __global__ void __launch_bounds__(256) k_assign(const float4* __restrict__ sorte
     }
 }
 
+// Lane-per-pair variant: four consecutive lanes share a particle, lane pr < 3 owns the aligned cell pair P0 + pr of every row of the
+// window (lane 3 idles).  The three vector reductions of a row then leave in ONE instruction from adjacent lanes, and the
+// load/store unit merges their 48 contiguous bytes into two 32-byte sectors instead of three separate sector packets: a third
+// fewer packets on the L1 -> L2 reduction path that bounds this kernel.  The windows are recomputed per lane (cheap).
+__device__ __forceinline__ float sel5(const float* a, int k)
+{
+    float v = 0.f;
+#pragma unroll
+    for (int q = 0; q < 5; ++q) v = (k == q) ? a[q] : v;
+    return v;
+}
+
+__global__ void __launch_bounds__(256) k_assign_pairs(const float4* __restrict__ sorted, long long Np, int N, float kf_ks, float offset, float* mesh)
+{
+    const long long gt = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long i = gt >> 2;
+    const int pr = (int)(gt & 3);
+    if (i >= Np || pr == 3) return;
+    const float4 p = sorted[i];
+    const AxisWin X = axis_window(kf_ks, p.x, offset), Y = axis_window(kf_ks, p.y, offset), Z = axis_window(kf_ks, p.z, offset);
+    const int P0 = X.c0 >> 1, off = X.c0 - 2 * P0, Nh = N / 2;
+    const int k0 = 2 * pr - off, k1 = k0 + 1;                  // window cells held by this lane's pair
+    const float xa0 = sel5(X.a, k0), xa1 = sel5(X.a, k1), xb0 = sel5(X.b, k0), xb1 = sel5(X.b, k1);
+    if (xa0 == 0.f && xa1 == 0.f && xb0 == 0.f && xb1 == 0.f) return;
+    int P = (P0 + pr) % Nh;
+    if (P < 0) P += Nh;
+    const long long xo = 4LL * P;
+#pragma unroll
+    for (int rz = 0; rz < 5; ++rz) {
+        if (Z.a[rz] == 0.f && Z.b[rz] == 0.f) continue;
+        const long long zo = (long long)wrapN(Z.c0 + rz, N) * N;
+#pragma unroll
+        for (int ry = 0; ry < 5; ++ry) {
+            const float wa = __fmul_rn(__fmul_rn(Y.a[ry], Z.a[rz]), p.w), wb = __fmul_rn(__fmul_rn(Y.b[ry], Z.b[rz]), p.w);
+            if (wa == 0.f && wb == 0.f) continue;
+            float* row = mesh + (zo + wrapN(Y.c0 + ry, N)) * (2LL * N);
+            const float v0 = xa0 * wa, v1 = xb0 * wb, v2 = xa1 * wa, v3 = xb1 * wb;
+            if (v0 != 0.f || v1 != 0.f || v2 != 0.f || v3 != 0.f) red_add_v4(row + xo, v0, v1, v2, v3);
+        }
+    }
+}
+
 size_t assign_workspace_bytes(long long Np, int N)
 {
     size_t hist = (((size_t)N * N + 1) * sizeof(unsigned int) + 255) / 256 * 256;
@@ -197,7 +240,9 @@ int assign_pcs_interlaced(const AssignIn& in, float* mesh, int zero_mesh, void* 
         k_hist<<<grid, blk, 0, st>>>(in, hist, sumw);
         k_scan<<<1, 1024, 0, st>>>(hist, (int)nrow);
         k_sort_scatter<<<grid, blk, 0, st>>>(in, hist, sorted);
-        k_assign<<<(unsigned)((in.Np + 255) / 256), 256, 0, st>>>(sorted, in.Np, in.N, in.kf_ks, in.offset, mesh);
+        static const int variant = [] { const char* e = getenv("PSB_ASSIGN_VARIANT"); return e ? atoi(e) : 1; }();
+        if (variant == 1) k_assign_pairs<<<(unsigned)((4 * in.Np + 255) / 256), 256, 0, st>>>(sorted, in.Np, in.N, in.kf_ks, in.offset, mesh);
+        else k_assign<<<(unsigned)((in.Np + 255) / 256), 256, 0, st>>>(sorted, in.Np, in.N, in.kf_ks, in.offset, mesh);
     }
     return cudaGetLastError() == cudaSuccess ? PSB_OK : PSB_ERR_CUDA;
 }
