@@ -73,24 +73,59 @@ __global__ void k_hist(AssignIn a, unsigned int* hist, double* sumw)
     }
 }
 
-// exclusive scan of n counters by one 1024-thread CTA (n <= ~1M: N^2 rows)
-__global__ void k_scan(unsigned int* data, int n)
+// exclusive scan of the n = N^2 row counters in three coalesced steps: per-tile sums, scan of the tile sums (one CTA), per-tile
+// exclusive scan + offset.  Tiles of SCAN_TILE counters, one CTA of 256 threads each (16 counters per thread).
+constexpr int SCAN_TILE = 4096;
+
+__device__ __forceinline__ unsigned int block_exclusive_scan_256(unsigned int v, unsigned int* total)
 {
-    __shared__ unsigned int part[1024];
-    const int chunk = (n + 1023) / 1024;
-    const int b = threadIdx.x * chunk, e = min(b + chunk, n);
-    unsigned int s = 0;
-    for (int i = b; i < e; ++i) s += data[i];
-    part[threadIdx.x] = s;
+    __shared__ unsigned int wsum[8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    unsigned int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) wsum[w] = x;
     __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-        unsigned int v = threadIdx.x >= o ? part[threadIdx.x - o] : 0u;
-        __syncthreads();
-        part[threadIdx.x] += v;
-        __syncthreads();
-    }
-    unsigned int run = threadIdx.x ? part[threadIdx.x - 1] : 0u;
-    for (int i = b; i < e; ++i) { unsigned int c = data[i]; data[i] = run; run += c; }
+    unsigned int base = 0, tot = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { const unsigned int sw = wsum[k]; if (k < w) base += sw; tot += sw; }
+    __syncthreads();
+    *total = tot;
+    return base + x - v;
+}
+
+__global__ void __launch_bounds__(256) k_scan_tile_sums(const unsigned int* __restrict__ data, int n, unsigned int* __restrict__ tile_sum)
+{
+    const int t0 = blockIdx.x * SCAN_TILE;
+    unsigned int s = 0;
+    for (int i = threadIdx.x; i < SCAN_TILE; i += 256) { const int e = t0 + i; if (e < n) s += data[e]; }
+    unsigned int tot;
+    block_exclusive_scan_256(s, &tot);
+    if (threadIdx.x == 0) tile_sum[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(256) k_scan_tiles(unsigned int* tile_sum, int ntile)
+{
+    // ntile <= 256 * 16 (N <= 4096): every thread owns a contiguous run of 16 tile sums
+    unsigned int loc[16], s = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { const int e = threadIdx.x * 16 + k; loc[k] = e < ntile ? tile_sum[e] : 0u; s += loc[k]; }
+    unsigned int tot;
+    unsigned int run = block_exclusive_scan_256(s, &tot);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { const int e = threadIdx.x * 16 + k; if (e < ntile) tile_sum[e] = run; run += loc[k]; }
+}
+
+__global__ void __launch_bounds__(256) k_scan_apply(unsigned int* __restrict__ data, int n, const unsigned int* __restrict__ tile_off)
+{
+    const int t0 = blockIdx.x * SCAN_TILE + threadIdx.x * 16;            // 16 consecutive counters per thread (64-byte runs)
+    unsigned int loc[16], s = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { loc[k] = t0 + k < n ? data[t0 + k] : 0u; s += loc[k]; }
+    unsigned int tot;
+    unsigned int run = tile_off[blockIdx.x] + block_exclusive_scan_256(s, &tot);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { if (t0 + k < n) data[t0 + k] = run; run += loc[k]; }
 }
 
 __global__ void k_sort_scatter(AssignIn a, unsigned int* cursor, float4* sorted)
@@ -230,6 +265,7 @@ int assign_pcs_interlaced(const AssignIn& in, float* mesh, int zero_mesh, void* 
     const size_t nrow = (size_t)in.N * in.N;
     const size_t hist_b = ((nrow + 1) * sizeof(unsigned int) + 255) / 256 * 256;
     unsigned int* hist = static_cast<unsigned int*>(ws);
+    unsigned int* tile_sum = hist + hist_b / sizeof(unsigned int);      // second counter area: scan tile sums (<= 4096 entries)
     float4* sorted = reinterpret_cast<float4*>(static_cast<char*>(ws) + 2 * hist_b);
     if (cudaMemsetAsync(hist, 0, hist_b, st) != cudaSuccess) return PSB_ERR_CUDA;
     if (cudaMemsetAsync(sumw, 0, sizeof(double), st) != cudaSuccess) return PSB_ERR_CUDA;
@@ -238,7 +274,11 @@ int assign_pcs_interlaced(const AssignIn& in, float* mesh, int zero_mesh, void* 
         const int blk = 256;
         const int grid = (int)((in.Np + blk - 1) / blk < 148 * 16 ? (in.Np + blk - 1) / blk : 148 * 16);
         k_hist<<<grid, blk, 0, st>>>(in, hist, sumw);
-        k_scan<<<1, 1024, 0, st>>>(hist, (int)nrow);
+        const int ntile = (int)((nrow + SCAN_TILE - 1) / SCAN_TILE);
+        if (ntile > 4096) return PSB_ERR_UNSUPPORTED_N;
+        k_scan_tile_sums<<<ntile, 256, 0, st>>>(hist, (int)nrow, tile_sum);
+        k_scan_tiles<<<1, 256, 0, st>>>(tile_sum, ntile);
+        k_scan_apply<<<ntile, 256, 0, st>>>(hist, (int)nrow, tile_sum);
         k_sort_scatter<<<grid, blk, 0, st>>>(in, hist, sorted);
         static const int variant = [] { const char* e = getenv("PSB_ASSIGN_VARIANT"); return e ? atoi(e) : 1; }();
         if (variant == 1) k_assign_pairs<<<(unsigned)((4 * in.Np + 255) / 256), 256, 0, st>>>(sorted, in.Np, in.N, in.kf_ks, in.offset, mesh);
