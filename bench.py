@@ -286,7 +286,7 @@ def run_b200(args):
                     'd2h_bytes_per_step': int(8 * (len(tri) + S + (S % 2))),
                     'api': 'pyspectrum_b200.pyspectrum.Bk_periodic_many over pinned host catalogues (float64 positions)',
                     'single_call_value': e2e1_ms * 1e-3 / ncat, 'single_call_api': 'Bk_periodic, one catalogue per call, no overlap'},
-            'gpu_launches': int(args.steps * (4 + 3 + 2 + 3 * ((S + 1) // 2) + 2)),
+            'gpu_launches': int(args.steps * (6 + 3 + 2 + 3 * ((S + 1) // 2) + 2)),      # K1 6, mesh FFT 3, shell power/scales 2, 3 per shell pair, K6 2
             'stages_ms': {'assign': float(stage_ms[0]), 'fft_fcomb': float(stage_ms[1]), 'shell_fields': float(stage_ms[2]),
                           'triangles': tri_ms},
             'assign_mpart_per_s': Np / (float(stage_ms[0]) * 1e-3) / 1e6,

@@ -17,7 +17,7 @@ print('B warp (stage 0): wait %.0f  cells %.0f  fence+arrive %.0f ; arrives %.0f
 print('former warp0 stage0 arrives %.0f cycles before MMA sees full[0]' % (mma[0]-f0[2])[8:40].mean())
 print('former warp0 h0: form+issue STTM %.0f, wait::st+fence+arrive %.0f | h1: %.0f, %.0f' % ((f0[3]-f0[1])[8:40].mean(), (f0[2]-f0[3])[8:40].mean(), (f0[7]-f0[5])[8:40].mean(), (f0[6]-f0[7])[8:40].mean()))
 
-if t.shape[0] > 4:
+if t.shape[0] > 4 and (t[4] > 0).any():
     fine = rel(t[4])       # warp 0, h=0: [1] I_i loads landed, [2] tile0 math done, [3] tile0 STTM issued, [4] tile1 math done, [5] tile1 STTM issued, [6] wait::st done
     w_end = f0[1]
     sl = slice(8, 40)
