@@ -97,6 +97,8 @@ class PeriodicPipeline(object):
         self._tw64 = None
         self.mmax = 3 * h * h
         self._irk, self._bins, self._nk, self._tiles, self._counts = {}, {}, {}, {}, {}
+        self._pin_pool = {}                               # free pinned result buffers by size (bispectrum_launch/finish)
+        self._copy_stream = None                          # upload stream of the *_many generators
 
     # ------------------------------------------------------------------ tables
     @property
@@ -340,17 +342,17 @@ class PeriodicPipeline(object):
                 'auto' = tc when the fields are packed and the shapes allow it.
         packed: whether `fields` holds packed hi/lo halves (default: the tag shell_fields put on the tensor)."""
         S = Nmax - Ncut // step + 1
-        self._field_rows = list(range(S)) if field_rows is None else list(field_rows)      # row of `fields` holding shell slot f
+        rows = list(range(S)) if field_rows is None else list(field_rows)                  # row of `fields` holding shell slot f
         if packed is None:
             packed = bool(getattr(fields, 'psb_packed', False))
         tc_ok = packed and fields.dtype == torch.float32 and fields.shape[1] % 64 == 0 and S <= 128
         if engine == 'tc' and not tc_ok:
             raise ValueError('tensor-core triangle kernel needs packed float32 fields, N^3 % 64 == 0 and <= 128 shells')
         if engine == 'tc' or (engine == 'auto' and tc_ok):
-            return self._triangle_sums_tc(fields, Nmax, Ncut, step)
+            return self._triangle_sums_tc(fields, Nmax, Ncut, step, rows)
         tri, tiles, ntiles = self.triangle_tiles(Nmax, Ncut, step)
         nf = (S + 3) // 4 * 4
-        ptrs = [fields[self._field_rows[min(f, S - 1)]].data_ptr() for f in range(nf)]
+        ptrs = [fields[rows[min(f, S - 1)]].data_ptr() for f in range(nf)]
         dptr = torch.tensor(ptrs, dtype=torch.int64).to(self.dev)
         sums = torch.zeros(len(tri), dtype=torch.float64, device=self.dev)
         wsb = self.L.psb_bk_triangle_workspace_bytes(ntiles)
@@ -421,10 +423,10 @@ class PeriodicPipeline(object):
             self._tiles[key] = (tri, NT, passes, layout)
         return self._tiles[key]
 
-    def _triangle_sums_tc(self, fields, Nmax, Ncut, step):
+    def _triangle_sums_tc(self, fields, Nmax, Ncut, step, rows):
         tri, NT, passes, layout = self.tc_passes(Nmax, Ncut, step)
         S = Nmax - Ncut // step + 1
-        dptr = torch.tensor([fields[self._field_rows[f]].data_ptr() for f in range(S)], dtype=torch.int64).to(self.dev)
+        dptr = torch.tensor([fields[rows[f]].data_ptr() for f in range(S)], dtype=torch.int64).to(self.dev)
         sums = torch.zeros(len(tri), dtype=torch.float64, device=self.dev)
         MT = passes[0][1]
         wsb = self.L.psb_bk_triangle_tc_workspace_bytes(MT, NT)
@@ -436,8 +438,7 @@ class PeriodicPipeline(object):
 
     def _pinned(self, n):
         """float64 pinned host buffer of n elements from a small free list (cudaHostAlloc per call would cost more than K4)."""
-        pool = self.__dict__.setdefault('_pin_pool', {})
-        free = pool.setdefault(n, [])
+        free = self._pin_pool.setdefault(n, [])
         return free.pop() if free else torch.empty(n, dtype=torch.float64, pin_memory=True)
 
     def bispectrum_launch(self, half, step, Ncut, Nmax, engine='auto', sumw=None):
