@@ -51,6 +51,62 @@ extern "C" int emu_fft_f32(float* data, int N, int dir, int estride) { return di
 extern "C" int emu_fft_f64(double* data, int N, int dir, int estride) { return dir > 0 ? run_fft<double, 1>(data, N, estride) : run_fft<double, -1>(data, N, estride); }
 extern "C" int emu_plan(int N, int* radices) { FftPlan p; if (!make_plan(N, &p)) return -1; for (int i = 0; i < p.nstages; ++i) radices[i] = p.radix[i]; return p.nstages; }
 
+
+// ---- composite in-register DFTs (Dft<16|18|20|32>) and the two-stage plans built from them (360 = 20 x 18, 256 = 16 x 16)
+template <int R, int DIR> static void run_dft(double* data) { Dft<R, DIR, double>::run(reinterpret_cast<Cx<double>*>(data)); }
+extern "C" int emu_dft(double* data, int R, int dir)
+{
+    switch (R) {
+        case 2: dir > 0 ? run_dft<2, 1>(data) : run_dft<2, -1>(data); return 0;
+        case 3: dir > 0 ? run_dft<3, 1>(data) : run_dft<3, -1>(data); return 0;
+        case 4: dir > 0 ? run_dft<4, 1>(data) : run_dft<4, -1>(data); return 0;
+        case 5: dir > 0 ? run_dft<5, 1>(data) : run_dft<5, -1>(data); return 0;
+        case 8: dir > 0 ? run_dft<8, 1>(data) : run_dft<8, -1>(data); return 0;
+        case 9: dir > 0 ? run_dft<9, 1>(data) : run_dft<9, -1>(data); return 0;
+        case 16: dir > 0 ? run_dft<16, 1>(data) : run_dft<16, -1>(data); return 0;
+        case 18: dir > 0 ? run_dft<18, 1>(data) : run_dft<18, -1>(data); return 0;
+        case 20: dir > 0 ? run_dft<20, 1>(data) : run_dft<20, -1>(data); return 0;
+        case 32: dir > 0 ? run_dft<32, 1>(data) : run_dft<32, -1>(data); return 0;
+        default: return -1;
+    }
+}
+
+// the fused-edge two-stage line FFT exactly as fft_lines_fused_kernel runs it: stage 1 from "global" (in), Ns = 1, no twiddles;
+// stage 2 with twiddles tw[q*j], outputs at j + q*M2
+template <typename T, int R1, int R2, int DIR> static void two_stage(const T* in_, T* out_)
+{
+    constexpr int N = R1 * R2, M1 = N / R1, M2 = N / R2;
+    const Cx<T>* in = reinterpret_cast<const Cx<T>*>(in_);
+    Cx<T>* out = reinterpret_cast<Cx<T>*>(out_);
+    std::vector<Cx<T>> s(N), tw(N);
+    for (int i = 0; i < N; ++i) { tw[i].x = (T)std::cos(2.0 * M_PI * i / N); tw[i].y = (T)std::sin(2.0 * M_PI * i / N); }
+    for (int j = 0; j < M1; ++j) {
+        Cx<T> v[R1];
+        for (int q = 0; q < R1; ++q) v[q] = in[j + q * M1];
+        Dft<R1, DIR, T>::run(v);
+        for (int q = 0; q < R1; ++q) s[j * R1 + q] = v[q];
+    }
+    for (int j = 0; j < M2; ++j) {
+        Cx<T> v[R2];
+        stage_read<R2, T>(s.data(), 1, N, j, v);
+        for (int q = 1; q < R2; ++q) { Cx<T> w = tw[q * j]; if (DIR < 0) w.y = -w.y; v[q] = v[q] * w; }
+        Dft<R2, DIR, T>::run(v);
+        for (int q = 0; q < R2; ++q) out[j + q * M2] = v[q];
+    }
+}
+extern "C" int emu_two_stage_f32(const float* in, float* out, int N, int dir)
+{
+    if (N == 360) { dir > 0 ? two_stage<float, 20, 18, 1>(in, out) : two_stage<float, 20, 18, -1>(in, out); return 0; }
+    if (N == 256) { dir > 0 ? two_stage<float, 16, 16, 1>(in, out) : two_stage<float, 16, 16, -1>(in, out); return 0; }
+    return -1;
+}
+extern "C" int emu_two_stage_f64(const double* in, double* out, int N, int dir)
+{
+    if (N == 360) { dir > 0 ? two_stage<double, 20, 18, 1>(in, out) : two_stage<double, 20, 18, -1>(in, out); return 0; }
+    if (N == 256) { dir > 0 ? two_stage<double, 16, 16, 1>(in, out) : two_stage<double, 16, 16, -1>(in, out); return 0; }
+    return -1;
+}
+
 #include "../../pyspectrum_b200/csrc/psb_fcomb_core.cuh"
 // full: complex64 (N,N,N) Fortran order [ix + N*(iy + N*iz)] BEFORE fcomb; half: output (N/2+1,N,N) Fortran order
 extern "C" void emu_fcomb(const float* full_, float* half_, int N, float sumw, int periodic)
