@@ -65,6 +65,60 @@ def triangle_list(Nmax, Ncut, step):
     return np.stack([I[m], J[m], L[m]], axis=1).astype(np.int32)      # C-order ravel == nested loop order
 
 
+def build_tc_plan(tri, s0, Nmax, layout=1):
+    """Host plan of the tensor-core triangle kernel (pure numpy): which pair row (i,j) sits in which TMEM lane and M tile.
+    layout 0: a lane holds one i and up to MT of its partners j (one per M tile): a thread loads I_i once for MT rows.
+    layout 1 (MT == 4 only): a lane holds a 2x2 block (i0,i1) x (j0,j1), rows (i0,j0), (i0,j1), (i1,j0), (i1,j1) in tiles 0..3:
+             four field vectors give four rows of products.
+    Lanes are cut into passes of 128.  Returns (NT, MT, layout_used, [(lane_ij int32 [128][5], tri_rc int32 [ntri][2]), ...]):
+    lane_ij holds field slots (shell - s0, -1 = unused), tri_rc the (row = tile*128 + lane, column = l - s0) of every triangle
+    owned by the pass, (-1,-1) otherwise."""
+    S = Nmax - s0 + 1
+    NT = (S + 15) // 16 * 16
+    MT = 4 if NT <= 64 else 256 // NT              # accumulator tiles that fit in 256 TMEM columns
+    if MT != 4:
+        layout = 0
+    partners = {}
+    for i, j, _ in tri:
+        partners.setdefault(int(i), set()).add(int(j))
+    lanes = []                                     # 5 field slots per lane (shell indices, -1 = unused) + its rows
+    if layout == 0:
+        for i in sorted(partners):
+            js = sorted(partners[i])
+            nl = (len(js) + MT - 1) // MT
+            for k in range(nl):
+                jl = [js[k + m * nl] if k + m * nl < len(js) else -1 for m in range(MT)]
+                lanes.append(([i] + jl + [-1] * (4 - MT), [(i, j) for j in jl]))
+    else:
+        ivals = sorted(partners)
+        for a in range(0, len(ivals), 2):
+            grp = ivals[a:a + 2]
+            i0, i1 = grp[0], (grp[1] if len(grp) > 1 else -1)
+            js = sorted(set().union(*[partners[i] for i in grp]))
+            nl = (len(js) + 1) // 2               # consecutive lanes take consecutive j: rows one apart -> conflict-free LDS.128
+            for k in range(nl):
+                j0, j1 = js[k], (js[k + nl] if k + nl < len(js) else -1)
+                lanes.append(([i0, i1, j0, j1, -1], [(i0, j0), (i0, j1), (i1, j0), (i1, j1)]))
+    passes = []
+    ti, tj, tl = tri[:, 0], tri[:, 1], tri[:, 2]
+    for l0 in range(0, len(lanes), 128):
+        sub = lanes[l0:l0 + 128]
+        lij = np.full((128, 5), -1, np.int32)
+        row_of = {}
+        for ln, (slots, rows) in enumerate(sub):
+            lij[ln] = [v - s0 if v >= 0 else -1 for v in slots]
+            for m, (i, j) in enumerate(rows):
+                if i >= 0 and j >= 0:
+                    row_of[(i, j)] = m * 128 + ln
+        rc = np.full((len(tri), 2), -1, np.int32)
+        for t in range(len(tri)):
+            r = row_of.get((int(ti[t]), int(tj[t])))
+            if r is not None:
+                rc[t] = (r, tl[t] - s0)
+        passes.append((lij, rc))
+    return NT, MT, layout, passes
+
+
 class PeriodicPipeline(object):
     """Device-resident pipeline for one (Ngrid) on the current CUDA device.  Holds the host-built tables
     (twiddles, fcomb phase/window tables, shell / bin index tables) and caches per-configuration data
@@ -366,61 +420,15 @@ class PeriodicPipeline(object):
         return sums
 
     def tc_passes(self, Nmax, Ncut, step, layout=None):
-        """Host plan of the tensor-core kernel: which pair row (i,j) sits in which TMEM lane and M tile.
-        layout 0: a lane holds one i and up to MT of its partners j (one per M tile): a thread loads I_i once for MT rows.
-        layout 1 (MT == 4): a lane holds a 2x2 block (i0,i1) x (j0,j1), rows (i0,j0), (i0,j1), (i1,j0), (i1,j1) in tiles 0..3:
-                 four field vectors give four rows of products.
-        Lanes are cut into passes of 128; per pass the (row, column) of every triangle."""
+        """Device copy of the tensor-core plan (`build_tc_plan`), cached per configuration."""
         if layout is None:
             layout = int(os.environ.get('PSB_TC_LAYOUT', '1'))       # 2x2 blocks: 17 % faster (profiles/r1_summary.md)
-        tri = triangle_list(Nmax, Ncut, step)
-        s0 = Ncut // step
-        S = Nmax - s0 + 1
-        NT = (S + 15) // 16 * 16
-        MT = 4 if NT <= 64 else 256 // NT          # accumulator tiles that fit in 256 TMEM columns
-        if MT != 4:
-            layout = 0
         key = ('tc', Nmax, Ncut, step, layout)
         if key not in self._tiles:
-            partners = {}
-            for i, j, _ in tri:
-                partners.setdefault(int(i), set()).add(int(j))
-            lanes = []                                     # 5 field slots per lane (shell indices, -1 = unused) + its rows
-            if layout == 0:
-                for i in sorted(partners):
-                    js = sorted(partners[i])
-                    nl = (len(js) + MT - 1) // MT
-                    for k in range(nl):
-                        jl = [js[k + m * nl] if k + m * nl < len(js) else -1 for m in range(MT)]
-                        lanes.append(([i] + jl + [-1] * (4 - MT), [(i, j) for j in jl]))
-            else:
-                ivals = sorted(partners)
-                for a in range(0, len(ivals), 2):
-                    grp = ivals[a:a + 2]
-                    i0, i1 = grp[0], (grp[1] if len(grp) > 1 else -1)
-                    js = sorted(set().union(*[partners[i] for i in grp]))
-                    nl = (len(js) + 1) // 2               # consecutive lanes take consecutive j: rows one apart -> conflict-free LDS.128
-                    for k in range(nl):
-                        j0, j1 = js[k], (js[k + nl] if k + nl < len(js) else -1)
-                        lanes.append(([i0, i1, j0, j1, -1], [(i0, j0), (i0, j1), (i1, j0), (i1, j1)]))
-            passes = []
-            ti, tj, tl = tri[:, 0], tri[:, 1], tri[:, 2]
-            for l0 in range(0, len(lanes), 128):
-                sub = lanes[l0:l0 + 128]
-                lij = np.full((128, 5), -1, np.int32)
-                row_of = {}
-                for ln, (slots, rows) in enumerate(sub):
-                    lij[ln] = [v - s0 if v >= 0 else -1 for v in slots]
-                    for m, (i, j) in enumerate(rows):
-                        if i >= 0 and j >= 0:
-                            row_of[(i, j)] = m * 128 + ln
-                rc = np.full((len(tri), 2), -1, np.int32)
-                for t in range(len(tri)):
-                    r = row_of.get((int(ti[t]), int(tj[t])))
-                    if r is not None:
-                        rc[t] = (r, tl[t] - s0)
-                passes.append((torch.from_numpy(lij).to(self.dev), MT, torch.from_numpy(rc).to(self.dev)))
-            self._tiles[key] = (tri, NT, passes, layout)
+            tri = triangle_list(Nmax, Ncut, step)
+            NT, MT, layout_used, passes = build_tc_plan(tri, Ncut // step, Nmax, layout)
+            dev_passes = [(torch.from_numpy(lij).to(self.dev), MT, torch.from_numpy(rc).to(self.dev)) for lij, rc in passes]
+            self._tiles[key] = (tri, NT, dev_passes, layout_used)
         return self._tiles[key]
 
     def _triangle_sums_tc(self, fields, Nmax, Ncut, step, rows):

@@ -158,3 +158,35 @@ def test_two_rank_gloo_timing_reduction():
         assert mx == [11.0, 5.0] and sm == [2.0, 1.0] and seed == 2 + rank
     from pyspectrum_b200 import dist as D
     assert D.seconds_per_catalogue(3.0, 5, 2) == 0.3
+
+
+@pytest.mark.parametrize('layout', [0, 1])
+@pytest.mark.parametrize('Nmax,Ncut,step', [(40, 3, 3), (12, 1, 1), (10, 3, 2), (11, 3, 2), (30, 3, 1), (7, 3, 3), (64, 3, 1), (72, 3, 1), (80, 3, 2), (5, 4, 4)])
+def test_tensor_core_plan_covers_every_triangle_once(Nmax, Ncut, step, layout):
+    """build_tc_plan (host plan of psb_bk_triangle_sums_tc): every triangle (i,j,l) is owned by exactly one pass, its row decodes
+    back to (i,j) through the lane's field slots in the declared layout, its column is l; rows are unique; lanes stay in range."""
+    from pyspectrum_b200 import pyspectrum as P
+    tri = P.triangle_list(Nmax, Ncut, step)
+    s0 = Ncut // step
+    S = Nmax - s0 + 1
+    NT, MT, used, passes = P.build_tc_plan(tri, s0, Nmax, layout)
+    assert NT % 16 == 0 and NT >= S and MT == (4 if NT <= 64 else 256 // NT) and MT * NT <= 256
+    assert used == (layout if MT == 4 else 0)
+    owner = np.zeros(len(tri), int)
+    for lij, rc in passes:
+        assert lij.shape == (128, 5) and lij.dtype == np.int32 and rc.shape == (len(tri), 2) and rc.dtype == np.int32
+        assert lij.max() < S and lij.min() >= -1
+        mine = rc[:, 0] >= 0
+        owner += mine
+        rows, cols = rc[mine, 0], rc[mine, 1]
+        assert rows.max() < MT * 128
+        m, ln = rows // 128, rows % 128
+        sl = lij[ln]
+        if used == 0:                                   # {i; j_0..j_3}
+            fi, fj = sl[:, 0], sl[np.arange(len(ln)), 1 + m]
+        else:                                           # {i0, i1, j0, j1}: tile m = 2*(which i) + (which j)
+            fi, fj = sl[np.arange(len(ln)), m // 2], sl[np.arange(len(ln)), 2 + m % 2]
+        assert np.array_equal(fi + s0, tri[mine, 0]) and np.array_equal(fj + s0, tri[mine, 1]) and np.array_equal(cols + s0, tri[mine, 2])
+        pairs = {(int(a), int(b)) for a, b in zip(tri[mine, 0], tri[mine, 1])}
+        assert len({int(r) for r in rows}) == len(pairs)            # one row per (i,j) pair
+    assert np.all(owner == 1)
