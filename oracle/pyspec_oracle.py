@@ -12,6 +12,12 @@ estimator path, used only as the parity checker and as the timed CPU baseline:
   _Bk_periodic        <- pyspectrum/pyspectrum.py:359-457
   _counts_Bk123       <- pyspectrum/pyspectrum.py:962-1030    (cold path, vectorised; no file I/O)
   counts_bruteforce   <- definition of the counts (closed triangles mod N), toy grids only
+  B0_survey           <- pyspectrum/pyspectrum.py:13-132      (without the Ngrid==360 assert)
+  _B0_survey          <- pyspectrum/pyspectrum.py:135-282
+  FFT_survey_mono     <- pyspectrum/pyspectrum.py:731-826
+  radecz_to_cartesian <- pyspectrum/util.py:27-51, ijl_order <- util.py:8-24, applyRSD <- util.py:54-75
+  FlatLambdaCDM       <- astropy.cosmology.FlatLambdaCDM(H0, Om0) (third party, un-pinned in setup.py:64, absent here):
+                         flat matter+Lambda, Tcmb0=0; comoving_distance by adaptive quadrature as astropy does
 
 Native pieces (assign_quad / fcomb_periodic / pk_pbox_rsd) come from
 oracle/estimator_oracle.c, a line-by-line C restatement of pyspectrum/estimator.f.
@@ -424,4 +430,148 @@ def Bk_periodic(xyz, w=None, Lbox=2600, Ngrid=360, step=3, Ncut=3, Nmax=40, work
     bispec['b123'] = bispec['b123'] * (2 * np.pi) ** 6 / kf ** 6 - b_shotnoise
     bispec['b123_sn'] = b_shotnoise
     bispec['q123'] = bispec['b123'] / (bispec['p0k1'] * bispec['p0k2'] + bispec['p0k1'] * bispec['p0k3'] + bispec['p0k2'] * bispec['p0k3'])
+    return bispec
+
+
+# ----------------------------------------------------------------------------------------
+# survey geometry and the util.py helpers either side of the path
+# ----------------------------------------------------------------------------------------
+class FlatLambdaCDM(object):
+    """astropy.cosmology.FlatLambdaCDM(H0, Om0) restated for the two members the reference uses (py:88, 769; ut:45, 68-71):
+    E(z) = sqrt(Om0 (1+z)^3 + 1 - Om0), comoving_distance = c/H0 * quad(1/E, 0, z) in Mpc."""
+
+    def __init__(self, H0=67.6, Om0=0.31):
+        self.H0, self.Om0, self.h = float(H0), float(Om0), float(H0) / 100.
+
+    def efunc(self, z):
+        return np.sqrt(self.Om0 * (1. + np.asarray(z, dtype=float)) ** 3 + (1. - self.Om0))
+
+    def comoving_distance(self, z):
+        from scipy.integrate import quad
+        zz = np.atleast_1d(np.asarray(z, dtype=float))
+        out = np.array([quad(lambda x: 1. / np.sqrt(self.Om0 * (1. + x) ** 3 + 1. - self.Om0), 0., zi,
+                             epsabs=0., epsrel=1e-13)[0] for zi in zz])
+        return 299792.458 / self.H0 * out
+
+
+def radecz_to_cartesian(radecz, cosmo=None):
+    """ut:27-51 (on a copy: the reference scales the caller's RA/Dec rows in place)."""
+    ra, dec, z = np.array(radecz, dtype=float)
+    ra *= np.pi / 180.
+    dec *= np.pi / 180.
+    rad = cosmo.comoving_distance(z) * cosmo.h
+    return np.array([rad * np.cos(dec) * np.cos(ra), rad * np.cos(dec) * np.sin(ra), rad * np.sin(dec)])
+
+
+def ijl_order(i_k, j_k, l_k, typ='GM'):
+    """ut:8-24."""
+    i_bq = np.arange(len(i_k))
+    i_bq_new = []
+    for l in np.sort(np.unique(l_k)):
+        for j in np.sort(np.unique(j_k[l_k == l])):
+            for i in np.sort(np.unique(i_k[(l_k == l) & (j_k == j)])):
+                i_bq_new.append(i_bq[(i_k == i) & (j_k == j) & (l_k == l)])
+    return np.array(i_bq_new)
+
+
+def applyRSD(xyz, vxyz, redshift, h=0.7, omega0_m=0.3, LOS=None, Lbox=None):
+    """ut:54-75 (with the FlatLambdaCDM the reference forgets to import)."""
+    i_los = {'x': 0, 'y': 1, 'z': 2}[LOS]
+    cosmo = FlatLambdaCDM(H0=100. * h, Om0=omega0_m)
+    rsd_factor = (1 + redshift) / (100 * cosmo.efunc(redshift))
+    xyz_rsd = xyz.copy()
+    xyz_rsd[i_los] += rsd_factor * vxyz[i_los] + Lbox
+    xyz_rsd[i_los] = (xyz_rsd[i_los] % Lbox)
+    return xyz_rsd
+
+
+def FFT_survey_mono(radecz, nb, w=None, P0_fkp=1e6, Lbox=2600., Ngrid=360, cosmo=None, workers=1):
+    """py:731-826.  The caller's w is not modified (py:799 does `w *= w_fkp`)."""
+    kf_ks = np.float32(float(Ngrid) / Lbox)
+    N = radecz.shape[1]
+    if cosmo is None:
+        cosmo = FlatLambdaCDM(H0=67.6, Om0=0.31)
+    w = np.ones(N) if w is None else np.array(w, dtype=float)
+    xyz = radecz_to_cartesian(radecz, cosmo=cosmo)
+    xyz_max, xyz_min = np.max(xyz, axis=1), np.min(xyz, axis=1)
+    assert np.sum(xyz_max >= 0.5 * Lbox) + np.sum(np.abs(xyz_min) >= 0.5 * Lbox) == 0, 'box not big enough!'
+    xyzs = np.zeros([3, N], dtype=np.float32, order='F')
+    for a in range(3):
+        xyzs[a, :] = xyz[a, :]
+    Ntot = np.sum(w)
+    w *= 1. / (1. + nb * P0_fkp)
+    I12, I13 = np.sum(w ** 2), np.sum(w ** 3)
+    I22, I23, I33 = np.sum(nb * w ** 2), np.sum(nb * w ** 3), np.sum(nb ** 2 * w ** 3)
+    _delta = np.zeros([2 * Ngrid, Ngrid, Ngrid], dtype=np.float32, order='F')
+    assign_quad(xyzs, w, _delta, kf_ks, 0.5 * Ngrid, 0, 0, 0, 0)
+    ifft_delta = _FFT(_delta, Ngrid, workers=workers)
+    fcomb_survey(ifft_delta, Ngrid)
+    return ifft_delta[:Ngrid // 2 + 1, :, :], Ntot, I12, I13, I22, I23, I33
+
+
+def _B0_survey(delta, alpha, I12, I13, I22, I23, I33, Nmax=40, Ncut=3, step=3, workers=1, counts=None):
+    """py:135-282.  `delta` = full complex field (data - alpha * randoms)."""
+    Ngrid = delta.shape[0]
+    irk = shell_index(Ngrid, step)
+    Nk = np.array([np.sum(irk == i) for i in np.arange(Nmax + 1)])
+    s = Ncut // step
+    tempdelta = delta.astype(np.complex64)                   # py:204 assigns into a complex64 tempK
+    fields = shell_fields(tempdelta, irk, range(s, Nmax + 1), workers=workers)
+    p0k = np.zeros(Nmax)
+    for j in range(s, Nmax + 1):
+        f64 = fields[j].astype(np.float64)
+        p0k[j - 1] = np.einsum('i,i', f64, f64) / Ngrid ** 3 / Nk[j]
+    p0k /= I22
+    p0k -= (1. + alpha) * I12 / I22
+    if counts is None:
+        counts = _counts_Bk123(Ngrid=Ngrid, Nmax=Nmax, Ncut=Ncut, step=step, workers=workers)
+    i_arr, j_arr, l_arr = [], [], []
+    p0k_i, p0k_j, p0k_l = [], [], []
+    b123_arr, q123_arr, cnts_arr = [], [], []
+    for (i, j, l) in triangle_list(Nmax, Ncut, step):
+        fac = _fac(i, j, l)
+        c = counts[i - 1, j - 1, l - 1]
+        if c > 0:
+            i_arr.append(i); j_arr.append(j); l_arr.append(l)
+            b = _triple(fields[i], fields[j], fields[l]) / c
+            b -= (p0k[i - 1] + p0k[j - 1] + p0k[l - 1]) * I23 + (1. - alpha ** 2) * I13
+            b /= I33
+            p0k_i.append(p0k[i - 1]); p0k_j.append(p0k[j - 1]); p0k_l.append(p0k[l - 1])
+            b123_arr.append(b)
+            q123_arr.append(b / (p0k[i - 1] * p0k[j - 1] + p0k[j - 1] * p0k[l - 1] + p0k[l - 1] * p0k[i - 1]))
+            cnts_arr.append(c / (fac * float(Ngrid ** 3)))
+        else:
+            p0k_i.append(0.); p0k_j.append(0.); p0k_l.append(0.)
+            b123_arr.append(0.); q123_arr.append(0.); cnts_arr.append(0.)
+    output = {}
+    output['i_k1'] = np.array(i_arr) * step
+    output['i_k2'] = np.array(j_arr) * step
+    output['i_k3'] = np.array(l_arr) * step
+    output['p0k1'] = np.array(p0k_i)
+    output['p0k2'] = np.array(p0k_j)
+    output['p0k3'] = np.array(p0k_l)
+    output['b123'] = np.array(b123_arr)
+    output['q123'] = np.array(q123_arr)
+    output['counts'] = np.array(cnts_arr)
+    return output
+
+
+def B0_survey(radecz, nbar, w=None, radecz_r=None, nbar_r=None, w_r=None, P0_fkp=1e6, Lbox=2600, Ngrid=360, step=3,
+              Ncut=3, Nmax=40, cosmo=None, workers=1, counts=None):
+    """py:13-132 (without the Ngrid==360 assert)."""
+    if cosmo is None:
+        cosmo = FlatLambdaCDM(H0=67.6, Om0=0.31)
+    kf = 2 * np.pi / Lbox
+    N = radecz.shape[1]
+    delta_d, Ngtot, I12d, I13d, I22d, I23d, I33d = FFT_survey_mono(radecz, nbar, w=w, P0_fkp=P0_fkp, Lbox=Lbox, Ngrid=Ngrid,
+                                                                    cosmo=cosmo, workers=workers)
+    deltak_d = reflect_delta(delta_d, Ngrid)
+    delta_r, Nrtot, I12r, I13r, I22r, I23r, I33r = FFT_survey_mono(radecz_r, nbar_r, w=w_r, P0_fkp=P0_fkp, Lbox=Lbox,
+                                                                    Ngrid=Ngrid, cosmo=cosmo, workers=workers)
+    deltak_r = reflect_delta(delta_r, Ngrid)
+    alpha = Ngtot / Nrtot
+    deltak = deltak_d - alpha * deltak_r                     # complex128 under numpy >= 2 (alpha is a float64 scalar)
+    bispec = _B0_survey(deltak, alpha, alpha * I12r, alpha * I13r, alpha * I22r, alpha * I23r, alpha * I33r, Nmax=Nmax,
+                        Ncut=Ncut, step=step, workers=workers, counts=counts)
+    bispec['meta'] = {'Lbox': Lbox, 'Ngrid': Ngrid, 'step': step, 'Ncut': Ncut, 'Nmax': Nmax, 'N': N, 'nbar': nbar, 'kf': kf}
     return bispec

@@ -6,6 +6,8 @@ Same public functions, arguments and output dictionaries as the reference:
     Pk_periodic_rsd  (pyspectrum.py:460-538, code='fortran' branch 628-641)
     Bk_periodic      (pyspectrum.py:285-356 + _Bk_periodic 359-457)
     FFT_periodic     (pyspectrum.py:909-959), reflect_delta (1134-1157), _counts_Bk123 (962-1030)
+    B0_survey        (pyspectrum.py:13-132 + _B0_survey 135-282 + FFT_survey_mono 731-826): the survey-geometry monopole
+                     bispectrum, same kernels with the assignment offset 0.5*Ngrid and fcomb_survey
 
 Behind them the f2py module `estimator` and the pyfftw calls are replaced by hand-written sm_100a
 kernels reached through the C ABI of include/psb200.h (ctypes; torch tensors are only device buffers
@@ -28,6 +30,7 @@ from . import _lib
 from ._lib import check
 
 __all__ = ['Pk_periodic', 'Pk_periodic_rsd', 'Bk_periodic', 'FFT_periodic', 'reflect_delta',
+           'B0_survey', 'FFT_survey_mono', '_B0_survey', '_Bk_periodic',
            '_counts_Bk123', 'dat_dir', 'PeriodicPipeline']
 
 _DAT_DIR = os.environ.get('PYSPECTRUM_B200_DAT', os.path.join(os.path.dirname(os.path.realpath(__file__)), 'dat'))
@@ -262,6 +265,29 @@ class PeriodicPipeline(object):
         mesh, sumw = self.assign(pos, aos, wt, Lbox)
         half = self.mesh_to_delta(mesh, sumw)
         return half, sumw
+
+    def fft_survey(self, xyz, w, Lbox):
+        """Survey-geometry delta_0(k) (pyspectrum.py:817-823): positions in (-L/2, L/2) shifted by half a box through the
+        assignment offset (0.5*Ngrid), no clipping, and fcomb_survey (no division by sum w; estimator.f:686)."""
+        pos, aos, wt = self.to_device(xyz, w)
+        mesh, sumw = self.assign(pos, aos, wt, Lbox, offset=0.5 * self.N, clip=False)
+        return self.mesh_to_delta(mesh, sumw, periodic=0)
+
+    def half_from_full(self, delta):
+        """Host full field (Ngrid,Ngrid,Ngrid) complex, indexed [kx,ky,kz] -> device half field of its Hermitian part
+        d_h(k) = (d(k) + conj(d(-k)))/2.  The reference's shell stage keeps Re(FFT(masked field)) (pyspectrum.py:202-215,
+        389-399), which is the transform of the Hermitian part, so this is exact for any input and the identity for the
+        output of reflect_delta."""
+        N, h = self.N, self.h
+        delta = np.asarray(delta)
+        if delta.shape != (N, N, N):
+            raise ValueError('delta must be (Ngrid,Ngrid,Ngrid) for this pipeline')
+        d = delta.astype(np.complex64, copy=False)
+        idx = (-np.arange(N)) % N
+        mirror = np.conj(d[idx[:h + 1]][:, idx][:, :, idx])
+        dh = np.complex64(0.5) * (d[:h + 1] + mirror)
+        arr = np.ascontiguousarray(dh.transpose(2, 1, 0))              # [kz][ky][kx]
+        return torch.from_numpy(arr.view(np.float32).reshape(N, N, h + 1, 2)).to(self.dev)
 
     # ------------------------------------------------------------------ K4
     def pk_monopole(self, half, Lbox):
@@ -820,3 +846,153 @@ def _bk_finish(h):
 def Bk_periodic(xyz, w=None, Lbox=2600, Ngrid=360, step=3, Ncut=3, Nmax=40, fft='pyfftw', nthreads=1, silent=True):
     """Bispectrum of a periodic box; see pyspectrum.py:285-356 for the contract."""
     return _bk_finish(_bk_launch(xyz, w, Lbox, Ngrid, step, Ncut, Nmax, fft, silent))
+
+
+# ----------------------------------------------------------------------------------------------
+# survey geometry: monopole bispectrum with the FKP / Scoccimarro (2015) normalisation  (SURVEY 8f rank 1)
+# ----------------------------------------------------------------------------------------------
+def _shell_fac(tri):
+    """Symmetry factor of pyspectrum.py:237-241 / 419-423 for the triples (i,j,l)."""
+    i, j, l = tri[:, 0], tri[:, 1], tri[:, 2]
+    fac = np.ones(len(tri))
+    fac[(j == l) & (i == j)] = 6.
+    fac[(i == j) & (j != l)] = 2.
+    fac[(i == l) & (l != j)] = 2.
+    fac[(j == l) & (l != i)] = 2.
+    return fac
+
+
+def _fft_survey_mono_dev(radecz, nb, w, P0_fkp, Lbox, Ngrid, cosmo, silent):
+    """Device half of FFT_survey_mono: returns (half field on the device, Ntot, I12, I13, I22, I23, I33)."""
+    from . import util as UT
+    radecz = np.asarray(radecz)
+    N = int(radecz.shape[1])
+    if cosmo is None:
+        cosmo = UT.FlatLambdaCDM(H0=67.6, Om0=0.31)                  # py:769-770
+    w = np.ones(N) if w is None else np.asarray(w, dtype=np.float64)
+    nb = np.asarray(nb, dtype=np.float64)
+    xyz = UT.radecz_to_cartesian(radecz, cosmo=cosmo)
+    xyz_max = np.max(xyz, axis=1)
+    xyz_min = np.min(xyz, axis=1)
+    if not silent:
+        print(['%.1f < %s < %.1f\n' % (mi, _axis, ma) for _axis, mi, ma in zip(['x', 'y', 'z'], xyz_min, xyz_max)])
+    assert np.sum(xyz_max >= 0.5 * Lbox) + np.sum(np.abs(xyz_min) >= 0.5 * Lbox) == 0, 'box not big enough!'
+    if not silent:
+        print('%i positions' % N)
+    Ntot = np.sum(w)                                                 # total weight without FKP (py:794)
+    w = w * (1. / (1. + nb * P0_fkp))                                # FKP weights (py:797-799); the caller's w is left alone
+    I12 = np.sum(w ** 2)
+    I13 = np.sum(w ** 3)
+    I22 = np.sum(nb * w ** 2)
+    I23 = np.sum(nb * w ** 3)
+    I33 = np.sum(nb ** 2 * w ** 3)
+    if not silent:
+        print('Ntot=%.2f' % Ntot)
+        for name, val in zip(['I12', 'I13', 'I22', 'I23', 'I33'], [I12, I13, I22, I23, I33]):
+            print('%s=%.2e' % (name, val))
+    assert np.all([(I12 >= 0), (I13 >= 0), (I22 >= 0), (I23 >= 0), (I33 >= 0)])
+    half = PeriodicPipeline.get(Ngrid).fft_survey(xyz, w, Lbox)
+    if not silent:
+        print('delta_0(k) complete')
+    return half, Ntot, I12, I13, I22, I23, I33
+
+
+def FFT_survey_mono(radecz, nb, w=None, P0_fkp=1e6, Lbox=2600., Ngrid=360, cosmo=None, fft='pyfftw', silent=True):
+    """pyspectrum.py:731-826: (RA, Dec, z) catalogue -> FKP-weighted delta_0(k) on the half grid, complex64
+    (Ngrid//2+1, Ngrid, Ngrid) indexed [kx,ky,kz], plus Ntot = sum w and the normalisation sums I12, I13, I22, I23, I33.
+    Unlike the reference, neither `w` (py:799 multiplies it by the FKP weight in place) nor the RA/Dec rows of `radecz`
+    (util.py:41-42 converts them to radians in place) are modified."""
+    half, Ntot, I12, I13, I22, I23, I33 = _fft_survey_mono_dev(radecz, nb, w, P0_fkp, Lbox, Ngrid, cosmo, silent)
+    a = half.cpu().numpy().view(np.complex64)[..., 0]                # (kz,ky,kx) C-order
+    return a.transpose(2, 1, 0), Ntot, I12, I13, I22, I23, I33
+
+
+def _b0_survey_dev(half, Ngrid, alpha, I12, I13, I22, I23, I33, Nmax, Ncut, step, fft, silent):
+    """Shell fields + triangle sums of a device half field and the survey normalisation of pyspectrum.py:216-281."""
+    s0 = Ncut // step
+    if s0 < 1:
+        raise ValueError('Ncut//step must be >= 1 (the reference wraps p0k[-1] there, SURVEY Q9)')
+    pipe = PeriodicPipeline.get(Ngrid)
+    Nk = pipe.shell_mode_counts(step, Nmax)
+    counts = pipe.counts(Nmax, Ncut, step, fft=fft, silent=silent)
+    sums, sumsq = pipe.bispectrum_sums(half, step, Ncut, Nmax)
+    tri = triangle_list(Nmax, Ncut, step)
+    p0k = np.zeros(Nmax)
+    for j in range(s0, Nmax + 1):
+        p0k[j - 1] = sumsq[j - s0] / Ngrid ** 3 / Nk[j]
+    p0k /= I22                                                       # py:218-220
+    p0k -= (1. + alpha) * I12 / I22
+    i, j, l = tri[:, 0], tri[:, 1], tri[:, 2]
+    c = counts[i - 1, j - 1, l - 1]
+    pos = c > 0
+    cs = np.where(pos, c, 1.)
+    pi_, pj_, pl_ = p0k[i - 1], p0k[j - 1], p0k[l - 1]
+    b = sums / cs
+    b = b - ((pi_ + pj_ + pl_) * I23 + (1. - alpha ** 2) * I13)      # py:250-253
+    b = b / I33
+    with np.errstate(divide='ignore', invalid='ignore'):
+        q = b / (pi_ * pj_ + pj_ * pl_ + pl_ * pi_)
+    out = {}
+    out['i_k1'] = i[pos].astype(np.int64) * step                     # index lists skip empty triangles, value lists do not
+    out['i_k2'] = j[pos].astype(np.int64) * step
+    out['i_k3'] = l[pos].astype(np.int64) * step
+    out['p0k1'] = np.where(pos, pi_, 0.)
+    out['p0k2'] = np.where(pos, pj_, 0.)
+    out['p0k3'] = np.where(pos, pl_, 0.)
+    out['b123'] = np.where(pos, b, 0.)
+    out['q123'] = np.where(pos, q, 0.)
+    out['counts'] = np.where(pos, c / (_shell_fac(tri) * float(Ngrid ** 3)), 0.)
+    return out
+
+
+def _B0_survey(delta, alpha, I12, I13, I22, I23, I33, Nmax=40, Ncut=3, step=3, fft='pyfftw', nthreads=1, silent=True):
+    """pyspectrum.py:135-282: bispectrum monopole of a full (Ngrid,Ngrid,Ngrid) delta(k) = data - alpha * randoms with
+    the survey shot-noise terms and normalisation.  `delta` is a host array indexed [kx,ky,kz] as reflect_delta returns."""
+    Ngrid = np.asarray(delta).shape[0]
+    half = PeriodicPipeline.get(Ngrid).half_from_full(delta)
+    return _b0_survey_dev(half, Ngrid, alpha, I12, I13, I22, I23, I33, Nmax, Ncut, step, fft, silent)
+
+
+def _Bk_periodic(delta, Nmax=40, Ncut=3, step=3, fft='pyfftw', nthreads=1, silent=True):
+    """pyspectrum.py:359-457: raw bispectrum (no units, no shot noise) of a full (Ngrid,Ngrid,Ngrid) delta(k) host array."""
+    Ngrid = np.asarray(delta).shape[0]
+    s0 = Ncut // step
+    if s0 < 1:
+        raise ValueError('Ncut//step must be >= 1 (the reference wraps p0k[-1] there, SURVEY Q9)')
+    pipe = PeriodicPipeline.get(Ngrid)
+    half = pipe.half_from_full(delta)
+    sums, sumsq = pipe.bispectrum_sums(half, step, Ncut, Nmax)
+    return _bk_epilogue(Ngrid, triangle_list(Nmax, Ncut, step), sums, sumsq, pipe.shell_mode_counts(step, Nmax),
+                        pipe.counts(Nmax, Ncut, step, fft=fft, silent=silent), step, Ncut, Nmax)
+
+
+def B0_survey(radecz, nbar, w=None, radecz_r=None, nbar_r=None, w_r=None, P0_fkp=1e6, Lbox=2600, Ngrid=360, step=3, Ncut=3,
+              Nmax=40, cosmo=None, fft='pyfftw', nthreads=1, silent=True):
+    """Bispectrum monopole for survey geometry (Scoccimarro 2015 estimator); see pyspectrum.py:13-132 for the contract.
+    Data and random catalogues are assigned and transformed on the GPU, delta = delta_d - alpha * delta_r is formed on the
+    device half fields (in float64, rounded once to complex64 -- what numpy >= 2 gives the reference at py:123 and 204), and
+    the shell / triangle stage is the one of Bk_periodic.  The `Ngrid == 360` assert (py:90) is relaxed as for Bk_periodic."""
+    if radecz_r is None:
+        raise ValueError('specify a random catalog')                 # the reference fails on radecz_r.shape (py:105)
+    if nbar_r is None:
+        raise ValueError('specify nbar for random catalog')
+    kf = 2 * np.pi / Lbox
+    N = int(np.asarray(radecz).shape[1])
+    if not silent:
+        print('--- %i positions in %i box ---' % (N, Lbox))
+        print('--- calculating the FFT for data ---')
+    half_d, Ngtot, I12d, I13d, I22d, I23d, I33d = _fft_survey_mono_dev(radecz, nbar, w, P0_fkp, Lbox, Ngrid, cosmo, silent)
+    if not silent:
+        print('--- calculating the FFT for random ---')
+    half_r, Nrtot, I12r, I13r, I22r, I23r, I33r = _fft_survey_mono_dev(radecz_r, nbar_r, w_r, P0_fkp, Lbox, Ngrid, cosmo, silent)
+    alpha = Ngtot / Nrtot
+    if not silent:
+        print('alpha=%e' % alpha)
+    half = (half_d.double() - float(alpha) * half_r.double()).float()
+    del half_d, half_r
+    if not silent:
+        print('--- calculating the bispectrum ---')
+    bispec = _b0_survey_dev(half, Ngrid, alpha, alpha * I12r, alpha * I13r, alpha * I22r, alpha * I23r, alpha * I33r,
+                            Nmax, Ncut, step, fft, True)
+    bispec['meta'] = {'Lbox': Lbox, 'Ngrid': Ngrid, 'step': step, 'Ncut': Ncut, 'Nmax': Nmax, 'N': N, 'nbar': nbar, 'kf': kf}
+    return bispec

@@ -1,0 +1,123 @@
+"""pyspectrum_b200.util -- host utilities either side of the estimator hot path (pySpectrum's pyspectrum/util.py).
+
+    ijl_order            (util.py:8-24)    triangle re-ordering to the 'GM' convention
+    radecz_to_cartesian  (util.py:27-51)   (RA, Dec, z) -> comoving Cartesian Mpc/h
+    applyRSD             (util.py:54-75)   redshift-space positions in a periodic box
+    read_fortFFT         (util.py:78-107)  Fortran-unformatted half field -> full Hermitian field
+
+Pure numpy host code (a few passes over the catalogue; nothing here is on the GPU path).  The reference takes
+its cosmology from astropy (`FlatLambdaCDM`, un-pinned, not in this image); `FlatLambdaCDM` below restates the
+two members the reference touches -- `comoving_distance` and `efunc` for a flat matter + Lambda universe, which is
+what `astropy.cosmology.FlatLambdaCDM(H0, Om0)` is with its default Tcmb0=0 (no radiation, no neutrinos) -- and any
+object with the same members (an astropy cosmology) is accepted in its place.
+
+Deliberate differences from the reference:
+  * `radecz_to_cartesian` does NOT convert the caller's RA/Dec rows to radians in place (util.py:41-42 does, so a
+    second call on the same array silently gives different positions);
+  * `applyRSD` works: the reference uses `FlatLambdaCDM` without importing it (NameError on every call);
+  * `read_fortFFT` uses integer division for the record shape (util.py:84 passes a float to reshape).
+"""
+import numpy as np
+
+__all__ = ['ijl_order', 'radecz_to_cartesian', 'applyRSD', 'read_fortFFT', 'FlatLambdaCDM']
+
+_C_KMS = 299792.458                                   # speed of light [km/s]
+_GL_X, _GL_W = np.polynomial.legendre.leggauss(24)    # per-panel Gauss-Legendre rule
+
+
+class FlatLambdaCDM(object):
+    """Flat LambdaCDM background: E(z)^2 = Om0 (1+z)^3 + (1 - Om0).  Members follow astropy's names."""
+
+    def __init__(self, H0=67.6, Om0=0.31):
+        self.H0 = float(H0)
+        self.Om0 = float(Om0)
+        self.Ode0 = 1. - self.Om0
+        self.h = self.H0 / 100.
+
+    def efunc(self, z):
+        z = np.asarray(z, dtype=np.float64)
+        return np.sqrt(self.Om0 * (1. + z) ** 3 + self.Ode0)
+
+    def comoving_distance(self, z):
+        """Line-of-sight comoving distance in Mpc: (c/H0) int_0^z dz'/E(z').  Composite 24-point Gauss-Legendre with
+        panels of at most 0.5 in z (the integrand is analytic; error < 1e-13 relative)."""
+        z = np.atleast_1d(np.asarray(z, dtype=np.float64))
+        out = np.zeros_like(z)
+        if z.size == 0:
+            return out
+        npanel = max(int(np.ceil(np.max(np.abs(z)) / 0.5)), 1)
+        for p in range(npanel):
+            a = z * (p / float(npanel))
+            b = z * ((p + 1) / float(npanel))
+            half = 0.5 * (b - a)
+            mid = 0.5 * (b + a)
+            zz = mid[:, None] + half[:, None] * _GL_X[None, :]
+            out += half * np.sum(_GL_W[None, :] / self.efunc(zz), axis=1)
+        return (_C_KMS / self.H0) * out
+
+
+def ijl_order(i_k, j_k, l_k, typ='GM'):
+    """util.py:8-24: indices that re-order triangles (i>=j>=l) with l slowest, then j, then i (Gil-Marin's order).
+    Returns an array of shape (Ntri, m) like the reference: one row per distinct (i,j,l), holding the indices of the
+    input entries with that triple (m=1 when the triples are unique)."""
+    i_k, j_k, l_k = np.asarray(i_k), np.asarray(j_k), np.asarray(l_k)
+    if typ != 'GM':
+        raise NotImplementedError
+    n = len(i_k)
+    # lexicographic sort on (l, j, i); stable, so duplicates keep their input order like the reference's masks
+    order = np.lexsort((i_k, j_k, l_k))
+    keys = np.stack([l_k[order], j_k[order], i_k[order]], axis=1)
+    if n == 0:
+        return np.array([])
+    new = np.ones(n, dtype=bool)
+    new[1:] = np.any(keys[1:] != keys[:-1], axis=1)
+    starts = np.flatnonzero(new)
+    groups = np.split(order, starts[1:])
+    return np.array(groups)
+
+
+def radecz_to_cartesian(radecz, cosmo=None):
+    """util.py:27-51: [3,N] (RA deg, Dec deg, z) -> [3,N] comoving Cartesian coordinates in Mpc/h."""
+    radecz = np.asarray(radecz)
+    assert radecz.shape[0] == 3, "radecz has to be have shape [3,N]"
+    if cosmo is None:
+        cosmo = FlatLambdaCDM(H0=67.6, Om0=0.31)      # the default of pyspectrum.py:88
+    ra = radecz[0] * (np.pi / 180.)
+    dec = radecz[1] * (np.pi / 180.)
+    rad = cosmo.comoving_distance(radecz[2])
+    rad = np.asarray(getattr(rad, 'value', rad), dtype=np.float64) * cosmo.h       # astropy returns a Quantity [Mpc]
+    return np.array([rad * np.cos(dec) * np.cos(ra),
+                     rad * np.cos(dec) * np.sin(ra),
+                     rad * np.sin(dec)])
+
+
+def applyRSD(xyz, vxyz, redshift, h=0.7, omega0_m=0.3, LOS=None, Lbox=None):
+    """util.py:54-75: x_s = (x + v (1+z)/(100 E(z)) + L) mod L along the line of sight, velocities in km/s."""
+    xyz, vxyz = np.asarray(xyz), np.asarray(vxyz)
+    assert xyz.shape[0] == 3
+    assert vxyz.shape[0] == 3
+    if LOS is None:
+        raise ValueError("specify line of sight")
+    if Lbox is None:
+        raise ValueError("specify box size")
+    i_los = {'x': 0, 'y': 1, 'z': 2}[LOS]
+    cosmo = FlatLambdaCDM(H0=100. * h, Om0=omega0_m)
+    rsd_factor = (1 + redshift) / (100 * cosmo.efunc(redshift))
+    xyz_rsd = xyz.copy()
+    xyz_rsd[i_los] += rsd_factor * vxyz[i_los] + Lbox
+    xyz_rsd[i_los] = (xyz_rsd[i_los] % Lbox)
+    return xyz_rsd
+
+
+def read_fortFFT(file=None):
+    """util.py:78-107: read `Ngrid` + the (Ngrid/2+1, Ngrid, Ngrid) complex64 half field from a Fortran-unformatted file
+    and return the full Hermitian field (same completion as pyspectrum.reflect_delta)."""
+    from .pyspectrum import reflect_delta
+    raw = np.fromfile(file, dtype=np.uint8)
+    n1 = int(np.frombuffer(raw[:4].tobytes(), '<i4')[0])
+    Ngrid = int(np.frombuffer(raw[4:4 + n1].tobytes(), '<i4')[0])
+    o = 4 + n1 + 4
+    n2 = int(np.frombuffer(raw[o:o + 4].tobytes(), '<i4')[0])
+    delt = np.frombuffer(raw[o + 4:o + 4 + n2].tobytes(), '<c8')
+    delt = np.reshape(delt, (Ngrid // 2 + 1, Ngrid, Ngrid), order='F')
+    return reflect_delta(delt, Ngrid=Ngrid)

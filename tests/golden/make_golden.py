@@ -6,6 +6,7 @@ Run in the build container only (needs /root/reference):
     python tests/golden/make_golden.py small      # seconds
     python tests/golden/make_golden.py counts     # converts the shipped counts.* files to integers
     python tests/golden/make_golden.py box360     # ~20 min, ~18 GB: Pk+Bk on dat/test_box.hdf5
+    python tests/golden/make_golden.py survey     # seconds: FFT_survey_mono / _B0_survey (B0_survey body) + util.py
 
 How: the reference package is copied to a scratch dir (its counts cold path writes into
 its own dat/ directory, pyspectrum.py:1026-1028), one token is fixed (pyspectrum.py:713,
@@ -14,7 +15,8 @@ numpy >= 1.13) and it is imported with three modules shimmed in sys.modules:
 
     pyfftw            -> scipy.fft (pocketfft) keeping complex64 / complex128
     estimator         -> oracle/estimator_oracle.c through ctypes (no gfortran here)
-    astropy.cosmology -> stub (only imported, never used on the periodic path)
+    astropy.cosmology -> FlatLambdaCDM restated in oracle/pyspec_oracle.py (flat matter+Lambda, scipy quad); astropy is
+                         un-pinned third-party code that is not installed here -- used by the survey path only
 
 So the goldens pin the *Python layer* of the reference exactly (binning, shells, triangle
 order, units, shot noise), on top of the C restatement of estimator.f.
@@ -78,13 +80,14 @@ def import_reference():
     est.assign_quad = lambda r, w, dtl, kf_ks, offset, ia, ib, ic, id, np_=None, ngrid=None: \
         O.assign_quad(r, w, dtl, kf_ks, offset, ia, ib, ic, id)
     est.fcomb_periodic = lambda dcl, n, ngrid=None: O.fcomb_periodic(dcl, n)
+    est.fcomb_survey = lambda dcl, ngrid=None: O.fcomb_survey(dcl)
     est.pk_pbox_rsd = lambda dtl, irsd, lbox, nbin, nmu, ngrid=None: O.pk_pbox_rsd(dtl, irsd, int(lbox), nbin, nmu)
     sys.modules['estimator'] = est
 
     # ---- astropy stub ----------------------------------------------------------------------
     astropy = types.ModuleType('astropy')
     cosmo = types.ModuleType('astropy.cosmology')
-    cosmo.FlatLambdaCDM = object
+    cosmo.FlatLambdaCDM = O.FlatLambdaCDM
     astropy.cosmology = cosmo
     sys.modules.update({'astropy': astropy, 'astropy.cosmology': cosmo})
 
@@ -202,10 +205,81 @@ def box360(pySpec):
     print('wrote box360.npz; Ntri =', len(bk['b123']))
 
 
+def survey_catalogue(seed, Nd, Nr):
+    """Deterministic toy survey: a cone in (RA, Dec, z) with clustered data (blobs) and uniform-in-volume randoms, a
+    redshift-dependent nbar(z) and (for the data) systematic weights."""
+    rng = np.random.default_rng(seed)
+
+    def cone(n):
+        ra = rng.uniform(110., 250., n)
+        dec = np.degrees(np.arcsin(rng.uniform(np.sin(np.radians(-5.)), np.sin(np.radians(60.)), n)))
+        z = (rng.uniform(0.2 ** 3, 0.55 ** 3, n)) ** (1. / 3.)
+        return np.array([ra, dec, z])
+    rand = cone(Nr)
+    par = cone(max(Nd // 30, 1))
+    kids = par[:, rng.integers(0, par.shape[1], Nd // 2)] + rng.normal(0, 1., (3, Nd // 2)) * np.array([[2.], [2.], [0.01]])
+    kids[2] = np.clip(kids[2], 0.2, 0.55)
+    kids[1] = np.clip(kids[1], -5., 60.)
+    data = np.concatenate([kids, cone(Nd - Nd // 2)], axis=1)
+    nz = lambda z: 3e-4 * np.exp(-((z - 0.35) / 0.2) ** 2)
+    w = rng.uniform(0.8, 1.3, Nd)
+    return data, nz(data[2]), w, rand, nz(rand[2])
+
+
+def survey(pySpec):
+    from pyspectrum import util as UT
+    from oracle import pyspec_oracle as O
+    for tag, N, L, Nd, Nr, seed, weighted, cfgs in [('A', 32, 3200., 3000, 12000, 21, False, [(3, 3, 4), (2, 3, 6)]),
+                                                     ('B', 36, 3000., 2500, 9000, 22, True, [(2, 2, 7), (1, 1, 8)])]:
+        radecz, nb, w, radecz_r, nb_r = survey_catalogue(seed, Nd, Nr)
+        d = {'radecz': radecz, 'nbar': nb, 'radecz_r': radecz_r, 'nbar_r': nb_r, 'Lbox': L, 'Ngrid': N, 'P0_fkp': 1e4}
+        if weighted:
+            d['w'] = w
+        P0 = 1e4
+        # the reference mutates radecz (degrees -> radians) and w (FKP) in place: always hand it copies
+        xyz = UT.radecz_to_cartesian(radecz.copy(), cosmo=O.FlatLambdaCDM(H0=67.6, Om0=0.31))
+        d['xyz'] = np.asarray(xyz)
+        wd = w.copy() if weighted else None
+        delta_d, Ngtot, I12d, I13d, I22d, I23d, I33d = pySpec.FFT_survey_mono(radecz.copy(), nb, w=wd, P0_fkp=P0, Lbox=L, Ngrid=N)
+        delta_r, Nrtot, I12r, I13r, I22r, I23r, I33r = pySpec.FFT_survey_mono(radecz_r.copy(), nb_r, w=None, P0_fkp=P0, Lbox=L, Ngrid=N)
+        d['delta_d'] = np.ascontiguousarray(delta_d)
+        d['delta_r'] = np.ascontiguousarray(delta_r)
+        d['sums_d'] = np.array([Ngtot, I12d, I13d, I22d, I23d, I33d])
+        d['sums_r'] = np.array([Nrtot, I12r, I13r, I22r, I23r, I33r])
+        # body of B0_survey (py:101-128; its Ngrid==360 assert, py:90, keeps the function itself from running here)
+        deltak_d = pySpec.reflect_delta(delta_d, Ngrid=N)
+        deltak_r = pySpec.reflect_delta(delta_r, Ngrid=N)
+        alpha = Ngtot / Nrtot
+        deltak = deltak_d - alpha * deltak_r
+        for (step, Ncut, Nmax) in cfgs:
+            bk = pySpec._B0_survey(deltak, alpha, alpha * I12r, alpha * I13r, alpha * I22r, alpha * I23r, alpha * I33r,
+                                   Nmax=Nmax, Ncut=Ncut, step=step)
+            pre = 'b0_s%d_c%d_m%d_' % (step, Ncut, Nmax)
+            for key in ['i_k1', 'i_k2', 'i_k3', 'p0k1', 'p0k2', 'p0k3', 'b123', 'q123', 'counts']:
+                d[pre + key] = np.asarray(bk[key])
+        np.savez_compressed(os.path.join(HERE, 'survey_%s.npz' % tag), **d)
+        print('wrote survey_%s.npz' % tag, len(d), 'arrays; alpha', alpha)
+    # ---- util.py -------------------------------------------------------------------------------
+    u = {}
+    rng = np.random.default_rng(31)
+    tri = np.array([(i, j, l) for i in range(1, 9) for j in range(1, i + 1) for l in range(max(i - j, 1), j + 1)])
+    perm = rng.permutation(len(tri))
+    u['ijl_in'] = tri[perm]
+    u['ijl_out'] = UT.ijl_order(tri[perm, 0], tri[perm, 1], tri[perm, 2], typ='GM')
+    UT.FlatLambdaCDM = O.FlatLambdaCDM              # util.py uses the name without importing it (NameError otherwise)
+    xyz = rng.uniform(0, 500., (3, 200))
+    vxyz = rng.normal(0, 600., (3, 200))
+    u['rsd_xyz'], u['rsd_vxyz'] = xyz, vxyz
+    for los in 'xyz':
+        u['rsd_out_' + los] = UT.applyRSD(xyz, vxyz, 0.5, h=0.7, omega0_m=0.3, LOS=los, Lbox=500.)
+    np.savez_compressed(os.path.join(HERE, 'util.npz'), **u)
+    print('wrote util.npz')
+
+
 if __name__ == '__main__':
     what = sys.argv[1] if len(sys.argv) > 1 else 'small'
     if what == 'counts':
         counts()
     else:
         ps = import_reference()
-        {'small': small, 'box360': box360}[what](ps)
+        {'small': small, 'box360': box360, 'survey': survey}[what](ps)

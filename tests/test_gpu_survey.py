@@ -1,0 +1,130 @@
+"""GPU parity tests of the survey-geometry monopole bispectrum (pyspectrum.py:13-282, 731-826) through
+the CUDA path: FFT_survey_mono / _B0_survey / B0_survey / _Bk_periodic of pyspectrum_b200.pyspectrum against goldens made
+by the UNMODIFIED reference (tests/golden/survey_{A,B}.npz) and against the CPU oracle on seeded catalogues.
+
+Tolerances.  Index lists and normalised counts: exact / 1e-13.  delta_0(k): 3e-6 of max|delta| (float32 scatter order).
+p0k: rtol 1e-5 on the pre-shot-noise value p + (1+alpha) I12/I22.  b123: |diff| <= 1e-5 * scale + 1e-6 * max(scale) with
+scale = |b123 + shot-noise term| -- delta = delta_d - alpha * delta_r cancels the survey window, which amplifies the
+float32 rounding of the two meshes: re-running the reference algorithm itself with the particles in a different order moves
+b123 by up to 0.3 of this bound (measured on these catalogues with the oracle), so nothing tighter is meaningful.
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+SURVEY_CFGS = {'A': [(3, 3, 4), (2, 3, 6)], 'B': [(2, 2, 7), (1, 1, 8)]}
+
+
+@pytest.fixture(scope='module')
+def mods():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from pyspectrum_b200 import pyspectrum as pySpec
+    from oracle import pyspec_oracle as O
+    return pySpec, O
+
+
+def _g(golden_dir, name):
+    return dict(np.load(os.path.join(golden_dir, name)))
+
+
+def _check_b0(bk, ref, alpha, I12, I13, I22, I23, I33):
+    for key in ['i_k1', 'i_k2', 'i_k3']:
+        assert np.array_equal(bk[key], ref[key]), key
+    np.testing.assert_allclose(bk['counts'], ref['counts'], rtol=1e-13)
+    sn_p = (1. + alpha) * I12 / I22
+    for key in ['p0k1', 'p0k2', 'p0k3']:
+        np.testing.assert_allclose(bk[key] + sn_p, ref[key] + sn_p, rtol=RTOL)
+    sn_b = ((ref['p0k1'] + ref['p0k2'] + ref['p0k3']) * I23 + (1. - alpha ** 2) * I13) / I33
+    scale = np.abs(ref['b123'] + sn_b)
+    assert np.all(np.abs(bk['b123'] - ref['b123']) <= RTOL * scale + 1e-6 * scale.max())
+
+
+@pytest.mark.parametrize('tag', ['A', 'B'])
+def test_survey_matches_reference_goldens(mods, golden_dir, tag):
+    pySpec, O = mods
+    g = _g(golden_dir, 'survey_%s.npz' % tag)
+    N, L, P0 = int(g['Ngrid']), float(g['Lbox']), float(g['P0_fkp'])
+    w = g.get('w')
+    radecz0 = g['radecz'].copy()
+    w0 = None if w is None else w.copy()
+    # ---- FFT_survey_mono: delta_0(k) and the normalisation sums, data and randoms
+    dd = pySpec.FFT_survey_mono(g['radecz'], g['nbar'], w=w, P0_fkp=P0, Lbox=L, Ngrid=N)
+    dr = pySpec.FFT_survey_mono(g['radecz_r'], g['nbar_r'], P0_fkp=P0, Lbox=L, Ngrid=N)
+    for out, dk, sk in [(dd, 'delta_d', 'sums_d'), (dr, 'delta_r', 'sums_r')]:
+        assert out[0].shape == g[dk].shape and out[0].dtype == np.complex64
+        assert np.abs(out[0] - g[dk]).max() <= 3e-6 * np.abs(g[dk]).max()
+        np.testing.assert_allclose(np.array(out[1:]), g[sk], rtol=1e-13)
+    assert np.array_equal(g['radecz'], radecz0) and (w is None or np.array_equal(w, w0))     # inputs are not modified
+    alpha = g['sums_d'][0] / g['sums_r'][0]
+    I12, I13, I22, I23, I33 = alpha * g['sums_r'][1:]
+    for (step, Ncut, Nmax) in SURVEY_CFGS[tag]:
+        pre = 'b0_s%d_c%d_m%d_' % (step, Ncut, Nmax)
+        ref = {k: g[pre + k] for k in ['i_k1', 'i_k2', 'i_k3', 'p0k1', 'p0k2', 'p0k3', 'b123', 'q123', 'counts']}
+        # ---- the public entry point
+        bk = pySpec.B0_survey(g['radecz'], g['nbar'], w=w, radecz_r=g['radecz_r'], nbar_r=g['nbar_r'], P0_fkp=P0, Lbox=L,
+                              Ngrid=N, step=step, Ncut=Ncut, Nmax=Nmax)
+        _check_b0(bk, ref, alpha, I12, I13, I22, I23, I33)
+        assert bk['meta']['Ngrid'] == N and bk['meta']['N'] == g['radecz'].shape[1] and bk['meta']['kf'] == 2 * np.pi / L
+        # ---- _B0_survey on the reference's own full field (reflect_delta of its half fields)
+        deltak = O.reflect_delta(g['delta_d'], N) - alpha * O.reflect_delta(g['delta_r'], N)
+        bk2 = pySpec._B0_survey(deltak, alpha, I12, I13, I22, I23, I33, Nmax=Nmax, Ncut=Ncut, step=step)
+        _check_b0(bk2, ref, alpha, I12, I13, I22, I23, I33)
+
+
+def test_survey_argument_errors(mods, golden_dir):
+    pySpec, _ = mods
+    g = _g(golden_dir, 'survey_A.npz')
+    N, L = int(g['Ngrid']), float(g['Lbox'])
+    with pytest.raises(ValueError):
+        pySpec.B0_survey(g['radecz'], g['nbar'], radecz_r=g['radecz_r'], Lbox=L, Ngrid=N)          # nbar_r missing (py:82-83)
+    with pytest.raises(ValueError):
+        pySpec.B0_survey(g['radecz'], g['nbar'], Lbox=L, Ngrid=N)                                  # no randoms
+    with pytest.raises(AssertionError):
+        pySpec.FFT_survey_mono(g['radecz'], g['nbar'], Lbox=1000., Ngrid=N)                        # 'box not big enough!'
+
+
+@pytest.mark.parametrize('N,Nd,Nr', [(48, 20000, 100000), (64, 50000, 200000)])
+def test_survey_matches_oracle_seeded(mods, N, Nd, Nr):
+    pySpec, O = mods
+    rng = np.random.default_rng(N)
+
+    def cone(n):
+        return np.array([rng.uniform(100., 260., n), np.degrees(np.arcsin(rng.uniform(-0.1, 0.9, n))),
+                         rng.uniform(0.15 ** 3, 0.6 ** 3, n) ** (1. / 3.)])
+    data, rand = cone(Nd), cone(Nr)
+    nz = lambda z: 2e-4 * (1. + z)
+    w = rng.uniform(0.9, 1.2, Nd)
+    kw = dict(P0_fkp=2e4, Lbox=3600., Ngrid=N, step=2, Ncut=3, Nmax=10)
+    bk = pySpec.B0_survey(data, nz(data[2]), w=w, radecz_r=rand, nbar_r=nz(rand[2]), **kw)
+    ref = O.B0_survey(data, nz(data[2]), w=w, radecz_r=rand, nbar_r=nz(rand[2]), **kw)
+    fr = O.FFT_survey_mono(rand, nz(rand[2]), P0_fkp=2e4, Lbox=3600., Ngrid=N)
+    alpha = np.sum(w) / fr[1]
+    _check_b0(bk, ref, alpha, *[alpha * x for x in fr[2:]])
+
+
+def test_bk_periodic_from_full_field(mods, golden_dir):
+    """_Bk_periodic (pyspectrum.py:359-457) on a host full field: the reference golden's raw (unit-less) bispectrum, and a
+    non-Hermitian input, for which the reference keeps Re(FFT) = the transform of the Hermitian part."""
+    pySpec, O = mods
+    g = _g(golden_dir, 'small_A.npz')
+    N, L = int(g['Ngrid']), float(g['Lbox'])
+    full = O.reflect_delta(g['delta_half'], N)
+    step, Ncut, Nmax = 2, 3, 6
+    raw = pySpec._counts_Bk123(Ngrid=N, Nmax=Nmax, Ncut=Ncut, step=step)
+    ref = O._Bk_periodic(full, Nmax=Nmax, Ncut=Ncut, step=step, counts=raw)
+    bk = pySpec._Bk_periodic(full, Nmax=Nmax, Ncut=Ncut, step=step)
+    assert np.array_equal(bk['i_k1'], ref['i_k1']) and np.array_equal(bk['i_k3'], ref['i_k3'])
+    np.testing.assert_allclose(bk['p0k1'], ref['p0k1'], rtol=RTOL)
+    assert np.all(np.abs(bk['b123'] - ref['b123']) <= RTOL * np.abs(ref['b123']) + 1e-7 * np.abs(ref['b123']).max())
+    rng = np.random.default_rng(3)
+    noise = (rng.normal(size=full.shape) + 1j * rng.normal(size=full.shape)).astype(np.complex64) * np.abs(full).mean()
+    ref = O._Bk_periodic(full + noise, Nmax=Nmax, Ncut=Ncut, step=step, counts=raw)
+    bk = pySpec._Bk_periodic(full + noise, Nmax=Nmax, Ncut=Ncut, step=step)
+    np.testing.assert_allclose(bk['p0k1'], ref['p0k1'], rtol=RTOL)
+    assert np.all(np.abs(bk['b123'] - ref['b123']) <= RTOL * np.abs(ref['b123']) + 1e-6 * np.abs(ref['b123']).max())
