@@ -38,10 +38,9 @@ class FlatLambdaCDM(object):
         z = np.asarray(z, dtype=np.float64)
         return np.sqrt(self.Om0 * (1. + z) ** 3 + self.Ode0)
 
-    def comoving_distance(self, z):
-        """Line-of-sight comoving distance in Mpc: (c/H0) int_0^z dz'/E(z').  Composite 24-point Gauss-Legendre with
-        panels of at most 0.5 in z (the integrand is analytic; error < 1e-13 relative)."""
-        z = np.atleast_1d(np.asarray(z, dtype=np.float64))
+    def _integral(self, z):
+        """int_0^z dz'/E(z') by composite 24-point Gauss-Legendre, panels of at most 0.5 in z (analytic integrand:
+        relative error < 1e-13)."""
         out = np.zeros_like(z)
         if z.size == 0:
             return out
@@ -53,6 +52,30 @@ class FlatLambdaCDM(object):
             mid = 0.5 * (b + a)
             zz = mid[:, None] + half[:, None] * _GL_X[None, :]
             out += half * np.sum(_GL_W[None, :] / self.efunc(zz), axis=1)
+        return out
+
+    def comoving_distance(self, z):
+        """Line-of-sight comoving distance in Mpc: (c/H0) int_0^z dz'/E(z').  Catalogue-sized inputs (random catalogues
+        hold 1e7-1e9 redshifts) go through a cubic Hermite table on 4097 nodes over [0, zmax] whose node values come from
+        the quadrature and whose slopes are the exact integrand 1/E (interpolation error ~ dz^4/384 times the fourth
+        derivative: below 1e-15)."""
+        z = np.atleast_1d(np.asarray(z, dtype=np.float64))
+        if z.size <= 8192 or np.min(z) < 0.:
+            return (_C_KMS / self.H0) * self._integral(z)
+        nn = 4096
+        zmax = float(np.max(z))
+        if zmax == 0.:
+            return np.zeros_like(z)
+        dz = zmax / nn
+        zn = np.arange(nn + 1) * dz
+        fn = self._integral(zn)
+        gn = 1. / self.efunc(zn)
+        k = np.minimum((z / dz).astype(np.int64), nn - 1)
+        t = z / dz - k
+        f0, f1, g0, g1 = fn[k], fn[k + 1], gn[k] * dz, gn[k + 1] * dz
+        t2 = t * t
+        t3 = t2 * t
+        out = (2. * t3 - 3. * t2 + 1.) * f0 + (t3 - 2. * t2 + t) * g0 + (-2. * t3 + 3. * t2) * f1 + (t3 - t2) * g1
         return (_C_KMS / self.H0) * out
 
 

@@ -32,6 +32,10 @@ def test_comoving_distance_known_answers():
     b = O.FlatLambdaCDM(H0=67.6, Om0=0.31).comoving_distance(zz)
     np.testing.assert_allclose(a, b, rtol=1e-12)
     assert UT.FlatLambdaCDM(H0=67.6, Om0=0.31).h == pytest.approx(0.676)
+    # catalogue-sized input: cubic Hermite table (exact slopes) vs the direct quadrature, absolute error in Mpc
+    cos = UT.FlatLambdaCDM(H0=67.6, Om0=0.31)
+    zbig = np.random.default_rng(1).uniform(0., 1.2, 20000)
+    assert np.abs(cos.comoving_distance(zbig) - (c / 67.6) * cos._integral(zbig)).max() < 1e-9
     assert UT.FlatLambdaCDM(H0=67.6, Om0=0.31).efunc(0.) == pytest.approx(1.)
 
 

@@ -7,6 +7,9 @@
   c3  Pk_periodic_rsd (rsd=z), ~1e8-particle lognormal catalogue with a z displacement, Ngrid=512 -> full oracle comparison
   c4  Bk_periodic, Ngrid=512, step=2, Ncut=3, Nmax=80 (46 700 triangles, 80 shells)     -> oracle on a subset of triangles
       (the reference algorithm needs 87 GB of float64 shell fields here; the oracle streams a few shells)
+  survey  B0_survey (survey geometry): 1e6 data + 5e6 randoms in a cone, Lbox=3600, Ngrid=360, step=3,
+      Ncut=3, Nmax=40 -> timing; parity against the oracle at Ngrid=96 on a 1/20 subsample (the oracle's float64 shell
+      store does not fit the time budget at 360)
 Prints one JSON line per config (timings by CUDA events / wall clock, parity figures)."""
 import json
 import os
@@ -156,8 +159,45 @@ def c4():
     print(json.dumps(out), flush=True)
 
 
+def survey():
+    from oracle import pyspec_oracle as O
+    rng = np.random.default_rng(7)
+
+    def cone(n):
+        return np.array([rng.uniform(100., 260., n), np.degrees(np.arcsin(rng.uniform(-0.1, 0.9, n))),
+                         rng.uniform(0.15 ** 3, 0.6 ** 3, n) ** (1. / 3.)])
+    nz = lambda z: 3e-4 * np.exp(-((z - 0.4) / 0.25) ** 2)
+    data, rand = cone(10 ** 6), cone(5 * 10 ** 6)
+    kw = dict(P0_fkp=1e4, Lbox=3600., step=3, Ncut=3, Nmax=40)
+    pySpec.PeriodicPipeline.get(360).counts(40, 3, 3)
+    t0 = time.perf_counter()
+    from pyspectrum_b200 import util as UT
+    UT.radecz_to_cartesian(rand)
+    t_host = time.perf_counter() - t0
+    bk, t = timed(lambda: pySpec.B0_survey(data, nz(data[2]), radecz_r=rand, nbar_r=nz(rand[2]), Ngrid=360, **kw), reps=3)
+    out = {'config': 'B0_survey 1e6 data + 5e6 randoms, L=3600, N=360, step=3, Ncut=3, Nmax=40', 'triangles': len(bk['b123']),
+           'e2e_pageable_host_s': t, 'host_radecz_to_cartesian_randoms_s': t_host,
+           'finite': bool(np.all(np.isfinite(bk['b123'])) and np.all(np.isfinite(bk['q123'])))}
+    if ORACLE:
+        d, r = data[:, ::20], rand[:, ::20]
+        kw2 = dict(P0_fkp=1e4, Lbox=3600., Ngrid=96, step=2, Ncut=3, Nmax=12)
+        t0 = time.perf_counter()
+        ref = O.B0_survey(d, nz(d[2]), radecz_r=r, nbar_r=nz(r[2]), workers=os.cpu_count(), **kw2)
+        out['oracle_s'] = time.perf_counter() - t0
+        got = pySpec.B0_survey(d, nz(d[2]), radecz_r=r, nbar_r=nz(r[2]), **kw2)
+        fr = O.FFT_survey_mono(r, nz(r[2]), P0_fkp=1e4, Lbox=3600., Ngrid=96)
+        alpha = d.shape[1] / fr[1]
+        I12, I13, I22, I23, I33 = [alpha * x for x in fr[2:]]
+        sn_b = ((ref['p0k1'] + ref['p0k2'] + ref['p0k3']) * I23 + (1. - alpha ** 2) * I13) / I33
+        scale = np.abs(ref['b123'] + sn_b)
+        out['idx_exact'] = bool(np.array_equal(got['i_k1'], ref['i_k1']) and np.array_equal(got['i_k3'], ref['i_k3']))
+        out['p0k1_raw_max_rel'] = float(np.abs((got['p0k1'] - ref['p0k1']) / (ref['p0k1'] + (1 + alpha) * I12 / I22)).max())
+        out['b123_max_err_over_tol'] = float((np.abs(got['b123'] - ref['b123']) / (1e-5 * scale + 1e-6 * scale.max())).max())
+    print(json.dumps(out), flush=True)
+
+
 if __name__ == '__main__':
     for name in sys.argv[1:]:
-        if name in ('c1', 'c3', 'c4'):
-            {'c1': c1, 'c3': c3, 'c4': c4}[name]()
+        if name in ('c1', 'c3', 'c4', 'survey'):
+            {'c1': c1, 'c3': c3, 'c4': c4, 'survey': survey}[name]()
             torch.cuda.empty_cache()
