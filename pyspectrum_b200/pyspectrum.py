@@ -30,7 +30,7 @@ from . import _lib
 from ._lib import check
 
 __all__ = ['Pk_periodic', 'Pk_periodic_rsd', 'Bk_periodic', 'FFT_periodic', 'reflect_delta',
-           'B0_survey', 'FFT_survey_mono', '_B0_survey', '_Bk_periodic',
+           'B0_survey', 'FFT_survey_mono', '_B0_survey', '_Bk_periodic', '_Pk_periodic_rsd', '_counts_Bk123_f77',
            '_counts_Bk123', 'dat_dir', 'PeriodicPipeline']
 
 _DAT_DIR = os.environ.get('PYSPECTRUM_B200_DAT', os.path.join(os.path.dirname(os.path.realpath(__file__)), 'dat'))
@@ -652,20 +652,10 @@ def Pk_periodic(xyz, w=None, Lbox=2600, Ngrid=360, fft='pyfftw', silent=True):
     return {'meta': meta, 'k': k, 'p0k': p0k - 1. / nbar, 'counts': counts, 'p0k_sn': 1. / nbar}
 
 
-def Pk_periodic_rsd(xyz, w=None, Lbox=2600, Ngrid=360, rsd=2, Nmubin=10, fft='pyfftw', code='fortran', silent=True):
-    """Power-spectrum multipoles + P(k,mu); see pyspectrum.py:460-538 for the contract."""
-    N = _npart(xyz)
-    nbar = float(N) / Lbox ** 3                      # py:510 (N, not sum w: SURVEY Q11)
-    kf = 2 * np.pi / Lbox
-    if rsd not in (0, 1, 2):
-        raise ValueError('rsd must be 0, 1 or 2')
-    pipe = PeriodicPipeline.get(Ngrid)
-    if not silent:
-        print('------------------')
-        print('%i positions in %i box' % (N, Lbox))
-        print('nbar = %f' % nbar)
-    half, _ = pipe.fft_periodic(xyz, w, Lbox)
-    Nbins = Ngrid // 2
+def _pk_rsd_from_half(pipe, half, Lbox, rsd, Nmubin):
+    """K4 multipoles of a device half field + the normalisation of estimator.f:246-262 and pyspectrum.py:634-640.
+    Returns (ks, p0k, p2k, p4k, nk, k_kmu, mu_kmu, p_kmu, n_kmu) like the reference's _Pk_periodic_rsd."""
+    Nbins = pipe.N // 2
     raw, kf32 = pipe.pk_multipoles(half, int(Lbox), rsd, Nmubin)      # Lbox is an INTEGER dummy: estimator.f:158
     raw = raw.cpu().numpy()
     nk = raw[:Nbins].copy()
@@ -687,6 +677,67 @@ def Pk_periodic_rsd(xyz, w=None, Lbox=2600, Ngrid=360, rsd=2, Nmubin=10, fft='py
     p2k *= pk_norm
     p4k *= pk_norm
     p_kmu *= pk_norm
+    return ks, p0k, p2k, p4k, nk, k_kmu, mu_kmu, p_kmu, n_kmu
+
+
+def _Pk_periodic_rsd(delta, Lbox=None, rsd=2, Nmubin=5, code='fortran'):
+    """pyspectrum.py:541-641, code='fortran' branch: multipoles and P(k,mu) of a host half field delta(k) of shape
+    (Ngrid//2+1, Ngrid, Ngrid) indexed [kx,ky,kz] (what FFT_periodic returns).  The reference's code='python' branch is a
+    debugging variant on the full grid (it prints every (k,mu) bin) and is not provided."""
+    if code != 'fortran':
+        raise NotImplementedError("only code='fortran' (estimator.pk_pbox_rsd, estimator.f:155-264) is provided")
+    if Lbox is None:
+        raise ValueError('Lbox is required (pk_pbox_rsd takes it as an integer, estimator.f:158)')
+    if rsd not in (0, 1, 2):
+        raise ValueError('rsd must be 0, 1 or 2')
+    delta = np.asarray(delta)
+    Ngrid = delta.shape[1]
+    if delta.shape != (Ngrid // 2 + 1, Ngrid, Ngrid):
+        raise ValueError('delta must be the half field (Ngrid//2+1, Ngrid, Ngrid)')
+    pipe = PeriodicPipeline.get(Ngrid)
+    arr = np.ascontiguousarray(delta.astype(np.complex64, copy=False).transpose(2, 1, 0))           # [kz][ky][kx]
+    half = torch.from_numpy(arr.view(np.float32).reshape(Ngrid, Ngrid, Ngrid // 2 + 1, 2)).to(pipe.dev)
+    return _pk_rsd_from_half(pipe, half, Lbox, rsd, Nmubin)
+
+
+def _counts_Bk123_f77(Ngrid=360, Nmax=40, Ncut=3, step=3, silent=True):
+    """pyspectrum.py:1033-1057: triangle counts through estimator.bk_counts (estimator.f:2-102), cached in the reference's
+    `.fort77` file.  Returned array is Fortran-ordered and indexed like the Fortran's coun(i<=j<=l) (NOT like _counts_Bk123).
+    The reference allocates a fixed (40,40,40) array (py:1049); here the array is (Nmax,Nmax,Nmax).  The cache file holds the
+    array in Fortran order and is read back the same way (the reference writes it with ndarray.tofile, i.e. in C order,
+    and reads it with order='F', so its cache hits return the transposed array)."""
+    from . import estimator as fEstimate
+    fcnt = ''.join(['counts', '.Ngrid', str(Ngrid), '.Nmax', str(Nmax), '.Ncut', str(Ncut), '.step', str(step), '.fort77'])
+    f_counts = os.path.join(dat_dir(), fcnt)
+    if os.path.isfile(f_counts):
+        return np.reshape(_read_fortran_record(f_counts, Nmax).ravel(), (Nmax, Nmax, Nmax), order='F')
+    if not silent:
+        print('-- %s does not exist --' % f_counts)
+        print('-- computing %s --' % f_counts)
+    counts = np.zeros((Nmax, Nmax, Nmax), dtype=np.float64, order='F')
+    fEstimate.bk_counts(counts, Ngrid, float(step), Ncut, Nmax)
+    try:
+        os.makedirs(dat_dir(), exist_ok=True)
+        _write_fortran_record(f_counts, counts.ravel(order='F'))
+    except OSError:
+        pass
+    return counts
+
+
+def Pk_periodic_rsd(xyz, w=None, Lbox=2600, Ngrid=360, rsd=2, Nmubin=10, fft='pyfftw', code='fortran', silent=True):
+    """Power-spectrum multipoles + P(k,mu); see pyspectrum.py:460-538 for the contract."""
+    N = _npart(xyz)
+    nbar = float(N) / Lbox ** 3                      # py:510 (N, not sum w: SURVEY Q11)
+    kf = 2 * np.pi / Lbox
+    if rsd not in (0, 1, 2):
+        raise ValueError('rsd must be 0, 1 or 2')
+    pipe = PeriodicPipeline.get(Ngrid)
+    if not silent:
+        print('------------------')
+        print('%i positions in %i box' % (N, Lbox))
+        print('nbar = %f' % nbar)
+    half, _ = pipe.fft_periodic(xyz, w, Lbox)
+    ks, p0k, p2k, p4k, nk, k_kmu, mu_kmu, p_kmu, n_kmu = _pk_rsd_from_half(pipe, half, Lbox, rsd, Nmubin)
     if not silent:
         print('--- correcting for shotnoise ---')
     meta = {'Lbox': Lbox, 'Ngrid': Ngrid, 'N': N, 'nbar': nbar, 'kf': kf}

@@ -89,8 +89,26 @@ def test_survey_argument_errors(mods, golden_dir):
         pySpec.FFT_survey_mono(g['radecz'], g['nbar'], Lbox=1000., Ngrid=N)                        # 'box not big enough!'
 
 
+def _shell_amplification(O, half_d, half, N, step, Nmax):
+    """Per shell j: rms|delta_d| / rms|delta_d - alpha delta_r| over the modes of the shell -- how much the subtraction of
+    the survey window amplifies the relative float32 rounding of the data (and random) mesh."""
+    irk = O.shell_index(N, step)[:N // 2 + 1]
+    amp = np.ones(Nmax + 1)
+    for j in range(1, Nmax + 1):
+        m = irk == j
+        if m.any():
+            amp[j] = max(1., np.sqrt(np.sum(np.abs(half_d[m]) ** 2) / np.sum(np.abs(half[m]) ** 2)))
+    return amp
+
+
 @pytest.mark.parametrize('N,Nd,Nr', [(48, 20000, 100000), (64, 50000, 200000)])
 def test_survey_matches_oracle_seeded(mods, N, Nd, Nr):
+    """Larger seeded cone against the oracle, in three steps, because delta = delta_d - alpha delta_r cancels the survey
+    window (here by a factor ~45 in the lowest shell) and with it amplifies the float32 summation-order noise of the two
+    meshes: the ORACLE itself, fed the same catalogue in a different particle order, moves b123 by up to 5.5x the plain
+    1e-5 bound on these catalogues (measured).  (1) the uncancelled fields delta_d, delta_r agree to 3e-6 of max|delta|;
+    (2) the shell / triangle stage on the oracle's own delta(k) agrees to the plain bound; (3) the whole of B0_survey agrees
+    to the bound scaled by the largest window amplification of the triangle's three shells."""
     pySpec, O = mods
     rng = np.random.default_rng(N)
 
@@ -100,12 +118,38 @@ def test_survey_matches_oracle_seeded(mods, N, Nd, Nr):
     data, rand = cone(Nd), cone(Nr)
     nz = lambda z: 2e-4 * (1. + z)
     w = rng.uniform(0.9, 1.2, Nd)
-    kw = dict(P0_fkp=2e4, Lbox=3600., Ngrid=N, step=2, Ncut=3, Nmax=10)
+    L, P0, step, Ncut, Nmax = 3600., 2e4, 2, 3, 10
+    kw = dict(P0_fkp=P0, Lbox=L, Ngrid=N, step=step, Ncut=Ncut, Nmax=Nmax)
+    # (1) uncancelled fields
+    od = O.FFT_survey_mono(data, nz(data[2]), w=w, P0_fkp=P0, Lbox=L, Ngrid=N)
+    orr = O.FFT_survey_mono(rand, nz(rand[2]), P0_fkp=P0, Lbox=L, Ngrid=N)
+    gd = pySpec.FFT_survey_mono(data, nz(data[2]), w=w, P0_fkp=P0, Lbox=L, Ngrid=N)
+    gr = pySpec.FFT_survey_mono(rand, nz(rand[2]), P0_fkp=P0, Lbox=L, Ngrid=N)
+    for got, ref in [(gd, od), (gr, orr)]:
+        assert np.abs(got[0] - ref[0]).max() <= 3e-6 * np.abs(ref[0]).max()
+        np.testing.assert_allclose(np.array(got[1:]), np.array(ref[1:]), rtol=1e-12)
+    alpha = od[1] / orr[1]
+    Is = [alpha * x for x in orr[2:]]
+    # (2) shell + triangle stage on the same delta(k)
+    counts = pySpec._counts_Bk123(Ngrid=N, Nmax=Nmax, Ncut=Ncut, step=step)
+    deltak = O.reflect_delta(od[0], N) - alpha * O.reflect_delta(orr[0], N)
+    ref2 = O._B0_survey(deltak, alpha, *Is, Nmax=Nmax, Ncut=Ncut, step=step, counts=counts)
+    _check_b0(pySpec._B0_survey(deltak, alpha, *Is, Nmax=Nmax, Ncut=Ncut, step=step), ref2, alpha, *Is)
+    # (3) end to end
     bk = pySpec.B0_survey(data, nz(data[2]), w=w, radecz_r=rand, nbar_r=nz(rand[2]), **kw)
-    ref = O.B0_survey(data, nz(data[2]), w=w, radecz_r=rand, nbar_r=nz(rand[2]), **kw)
-    fr = O.FFT_survey_mono(rand, nz(rand[2]), P0_fkp=2e4, Lbox=3600., Ngrid=N)
-    alpha = np.sum(w) / fr[1]
-    _check_b0(bk, ref, alpha, *[alpha * x for x in fr[2:]])
+    ref = O.B0_survey(data, nz(data[2]), w=w, radecz_r=rand, nbar_r=nz(rand[2]), counts=counts, **kw)
+    half = np.asarray(od[0]) - alpha * np.asarray(orr[0])
+    amp = _shell_amplification(O, np.asarray(od[0]), half, N, step, Nmax)
+    tri = O.triangle_list(Nmax, Ncut, step)
+    amp3 = np.maximum(np.maximum(amp[tri[:, 0]], amp[tri[:, 1]]), amp[tri[:, 2]])
+    assert amp3.max() > 5.                                            # the catalogue does exercise the cancellation
+    for key in ['i_k1', 'i_k2', 'i_k3']:
+        assert np.array_equal(bk[key], ref[key])
+    sn_p = (1. + alpha) * Is[0] / Is[2]
+    assert np.all(np.abs(bk['p0k1'] - ref['p0k1']) <= RTOL * amp[tri[:, 0]] * np.abs(ref['p0k1'] + sn_p))
+    sn_b = ((ref['p0k1'] + ref['p0k2'] + ref['p0k3']) * Is[3] + (1. - alpha ** 2) * Is[1]) / Is[4]
+    scale = np.abs(ref['b123'] + sn_b)
+    assert np.all(np.abs(bk['b123'] - ref['b123']) <= amp3 * (RTOL * scale + 1e-6 * scale.max()))
 
 
 def test_bk_periodic_from_full_field(mods, golden_dir):
@@ -128,3 +172,39 @@ def test_bk_periodic_from_full_field(mods, golden_dir):
     bk = pySpec._Bk_periodic(full + noise, Nmax=Nmax, Ncut=Ncut, step=step)
     np.testing.assert_allclose(bk['p0k1'], ref['p0k1'], rtol=RTOL)
     assert np.all(np.abs(bk['b123'] - ref['b123']) <= RTOL * np.abs(ref['b123']) + 1e-6 * np.abs(ref['b123']).max())
+
+
+def test_pk_periodic_rsd_from_half_field(mods, golden_dir):
+    """_Pk_periodic_rsd (pyspectrum.py:541-641, code='fortran') on the reference golden's own half field."""
+    pySpec, O = mods
+    g = _g(golden_dir, 'small_B.npz')
+    N, L = int(g['Ngrid']), float(g['Lbox'])
+    for rsd in (0, 1, 2):
+        ks, p0k, p2k, p4k, nk, k_kmu, mu_kmu, p_kmu, n_kmu = pySpec._Pk_periodic_rsd(g['delta_half'], Lbox=L, rsd=rsd, Nmubin=5)
+        pre = 'rsd%d_mu5_' % rsd
+        sn = g[pre + 'p_sn'][0]
+        assert np.array_equal(nk, g[pre + 'counts']) and np.array_equal(n_kmu, g[pre + 'counts_kmu'])
+        np.testing.assert_allclose(ks, g[pre + 'k'], rtol=1e-6)
+        np.testing.assert_allclose(p0k, g[pre + 'p0k'] + sn, rtol=RTOL)            # the golden is shot-noise corrected
+        scale = np.abs(g[pre + 'p0k'] + sn)
+        assert np.all(np.abs(p2k - g[pre + 'p2k']) <= 5 * RTOL * scale)
+        assert np.all(np.abs(p4k - g[pre + 'p4k']) <= 9 * RTOL * scale)
+        m = n_kmu > 0
+        np.testing.assert_allclose(p_kmu[m], (g[pre + 'p_kmu'] + sn)[m], rtol=RTOL)
+    with pytest.raises(NotImplementedError):
+        pySpec._Pk_periodic_rsd(g['delta_half'], Lbox=L, code='python')
+    with pytest.raises(ValueError):
+        pySpec._Pk_periodic_rsd(g['delta_half'][:, :, :-1], Lbox=L)
+
+
+def test_counts_f77_entry_point(mods, tmp_path, monkeypatch):
+    """_counts_Bk123_f77 (pyspectrum.py:1033-1057): estimator.bk_counts layout coun(i<=j<=l), cached as a Fortran record."""
+    pySpec, O = mods
+    monkeypatch.setattr(pySpec, '_DAT_DIR', str(tmp_path))
+    N, nmax = 24, 3
+    c = pySpec._counts_Bk123_f77(Ngrid=N, Nmax=nmax, Ncut=3, step=3)
+    cb = O.counts_bruteforce(N, nmax, 3, 3)
+    for (i, j, l) in O.triangle_list(nmax, 3, 3):
+        assert c[l - 1, j - 1, i - 1] == cb[i - 1, j - 1, l - 1] * N ** 3
+    assert os.path.isfile(os.path.join(str(tmp_path), 'counts.Ngrid24.Nmax3.Ncut3.step3.fort77'))
+    assert np.array_equal(pySpec._counts_Bk123_f77(Ngrid=N, Nmax=nmax, Ncut=3, step=3), c)      # cache hit: same array
