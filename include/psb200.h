@@ -68,6 +68,18 @@ int psb_assign_pcs_interlaced(const void* pos, int pos_f64, int pos_aos, const v
                               int64_t np, int ngrid, double lbox_clip, float kf_ks, float offset,
                               float* mesh, int zero_mesh, void* ws, size_t ws_bytes, double* sumw, void* stream);
 
+/* Survey-geometry catalogue pre-step, one pass on the device (pyspectrum.py:776-806 + util.py:27-51):
+ * (RA, Dec, z) -> comoving Cartesian float32 positions, FKP weights, normalisation sums, bounding box.
+ *   radecz      device float64 [3][np]: RA [deg], Dec [deg], redshift
+ *   nbar, w     device float64 [np]; w may be NULL (all ones)
+ *   dist_table  device float64 [nnodes][2]: cubic Hermite nodes over z in [0, zmax], {D(z_k), D'(z_k) dz} with D the
+ *               line-of-sight comoving distance in Mpc/h of the caller's cosmology and dz = zmax/(nnodes-1)
+ *   xyz_f32     out, device float32 [3][np] (the layout psb_assign_pcs_interlaced takes with pos_f64=0, pos_aos=0)
+ *   w_f32       out, device float32 [np]: w / (1 + nbar p0_fkp)
+ *   out12       out, device float64 [12]: Ntot = sum w, I12, I13, I22, I23, I33 (py:794, 802-806), min x,y,z, max x,y,z */
+int psb_survey_prepare(const double* radecz, const double* nbar, const double* w, int64_t np, const double* dist_table, int nnodes,
+                       double zmax, double p0_fkp, float* xyz_f32, float* w_f32, double* out12, void* stream);
+
 /* K2+K3  pyspectrum.py:1060-1080 + estimator.f:605-675 + the [:N/2+1] slice (py:959).
  *   mesh_c64  in: (A + iB) on [z][y][x]; destroyed (x and y passes run in place)
  *   half_c64  out: delta(k) on [kz][ky][kx], kx = 0..N/2 (the reference's Fortran (N/2+1,N,N) array)

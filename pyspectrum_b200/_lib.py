@@ -47,6 +47,7 @@ PROTOTYPES = {
     'psb_irk_table_f32': (_i, [_f, _i, _vp]),
     'psb_assign_workspace_bytes': (_sz, [_i64, _i]),
     'psb_assign_pcs_interlaced': (_i, [_vp, _i, _i, _vp, _i, _i64, _i, _d, _f, _f, _vp, _i, _vp, _sz, _vp, _vp]),
+    'psb_survey_prepare': (_i, [_vp, _vp, _vp, _i64, _vp, _i, _d, _d, _vp, _vp, _vp, _vp]),
     'psb_fft_mesh_to_delta': (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp]),
     'psb_fft_c2c_3d': (_i, [_vp, _i, _i, _vp, _vp]),
     'psb_fcomb': (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _vp]),

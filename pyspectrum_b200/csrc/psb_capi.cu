@@ -238,6 +238,14 @@ int psb_bk_build_tiles(const int32_t* tri, int ntri, int s0, int32_t* tiles, int
     return PSB_OK;
 }
 
+int psb_survey_prepare(const double* radecz, const double* nbar, const double* w, int64_t np, const double* dist_table, int nnodes,
+                       double zmax, double p0_fkp, float* xyz_f32, float* w_f32, double* out12, void* stream)
+{
+    if (!radecz || !nbar || !dist_table || !xyz_f32 || !w_f32 || !out12 || nnodes < 2) return PSB_ERR_ARG;
+    return psb::survey_prepare(radecz, nbar, w, (long long)np, dist_table, nnodes - 1, zmax, p0_fkp, xyz_f32, w_f32, out12,
+                               (cudaStream_t)stream);
+}
+
 // ---------------------------------------------------------------- f2py-shaped host drop-ins
 int psb_host_assign_quad(const float* r, const float* w, float* dtl, int64_t np, int N, float kf_ks, float offset,
                          int ia, int ib, int ic, int id)

@@ -61,4 +61,8 @@ size_t triangle_tc_workspace_bytes(int MT, int NT);
 int triangle_sums_tc_pass(const float* const* fields, int S, long long ncell, const int* lane_ij, int lane_layout, int MT, int NT,
                           const int* tri_rc, int ntri, double* sums, void* ws, size_t ws_bytes, cudaStream_t st);
 
+// survey-geometry catalogue pre-step (psb_survey.cu)
+int survey_prepare(const double* radecz, const double* nb, const double* w, long long np, const double* tab, int nn, double zmax,
+                   double p0_fkp, float* xyz, float* wout, double* out12, cudaStream_t st);
+
 }  // namespace psb

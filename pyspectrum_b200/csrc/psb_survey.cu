@@ -1,0 +1,116 @@
+// psb_survey.cu -- catalogue pre-step of the survey-geometry path, one pass over the catalogue on the device:
+//   (RA, Dec, z) -> comoving Cartesian Mpc/h        pyspectrum/util.py:27-51   (radecz_to_cartesian)
+//   cast to float32 positions                       pyspectrum/pyspectrum.py:789-792
+//   FKP weights w / (1 + nbar P0)                   pyspectrum/pyspectrum.py:797-799
+//   Ntot, I12, I13, I22, I23, I33                   pyspectrum/pyspectrum.py:794, 802-806
+//   min / max of x, y, z (float64)                  pyspectrum/pyspectrum.py:779-785 ('box not big enough!')
+// The line-of-sight comoving distance comes from a cubic Hermite table over [0, zmax] built by the host from the
+// caller's cosmology object (node values D(z_k) h and exact slopes c h / (H0 E(z_k)) dz); 4097 nodes keep the
+// interpolation error below 1e-12 relative.  HBM bound: 40 B read + 16 B written per object.
+#include <cuda_runtime.h>
+#include "psb_kernels.h"
+
+namespace psb {
+
+__device__ __forceinline__ unsigned long long ordered_key(double x)
+{
+    const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);             // monotone map double -> uint64
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// out_sums: [0..5] = Ntot, I12, I13, I22, I23, I33 (float64, atomically accumulated: zero them first)
+// out_keys: [0..2] = ordered keys of min x,y,z (initialise to ~0), [3..5] = of max x,y,z (initialise to 0)
+__global__ void __launch_bounds__(256) k_survey_prepare(const double* __restrict__ ra, const double* __restrict__ dec,
+                                                        const double* __restrict__ zr, const double* __restrict__ nb,
+                                                        const double* __restrict__ w, long long np,
+                                                        const double* __restrict__ tab, int nn, double inv_dz, double p0,
+                                                        float* __restrict__ xyz, float* __restrict__ wout,
+                                                        double* out_sums, unsigned long long* out_keys)
+{
+    const double deg = 3.141592653589793 / 180.;
+    double s[6] = { 0, 0, 0, 0, 0, 0 };
+    double mn[3] = { 1e300, 1e300, 1e300 }, mx[3] = { -1e300, -1e300, -1e300 };
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < np; i += (long long)gridDim.x * blockDim.x) {
+        const double z = zr[i];
+        const double u = z * inv_dz;
+        int k = (int)u;
+        k = k < 0 ? 0 : (k > nn - 1 ? nn - 1 : k);
+        const double t = u - (double)k, t2 = t * t, t3 = t2 * t;
+        const double2 n0 = reinterpret_cast<const double2*>(tab)[k], n1 = reinterpret_cast<const double2*>(tab)[k + 1];
+        const double rad = (2. * t3 - 3. * t2 + 1.) * n0.x + (t3 - 2. * t2 + t) * n0.y + (-2. * t3 + 3. * t2) * n1.x + (t3 - t2) * n1.y;
+        double sd, cd, sr, cr;
+        sincos(__dmul_rn(dec[i], deg), &sd, &cd);
+        sincos(__dmul_rn(ra[i], deg), &sr, &cr);
+        const double rc = __dmul_rn(rad, cd);
+        const double p[3] = { __dmul_rn(rc, cr), __dmul_rn(rc, sr), __dmul_rn(rad, sd) };
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            xyz[a * np + i] = (float)p[a];
+            mn[a] = fmin(mn[a], p[a]);
+            mx[a] = fmax(mx[a], p[a]);
+        }
+        const double w0 = w ? w[i] : 1.0, n = nb[i];
+        const double wf = __dmul_rn(w0, __ddiv_rn(1.0, __dadd_rn(1.0, __dmul_rn(n, p0))));
+        wout[i] = (float)wf;
+        const double w2 = __dmul_rn(wf, wf), w3 = __dmul_rn(w2, wf);
+        s[0] += w0; s[1] += w2; s[2] += w3; s[3] += __dmul_rn(n, w2); s[4] += __dmul_rn(n, w3); s[5] += __dmul_rn(__dmul_rn(n, n), w3);
+    }
+    __shared__ double red[6][8];
+    __shared__ unsigned long long kred[6][8];
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) { const double v = warp_sum(s[a]); if (lane == 0) red[a][wp] = v; }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        unsigned long long lo = ordered_key(mn[a]), hi = ordered_key(mx[a]);
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long l2 = __shfl_down_sync(0xffffffffu, lo, o), h2 = __shfl_down_sync(0xffffffffu, hi, o);
+            lo = l2 < lo ? l2 : lo; hi = h2 > hi ? h2 : hi;
+        }
+        if (lane == 0) { kred[a][wp] = lo; kred[3 + a][wp] = hi; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        double v = 0;
+        for (int k = 0; k < 8; ++k) v += red[threadIdx.x][k];
+        atomicAdd(&out_sums[threadIdx.x], v);
+        unsigned long long key = kred[threadIdx.x][0];
+        for (int k = 1; k < 8; ++k) { const unsigned long long o = kred[threadIdx.x][k]; key = threadIdx.x < 3 ? (o < key ? o : key) : (o > key ? o : key); }
+        if (threadIdx.x < 3) atomicMin(&out_keys[threadIdx.x], key); else atomicMax(&out_keys[threadIdx.x], key);
+    }
+}
+
+__global__ void k_survey_finish(double* out, const unsigned long long* keys)
+{
+    const int a = threadIdx.x;
+    if (a < 6) {
+        const unsigned long long k = keys[a];
+        const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+        out[6 + a] = __longlong_as_double((long long)b);
+    }
+}
+
+int survey_prepare(const double* radecz, const double* nb, const double* w, long long np, const double* tab, int nn, double zmax,
+                   double p0_fkp, float* xyz, float* wout, double* out12, cudaStream_t st)
+{
+    if (np < 1 || nn < 1 || !(zmax > 0.)) return PSB_ERR_ARG;
+    unsigned long long init[6] = { ~0ull, ~0ull, ~0ull, 0ull, 0ull, 0ull };
+    // out12[0..5] sums, out12[6..11] receive min xyz / max xyz; the keys live in out12[6..11] until k_survey_finish decodes them
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(out12 + 6);
+    if (cudaMemsetAsync(out12, 0, 6 * sizeof(double), st) != cudaSuccess) return PSB_ERR_CUDA;
+    if (cudaMemcpyAsync(keys, init, sizeof(init), cudaMemcpyHostToDevice, st) != cudaSuccess) return PSB_ERR_CUDA;
+    long long nblk = (np + 255) / 256;
+    if (nblk > 148 * 8) nblk = 148 * 8;
+    k_survey_prepare<<<(unsigned)nblk, 256, 0, st>>>(radecz, radecz + np, radecz + 2 * np, nb, w, np, tab, nn, (double)nn / zmax, p0_fkp,
+                                                     xyz, wout, out12, keys);
+    k_survey_finish<<<1, 32, 0, st>>>(out12, keys);
+    return cudaGetLastError() == cudaSuccess ? PSB_OK : PSB_ERR_CUDA;
+}
+
+}  // namespace psb

@@ -266,6 +266,46 @@ class PeriodicPipeline(object):
         half = self.mesh_to_delta(mesh, sumw)
         return half, sumw
 
+    @staticmethod
+    def survey_distance_table(cosmo, zmax, nnodes=4097):
+        """Cubic Hermite nodes {D(z_k), D'(z_k) dz} of the line-of-sight comoving distance in Mpc/h over [0, zmax] for the
+        caller's cosmology object (anything with `comoving_distance(z)` [Mpc, plain array or astropy Quantity] and `h`).
+        The slopes come from a not-a-knot cubic spline through the nodes (error ~ dz^3: far below float32 positions)."""
+        from scipy.interpolate import CubicSpline
+        zn = np.linspace(0., float(zmax), nnodes)
+        D = cosmo.comoving_distance(zn)
+        D = np.asarray(getattr(D, 'value', D), dtype=np.float64) * float(getattr(cosmo.h, 'value', cosmo.h))
+        slope = CubicSpline(zn, D)(zn, 1) * (float(zmax) / (nnodes - 1))
+        return np.ascontiguousarray(np.stack([D, slope], axis=1))
+
+    def survey_prepare(self, radecz, nb, w, P0_fkp, cosmo):
+        """Catalogue pre-step of the survey path on the device (psb_survey_prepare): returns (xyz float32 [3,Np] device,
+        FKP weights float32 [Np] device, host float64[12] = Ntot, I12, I13, I22, I23, I33, min xyz, max xyz)."""
+        radecz = np.ascontiguousarray(radecz, dtype=np.float64)
+        if radecz.ndim != 2 or radecz.shape[0] != 3:
+            raise ValueError('radecz has to be have shape [3,N]')
+        Np = int(radecz.shape[1])
+        zmin, zmax = float(radecz[2].min()), float(radecz[2].max())
+        if not (zmin >= 0.) or not np.isfinite(zmax):
+            raise ValueError('redshifts must be finite and >= 0')
+        zmax = max(zmax, 1e-6)
+        tab = torch.from_numpy(self.survey_distance_table(cosmo, zmax)).to(self.dev)
+        rdz = torch.from_numpy(radecz).to(self.dev, non_blocking=True)
+        nbd = torch.from_numpy(np.ascontiguousarray(nb, dtype=np.float64)).to(self.dev, non_blocking=True)
+        if nbd.numel() != Np:
+            raise ValueError('nbar must have one entry per object')
+        wd = None
+        if w is not None:
+            wd = torch.from_numpy(np.ascontiguousarray(w, dtype=np.float64)).to(self.dev, non_blocking=True)
+            if wd.numel() != Np:
+                raise ValueError('w must have one entry per object')
+        xyz = torch.empty((3, Np), dtype=torch.float32, device=self.dev)
+        wf = torch.empty(Np, dtype=torch.float32, device=self.dev)
+        out = torch.empty(12, dtype=torch.float64, device=self.dev)
+        check(self.L.psb_survey_prepare(_ptr(rdz), _ptr(nbd), _ptr(wd), Np, _ptr(tab), tab.shape[0], zmax, float(P0_fkp),
+                                        _ptr(xyz), _ptr(wf), _ptr(out), _stream()), 'psb_survey_prepare')
+        return xyz, wf, out.cpu().numpy()
+
     def fft_survey(self, xyz, w, Lbox):
         """Survey-geometry delta_0(k) (pyspectrum.py:817-823): positions in (-L/2, L/2) shifted by half a box through the
         assignment offset (0.5*Ngrid), no clipping, and fcomb_survey (no division by sum w; estimator.f:686)."""
@@ -917,32 +957,26 @@ def _fft_survey_mono_dev(radecz, nb, w, P0_fkp, Lbox, Ngrid, cosmo, silent):
     """Device half of FFT_survey_mono: returns (half field on the device, Ntot, I12, I13, I22, I23, I33)."""
     from . import util as UT
     radecz = np.asarray(radecz)
+    assert radecz.shape[0] == 3, "radecz has to be have shape [3,N]"
     N = int(radecz.shape[1])
     if cosmo is None:
         cosmo = UT.FlatLambdaCDM(H0=67.6, Om0=0.31)                  # py:769-770
-    w = np.ones(N) if w is None else np.asarray(w, dtype=np.float64)
-    nb = np.asarray(nb, dtype=np.float64)
-    xyz = UT.radecz_to_cartesian(radecz, cosmo=cosmo)
-    xyz_max = np.max(xyz, axis=1)
-    xyz_min = np.min(xyz, axis=1)
+    pipe = PeriodicPipeline.get(Ngrid)
+    # util.radecz_to_cartesian, the float32 cast (py:789-792), the FKP weights (py:797-799; the caller's w is left alone)
+    # and the sums of py:794-806 in one pass over the catalogue on the device
+    xyz, wf, out = pipe.survey_prepare(radecz, nb, w, P0_fkp, cosmo)
+    Ntot, I12, I13, I22, I23, I33 = [float(v) for v in out[:6]]
+    xyz_min, xyz_max = out[6:9], out[9:12]
     if not silent:
         print(['%.1f < %s < %.1f\n' % (mi, _axis, ma) for _axis, mi, ma in zip(['x', 'y', 'z'], xyz_min, xyz_max)])
     assert np.sum(xyz_max >= 0.5 * Lbox) + np.sum(np.abs(xyz_min) >= 0.5 * Lbox) == 0, 'box not big enough!'
     if not silent:
         print('%i positions' % N)
-    Ntot = np.sum(w)                                                 # total weight without FKP (py:794)
-    w = w * (1. / (1. + nb * P0_fkp))                                # FKP weights (py:797-799); the caller's w is left alone
-    I12 = np.sum(w ** 2)
-    I13 = np.sum(w ** 3)
-    I22 = np.sum(nb * w ** 2)
-    I23 = np.sum(nb * w ** 3)
-    I33 = np.sum(nb ** 2 * w ** 3)
-    if not silent:
         print('Ntot=%.2f' % Ntot)
         for name, val in zip(['I12', 'I13', 'I22', 'I23', 'I33'], [I12, I13, I22, I23, I33]):
             print('%s=%.2e' % (name, val))
     assert np.all([(I12 >= 0), (I13 >= 0), (I22 >= 0), (I23 >= 0), (I33 >= 0)])
-    half = PeriodicPipeline.get(Ngrid).fft_survey(xyz, w, Lbox)
+    half = pipe.fft_survey(xyz, wf, Lbox)
     if not silent:
         print('delta_0(k) complete')
     return half, Ntot, I12, I13, I22, I23, I33

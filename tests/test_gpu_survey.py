@@ -59,7 +59,7 @@ def test_survey_matches_reference_goldens(mods, golden_dir, tag):
     for out, dk, sk in [(dd, 'delta_d', 'sums_d'), (dr, 'delta_r', 'sums_r')]:
         assert out[0].shape == g[dk].shape and out[0].dtype == np.complex64
         assert np.abs(out[0] - g[dk]).max() <= 3e-6 * np.abs(g[dk]).max()
-        np.testing.assert_allclose(np.array(out[1:]), g[sk], rtol=1e-13)
+        np.testing.assert_allclose(np.array(out[1:]), g[sk], rtol=1e-12)
     assert np.array_equal(g['radecz'], radecz0) and (w is None or np.array_equal(w, w0))     # inputs are not modified
     alpha = g['sums_d'][0] / g['sums_r'][0]
     I12, I13, I22, I23, I33 = alpha * g['sums_r'][1:]
@@ -208,3 +208,30 @@ def test_counts_f77_entry_point(mods, tmp_path, monkeypatch):
         assert c[l - 1, j - 1, i - 1] == cb[i - 1, j - 1, l - 1] * N ** 3
     assert os.path.isfile(os.path.join(str(tmp_path), 'counts.Ngrid24.Nmax3.Ncut3.step3.fort77'))
     assert np.array_equal(pySpec._counts_Bk123_f77(Ngrid=N, Nmax=nmax, Ncut=3, step=3), c)      # cache hit: same array
+
+
+@pytest.mark.parametrize('Np,weighted', [(1, False), (777, True), (300000, True)])
+def test_survey_prepare_kernel(mods, Np, weighted):
+    """psb_survey_prepare (one pass on the device) against util.radecz_to_cartesian + the numpy lines of py:789-806."""
+    pySpec, O = mods
+    from pyspectrum_b200 import util as UT
+    rng = np.random.default_rng(Np)
+    radecz = np.array([rng.uniform(0., 360., Np), rng.uniform(-90., 90., Np), rng.uniform(0., 1.5, Np)])
+    nb = rng.uniform(1e-5, 5e-4, Np)
+    w = rng.uniform(0.5, 2., Np) if weighted else None
+    cosmo = UT.FlatLambdaCDM(H0=70., Om0=0.3)
+    xyz, wf, out = pySpec.PeriodicPipeline.get(24).survey_prepare(radecz, nb, w, 1e4, cosmo)
+    ref = O.radecz_to_cartesian(radecz, O.FlatLambdaCDM(70., 0.3))
+    xyz = xyz.cpu().numpy()
+    assert xyz.dtype == np.float32 and xyz.shape == (3, Np)
+    # float32 cast of a float64 value that agrees to ~1e-12: identical or one float32 ulp apart
+    assert np.all(np.abs(xyz - ref.astype(np.float32)) <= np.spacing(np.abs(ref).astype(np.float32)) + 1e-8)
+    w0 = np.ones(Np) if w is None else w
+    wref = w0 * (1. / (1. + nb * 1e4))
+    assert np.array_equal(wf.cpu().numpy(), wref.astype(np.float32))
+    sums = [w0.sum(), (wref ** 2).sum(), (wref ** 3).sum(), (nb * wref ** 2).sum(), (nb * wref ** 3).sum(), (nb ** 2 * wref ** 3).sum()]
+    np.testing.assert_allclose(out[:6], sums, rtol=1e-12)
+    np.testing.assert_allclose(out[6:9], ref.min(axis=1), rtol=1e-10, atol=1e-8)
+    np.testing.assert_allclose(out[9:12], ref.max(axis=1), rtol=1e-10, atol=1e-8)
+    with pytest.raises(ValueError):
+        pySpec.PeriodicPipeline.get(24).survey_prepare(-radecz, nb, w, 1e4, cosmo)               # negative redshift
