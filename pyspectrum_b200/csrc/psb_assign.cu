@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(256) k_assign(const float4* __restrict__ sorte
     }
 }
 
-// Lane-per-pair variant: four consecutive lanes share a particle, lane pr < 3 owns the aligned cell pair P0 + pr of every row of the
+// Lane-per-pair variant (PSB_ASSIGN_VARIANT=1; also the path for N > 1024): four consecutive lanes share a particle, lane pr < 3 owns the aligned cell pair P0 + pr of every row of the
 // window (lane 3 idles).  The three vector reductions of a row then leave in ONE instruction from adjacent lanes, and the
 // load/store unit merges their 48 contiguous bytes into two 32-byte sectors instead of three separate sector packets: a third
 // fewer packets on the L1 -> L2 reduction path that bounds this kernel.  The windows are recomputed per lane (cheap).
@@ -252,6 +252,56 @@ __global__ void __launch_bounds__(256) k_assign_pairs(const float4* __restrict__
     }
 }
 
+// Three-lanes-per-particle variant (default): lanes 3g, 3g+1, 3g+2 of a warp own the three aligned cell pairs of particle g
+// (10 particles per warp, lanes 30/31 idle: 94 % of the lanes work instead of 75 % with four lanes per particle), so the merged
+// 48-byte row reductions of k_assign_pairs are kept while a warp instruction serves 10 particles instead of 8.  The inner loop
+// is trimmed to what ncu showed it spends its issue slots on (k_assign_pairs: 78 % issue utilisation, 1435 instructions per
+// lane and particle, REDG only 1.7 % of them): periodic wraps by compare-and-subtract from one wrapped base cell instead of a
+// modulo per row, 32-bit element offsets (2 N^3 < 2^32), weights pre-multiplied per z row, and the four "product != 0" tests of
+// a reduction replaced by tests on its factors.
+__global__ void __launch_bounds__(256) k_assign_tri(const float4* __restrict__ sorted, long long Np, int N, float kf_ks, float offset, float* mesh)
+{
+    const int lane = threadIdx.x & 31;
+    const int g = lane / 3, pr = lane - 3 * g;
+    const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long i = warp * 10 + g;
+    if (g >= 10 || i >= Np) return;
+    const float4 p = sorted[i];
+    const AxisWin X = axis_window(kf_ks, p.x, offset), Y = axis_window(kf_ks, p.y, offset), Z = axis_window(kf_ks, p.z, offset);
+    const int P0 = X.c0 >> 1, off = X.c0 - 2 * P0, Nh = N / 2;
+    const int k0 = 2 * pr - off, k1 = k0 + 1;                  // window cells held by this lane's pair
+    const float xa0 = sel5(X.a, k0), xa1 = sel5(X.a, k1), xb0 = sel5(X.b, k0), xb1 = sel5(X.b, k1);
+    const bool nza = xa0 != 0.f || xa1 != 0.f, nzb = xb0 != 0.f || xb1 != 0.f;
+    if (!nza && !nzb) return;
+    int P = (P0 + pr) % Nh;
+    if (P < 0) P += Nh;
+    const int y0 = wrapN(Y.c0, N), z0 = wrapN(Z.c0, N);
+    const unsigned rowlen = 2u * (unsigned)N;
+    unsigned yoff[5];
+    float za[5], zb[5];
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+        int yy = y0 + r;
+        yy = yy >= N ? yy - N : yy;
+        yoff[r] = (unsigned)yy * rowlen + 4u * (unsigned)P;
+        za[r] = Z.a[r] * p.w;
+        zb[r] = Z.b[r] * p.w;
+    }
+#pragma unroll
+    for (int rz = 0; rz < 5; ++rz) {
+        if (za[rz] == 0.f && zb[rz] == 0.f) continue;
+        int zz = z0 + rz;
+        zz = zz >= N ? zz - N : zz;
+        const unsigned zoff = (unsigned)zz * (unsigned)N * rowlen;
+#pragma unroll
+        for (int ry = 0; ry < 5; ++ry) {
+            const float wa = Y.a[ry] * za[rz], wb = Y.b[ry] * zb[rz];
+            if (!((nza && wa != 0.f) || (nzb && wb != 0.f))) continue;
+            red_add_v4(mesh + (zoff + yoff[ry]), xa0 * wa, xb0 * wb, xa1 * wa, xb1 * wb);
+        }
+    }
+}
+
 size_t assign_workspace_bytes(long long Np, int N)
 {
     size_t hist = (((size_t)N * N + 1) * sizeof(unsigned int) + 255) / 256 * 256;
@@ -280,8 +330,9 @@ int assign_pcs_interlaced(const AssignIn& in, float* mesh, int zero_mesh, void* 
         k_scan_tiles<<<1, 256, 0, st>>>(tile_sum, ntile);
         k_scan_apply<<<ntile, 256, 0, st>>>(hist, (int)nrow, tile_sum);
         k_sort_scatter<<<grid, blk, 0, st>>>(in, hist, sorted);
-        static const int variant = [] { const char* e = getenv("PSB_ASSIGN_VARIANT"); return e ? atoi(e) : 1; }();
-        if (variant == 1) k_assign_pairs<<<(unsigned)((4 * in.Np + 255) / 256), 256, 0, st>>>(sorted, in.Np, in.N, in.kf_ks, in.offset, mesh);
+        static const int variant = [] { const char* e = getenv("PSB_ASSIGN_VARIANT"); return e ? atoi(e) : 2; }();
+        if (variant == 2 && in.N <= 1024) k_assign_tri<<<(unsigned)((in.Np + 79) / 80), 256, 0, st>>>(sorted, in.Np, in.N, in.kf_ks, in.offset, mesh);
+        else if (variant == 1) k_assign_pairs<<<(unsigned)((4 * in.Np + 255) / 256), 256, 0, st>>>(sorted, in.Np, in.N, in.kf_ks, in.offset, mesh);
         else k_assign<<<(unsigned)((in.Np + 255) / 256), 256, 0, st>>>(sorted, in.Np, in.N, in.kf_ks, in.offset, mesh);
     }
     return cudaGetLastError() == cudaSuccess ? PSB_OK : PSB_ERR_CUDA;
