@@ -81,3 +81,69 @@ def test_f2py_shape_and_order_checks():
         O.assign_quad(np.zeros((3, 1), np.float32), np.ones(1, np.float32), np.zeros((8, 4, 4), np.float32), 1., 0, 0, 0, 0, 0)
     with pytest.raises(ValueError):
         O.fcomb_periodic(np.zeros((4, 4, 4), np.complex64), 1.)
+
+
+# ---------------------------------------------------------------------------- survey-geometry pieces (estimator.f:677-745, py:817-823)
+def test_fcomb_survey_is_fcomb_periodic_with_unit_weight():
+    """The two subroutines differ only in cf: 1/(6^3 4 N) (f:614) against 1/(6^3 4) (f:686)."""
+    rng = np.random.default_rng(8)
+    N = 12
+    F = np.asfortranarray((rng.normal(size=(N, N, N)) + 1j * rng.normal(size=(N, N, N))).astype(np.complex64))
+    a, b = F.copy(order='F'), F.copy(order='F')
+    O.fcomb_survey(a, N)
+    O.fcomb_periodic(b, 1.)
+    assert np.array_equal(a, b)
+    c = F.copy(order='F')
+    O.fcomb_periodic(c, 4.)                                   # exact power of two: the same values scaled
+    assert np.array_equal(c * np.float32(4.), a)
+
+
+def test_assign_offset_is_a_half_box_shift():
+    """assign_quad(offset = N/2) on positions in (-L/2, L/2) (py:819) = assign_quad(offset = 0) on positions + L/2,
+    when the shift is exact in float32 (kf_ks = 1, half-integer offsets)."""
+    rng = np.random.default_rng(4)
+    N = 16
+    r = np.asfortranarray(rng.uniform(-7.5, 7.5, (3, 500)).astype(np.float32))
+    w = rng.uniform(0.5, 2., 500).astype(np.float32)
+    a = np.zeros((2 * N, N, N), np.float32, order='F')
+    b = np.zeros((2 * N, N, N), np.float32, order='F')
+    O.assign_quad(r, w, a, np.float32(1.), 0.5 * N, 0, 0, 0, 0)
+    O.assign_quad(np.asfortranarray(r + np.float32(8.)), w, b, np.float32(1.), 0., 0, 0, 0, 0)
+    assert np.abs(a - b).max() <= 2e-6 * np.abs(b).max()     # (r + 1) + 8 vs (r + 8) + 1: one float32 rounding apart
+    assert abs(a[::2].sum(dtype=np.float64) / w.sum(dtype=np.float64) - 216.) < 1e-3
+
+
+def test_survey_delta_of_one_object_is_a_plane_wave():
+    """One object at x (relative to the box centre): delta_0(k) = w_fkp e^{+i k.(x + L/2)} up to window/aliasing (py:817-823)."""
+    N, L = 24, 1000.
+    cos = O.FlatLambdaCDM(67.6, 0.31)
+    radecz = np.array([[35.], [12.], [0.1]])
+    nb = np.array([2e-4])
+    d, Ntot, I12, I13, I22, I23, I33 = O.FFT_survey_mono(radecz, nb, P0_fkp=1e4, Lbox=L, Ngrid=N, cosmo=cos)
+    wf = 1. / (1. + 2e-4 * 1e4)
+    assert Ntot == 1. and np.isclose(I12, wf ** 2) and np.isclose(I33, nb[0] ** 2 * wf ** 3)
+    x = O.radecz_to_cartesian(radecz, cos)[:, 0] + 0.5 * L
+    assert abs(d[0, 0, 0] - wf) < 1e-6
+    k = np.arange(N // 2 + 1)
+    kk = np.array([i if i <= N // 2 else i - N for i in range(N)])
+    ph = wf * np.exp(1j * 2 * np.pi / L * (k[:, None, None] * x[0] + kk[None, :, None] * x[1] + kk[None, None, :] * x[2]))
+    kmag = np.sqrt(k[:, None, None] ** 2 + kk[None, :, None] ** 2 + kk[None, None, :] ** 2)
+    assert np.abs(d - ph)[kmag < N / 4].max() < 1e-3 * wf
+
+
+def test_pk_pbox_rsd_single_mode_lands_in_its_bin():
+    """One mode pair +-k with |delta|^2 = 1 on the half grid: nk counts both partners, k = kf |k|, P0 kf^3 = mean |delta|^2 and
+    the quadrupole follows L2(mu) with mu = kz/|k| for the line of sight along z (estimator.f:196-262)."""
+    N, Lbox, nbin, nmu = 16, 100, 8, 4
+    d = np.zeros((N // 2 + 1, N, N), np.complex64, order='F')
+    kx, ky, kz = 2, 1, 2                                        # |k| = 3 exactly
+    d[kx, ky, kz] = 1.
+    k, p0, p2, p4, nk, km, mk, pkm, nkm = O.pk_pbox_rsd(d, 2, Lbox, nbin, nmu)
+    kf = 2 * np.pi / Lbox
+    b = 2                                                       # nint(nbin * 3 / (N/2)) - 1 = bin index 3 -> slot 2
+    assert nk[b] > 0 and np.isclose(k[b], kf * 3., rtol=0.1)    # mean |k| over all 98 modes with 2.5 <= |k| < 3.5
+    tot = p0 * nk * np.float64(np.float32(kf) ** 3)
+    assert np.isclose(tot[b], 2., rtol=1e-5) and np.allclose(np.delete(tot, b), 0.)      # both partners of the pair counted
+    mu = kz / 3.
+    assert np.isclose(p2[b] / p0[b], 5. * (-0.5 + 1.5 * mu * mu), rtol=1e-5)
+    assert np.isclose(p4[b] / p0[b], 9. * (0.375 - 3.75 * mu ** 2 + 4.375 * mu ** 4), rtol=1e-4)
