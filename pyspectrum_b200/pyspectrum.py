@@ -793,11 +793,7 @@ def _bk_epilogue(Ngrid, tri, sums, sumsq, Nk, counts, step, Ncut, Nmax):
     for j in range(s0, Nmax + 1):
         p0k[j - 1] = sumsq[j - s0] / Ngrid ** 3 / Nk[j]
     i, j, l = tri[:, 0], tri[:, 1], tri[:, 2]
-    fac = np.ones(len(tri))
-    fac[(j == l) & (i == j)] = 6.
-    fac[(i == j) & (j != l)] = 2.
-    fac[(i == l) & (l != j)] = 2.
-    fac[(j == l) & (l != i)] = 2.
+    fac = _shell_fac(tri)
     c = counts[i - 1, j - 1, l - 1]
     pos = c > 0
     cs = np.where(pos, c, 1.)

@@ -291,3 +291,26 @@ def test_survey_distance_table_accuracy():
         d = (2 * t3 - 3 * t2 + 1) * tab[k, 0] + (t3 - 2 * t2 + t) * tab[k, 1] + (-2 * t3 + 3 * t2) * tab[k + 1, 0] + (t3 - t2) * tab[k + 1, 1]
         ref = cos.comoving_distance(z) * cos.h
         assert np.abs(d - ref).max() < 1e-9 * ref.max()
+
+
+def test_product_bk_periodic_host_logic_with_stubbed_device(golden_dir, monkeypatch):
+    """_Bk_periodic (pyspectrum.py:359-457) and its epilogue on the reference golden's field, device stages stubbed as above."""
+    from pyspectrum_b200 import pyspectrum as pySpec
+    g = dict(np.load(os.path.join(golden_dir, 'small_A.npz')))
+    N, L = int(g['Ngrid']), float(g['Lbox'])
+    stub = _StubPipe(N)
+    monkeypatch.setattr(pySpec.PeriodicPipeline, 'get', classmethod(lambda cls, Ngrid: stub))
+    full = O.reflect_delta(g['delta_half'], N)
+    for (step, Ncut, Nmax) in [(3, 3, 4), (2, 3, 6), (1, 1, 8)]:
+        pre = 'bk_s%d_c%d_m%d_' % (step, Ncut, Nmax)
+        bk = pySpec._Bk_periodic(full, Nmax=Nmax, Ncut=Ncut, step=step)
+        nbar = g['xyz'].shape[1] / L ** 3
+        kf = 2 * np.pi / L
+        for key in ['i_k1', 'i_k2', 'i_k3']:
+            assert np.array_equal(bk[key], g[pre + key])
+        np.testing.assert_allclose(bk['counts'], g[pre + 'counts'], rtol=1e-12)
+        np.testing.assert_allclose(bk['p0k1'] * (2 * np.pi) ** 3 / kf ** 3 - 1. / nbar, g[pre + 'p0k1'], rtol=1e-9)
+        raw = (g[pre + 'b123'] + g[pre + 'b123_sn']) * kf ** 6 / (2 * np.pi) ** 6
+        np.testing.assert_allclose(bk['b123'], raw, rtol=1e-8, atol=1e-10 * np.abs(raw).max())
+    with pytest.raises(ValueError):
+        pySpec._Bk_periodic(full, Nmax=4, Ncut=1, step=3)           # Ncut//step == 0

@@ -1,3 +1,9 @@
+#!/usr/bin/env python
+"""Opcode mix of the kernels in an ncu report: share of executed warp instructions and (in brackets) of stall samples per SASS opcode.
+
+    ncu -i gpurun_out/x.ncu-rep --page source --csv --print-source sass > /tmp/x.csv
+    python tools/ncu_opcode_mix.py /tmp/x.csv
+"""
 import csv,collections,re,sys
 rows=list(csv.reader(open(sys.argv[1])))
 sections=[];cur=None;i=0
