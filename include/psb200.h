@@ -92,6 +92,20 @@ int psb_fft_c2c_3d(float* data_c64, int ngrid, int dir, const float* tw_c64, voi
 int psb_fcomb(const float* full_c64, float* half_c64, int ngrid, const double* rec_c128, const float* wk,
               const double* sumw, int periodic, void* stream);
 
+/* Slab-decomposed K2+K3 for ONE catalogue sharded over G GPUs (pyspectrum_b200/multigpu.py).  A rank owns nz = N/G
+ * z-planes of the reduced mesh (A + iB) and, after the exchange, ny = N/G ky-rows of k-space; hp = N/2+1 rounded up to even.
+ *   psb_fft_slab_xy    in-place x and y passes of data [nz][N][N] (dir=+1: FFTW_BACKWARD as py:1064-1075)
+ *   psb_slab_split_ab  d [nz][N][N] -> p = A^xy, q = B^xy on [nz][N][hp] (kx = 0..N/2; the conjugate partner is in the same plane)
+ *   (caller: all-to-all  [nz][N][hp] -> [N][ny][hp])
+ *   psb_fft_slab_z     in-place z pass of an array [N][ny][nx] (nx even)
+ *   psb_slab_fcomb     p, q [N][ny][hp] -> rows ky0..ky0+ny-1 of the half field, half [N][ny][N/2+1], through the same closed
+ *                      form of estimator.f:605-745 as psb_fft_mesh_to_delta (F(k) = p + iq, F(-k) = conj p + i conj q) */
+int psb_fft_slab_xy(float* data_c64, int ngrid, int nz, int dir, const float* tw_c64, void* stream);
+int psb_fft_slab_z(float* data_c64, int ngrid, int ny, int nx, int dir, const float* tw_c64, void* stream);
+int psb_slab_split_ab(const float* d_c64, float* p_c64, float* q_c64, int ngrid, int nz, int hp, void* stream);
+int psb_slab_fcomb(const float* p_c64, const float* q_c64, float* half_c64, int ngrid, int ky0, int ny, int hp,
+                   const double* rec_c128, const float* wk, const double* sumw, int periodic, void* stream);
+
 /* K4  power spectra from the half field.
  * psb_pk_monopole   : pyspectrum.py:690-716.  out (float64) = nk[nbin], sum|k|[nbin], sum|delta|^2[nbin]
  * psb_pk_multipoles : estimator.f:196-244 (raw sums, before f:246-262).  out (float64) =

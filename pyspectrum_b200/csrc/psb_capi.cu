@@ -154,6 +154,33 @@ int psb_fcomb(const float* full, float* half, int N, const double* rec, const fl
                             reinterpret_cast<const Cx<double>*>(rec), wk, sumw, periodic, S(stream));
 }
 
+int psb_fft_slab_xy(float* data, int N, int nz, int dir, const float* tw, void* stream)
+{
+    if (!data || !tw || (dir != 1 && dir != -1)) return PSB_ERR_ARG;
+    return fft_slab_xy(reinterpret_cast<Cx<float>*>(data), N, nz, dir, reinterpret_cast<const Cx<float>*>(tw), S(stream));
+}
+
+int psb_fft_slab_z(float* data, int N, int ny, int nx, int dir, const float* tw, void* stream)
+{
+    if (!data || !tw || (dir != 1 && dir != -1)) return PSB_ERR_ARG;
+    return fft_slab_z(reinterpret_cast<Cx<float>*>(data), N, ny, nx, dir, reinterpret_cast<const Cx<float>*>(tw), S(stream));
+}
+
+int psb_slab_split_ab(const float* d, float* p, float* q, int N, int nz, int hp, void* stream)
+{
+    if (!d || !p || !q) return PSB_ERR_ARG;
+    return slab_split_ab(reinterpret_cast<const Cx<float>*>(d), reinterpret_cast<Cx<float>*>(p), reinterpret_cast<Cx<float>*>(q), N, nz, hp,
+                         S(stream));
+}
+
+int psb_slab_fcomb(const float* p, const float* q, float* half, int N, int ky0, int ny, int hp, const double* rec, const float* wk,
+                   const double* sumw, int periodic, void* stream)
+{
+    if (!p || !q || !half || !rec || !wk || (periodic && !sumw)) return PSB_ERR_ARG;
+    return slab_fcomb(reinterpret_cast<const Cx<float>*>(p), reinterpret_cast<const Cx<float>*>(q), reinterpret_cast<Cx<float>*>(half), N, ky0,
+                      ny, hp, reinterpret_cast<const Cx<double>*>(rec), wk, sumw, periodic, S(stream));
+}
+
 int psb_pk_monopole(const float* half, int N, const uint16_t* bin, int nbin, double kf, double* out, void* stream)
 {
     if (!half || !bin || !out) return PSB_ERR_ARG;

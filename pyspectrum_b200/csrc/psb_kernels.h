@@ -61,6 +61,13 @@ size_t triangle_tc_workspace_bytes(int MT, int NT);
 int triangle_sums_tc_pass(const float* const* fields, int S, long long ncell, const int* lane_ij, int lane_layout, int MT, int NT,
                           const int* tri_rc, int ntri, double* sums, void* ws, size_t ws_bytes, cudaStream_t st);
 
+// slab-decomposed mesh -> delta(k) building blocks of the sharded path (psb_fft_mesh.cu)
+int fft_slab_xy(Cx<float>* data, int N, int nz, int dir, const Cx<float>* tw, cudaStream_t st);
+int fft_slab_z(Cx<float>* data, int N, int ny, int nx, int dir, const Cx<float>* tw, cudaStream_t st);
+int slab_split_ab(const Cx<float>* d, Cx<float>* P, Cx<float>* Q, int N, int nz, int hp, cudaStream_t st);
+int slab_fcomb(const Cx<float>* P, const Cx<float>* Q, Cx<float>* half, int N, int ky0, int ny, int hp, const Cx<double>* rec,
+               const float* Wk, const double* sumw, int periodic, cudaStream_t st);
+
 // survey-geometry catalogue pre-step (psb_survey.cu)
 int survey_prepare(const double* radecz, const double* nb, const double* w, long long np, const double* tab, int nn, double zmax,
                    double p0_fkp, float* xyz, float* wout, double* out12, cudaStream_t st);

@@ -11,6 +11,14 @@ Design ("alternative for grids that fit one GPU's memory", and what m
   5. slab-local triangle sums (K6) and shell powers -> all-reduce of Ntri + S float64   [exchange 3: ~50-400 kB]
   6. the float64 exact triangle counts use the same steps 3-5 with delta == 1
 
+Steps 1-2 have a slab-decomposed alternative (`sharded_delta(..., fft='slab')` or PSB_SHARDED_FFT=slab): the mesh is
+reduce-scattered into z-slabs instead of all-reduced, every rank transforms its slab along x and y, separates the two
+interlaced grids' spectra inside each plane (P = A^xy, Q = B^xy: the conjugate partner (-kx,-ky) is local), one all-to-all turns
+z-slabs into ky-slabs, the z pass and the point-wise fcomb follow, and an all-gather rebuilds the replicated half field that
+steps 3-5 use.  No conjugate-partner exchange; the FFT work is divided by G instead of replicated.  The building blocks are
+validated on one GPU with emulated ranks (tests/test_gpu_slab.py) and the exchange bookkeeping on gloo; the default stays
+'replicated' until the slab path has been timed on a multi-GPU box.
+
 Every kernel is the single-GPU one; only the orchestration differs.  The collectives are torch.distributed calls so the
 same code runs under NCCL (GPU) and gloo (the CPU tests of the host logic: tests/test_multigpu_host.py)."""
 import numpy as np
@@ -56,6 +64,102 @@ def exchange_to_slabs(fields_local, world):
     return out.view(nrow * world, slab)
 
 
+# ------------------------------------------------------------------------------------------ slab-decomposed mesh -> delta(k)
+def slab_geometry(N, world):
+    """(planes per rank, padded half-row length): N must divide by the number of ranks; rows hold kx = 0..N/2 padded to even."""
+    if N % world:
+        raise ValueError('Ngrid must be a multiple of the number of ranks for the slab FFT')
+    return N // world, (N // 2 + 2) // 2 * 2
+
+
+def z_to_y_chunks(t, world):
+    """t: [nz, N, hp, 2] (a rank's z-planes, all ky) -> send buffer [world, nz, ny, hp, 2]: chunk q = the ky range of rank q."""
+    nz, N, hp, two = t.shape
+    ny = N // world
+    return t.view(nz, world, ny, hp, two).permute(1, 0, 2, 3, 4).contiguous()
+
+
+def z_to_y_slabs(t, world):
+    """All-to-all of z-slabs into ky-slabs: [nz, N, hp, 2] on every rank -> [N, ny, hp, 2] (all z of this rank's ky range)."""
+    nz, N, hp, two = t.shape
+    send = z_to_y_chunks(t, world)
+    if world == 1:
+        return send.view(N, N, hp, two)
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send)                   # recv[g] = rank g's planes (z = g*nz .. ) of my ky range
+    return recv.view(world * nz, N // world, hp, two)
+
+
+def slab_phase1(pipe, mesh_slab):
+    """x and y passes of a reduced z-slab [nz, N, N, 2] (destroyed) + separation -> (P, Q) each [nz, N, hp, 2]."""
+    N = pipe.N
+    nz = mesh_slab.shape[0]
+    hp = (N // 2 + 2) // 2 * 2
+    st = P._stream()
+    P.check(pipe.L.psb_fft_slab_xy(P._ptr(mesh_slab), N, nz, 1, P._ptr(pipe.tw32), st), 'psb_fft_slab_xy')
+    p = torch.empty((nz, N, hp, 2), dtype=torch.float32, device=pipe.dev)
+    q = torch.empty_like(p)
+    P.check(pipe.L.psb_slab_split_ab(P._ptr(mesh_slab), P._ptr(p), P._ptr(q), N, nz, hp, st), 'psb_slab_split_ab')
+    return p, q
+
+
+def slab_phase2(pipe, py, qy, ky0, sumw, periodic=1):
+    """z passes of a ky-slab of P and Q [N, ny, hp, 2] (in place) + fcomb -> rows ky0.. of the half field, [N, ny, N/2+1, 2]."""
+    N = pipe.N
+    ny, hp = py.shape[1], py.shape[2]
+    st = P._stream()
+    for t in (py, qy):
+        P.check(pipe.L.psb_fft_slab_z(P._ptr(t), N, ny, hp, 1, P._ptr(pipe.tw32), st), 'psb_fft_slab_z')
+    half = torch.empty((N, ny, N // 2 + 1, 2), dtype=torch.float32, device=pipe.dev)
+    P.check(pipe.L.psb_slab_fcomb(P._ptr(py), P._ptr(qy), P._ptr(half), N, ky0, ny, hp, P._ptr(pipe.rec), P._ptr(pipe.wk), P._ptr(sumw),
+                                  periodic, st), 'psb_slab_fcomb')
+    return half
+
+
+def slab_mesh_to_delta_emulated(pipe, mesh, sumw, world, periodic=1):
+    """The slab pipeline for `world` emulated ranks on ONE device (the exchanges are slices): mesh [N,N,N,2] -> half field
+    [N,N,N/2+1,2].  Used to validate the building blocks without a multi-GPU box."""
+    N = pipe.N
+    nz, hp = slab_geometry(N, world)
+    pq = [slab_phase1(pipe, mesh[g * nz:(g + 1) * nz].clone()) for g in range(world)]
+    half = torch.empty((N, N, N // 2 + 1, 2), dtype=torch.float32, device=pipe.dev)
+    for r in range(world):
+        py = torch.cat([z_to_y_chunks(pq[g][0], world)[r] for g in range(world)], dim=0)
+        qy = torch.cat([z_to_y_chunks(pq[g][1], world)[r] for g in range(world)], dim=0)
+        half[:, r * nz:(r + 1) * nz] = slab_phase2(pipe, py, qy, r * nz, sumw, periodic)
+    return half
+
+
+def slab_mesh_to_delta(pipe, mesh, sumw, periodic=1):
+    """Distributed slab pipeline: every rank passes its UNREDUCED full mesh [N,N,N,2] (destroyed); returns the replicated half
+    field.  reduce-scatter (z-slabs) -> x,y passes + separation -> all-to-all -> z pass + fcomb -> all-gather."""
+    world = _world()
+    N = pipe.N
+    nz, hp = slab_geometry(N, world)
+    rank = dist.get_rank() if world > 1 else 0
+    if world > 1:
+        slab = torch.empty((nz, N, N, 2), dtype=torch.float32, device=pipe.dev)
+        dist.reduce_scatter_tensor(slab, mesh)
+    else:
+        slab = mesh
+    p, q = slab_phase1(pipe, slab)
+    del slab
+    py, qy = z_to_y_slabs(p, world), z_to_y_slabs(q, world)
+    del p, q
+    mine = slab_phase2(pipe, py, qy, rank * nz, sumw, periodic)
+    return gather_ky_slabs(mine, world)
+
+
+def gather_ky_slabs(mine, world):
+    """All-gather of the ky-slabs [N, ny, hx, 2] of the half field into the replicated [N, N, hx, 2] array."""
+    if world == 1:
+        return mine
+    N, ny, hx, two = mine.shape
+    gathered = torch.empty((world * N, ny, hx, two), dtype=mine.dtype, device=mine.device)     # rank-major concatenation
+    dist.all_gather_into_tensor(gathered, mine.contiguous())
+    return gathered.view(world, N, ny, hx, two).permute(1, 0, 2, 3, 4).reshape(N, world * ny, hx, two)
+
+
 def _allreduce(t, op=dist.ReduceOp.SUM):
     if dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(t, op=op)
@@ -66,12 +170,19 @@ def _world():
     return dist.get_world_size() if dist.is_initialized() else 1
 
 
-def sharded_delta(pipe, xyz_local, w_local, Lbox):
-    """Steps 1-2: returns (half field, global sum of weights as a device tensor)."""
+def sharded_delta(pipe, xyz_local, w_local, Lbox, fft=None):
+    """Steps 1-2: returns (half field, global sum of weights as a device tensor).  fft = 'replicated' (all-reduce of the mesh,
+    every rank transforms all of it) or 'slab' (see the module docstring); default from PSB_SHARDED_FFT, else 'replicated'."""
+    import os
+    fft = fft or os.environ.get('PSB_SHARDED_FFT', 'replicated')
+    if fft not in ('replicated', 'slab'):
+        raise ValueError("fft must be 'replicated' or 'slab'")
     pos, aos, wt = pipe.to_device(xyz_local, w_local)
     mesh, sumw = pipe.assign(pos, aos, wt, Lbox)
-    _allreduce(mesh)
     _allreduce(sumw)
+    if fft == 'slab' and pipe.N % _world() == 0:
+        return slab_mesh_to_delta(pipe, mesh, sumw), sumw
+    _allreduce(mesh)
     half = pipe.mesh_to_delta(mesh, sumw)
     return half, sumw
 

@@ -69,3 +69,51 @@ def test_exchange_single_rank_is_a_reshape():
     rows = slab_field_rows(4, 1, 2)
     for f in range(4):
         assert torch.equal(slabs[rows[f]], local[f])
+
+
+def _slab_worker(rank, world, port, out):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    import torch.distributed as dist
+    dist.init_process_group('gloo')
+    from pyspectrum_b200.multigpu import slab_geometry, z_to_y_slabs, gather_ky_slabs
+    N = 8
+    nz, hp = slab_geometry(N, world)
+    z, y, x, c = torch.meshgrid(torch.arange(N), torch.arange(N), torch.arange(hp), torch.arange(2), indexing='ij')
+    T = (z * 10000 + y * 100 + x * 2 + c).float()                 # global array [z][ky][kx][re/im]
+    mine = T[rank * nz:(rank + 1) * nz].contiguous()              # this rank's z-slab
+    ys = z_to_y_slabs(mine, world)                                # -> all z of this rank's ky range
+    ok = bool(torch.equal(ys, T[:, rank * nz:(rank + 1) * nz]))
+    full = gather_ky_slabs(ys, world)                             # -> replicated
+    ok &= bool(torch.equal(full, T))
+    out.put((rank, ok, tuple(ys.shape)))
+    dist.destroy_process_group()
+
+
+def test_slab_exchange_two_ranks_gloo():
+    """z-slabs -> ky-slabs all-to-all and the ky-slab all-gather of the slab-decomposed FFT (multigpu.slab_mesh_to_delta)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 31700 + os.getpid() % 2000
+    ps = [ctx.Process(target=_slab_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in ps]
+    res = sorted(q.get(timeout=120) for _ in ps)
+    [p.join(60) for p in ps]
+    assert all(p.exitcode == 0 for p in ps)
+    for rank, ok, shape in res:
+        assert ok and shape == (8, 4, 6, 2)
+
+
+def test_slab_geometry_and_single_rank_exchange():
+    from pyspectrum_b200.multigpu import slab_geometry, z_to_y_slabs, z_to_y_chunks, gather_ky_slabs
+    assert slab_geometry(360, 2) == (180, 182) and slab_geometry(1024, 8) == (128, 514) and slab_geometry(24, 4) == (6, 14)
+    try:
+        slab_geometry(360, 7)
+        assert False
+    except ValueError:
+        pass
+    t = torch.arange(4 * 8 * 6 * 2, dtype=torch.float32).view(4, 8, 6, 2)
+    ch = z_to_y_chunks(t, 2)                                      # chunk q = ky range q of these planes
+    assert torch.equal(ch[0], t[:, :4]) and torch.equal(ch[1], t[:, 4:])
+    full = torch.arange(8 * 8 * 6 * 2, dtype=torch.float32).view(8, 8, 6, 2)
+    assert torch.equal(z_to_y_slabs(full, 1), full) and torch.equal(gather_ky_slabs(full, 1), full)
