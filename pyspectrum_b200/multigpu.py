@@ -15,9 +15,12 @@ Steps 1-2 have a slab-decomposed alternative (`sharded_delta(..., fft='slab')` o
 reduce-scattered into z-slabs instead of all-reduced, every rank transforms its slab along x and y, separates the two
 interlaced grids' spectra inside each plane (P = A^xy, Q = B^xy: the conjugate partner (-kx,-ky) is local), one all-to-all turns
 z-slabs into ky-slabs, the z pass and the point-wise fcomb follow, and an all-gather rebuilds the replicated half field that
-steps 3-5 use.  No conjugate-partner exchange; the FFT work is divided by G instead of replicated.  The building blocks are
-validated on one GPU with emulated ranks (tests/test_gpu_slab.py) and the exchange bookkeeping on gloo; the default stays
-'replicated' until the slab path has been timed on a multi-GPU box.
+steps 3-5 use.  No conjugate-partner exchange; the FFT work is divided by G instead of replicated.  Validated on one GPU with
+emulated ranks (tests/test_gpu_slab.py: 2e-6 of max|delta| against the single-GPU K2+K3 for G = 1..8), the exchange bookkeeping
+on gloo (tests/test_multigpu_host.py), and under NCCL on 2 GPUs at C2 (tools/run_sharded.py: same outputs as the single-GPU
+path, 21.4 vs 20.9 ms -- at 360^3 on two GPUs the extra exchanges cost what the halved FFT saves).  It is meant for 1024^3 on 8
+GPUs, where the 8.6 GB mesh all-reduce and the replicated 25 ms FFT dominate P(k); the default stays 'replicated' until that
+configuration has been timed (profiles/r1_multigpu.jsonl).
 
 Every kernel is the single-GPU one; only the orchestration differs.  The collectives are torch.distributed calls so the
 same code runs under NCCL (GPU) and gloo (the CPU tests of the host logic: tests/test_multigpu_host.py)."""
