@@ -124,3 +124,43 @@ extern "C" void emu_fcomb(const float* full_, float* half_, int N, float sumw, i
         H[ix + (size_t)(h + 1) * (iy + (size_t)N * iz)] = fcomb_value(N, ix, iy, iz, Fk, Fm, rec.data(), Wk.data(), cf);
     }
 }
+
+// Slab-decomposed fcomb (psb_fft_mesh.cu: k_slab_split_ab / k_slab_fcomb), element for element the arithmetic of the two kernels.
+// d: [nz][N][N] complex64 after the x and y passes -> p, q: [nz][N][hp]
+extern "C" void emu_slab_split(const float* d_, float* p_, float* q_, int N, int nz, int hp)
+{
+    const Cx<float>* d = reinterpret_cast<const Cx<float>*>(d_);
+    Cx<float>* P = reinterpret_cast<Cx<float>*>(p_);
+    Cx<float>* Q = reinterpret_cast<Cx<float>*>(q_);
+    const int h = N / 2;
+    for (long long z = 0; z < nz; ++z) for (int ky = 0; ky < N; ++ky) for (int kx = 0; kx < hp; ++kx) {
+        Cx<float> p = mk<float>(0.f, 0.f), q = p;
+        if (kx <= h) {
+            const Cx<float> Dk = d[(z * N + ky) * N + kx];
+            const Cx<float> Dm = d[(z * N + kneg(ky, N)) * N + kneg(kx, N)];
+            p = mk<float>(0.5f * (Dk.x + Dm.x), 0.5f * (Dk.y - Dm.y));
+            q = mk<float>(0.5f * (Dk.y + Dm.y), -0.5f * (Dk.x - Dm.x));
+        }
+        P[(z * N + ky) * hp + kx] = p;
+        Q[(z * N + ky) * hp + kx] = q;
+    }
+}
+// p, q: [N][ny][hp] after the z pass -> half: [N][ny][N/2+1] = rows ky0.. of the half field
+extern "C" void emu_slab_fcomb(const float* p_, const float* q_, float* half_, int N, int ky0, int ny, int hp, float sumw, int periodic)
+{
+    const Cx<float>* P = reinterpret_cast<const Cx<float>*>(p_);
+    const Cx<float>* Q = reinterpret_cast<const Cx<float>*>(q_);
+    Cx<float>* H = reinterpret_cast<Cx<float>*>(half_);
+    const int h = N / 2;
+    std::vector<Cx<double>> rec(h + 1);
+    std::vector<float> Wk(h + 1);
+    fcomb_build_tables(N, rec.data(), Wk.data());
+    const float cf = periodic ? 1.f / (864.f * sumw) : 1.f / 864.f;
+    for (int iz = 0; iz < N; ++iz) for (int yl = 0; yl < ny; ++yl) for (int ix = 0; ix <= h; ++ix) {
+        const size_t s = ((size_t)iz * ny + yl) * hp + ix;
+        const Cx<float> p = P[s], q = Q[s];
+        const Cx<float> Fk = mk<float>(p.x - q.y, p.y + q.x);
+        const Cx<float> Fm = mk<float>(p.x + q.y, q.x - p.y);
+        H[((size_t)iz * ny + yl) * (h + 1) + ix] = fcomb_value(N, ix, ky0 + yl, iz, Fk, Fm, rec.data(), Wk.data(), cf);
+    }
+}

@@ -84,3 +84,56 @@ def test_fcomb_closed_form_matches_sequential_oracle(emu, N, periodic):
         O.fcomb_survey(ref, N)
     ref_half = ref[:N // 2 + 1, :, :].transpose(2, 1, 0)                                         # -> [iz,iy,ix]
     assert np.array_equal(half.view(np.uint32), np.ascontiguousarray(ref_half).view(np.uint32))
+
+
+@pytest.mark.parametrize('N,world', [(12, 1), (12, 2), (24, 4), (36, 3)])
+@pytest.mark.parametrize('periodic', [1, 0])
+def test_slab_decomposed_fcomb_matches_oracle(emu, N, world, periodic):
+    """The sharded path's slab pipeline (multigpu.slab_mesh_to_delta: x,y passes per z-slab, separation of the two grids' spectra,
+    z-slabs -> ky-slabs, z pass, fcomb rebuilt from P and Q) with numpy FFTs standing in for the line-FFT kernels and the two
+    element-wise kernels emulated: equals the oracle's sequential fcomb on the full transform to float32 rounding on EVERY mode,
+    the self-conjugate planes (last write wins) included."""
+    from pyspectrum_b200.multigpu import slab_geometry, z_to_y_chunks
+    from oracle import pyspec_oracle as O
+    import torch
+    rng = np.random.default_rng(N + world)
+    L, Np = 50., 3000
+    xyz = rng.uniform(0, L, (3, Np))
+    xyz[:, :Np // 2] = (xyz[:, :Np // 2] * 0.3 + 10.) % L
+    w = rng.uniform(0.5, 2., Np)
+    sumw = float(np.sum(w))
+    mesh = O.assign_mesh(xyz, w, L, N)                                            # (2N,N,N) Fortran order
+    ref = O._FFT(mesh, N)
+    if periodic:
+        O.fcomb_periodic(ref, sumw, N)
+    else:
+        O.fcomb_survey(ref, N)
+    ref_half = np.ascontiguousarray(ref[:N // 2 + 1].transpose(2, 1, 0))          # [kz][ky][kx]
+    d = (np.ascontiguousarray(mesh[0::2].transpose(2, 1, 0)) + 1j * np.ascontiguousarray(mesh[1::2].transpose(2, 1, 0))).astype(np.complex64)
+    nz, hp = slab_geometry(N, world)
+    emu.emu_slab_split.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int] * 3
+    emu.emu_slab_fcomb.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int] * 4 + [ctypes.c_float, ctypes.c_int]
+    pq = []
+    for g in range(world):                                                        # phase 1 on every emulated rank
+        s = d[g * nz:(g + 1) * nz]
+        D = np.ascontiguousarray(np.fft.ifft2(s, axes=(1, 2), norm='forward').astype(np.complex64))
+        p = np.zeros((nz, N, hp), np.complex64)
+        q = np.zeros((nz, N, hp), np.complex64)
+        emu.emu_slab_split(_ptr(D), _ptr(p), _ptr(q), N, nz, hp)
+        pq.append((p, q))
+    half = np.zeros((N, N, N // 2 + 1), np.complex64)
+    for r in range(world):                                                        # exchange (the product's own chunking) + phase 2
+        def gather(i):
+            parts = [z_to_y_chunks(torch.from_numpy(pq[g][i].view(np.float32).reshape(nz, N, hp, 2)), world)[r].numpy() for g in range(world)]
+            a = np.concatenate(parts, axis=0)                                     # [N z][ny][hp][2]
+            return np.ascontiguousarray(a).view(np.complex64)[..., 0]
+        py = np.ascontiguousarray(np.fft.ifft(gather(0), axis=0, norm='forward').astype(np.complex64))
+        qy = np.ascontiguousarray(np.fft.ifft(gather(1), axis=0, norm='forward').astype(np.complex64))
+        out = np.zeros((N, nz, N // 2 + 1), np.complex64)
+        emu.emu_slab_fcomb(_ptr(py), _ptr(qy), _ptr(out), N, r * nz, nz, hp, ctypes.c_float(sumw), periodic)
+        half[:, r * nz:(r + 1) * nz] = out
+    scale = np.abs(ref_half).max()
+    assert np.abs(half - ref_half).max() <= 2e-6 * scale
+    h = N // 2
+    for plane in (half[:, :, 0] - ref_half[:, :, 0], half[:, :, h] - ref_half[:, :, h], half[:, h] - ref_half[:, h], half[h] - ref_half[h]):
+        assert np.abs(plane).max() <= 2e-6 * scale
