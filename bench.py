@@ -264,8 +264,8 @@ def run_b200(args):
                                     'frac_algorithmic': ach_tf / tf_peak, 'frac_issued': 9.4 * ach_tf / tf_peak},
                     'note': 'algorithmic bytes = 4 Nshell N^3 (every field read once), algorithmic flops = (Npair + 2 Ntri) N^3 '
                             '(SURVEY 8d); as a GEMM the kernel issues 3 split MMAs on a dense 512 x 48 tile per 16 cells = 9.4x '
-                            'the algorithmic flops; it is limited by the CUDA-core formation of the fp16 pair-product operand '
-                            '(handshake/latency chain, profiles/r1_summary.md), not by HBM or the tensor pipe'}
+                            'the algorithmic flops; it is limited by the SM load/store data path (shared-memory and TMEM wavefronts of '
+                            'forming the fp16 pair-product operand, DESIGN.md K6 / profiles/r1_summary.md), not by HBM or the tensor pipe'}
         else:
             roof = {'kernel': 'k_tri (K6 triangle sums, FFMA path)', 'bound': 'hbm', 'achieved': ach_gbs, 'peak': hbm_peak,
                     'unit': 'GB/s', 'frac': ach_gbs / hbm_peak, 'traffic': None, 'peak_source': peak_src,
