@@ -4,7 +4,6 @@ version run exactly as they would under NCCL (whose collectives are covered on g
 Reference = the single-GPU K2+K3 (psb_fft_mesh_to_delta), itself pinned to the oracle in tests/test_gpu_parity.py.
 Tolerance: 2e-6 of max|delta| (the slab path rebuilds F(k) from the separated spectra: one more float32 rounding),
 including the self-conjugate planes where the Fortran's last write wins."""
-import ctypes
 
 import numpy as np
 import pytest

@@ -2,7 +2,6 @@
 pair dealing, the all-to-all to slabs and the row bookkeeping that K6 relies on."""
 import os
 
-import numpy as np
 import torch
 
 
