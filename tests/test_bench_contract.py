@@ -1,0 +1,32 @@
+"""CPU: the reference arm of bench.py (the CPU oracle timed on the host cores) prints ONE JSON line with the keys the driver reads."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_one_contract_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0'],
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip().startswith('{')]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ['impl', 'metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling', 'vs_baseline',
+                'dtype', 'data', 'config', 'cpu_baseline', 'e2e']:
+        assert key in d, key
+    assert d['impl'] == 'reference' and d['higher_is_better'] is False and d['vs_baseline'] is None and d['unit'] == 's/catalog'
+    assert d['value'] > 0 and abs(d['ms_per_step'] - 1e3 * d['value']) < 1e-6 * d['ms_per_step']
+    assert 'workload' in d['config'] and 'model' not in d['config']
+    cb = d['cpu_baseline']
+    assert cb['kind'] in ('port', 'reference') and cb['cores'] >= 1 and cb['value'] == d['value'] and 'sample' in cb
+    assert d['e2e'] == {'value': d['value'], 'unit': d['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+
+
+def test_reference_arm_other_ranks_do_nothing():
+    env = dict(os.environ, RANK='1', WORLD_SIZE='2')
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--gpus', '2', '--steps', '1', '--warmup', '0'],
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300, cwd=ROOT, env=env)
+    assert out.returncode == 0 and not [l for l in out.stdout.splitlines() if l.strip().startswith('{')]
