@@ -271,7 +271,8 @@ def run_b200(args):
                     'unit': 'GB/s', 'frac': ach_gbs / hbm_peak, 'traffic': None, 'peak_source': peak_src,
                     'note': 'FMA-pipe bound (84 flop/B): see fma_* keys', 'fma_achieved_tflops': ach_tf,
                     'fma_peak_tflops': fma_peak, 'fma_frac': ach_tf / fma_peak}
-        cpu = None if os.environ.get('PSB_BENCH_NO_CPU') else cpu_baseline_sample(threads=1)
+        # the CPU baseline leg runs on rank 0 of the single-GPU run only (the multi-GPU runs would just repeat it)
+        cpu = None if (world > 1 or os.environ.get('PSB_BENCH_NO_CPU')) else cpu_baseline_sample(threads=1)
         line = {
             'metric': METRIC, 'value': dev_ms * 1e-3 / ncat, 'unit': 's/catalog', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dev_ms / args.steps,
