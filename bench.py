@@ -14,8 +14,11 @@ b200 arm      one "step" = one full pass of the hot path over one catalogue:
               N > 1    : one process per GPU (torchrun), every rank works on its own catalogue, no data-path
                          collective (catalogues are independent) -> weak scaling; time = max over ranks.
 reference arm the CPU oracle (oracle/: C restatement of estimator.f + pocketfft + the reference's Python
-              algorithm) on the host cores, every step a bounded sample of the same workload, extrapolated
-              linearly per shell / per triangle (the full reference run takes ~15 min and ~17 GB).
+              algorithm) on ALL host threads, every step ONE WHOLE catalogue of the same recipe and seed as the
+              b200 arm (no sampling, no extrapolation: ~40 s per step on 16 threads, 8 GB of float32 shell fields).
+              The number of timed steps is capped so that the arm ends within a few minutes; `steps` says how many ran.
+Both arms draw the catalogue from the same seeded host generator (`lognormal_catalogue_numpy`), so they work on
+bit-identical particles.
 """
 import argparse
 import json
@@ -70,8 +73,9 @@ def lognormal_catalogue_torch(seed, dev, Np_target=10 ** 7, Lbox=2600., Ng=360):
     return xyz.contiguous()                                 # (3, Np) float64 on device
 
 
-def lognormal_catalogue_numpy(seed, Np_target, Lbox=2600., Ng=180):
-    """Host version for the reference arm (smaller generating grid: the catalogue only has to be clustered)."""
+def lognormal_catalogue_numpy(seed, Np_target, Lbox=2600., Ng=360):
+    """SURVEY 8d config C2 on the host (numpy + pocketfft): the ONE catalogue recipe both arms use (same seed -> identical
+    particles for the b200 arm, the reference arm and the sampled single-core baseline).  Outside every timed region."""
     import scipy.fft as sfft
     rng = np.random.default_rng(seed)
     kf = 2 * np.pi / Lbox
@@ -153,10 +157,13 @@ def run_b200(args):
 
     L, N, step, Ncut, Nmax = CFG['Lbox'], CFG['Ngrid'], CFG['step'], CFG['Ncut'], CFG['Nmax']
     s0 = Ncut // step
-    xyz_dev = lognormal_catalogue_torch(D.catalogue_seed(2, rank), dev, CFG['Np_target'], L, N)
-    Np = xyz_dev.shape[1]
+    # the same seeded host recipe as the reference arm (rank 0: bit-identical particles); other ranks get their own seed
+    xyz_np = lognormal_catalogue_numpy(2 + 1000 * rank, CFG['Np_target'], L, N)
+    Np = xyz_np.shape[1]
     xyz_host = torch.empty((3, Np), dtype=torch.float64, pin_memory=True)
-    xyz_host.copy_(xyz_dev)
+    xyz_host.copy_(torch.from_numpy(xyz_np))
+    del xyz_np
+    xyz_dev = xyz_host.to(dev)
     torch.cuda.synchronize()
     pipe = pySpec.PeriodicPipeline.get(N)
     pipe.counts(Nmax, Ncut, step)          # exact triangle counts: once per configuration, cached
@@ -277,12 +284,11 @@ def run_b200(args):
             'metric': METRIC, 'value': dev_ms * 1e-3 / ncat, 'unit': 's/catalog', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dev_ms / args.steps,
             'higher_is_better': False, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
-            'data': 'synthetic lognormal catalogue (seeded, generated on device), %d particles per catalogue' % Np,
-            'config': {'workload': 'BASELINE configs[1]: Bk_periodic, Lbox=2600, Ngrid=360, step=3, Ncut=3, Nmax=40',
-                       'particles': Np, 'triangles': int(len(tri)), 'shells': S,
-                       'parallelism': 'one catalogue per GPU (independent catalogues, no data-path collective)',
-                       'l2': 'inputs larger than L2 (8 GB of shell fields, 240 MB of positions vs 126 MB): no flush needed',
-                       'counts': 'exact triangle counts cached per configuration (computed once in float64 before timing)'},
+            'data': 'synthetic lognormal catalogue (seeded, host generator shared by both arms), %d particles per catalogue' % Np,
+            'config': shared_config(Np, len(tri), S),
+            'parallelism': 'one catalogue per GPU (independent catalogues, no data-path collective)',
+            'counts': 'exact triangle counts cached per configuration (computed once in float64 before timing; the reference reads '
+                      'them from its shipped cache file)',
             'e2e': {'value': e2e_ms * 1e-3 / ncat, 'unit': 's/catalog', 'h2d_bytes_per_step': int(3 * Np * 8),
                     'd2h_bytes_per_step': int(8 * (len(tri) + S + (S % 2))),
                     'api': 'pyspectrum_b200.pyspectrum.Bk_periodic_many over pinned host catalogues (float64 positions)',
@@ -343,26 +349,84 @@ def cpu_baseline_sample(threads=1, nshell_sample=4, ntri_sample=24, np_sample=2 
             'parts_s': {'assign': t_assign, 'fft_fcomb_reflect': t_other, 'shells': t_shell * S, 'triangles': t_tri * 6350}}
 
 
+def shared_config(Np, ntri, S):
+    """The `config` object both arms print (the driver compares them)."""
+    return {'workload': 'BASELINE configs[1]: Bk_periodic, Lbox=2600, Ngrid=360, step=3, Ncut=3, Nmax=40',
+            'catalogue': 'lognormal_catalogue_numpy(seed 2 + 1000 rank, Np_target 1e7, Lbox 2600, Ng 360)',
+            'particles': int(Np), 'triangles': int(ntri), 'shells': int(S),
+            'l2': 'inputs larger than L2 / the host LLC (8 GB of shell fields, 240 MB of positions vs 126 MB of L2): no flush needed'}
+
+
+def reference_counts():
+    """Triangle counts for C2 as the reference reads them from its shipped cache file (py:968-972): the committed copy of
+    counts.Ngrid360.Nmax40.Ncut3.step3.pyfftw (tests/golden/, exact integers)."""
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'counts_N360_Nmax40_Ncut3_step3.npz'))
+    counts = np.zeros((CFG['Nmax'],) * 3)
+    ijl = g['ijl'].astype(int)
+    counts[ijl[:, 0] - 1, ijl[:, 1] - 1, ijl[:, 2] - 1] = g['raw']
+    return counts
+
+
 def run_reference(args):
+    """The reference's own CPU algorithm for the path (oracle port: estimator.f restated in C + pocketfft + the Python layer of
+    pyspectrum.py) on all host threads, ONE WHOLE catalogue per step, same catalogue as the b200 arm's rank 0."""
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
         return
+    from oracle import pyspec_oracle as O
+    O.build()
     threads = os.cpu_count() or 1
-    for _ in range(min(args.warmup, 1)):
-        cpu_baseline_sample(threads=threads, nshell_sample=2, ntri_sample=4)
-    vals = []
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        vals.append(cpu_baseline_sample(threads=threads))
-        if time.perf_counter() - t0 > 240:          # keep the whole arm within a few minutes
+    L, N, step, Ncut, Nmax = CFG['Lbox'], CFG['Ngrid'], CFG['step'], CFG['Ncut'], CFG['Nmax']
+    smoke = bool(os.environ.get('PSB_REF_SMOKE'))        # tests/test_bench_contract.py only: 6 shells instead of 40, 2e5 particles
+    if smoke:
+        Nmax = 6
+    xyz = lognormal_catalogue_numpy(2, 2 * 10 ** 5 if smoke else CFG['Np_target'], L, N)
+    counts = reference_counts()[:Nmax, :Nmax, :Nmax]
+    ntri_expected = len(O.triangle_list(Nmax, Ncut, step))
+    assert smoke or ntri_expected == 6350
+    budget_s = float(os.environ.get('PSB_REF_BUDGET_S', 170.))
+
+    def one_step():
+        tm = {}
+        t0 = time.perf_counter()
+        out = O.Bk_periodic(xyz, Lbox=L, Ngrid=N, step=step, Ncut=Ncut, Nmax=Nmax, workers=threads, counts=counts,
+                            timings=tm, pool_threads=threads)
+        dt = time.perf_counter() - t0
+        assert len(out['b123']) == ntri_expected and np.all(np.isfinite(out['b123']))
+        return dt, tm
+
+    t_arm = time.perf_counter()
+    nwarm = 0
+    est = None
+    if args.warmup > 0:                                  # one whole untimed catalogue (pages in the library and 8 GB of buffers)
+        est, _ = one_step()
+        nwarm = 1
+    vals, parts = [], []
+    while len(vals) < args.steps:
+        spent = time.perf_counter() - t_arm
+        if vals and spent + (est or vals[-1]) > budget_s:   # cap: the arm has to end within a few minutes; `steps` reports the count
             break
-    v = float(np.mean([x['value'] for x in vals]))
-    cb = dict(vals[-1]); cb['value'] = v
+        dt, tm = one_step()
+        vals.append(dt)
+        parts.append(tm)
+        est = dt
+    v = float(np.mean(vals))
+    S = Nmax - Ncut // step + 1
+    parts_s = {k: float(np.mean([p.get(k, 0.) for p in parts])) for k in parts[0]}
+    cb = {'value': v, 'unit': 's/catalog', 'cores': threads, 'kind': 'port',
+          'sample': ('SMOKE RUN (PSB_REF_SMOKE, contract test only: Nmax=6) -- ' if smoke else '') +
+                    'the whole catalogue (%d particles), all %d shell FFTs, all %d triangle sums: nothing sampled or '
+                    'extrapolated; %d timed step(s) of %d requested (capped to keep the arm within %.0f s)'
+                    % (xyz.shape[1], S, ntri_expected, len(vals), args.steps, budget_s),
+          'parts_s': parts_s, 'steps_s': [float(x) for x in vals]}
     line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 's/catalog', 'n_gpus': int(os.environ.get('WORLD_SIZE', args.gpus)),
-            'steps': len(vals), 'warmup': min(args.warmup, 1), 'ms_per_step': v * 1e3, 'higher_is_better': False,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic lognormal catalogue (seeded, host)',
-            'config': {'workload': 'BASELINE configs[1]: Bk_periodic, Lbox=2600, Ngrid=360, step=3, Ncut=3, Nmax=40',
-                       'note': 'CPU oracle port of the reference on all host threads; each step is a bounded sample extrapolated linearly'},
+            'steps': len(vals), 'warmup': nwarm, 'ms_per_step': v * 1e3, 'higher_is_better': False,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic lognormal catalogue (seeded, host generator shared by both arms), %d particles per catalogue' % xyz.shape[1],
+            'config': shared_config(xyz.shape[1], ntri_expected, S),
+            'note': 'CPU oracle port of the reference (estimator.f restated in C, pocketfft for FFTW, the Python layer of pyspectrum.py) '
+                    'on all host threads: FFTs with workers=%d, triangle sums in a %d-thread pool, assignment serial as in the Fortran; '
+                    'counts from the shipped cache file as the reference does' % (threads, threads),
             'cpu_baseline': cb, 'e2e': {'value': v, 'unit': 's/catalog', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line))

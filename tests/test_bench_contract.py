@@ -9,7 +9,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_reference_arm_prints_one_contract_line():
     out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0'],
-                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600, cwd=ROOT)
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600, cwd=ROOT,
+                         env=dict(os.environ, PSB_REF_SMOKE='1'))       # same code path, 6 shells instead of 40 (the full arm takes minutes)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.strip().startswith('{')]
     assert len(lines) == 1
@@ -17,6 +18,7 @@ def test_reference_arm_prints_one_contract_line():
     for key in ['impl', 'metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling', 'vs_baseline',
                 'dtype', 'data', 'config', 'cpu_baseline', 'e2e']:
         assert key in d, key
+    assert d['steps'] == 1 and d['warmup'] == 0 and 'nothing sampled' in d['cpu_baseline']['sample']
     assert d['impl'] == 'reference' and d['higher_is_better'] is False and d['vs_baseline'] is None and d['unit'] == 's/catalog'
     assert d['value'] > 0 and abs(d['ms_per_step'] - 1e3 * d['value']) < 1e-6 * d['ms_per_step']
     assert 'workload' in d['config'] and 'model' not in d['config']
