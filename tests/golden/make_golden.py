@@ -36,7 +36,9 @@ REF = '/root/reference'
 SCRATCH = '/tmp/pyspectrum_ref_copy'
 
 
-def import_reference():
+def import_reference(estimator_module=None):
+    """estimator_module: what `import estimator` resolves to inside the reference (default: the oracle's C restatement;
+    tests/test_gpu_boundary.py passes pyspectrum_b200.estimator, the CUDA drop-in)."""
     from oracle import pyspec_oracle as O
     if os.path.isdir(SCRATCH):
         shutil.rmtree(SCRATCH)
@@ -82,7 +84,7 @@ def import_reference():
     est.fcomb_periodic = lambda dcl, n, ngrid=None: O.fcomb_periodic(dcl, n)
     est.fcomb_survey = lambda dcl, ngrid=None: O.fcomb_survey(dcl)
     est.pk_pbox_rsd = lambda dtl, irsd, lbox, nbin, nmu, ngrid=None: O.pk_pbox_rsd(dtl, irsd, int(lbox), nbin, nmu)
-    sys.modules['estimator'] = est
+    sys.modules['estimator'] = est if estimator_module is None else estimator_module
 
     # ---- astropy stub ----------------------------------------------------------------------
     astropy = types.ModuleType('astropy')
@@ -92,6 +94,8 @@ def import_reference():
     sys.modules.update({'astropy': astropy, 'astropy.cosmology': cosmo})
 
     sys.path.insert(0, SCRATCH)
+    for m in [m for m in sys.modules if m == 'pyspectrum' or m.startswith('pyspectrum.')]:
+        del sys.modules[m]                                   # a fresh import binds the estimator module given above
     from pyspectrum import pyspectrum as pySpec
     assert pySpec.__file__.startswith(SCRATCH)
     return pySpec
