@@ -115,6 +115,14 @@ int psb_pk_monopole(const float* half_c64, int ngrid, const uint16_t* bin_of_m, 
 int psb_pk_multipoles(const float* half_c64, int ngrid, const uint16_t* bin_of_m, int nbin, int nmu,
                       float kf32, const float* trig4_host, double* out, void* stream);
 
+/* code='python' branch of _Pk_periodic_rsd (pyspectrum.py:545-626): float64 (k,mu) estimator over ALL modes of a FULL field
+ * full_c64 [kx][ky][kz] (what reflect_delta returns, C order) with |k_a| = min(i, N-i), mu bin ceil(mu * nmu);
+ * bin_of_m = int(nbin*rk/phys_nyq + 0.5) host table (py:560), trig4_host = {cos theta_obs, sin theta_obs, cos phi_obs, sin phi_obs}
+ * in float64 (py:563-564, 577-578).  out (float64) = nk, sum rk, sum|d|^2, sum|d|^2 L2, sum|d|^2 L4 [nbin] (the last two over the
+ * mu-binned modes only, as py:606-607), then N_kmu, sum rk, sum mu, sum|d|^2 as [nbin][nmu]. */
+int psb_pk_kmu_python(const float* full_c64, int ngrid, const uint16_t* bin_of_m, int nbin, int nmu, double kf,
+                      const double* trig4_host, double* out, void* stream);
+
 /* K5  pyspectrum.py:373-404.  nk[j] = number of modes of the FULL grid in shell j (py:380). */
 int psb_shell_mode_counts(int ngrid, const uint16_t* irk_of_m, int nshell, uint64_t* nk, void* stream);
 /* One packed pair of shells (sa -> real part, sb -> imaginary part, sb<0: none), pruned to |k_i| <= R:

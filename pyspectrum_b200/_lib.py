@@ -35,7 +35,7 @@ def build(force=False, verbose=False):
 _c = ctypes
 _vp, _i, _i64, _f, _d, _sz = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_float, _c.c_double, _c.c_size_t
 
-# name -> (restype, argtypes); mirrors include/psb200.h one to one (tests/test_cabi_symbols.py checks it)
+# name -> (restype, argtypes); mirrors include/psb200.h one to one (tests/test_cabi_and_host.py checks it)
 PROTOTYPES = {
     'psb_version': (_i, []),
     'psb_error_string': (_c.c_char_p, [_i]),
@@ -57,6 +57,7 @@ PROTOTYPES = {
     'psb_slab_fcomb': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp]),
     'psb_pk_monopole': (_i, [_vp, _i, _vp, _i, _d, _vp, _vp]),
     'psb_pk_multipoles': (_i, [_vp, _i, _vp, _i, _i, _f, _vp, _vp, _vp]),
+    'psb_pk_kmu_python': (_i, [_vp, _i, _vp, _i, _i, _d, _vp, _vp, _vp]),
     'psb_shell_mode_counts': (_i, [_i, _vp, _i, _vp, _vp]),
     'psb_bk_shell_pair_f32': (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     'psb_bk_shell_power': (_i, [_vp, _i, _vp, _i, _vp, _vp]),

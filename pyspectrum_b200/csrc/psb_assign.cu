@@ -322,7 +322,7 @@ int assign_pcs_interlaced(const AssignIn& in, float* mesh, int zero_mesh, void* 
     if (zero_mesh && cudaMemsetAsync(mesh, 0, sizeof(float) * 2 * nrow * in.N, st) != cudaSuccess) return PSB_ERR_CUDA;
     if (in.Np > 0) {
         const int blk = 256;
-        const int grid = (int)((in.Np + blk - 1) / blk < 148 * 16 ? (in.Np + blk - 1) / blk : 148 * 16);
+        const int grid = (int)((in.Np + blk - 1) / blk < sm_count() * 16 ? (in.Np + blk - 1) / blk : sm_count() * 16);
         k_hist<<<grid, blk, 0, st>>>(in, hist, sumw);
         const int ntile = (int)((nrow + SCAN_TILE - 1) / SCAN_TILE);
         if (ntile > 4096) return PSB_ERR_UNSUPPORTED_N;

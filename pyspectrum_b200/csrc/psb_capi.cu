@@ -11,6 +11,19 @@
 
 using namespace psb;
 
+namespace psb {
+// one process drives one GPU (torchrun, one rank per device): the count of the first device seen is kept
+int sm_count()
+{
+    static const int n = [] {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v < 1) v = 148;
+        return v;
+    }();
+    return n;
+}
+}  // namespace psb
+
 namespace {
 
 struct DevBuf {
@@ -196,6 +209,11 @@ int psb_pk_multipoles(const float* half, int N, const uint16_t* bin, int nbin, i
     in.half = reinterpret_cast<const Cx<float>*>(half); in.N = N; in.bin = bin; in.Nbin = nbin; in.mode = 1; in.kf32 = kf32; in.Nmu = nmu;
     in.costh = trig4[0]; in.sinth = trig4[1]; in.cosph = trig4[2]; in.sinph = trig4[3];
     return binned_spectra(in, out, S(stream));
+}
+
+int psb_pk_kmu_python(const float* full, int N, const uint16_t* bin, int nbin, int nmu, double kf, const double* trig4, double* out, void* stream)
+{
+    return kmu_python(reinterpret_cast<const Cx<float>*>(full), N, bin, nbin, nmu, kf, trig4, out, S(stream));
 }
 
 int psb_shell_mode_counts(int N, const uint16_t* irk, int nshell, uint64_t* nk, void* stream)

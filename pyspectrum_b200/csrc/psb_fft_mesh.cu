@@ -74,7 +74,7 @@ int fcomb_standalone(const Cx<float>* full, Cx<float>* half, int N, const Cx<dou
                      const double* sumw, int periodic, cudaStream_t st)
 {
     if (N < 2 || N % 2) return PSB_ERR_ARG;
-    k_fcomb<<<148 * 8, 256, 0, st>>>(full, half, N, rec, Wk, sumw, periodic);
+    k_fcomb<<<sm_count() * 8, 256, 0, st>>>(full, half, N, rec, Wk, sumw, periodic);
     return cudaGetLastError() == cudaSuccess ? PSB_OK : PSB_ERR_CUDA;
 }
 
@@ -150,7 +150,7 @@ __global__ void k_slab_split_ab(const Cx<float>* __restrict__ d, Cx<float>* __re
 int slab_split_ab(const Cx<float>* d, Cx<float>* P, Cx<float>* Q, int N, int nz, int hp, cudaStream_t st)
 {
     if (N < 2 || (N & 1) || nz < 1 || hp < N / 2 + 1) return PSB_ERR_ARG;
-    k_slab_split_ab<<<148 * 8, 256, 0, st>>>(d, P, Q, N, nz, hp);
+    k_slab_split_ab<<<sm_count() * 8, 256, 0, st>>>(d, P, Q, N, nz, hp);
     return cudaGetLastError() == cudaSuccess ? PSB_OK : PSB_ERR_CUDA;
 }
 
@@ -176,7 +176,7 @@ int slab_fcomb(const Cx<float>* P, const Cx<float>* Q, Cx<float>* half, int N, i
                const float* Wk, const double* sumw, int periodic, cudaStream_t st)
 {
     if (N < 2 || (N & 1) || ny < 1 || ky0 < 0 || ky0 + ny > N || hp < N / 2 + 1) return PSB_ERR_ARG;
-    k_slab_fcomb<<<148 * 8, 256, 0, st>>>(P, Q, half, N, ky0, ny, hp, rec, Wk, sumw, periodic);
+    k_slab_fcomb<<<sm_count() * 8, 256, 0, st>>>(P, Q, half, N, ky0, ny, hp, rec, Wk, sumw, periodic);
     return cudaGetLastError() == cudaSuccess ? PSB_OK : PSB_ERR_CUDA;
 }
 

@@ -5,6 +5,9 @@
 
 namespace psb {
 
+// SMs of the current device (148 on B200), cached: grid-stride and persistent kernels size their grids as multiples of it
+int sm_count();
+
 struct AssignIn {
     const void* pos;      // positions
     int pos_f64;          // 1: float64, 0: float32
@@ -46,6 +49,9 @@ struct SpectraIn {
 // out layout (all float64): mode 0: nk[Nbin], ksum[Nbin], psum[Nbin]
 //                           mode 1: nk,k,p0,p2,p4 [Nbin] then nkm,km,mk,pkm [Nmu][Nbin] (Fortran (Nbin,Nmu))
 int binned_spectra(const SpectraIn& in, double* out, cudaStream_t st);
+// code='python' (k,mu) estimator on a full field [kx][ky][kz] (pyspectrum.py:545-626); trig4 = cos/sin theta_obs, cos/sin phi_obs (float64)
+int kmu_python(const Cx<float>* full, int N, const unsigned short* bin, int Nbin, int Nmu, double kf, const double* trig4, double* out,
+               cudaStream_t st);
 int shell_power(const Cx<float>* half, int N, const unsigned short* irk, int nshell, double* psum, cudaStream_t st);
 int shell_scales(const double* psum, int nshell, float target_rms, float* scales, cudaStream_t st);
 int shell_mode_counts(int N, const unsigned short* irk, int nshell_max, unsigned long long* nk, cudaStream_t st);

@@ -134,15 +134,92 @@ int binned_spectra(const SpectraIn& in, double* out, cudaStream_t st)
         const size_t smem = 3 * (size_t)in.Nbin * sizeof(double);
         if (smem > 200 * 1024) return PSB_ERR_ARG;
         if (cudaFuncSetAttribute(k_spectra<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PSB_ERR_CUDA;
-        k_spectra<0><<<148 * 4, 256, smem, st>>>(in, out, 0);
+        k_spectra<0><<<sm_count() * 4, 256, smem, st>>>(in, out, 0);
     } else {
         size_t smem = nout * sizeof(double);
         int tab_smem = 1;
         if (smem > 96 * 1024) { smem = 5 * (size_t)in.Nbin * sizeof(double); tab_smem = 0; }       // big (k,mu) tables stay in global memory
         if (smem > 200 * 1024) return PSB_ERR_ARG;
         if (cudaFuncSetAttribute(k_spectra<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PSB_ERR_CUDA;
-        k_spectra<1><<<148 * 2, 256, smem, st>>>(in, out, tab_smem);
+        k_spectra<1><<<sm_count() * 2, 256, smem, st>>>(in, out, tab_smem);
     }
+    return cudaGetLastError() == cudaSuccess ? PSB_OK : PSB_ERR_CUDA;
+}
+
+// code='python' variant of _Pk_periodic_rsd (pyspectrum.py:545-626): a float64 loop over ALL N^3 modes of a full (reflected) field
+// indexed [kx][ky][kz] with the absolute wave numbers |k_a| = min(i, N-i) (so mu >= 0), mu bin imu = ceil(mu/dmu) (mu = 0 falls in
+// no bin and, as in the reference, contributes to neither the (k,mu) table nor p2k/p4k), Legendre sums over the mu-binned modes
+// only.  Every float64 operation is written with a round-to-nearest intrinsic in numpy's evaluation order (no FMA contraction):
+// the bin counts are bit exact.  A debugging variant in the reference (it prints every bin) -> plain global float64 atomics for
+// the (k,mu) table, per-CTA shared bins for the five per-k sums.
+struct KmuPyIn {
+    const Cx<float>* full; int N; const unsigned short* bin; int Nbin, Nmu;
+    double kf, dmu, cos_th, sin_th, cos_ph, sin_ph;
+};
+
+__global__ void __launch_bounds__(256) k_kmu_python(KmuPyIn in, double* out)
+{
+    extern __shared__ double sbin[];                       // nk, ksum, p0, p2, p4 [Nbin]
+    const int N = in.N, Nbin = in.Nbin, Nmu = in.Nmu;
+    for (int i = threadIdx.x; i < 5 * Nbin; i += blockDim.x) sbin[i] = 0.0;
+    __syncthreads();
+    double* tab = out + 5 * (long long)Nbin;               // Nkmu, kkmu, mukmu, pkmu [Nbin][Nmu]
+    const long long tb = (long long)Nbin * Nmu, ntot = (long long)N * N * N;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < ntot; e += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(e % N);
+        const long long r = e / N;
+        const int b_ = (int)(r % N), a = (int)(r / N);
+        const int ia = a < N - a ? a : N - a, ib = b_ < N - b_ ? b_ : N - b_, ic = c < N - c ? c : N - c;
+        const int m = ia * ia + ib * ib + ic * ic;
+        const int bin = in.bin[m];
+        if (bin < 1 || bin > Nbin) continue;
+        const double rk = __dmul_rn(in.kf, __dsqrt_rn((double)m));
+        const double rkx = __dmul_rn(in.kf, (double)ia), rky = __dmul_rn(in.kf, (double)ib), rkz = __dmul_rn(in.kf, (double)ic);
+        const double cos_t = __ddiv_rn(rkz, rk);
+        const double sin_t = __dsqrt_rn(__dsub_rn(1.0, __dmul_rn(cos_t, cos_t)));
+        double cc = 0.0;
+        if (sin_t > 0.0) {
+            const double den = __dmul_rn(rk, sin_t);
+            cc = __dadd_rn(__dmul_rn(in.sin_ph, __ddiv_rn(rky, den)), __dmul_rn(in.cos_ph, __ddiv_rn(rkx, den)));
+        }
+        const double mu = __dadd_rn(__dmul_rn(in.cos_th, cos_t), __dmul_rn(__dmul_rn(in.sin_th, sin_t), cc));
+        const int imu = (int)ceil(__ddiv_rn(mu, in.dmu));
+        const Cx<float> d = in.full[e];
+        const float ab = (float)sqrt((double)d.x * (double)d.x + (double)d.y * (double)d.y);       // np.absolute(complex64)
+        const double pk = (double)__fmul_rn(ab, ab);
+        atomicAdd(&sbin[bin - 1], 1.0);
+        atomicAdd(&sbin[Nbin + bin - 1], rk);
+        atomicAdd(&sbin[2 * Nbin + bin - 1], pk);
+        if (imu >= 1 && imu <= Nmu) {
+            const double mu2 = __dmul_rn(mu, mu);
+            const double L2 = __dadd_rn(-0.5, __dmul_rn(1.5, mu2));
+            const double L4 = __dadd_rn(__dsub_rn(0.375, __dmul_rn(3.75, mu2)), __dmul_rn(4.375, __dmul_rn(mu2, mu2)));
+            atomicAdd(&sbin[3 * Nbin + bin - 1], __dmul_rn(pk, L2));
+            atomicAdd(&sbin[4 * Nbin + bin - 1], __dmul_rn(pk, L4));
+            double* t = tab + (long long)(bin - 1) * Nmu + (imu - 1);
+            atomicAdd(t, 1.0);
+            atomicAdd(t + tb, rk);
+            atomicAdd(t + 2 * tb, mu);
+            atomicAdd(t + 3 * tb, pk);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 5 * Nbin; i += blockDim.x)
+        if (sbin[i] != 0.0) atomicAdd(&out[i], sbin[i]);
+}
+
+int kmu_python(const Cx<float>* full, int N, const unsigned short* bin, int Nbin, int Nmu, double kf, const double* trig4, double* out,
+               cudaStream_t st)
+{
+    if (!full || !bin || !out || !trig4 || N < 2 || N % 2 || Nbin < 1 || Nmu < 1) return PSB_ERR_ARG;
+    const size_t nout = (5 + 4 * (size_t)Nmu) * Nbin, smem = 5 * (size_t)Nbin * sizeof(double);
+    if (smem > 200 * 1024) return PSB_ERR_ARG;
+    if (cudaMemsetAsync(out, 0, nout * sizeof(double), st) != cudaSuccess) return PSB_ERR_CUDA;
+    if (cudaFuncSetAttribute(k_kmu_python, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PSB_ERR_CUDA;
+    KmuPyIn in;
+    in.full = full; in.N = N; in.bin = bin; in.Nbin = Nbin; in.Nmu = Nmu; in.kf = kf; in.dmu = 1.0 / (double)Nmu;
+    in.cos_th = trig4[0]; in.sin_th = trig4[1]; in.cos_ph = trig4[2]; in.sin_ph = trig4[3];
+    k_kmu_python<<<sm_count() * 4, 256, smem, st>>>(in, out);
     return cudaGetLastError() == cudaSuccess ? PSB_OK : PSB_ERR_CUDA;
 }
 
@@ -170,7 +247,7 @@ int shell_mode_counts(int N, const unsigned short* irk, int nshell, unsigned lon
 {
     if (N < 2 || N % 2 || nshell < 1 || nshell > 8192) return PSB_ERR_ARG;
     if (cudaMemsetAsync(nk, 0, nshell * sizeof(unsigned long long), st) != cudaSuccess) return PSB_ERR_CUDA;
-    k_shell_counts<<<148 * 4, 256, nshell * sizeof(unsigned int), st>>>(N, irk, nshell, nk);
+    k_shell_counts<<<sm_count() * 4, 256, nshell * sizeof(unsigned int), st>>>(N, irk, nshell, nk);
     return cudaGetLastError() == cudaSuccess ? PSB_OK : PSB_ERR_CUDA;
 }
 
@@ -229,7 +306,7 @@ int shell_power(const Cx<float>* half, int N, const unsigned short* irk, int nsh
 {
     if (!half || !irk || !psum || N < 2 || N % 2 || nshell < 1 || nshell > SHELL_POWER_MAXBINS) return PSB_ERR_ARG;
     if (cudaMemsetAsync(psum, 0, nshell * sizeof(double), st) != cudaSuccess) return PSB_ERR_CUDA;
-    k_shell_power<<<148 * 4, 256, 0, st>>>(half, N, irk, nshell, psum);
+    k_shell_power<<<sm_count() * 4, 256, 0, st>>>(half, N, irk, nshell, psum);
     return cudaGetLastError() == cudaSuccess ? PSB_OK : PSB_ERR_CUDA;
 }
 

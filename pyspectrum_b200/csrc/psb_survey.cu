@@ -106,7 +106,7 @@ int survey_prepare(const double* radecz, const double* nb, const double* w, long
     if (cudaMemsetAsync(out12, 0, 6 * sizeof(double), st) != cudaSuccess) return PSB_ERR_CUDA;
     if (cudaMemcpyAsync(keys, init, sizeof(init), cudaMemcpyHostToDevice, st) != cudaSuccess) return PSB_ERR_CUDA;
     long long nblk = (np + 255) / 256;
-    if (nblk > 148 * 8) nblk = 148 * 8;
+    if (nblk > sm_count() * 8) nblk = sm_count() * 8;
     k_survey_prepare<<<(unsigned)nblk, 256, 0, st>>>(radecz, radecz + np, radecz + 2 * np, nb, w, np, tab, nn, (double)nn / zmax, p0_fkp,
                                                      xyz, wout, out12, keys);
     k_survey_finish<<<1, 32, 0, st>>>(out12, keys);

@@ -97,7 +97,7 @@ __global__ void k_tri_fold(const double* __restrict__ partial, int ncta, const i
     sums[slot] = s;
 }
 
-static int tri_ctas() { return 148; }
+static int tri_ctas() { return sm_count(); }
 
 size_t triangle_workspace_bytes(int ntiles)
 {

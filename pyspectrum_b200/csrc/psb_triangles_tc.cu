@@ -13,19 +13,23 @@
 // contiguous x range; tensor-core accumulation rounds toward zero, so TMEM is drained into float64
 // every p.flush_ksteps*16 cells (double-buffered accumulator sets: the drain overlaps the next MMAs).
 //
-// Warp roles (704 threads, 1 CTA/SM):
-//   warps 0..15  A formers, warp = 4*g + q.  Work unit n = (sub-chunk, K-step k, tile pair tp); group g takes n = g (mod 4), i.e.
-//                tiles {2tp,2tp+1} of K-steps kp and kp+2 of every 64-cell sub-chunk (two operand stages -> double buffered); a
-//                thread owns one TMEM lane in both tiles (rows sharing the field i), forms the pair products in packed half2
-//                (already hi/lo split) and writes them straight into TMEM (one tcgen05.st.x16 per tile) as the A operand; the
-//                groups take turns draining the accumulator tiles.  (PSB_TC_GROUPS=6 runs 24 former warps: same speed.)
-//                (A 2x2-block variant -- four rows from four field vectors, 1/3 less shared-memory traffic -- measured slower:
-//                the kernel is bound by the per-stage handshake/latency chain, not by shared-memory throughput; profiles/.)
+// Warp roles (NG = 4 former groups: 20 warps = 640 threads at 96 registers, 1 CTA/SM; Roles<NG> below):
+//   warps 0..15  A formers, warp = 4*g + q (group g, TMEM lane quarter q).  Default lane layout 1 (MT == 4): a thread owns one TMEM
+//                lane = a 2x2 block of pair rows (i0,i1) x (j0,j1), one row in each of the four M tiles; a work unit is one K-step
+//                (16 cells) of ALL four tiles, group g takes operand stage g of every 64-cell sub-chunk: four field vectors give four
+//                rows of products (1 shared-memory word per product), formed in packed half2 already hi/lo split and written
+//                straight into TMEM as the A operand (one tcgen05.st.x16 per tile).  Lane layout 0 (more than 64 shells: 2-3
+//                accumulator tiles): a lane holds one i and one j per tile, a unit is one K-step of a tile pair.  The groups take
+//                turns draining the accumulator tiles.  (PSB_TC_GROUPS=6 runs 24 former warps in layout 0: same speed.)
+//   warps 16,17  B formers (two operand stages each): packed fields -> fp16 hi/lo K-major core-matrix tiles in shared memory
+//   warp 18      TMA producer: cp.async.bulk (UBLKCP) of [S][XCH] field chunks, one row per lane
 //   warp 19      MMA issuer (one elected lane): tcgen05.mma.cta_group::1.kind::f16 with A from TMEM, B from smem; tcgen05.commit
-//   warp 18      TMA producer: cp.async.bulk (UBLKCP) of [S][64] fp32 field chunks, one row per lane
-//   warps 16,17,20,21 B formers (one per operand stage): fields -> fp16 hi/lo K-major core-matrix tiles in shared memory
-// Pipelines: chunk ring (TMA -> formers/B), four operand stages = the four K-steps of a chunk (formers/B -> MMA),
-// accumulators (MMA -> drain, one chunk late so nobody waits).
+// Pipelines: chunk ring (TMA -> formers/B), four operand stages = the four K-steps of a sub-chunk (formers/B -> MMA),
+// accumulators (MMA -> drain, one period late so nobody waits).
+// Truncation: the tensor core rounds its fp32 accumulation toward zero; between two drains an accumulator takes
+// 12*flush_chunks MMAs and comes out short by ~1.8e-8 per MMA relative to its own value (measured: mean -8.8e-7 of |S| at 48
+// MMAs).  The drain adds the TMEM value times (1 + bias_comp) to the fp32 shared accumulators (one FFMA, round to nearest),
+// which removes the systematic part; what is left is the zero-mean spread.
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <cstdlib>
@@ -58,13 +62,13 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 }
 // try_wait suspends the thread in hardware up to the hinted time, so waiting warps do not burn the issue
 // slots the MMA-issuing warp needs (polling formers made that warp the bottleneck: profiles/r1)
-__constant__ unsigned int c_wait_hint_ns = 20000u;
-
 // backoff_ns > 0: roles with slack (B formers, TMA producer) sleep between probes -- the hardware try_wait returns every ~85 cycles,
 // and eight spinning warps were issuing a third of all instructions of the SM (profiles/r1_summary.md)
+constexpr uint32_t WAIT_HINT_NS = 20000u;
+
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsigned backoff_ns = 0)
 {
-    const uint32_t hint = c_wait_hint_ns;
+    const uint32_t hint = WAIT_HINT_NS;
     const uint32_t a = smem_u32(bar);
     uint32_t done = 0;
     unsigned spins = 0;
@@ -189,6 +193,7 @@ struct Params {
     long long nchunk;             // ncell / XCH (chunk size of the launched instantiation)
     int flush_chunks;             // TMEM accumulators are drained (fp32, round-to-nearest) every flush_chunks 64-cell sub-chunks
     int gflush_drains;            // the fp32 accumulators go to float64 global every gflush_drains drains
+    float bias_gain;              // 1 + bias_comp: multiplies every drained TMEM value (compensates the truncating accumulation)
     double* partial;              // [gridDim.x][NT][MT*128] float64 partial sums (zeroed by the host)
     long long* trace;             // optional clock64 timeline of CTA 0 (profiling only): [role 0..4][event][sub-chunk]
     unsigned backoff_ns;          // sleep between barrier probes of the roles with slack (B formers; x5 for the TMA producer)
@@ -220,6 +225,7 @@ __device__ __forceinline__ void drain_accumulators(const Params& p, uint64_t* ac
     mbar_wait(acc_full, (uint32_t)(period & 1));
     tc_fence_after();
     const bool to_global = ((period + 1) % p.gflush_drains == 0) || final_drain;
+    const float bg = p.bias_gain;
     if (live && !(p.debug & 8)) {
         double* dst = p.partial + (size_t)blockIdx.x * MR * NT + (size_t)row;     // [col][row]: coalesced
         // one 16-column TMEM load per round trip: keeping two or three in flight needs 32-48 more live registers and spills at the
@@ -232,8 +238,8 @@ __device__ __forceinline__ void drain_accumulators(const Params& p, uint64_t* ac
             for (int q4 = 0; q4 < 4; ++q4) {
                 float4* sp = &accs[(size_t)(c0 / 4 + q4) * MR + row];
                 float4 cur = *sp;
-                cur.x += __uint_as_float(r[4 * q4]); cur.y += __uint_as_float(r[4 * q4 + 1]);
-                cur.z += __uint_as_float(r[4 * q4 + 2]); cur.w += __uint_as_float(r[4 * q4 + 3]);
+                cur.x = fmaf(__uint_as_float(r[4 * q4]), bg, cur.x); cur.y = fmaf(__uint_as_float(r[4 * q4 + 1]), bg, cur.y);
+                cur.z = fmaf(__uint_as_float(r[4 * q4 + 2]), bg, cur.z); cur.w = fmaf(__uint_as_float(r[4 * q4 + 3]), bg, cur.w);
                 if (to_global) {
                     dst[(size_t)(c0 + 4 * q4 + 0) * MR] += (double)cur.x;
                     dst[(size_t)(c0 + 4 * q4 + 1) * MR] += (double)cur.y;
@@ -570,7 +576,26 @@ __global__ void k_tri_tc_fold(const double* __restrict__ partial, int ncta, int 
 
 }  // namespace tc
 
-size_t triangle_tc_workspace_bytes(int MT, int NT) { return (size_t)148 * MT * 128 * NT * sizeof(double); }
+// tuning / profiling knobs, read from the environment ONCE (not per launch)
+struct TcEnv {
+    int groups = 4, debug = 0, flush_chunks = 4, gflush_drains = 64;
+    unsigned backoff_ns = 0;
+    double bias_per_mma = 1.83e-8;           // measured: -8.8e-7 of |S| after 48 accumulating MMAs (profiles/r1_summary.md)
+    const char* trace_path = nullptr;
+    TcEnv()
+    {
+        if (const char* e = getenv("PSB_TC_GROUPS")) { if (atoi(e) == 6) groups = 6; }
+        if (const char* e = getenv("PSB_TC_BACKOFF")) backoff_ns = (unsigned)strtoul(e, nullptr, 10);
+        if (const char* e = getenv("PSB_TC_DEBUG")) debug = atoi(e);
+        if (const char* e = getenv("PSB_TC_FLUSH")) { int v = atoi(e); if (v >= 1 && v <= 4096) flush_chunks = v; }
+        if (const char* e = getenv("PSB_TC_GFLUSH")) { int v = atoi(e); if (v >= 1 && v <= 65536) gflush_drains = v; }
+        if (const char* e = getenv("PSB_TC_BIAS")) bias_per_mma = atof(e);
+        trace_path = getenv("PSB_TC_TRACE");
+    }
+};
+static const TcEnv& tc_env() { static const TcEnv e; return e; }
+
+size_t triangle_tc_workspace_bytes(int MT, int NT) { return (size_t)sm_count() * MT * 128 * NT * sizeof(double); }
 
 // One pass: 128 lanes x MT tiles of pair rows (lane_ij) against all NT columns.  tri_rc[t] = (row, col) or (-1,-1).
 int triangle_sums_tc_pass(const float* const* fields, int S, long long ncell, const int* lane_ij, int lane_layout, int MT, int NT,
@@ -579,7 +604,9 @@ int triangle_sums_tc_pass(const float* const* fields, int S, long long ncell, co
     using namespace tc;
     const int tile_cols = NT <= 64 ? 64 : NT;           // accumulator tiles packed at NT columns: 3 tiles for 65..80 shells, 2 above
     if (S < 1 || S > NT || NT % 16 || NT > 128 || MT < 1 || MT > 256 / tile_cols || ncell % 64) return PSB_ERR_ARG;
-    if (ncell / 64 / 148 >= (1LL << 28)) return PSB_ERR_ARG;
+    const TcEnv& env = tc_env();
+    const int ncta = sm_count();
+    if (ncell / 64 / ncta >= (1LL << 28)) return PSB_ERR_ARG;
     if (ws_bytes < triangle_tc_workspace_bytes(MT, NT)) return PSB_ERR_WORKSPACE;
     const int MR = MT * 128;
     auto smem_for = [&](int xch) {
@@ -594,8 +621,7 @@ int triangle_sums_tc_pass(const float* const* fields, int S, long long ncell, co
     if (smem_for(256) > 227 * 1024 || ncell % 256) XCH = 64;
     const size_t smem = smem_for(XCH);
     if (smem > 227 * 1024 || ncell % XCH) return PSB_ERR_ARG;
-    int NG = 4;                                            // former groups: 4 (704 threads) or 6 (960 threads, 64 registers)
-    if (const char* e = getenv("PSB_TC_GROUPS")) { if (atoi(e) == 6) NG = 6; }
+    int NG = env.groups;                                   // former groups: 4 (640 threads) or 6 (960 threads, 64 registers)
     void (*kern)(Params) = nullptr;
     if (lane_layout == 1) { if (MT != 4) return PSB_ERR_ARG; NG = 4; kern = XCH == 256 ? k_tri_tc<256, 4, true> : k_tri_tc<64, 4, true>; }
     else if (NG == 6) kern = XCH == 256 ? k_tri_tc<256, 6, false> : k_tri_tc<64, 6, false>;
@@ -603,23 +629,17 @@ int triangle_sums_tc_pass(const float* const* fields, int S, long long ncell, co
     const int NTHR = NG == 6 ? Roles<6>::NTHR : Roles<4>::NTHR;
     const long long nchunk_launch = ncell / XCH;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PSB_ERR_CUDA;
-    const int ncta = 148;
     if (cudaMemsetAsync(ws, 0, triangle_tc_workspace_bytes(MT, NT), st) != cudaSuccess) return PSB_ERR_CUDA;
     Params p;
     p.fields = fields; p.S = S; p.NT = NT; p.MT = MT; p.tile_cols = tile_cols; p.lane_ij = lane_ij; p.nchunk = nchunk_launch;
     p.partial = static_cast<double*>(ws);
-    p.debug = 0;
-    p.backoff_ns = 0;
-    if (const char* e = getenv("PSB_TC_BACKOFF")) p.backoff_ns = (unsigned)strtoul(e, nullptr, 10);
-    { unsigned int hint = 20000u; if (const char* e = getenv("PSB_TC_HINT")) hint = (unsigned)strtoul(e, nullptr, 10);
-      cudaMemcpyToSymbolAsync(c_wait_hint_ns, &hint, sizeof(hint), 0, cudaMemcpyHostToDevice, st); }
-    if (const char* e = getenv("PSB_TC_DEBUG")) p.debug = atoi(e);
-    p.flush_chunks = 4;          // 16 K-steps = 48 accumulating MMAs per accumulator between round-to-nearest drains
-    p.gflush_drains = 64;
-    if (const char* e = getenv("PSB_TC_FLUSH")) { int v = atoi(e); if (v >= 1 && v <= 4096) p.flush_chunks = v; }
-    if (const char* e = getenv("PSB_TC_GFLUSH")) { int v = atoi(e); if (v >= 1 && v <= 65536) p.gflush_drains = v; }
+    p.debug = env.debug;
+    p.backoff_ns = env.backoff_ns;
+    p.flush_chunks = env.flush_chunks;          // default 4: 16 K-steps = 48 accumulating MMAs per accumulator between round-to-nearest drains
+    p.gflush_drains = env.gflush_drains;
+    p.bias_gain = (float)(1.0 + env.bias_per_mma * 12.0 * env.flush_chunks);
     p.trace = nullptr;
-    const char* trace_path = getenv("PSB_TC_TRACE");
+    const char* trace_path = env.trace_path;
     if (trace_path) { cudaMalloc(&p.trace, 5 * 8 * 64 * sizeof(long long)); cudaMemset(p.trace, 0, 5 * 8 * 64 * sizeof(long long)); }
     kern<<<ncta, NTHR, smem, st>>>(p);
     if (trace_path) {

@@ -16,7 +16,7 @@ and the stream).  There is no CPU fallback: without libpsb200.so or a CUDA devic
 Deliberate differences from the reference (all in DESIGN.md):
   * `Ngrid == 360` assert of Bk_periodic (py:332) is relaxed to "even N = 2^a 3^b 5^c";
   * Pk_periodic bins |delta_fft|^2 (py:713 indexes the wrong array and raises on numpy >= 1.13);
-  * `fft`, `nthreads`, `code` are accepted and ignored;
+  * `fft`, `nthreads` are accepted and ignored; `code='python'` selects the float64 (k,mu) estimator of py:545-626;
   * triangle counts are exact integers computed in float64 on the GPU and cached (memory + a file in the
     reference's own Fortran-record format) instead of the reference's pure-Python cold path.
 """
@@ -175,12 +175,13 @@ class PeriodicPipeline(object):
             self._irk[step] = torch.from_numpy(irk.astype(np.uint16)).to(self.dev)
         return self._irk[step]
 
-    def pk_bin_table(self, Lbox):
-        """Pk_periodic's bin index (pyspectrum.py:696-703) as a function of m."""
-        key = ('pk', float(Lbox))
+    def pk_bin_table(self, Lbox, kf=None):
+        """Pk_periodic's bin index (pyspectrum.py:696-703; same expression at py:560) as a function of m."""
+        if kf is None:
+            kf = 2 * np.pi / float(Lbox)
+        key = ('pk', float(kf))
         if key not in self._bins:
             Nbins = self.N // 2
-            kf = 2 * np.pi / float(Lbox)
             phys_nyq = kf * float(self.N) / 2.
             rk = kf * np.sqrt(np.arange(self.mmax + 1))
             irk = (Nbins * rk / phys_nyq + 0.5).astype(int)
@@ -348,6 +349,17 @@ class PeriodicPipeline(object):
         check(self.L.psb_pk_multipoles(_ptr(half), self.N, _ptr(self.rsd_bin_table(Nbins)), Nbins, int(Nmubin),
                                        kf32, _np_ptr(trig), _ptr(out), _stream()), 'psb_pk_multipoles')
         return out, kf32
+
+    def pk_kmu_python(self, full, kf, rsd, Nmubin):
+        """code='python' (k,mu) estimator (pyspectrum.py:545-626) on a device FULL field [kx,ky,kz,2] float32: raw float64 sums."""
+        Nbins = self.N // 2
+        out = torch.empty((5 + 4 * Nmubin) * Nbins, dtype=torch.float64, device=self.dev)
+        theta_obs = [0.5 * np.pi, 0.5 * np.pi, 0.][rsd]                    # py:563-564
+        phi_obs = [0., 0.5 * np.pi, 0.][rsd]
+        trig = np.array([np.cos(theta_obs), np.sin(theta_obs), np.cos(phi_obs), np.sin(phi_obs)], dtype=np.float64)
+        check(self.L.psb_pk_kmu_python(_ptr(full), self.N, _ptr(self.pk_bin_table(None, kf=kf)), Nbins, int(Nmubin), float(kf),
+                                       _np_ptr(trig), _ptr(out), _stream()), 'psb_pk_kmu_python')
+        return out
 
     # ------------------------------------------------------------------ K5
     def shell_mode_counts(self, step, Nmax):
@@ -721,11 +733,42 @@ def _pk_rsd_from_half(pipe, half, Lbox, rsd, Nmubin):
 
 
 def _Pk_periodic_rsd(delta, Lbox=None, rsd=2, Nmubin=5, code='fortran'):
-    """pyspectrum.py:541-641, code='fortran' branch: multipoles and P(k,mu) of a host half field delta(k) of shape
-    (Ngrid//2+1, Ngrid, Ngrid) indexed [kx,ky,kz] (what FFT_periodic returns).  The reference's code='python' branch is a
-    debugging variant on the full grid (it prints every (k,mu) bin) and is not provided."""
+    """pyspectrum.py:541-641.
+    code='fortran' (py:628-641): multipoles and P(k,mu) of a host HALF field delta(k) of shape (Ngrid//2+1, Ngrid, Ngrid) indexed
+        [kx,ky,kz] (what FFT_periodic returns) through the kernel that replaces estimator.pk_pbox_rsd (estimator.f:155-264).
+    code='python' (py:545-626): the float64 (k,mu) estimator on a FULL field (Ngrid,Ngrid,Ngrid) indexed [kx,ky,kz] (what
+        reflect_delta returns): |k_a| = min(i, N-i) so mu >= 0, mu bins ceil(mu*Nmubin), Legendre sums over the mu-binned modes;
+        Lbox=None gives k in units of the fundamental mode.  Same outputs as the reference's branch (which also prints every
+        (i,j) bin pair; that is not reproduced)."""
+    if code == 'python':
+        if rsd not in (0, 1, 2):
+            raise ValueError('rsd must be 0, 1 or 2')
+        delta = np.asarray(delta)
+        Ngrid = delta.shape[0]
+        if delta.shape != (Ngrid, Ngrid, Ngrid):
+            raise ValueError("code='python' takes the full field (Ngrid,Ngrid,Ngrid), e.g. reflect_delta's output")
+        pipe = PeriodicPipeline.get(Ngrid)
+        kf = 1. if Lbox is None else 2 * np.pi / float(Lbox)                  # py:552-555
+        arr = np.ascontiguousarray(delta.astype(np.complex64, copy=False))
+        full = torch.from_numpy(arr.view(np.float32).reshape(Ngrid, Ngrid, Ngrid, 2)).to(pipe.dev)
+        raw = pipe.pk_kmu_python(full, kf, rsd, Nmubin).cpu().numpy()
+        Nbins = Ngrid // 2
+        nks, ksum, p0, p2, p4 = [raw[a * Nbins:(a + 1) * Nbins].copy() for a in range(5)]
+        tb = Nbins * Nmubin
+        N_kmu, kk, mm, pp = [raw[5 * Nbins + a * tb:5 * Nbins + (a + 1) * tb].reshape(Nbins, Nmubin).copy() for a in range(4)]
+        ok = nks > 0
+        nk1 = np.where(ok, nks, 1.)
+        ks = np.where(ok, ksum / nk1, 0.)
+        pk_norm = (2. * np.pi) ** 3
+        p0k = np.where(ok, p0 / nk1 / kf ** 3, 0.) * pk_norm
+        p2k = np.where(ok, p2 / nk1 / kf ** 3 * 5., 0.) * pk_norm              # py:606-607
+        p4k = np.where(ok, p4 / nk1 / kf ** 3 * 9., 0.) * pk_norm
+        okm = N_kmu > 0
+        n1 = np.where(okm, N_kmu, 1.)
+        return (ks, p0k, p2k, p4k, nks, np.where(okm, kk / n1, 0.), np.where(okm, mm / n1, 0.),
+                np.where(okm, pp / n1 / kf ** 3, 0.) * pk_norm, N_kmu)
     if code != 'fortran':
-        raise NotImplementedError("only code='fortran' (estimator.pk_pbox_rsd, estimator.f:155-264) is provided")
+        raise ValueError("code must be 'fortran' or 'python'")
     if Lbox is None:
         raise ValueError('Lbox is required (pk_pbox_rsd takes it as an integer, estimator.f:158)')
     if rsd not in (0, 1, 2):
@@ -777,7 +820,16 @@ def Pk_periodic_rsd(xyz, w=None, Lbox=2600, Ngrid=360, rsd=2, Nmubin=10, fft='py
         print('%i positions in %i box' % (N, Lbox))
         print('nbar = %f' % nbar)
     half, _ = pipe.fft_periodic(xyz, w, Lbox)
-    ks, p0k, p2k, p4k, nk, k_kmu, mu_kmu, p_kmu, n_kmu = _pk_rsd_from_half(pipe, half, Lbox, rsd, Nmubin)
+    if code == 'python':
+        # the reference hands the HALF field to its full-grid python branch (py:519-522 -> IndexError at py:591); the evident
+        # intent is the reflected field, which is what is passed here
+        a = half.cpu().numpy().view(np.complex64)[..., 0].transpose(2, 1, 0)
+        ks, p0k, p2k, p4k, nk, k_kmu, mu_kmu, p_kmu, n_kmu = _Pk_periodic_rsd(reflect_delta(a, Ngrid), Lbox=Lbox, rsd=rsd,
+                                                                                Nmubin=Nmubin, code='python')
+    elif code == 'fortran':
+        ks, p0k, p2k, p4k, nk, k_kmu, mu_kmu, p_kmu, n_kmu = _pk_rsd_from_half(pipe, half, Lbox, rsd, Nmubin)
+    else:
+        raise ValueError("code must be 'fortran' or 'python'")
     if not silent:
         print('--- correcting for shotnoise ---')
     meta = {'Lbox': Lbox, 'Ngrid': Ngrid, 'N': N, 'nbar': nbar, 'kf': kf}

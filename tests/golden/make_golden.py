@@ -6,6 +6,7 @@ Run in the build container only (needs /root/reference):
     python tests/golden/make_golden.py small      # seconds
     python tests/golden/make_golden.py counts     # converts the shipped counts.* files to integers
     python tests/golden/make_golden.py box360     # ~20 min, ~18 GB: Pk+Bk on dat/test_box.hdf5
+    python tests/golden/make_golden.py kmupy      # seconds: _Pk_periodic_rsd(code="python"), pure numpy in the reference
     python tests/golden/make_golden.py survey     # seconds: FFT_survey_mono / _B0_survey (B0_survey body) + util.py
 
 How: the reference package is copied to a scratch dir (its counts cold path writes into
@@ -166,6 +167,26 @@ def small(pySpec):
     return out
 
 
+def kmupy(pySpec):
+    """code='python' branch of _Pk_periodic_rsd (py:545-626): pure numpy in the reference, so these goldens involve NO restatement
+    at all beyond the stored delta(k) it is fed (small_*.npz, reflected by the reference's own reflect_delta)."""
+    import contextlib
+    import io
+    d = {}
+    for tag in 'ABC':
+        g = np.load(os.path.join(HERE, 'small_%s.npz' % tag))
+        N, L = int(g['Ngrid']), float(g['Lbox'])
+        full = pySpec.reflect_delta(g['delta_half'], Ngrid=N)
+        for rsd, nmu, Lb in [(2, 5, L), (0, 5, L), (1, 4, None), (2, 10, None)]:
+            with contextlib.redirect_stdout(io.StringIO()):           # py:601 prints every (i,j)
+                out = pySpec._Pk_periodic_rsd(full, Lbox=Lb, rsd=rsd, Nmubin=nmu, code='python')
+            pre = '%s_rsd%d_mu%d_L%s_' % (tag, rsd, nmu, 'none' if Lb is None else 'box')
+            for key, val in zip(['k', 'p0k', 'p2k', 'p4k', 'nk', 'k_kmu', 'mu_kmu', 'p_kmu', 'n_kmu'], out):
+                d[pre + key] = np.asarray(val)
+    np.savez_compressed(os.path.join(HERE, 'kmu_python.npz'), **d)
+    print('wrote kmu_python.npz', len(d), 'arrays')
+
+
 def counts():
     """Shipped caches -> exact integers: counts/N^3 rounds to an integer to <3e-14."""
     from scipy.io import FortranFile
@@ -286,4 +307,4 @@ if __name__ == '__main__':
         counts()
     else:
         ps = import_reference()
-        {'small': small, 'box360': box360, 'survey': survey}[what](ps)
+        {'small': small, 'box360': box360, 'survey': survey, 'kmupy': kmupy}[what](ps)

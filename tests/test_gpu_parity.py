@@ -241,12 +241,14 @@ def test_edge_cases(mods):
 
 
 @pytest.mark.parametrize('N,Np,step,Ncut,Nmax', [(32, 20000, 1, 1, 12), (48, 60000, 2, 3, 10), (48, 60000, 2, 3, 11), (64, 100000, 1, 3, 30),     # 11: odd shell count
+                                                 (36, 30000, 1, 1, 14), (100, 200000, 2, 3, 20),   # N^3 % 256 != 0: 64-cell chunks (XCH = 64)
                                                  (192, 400000, 1, 3, 72)])      # 70 shells: three accumulator tiles of 80 columns
 def test_triangle_engines_vs_float64(mods, N, Np, step, Ncut, Nmax):
     """K6 alone: the tcgen05 split-fp16 kernel and the FFMA kernel against a float64 torch evaluation of
     sum_x I_i I_j I_l on the SAME stored fields.  Error bound stated relative to the 'noise norm'
     sqrt(sum_x (I_i I_j I_l)^2) plus |S|: the FFMA kernel's rounding noise scales with the norm (2e-6); the tensor-core
-    kernel additionally carries the round-toward-zero bias of 48 in-TMEM accumulations, proportional to |S| (8e-6)."""
+    kernel's in-TMEM accumulation rounds toward zero (48 MMAs between drains); the systematic part (-8.8e-7 of |S|) is compensated
+    in the drain, the zero-mean rest stays below 8e-6 for every shape, the 65-128-shell layouts included."""
     import torch
     pySpec, _, _ = mods
     L = 300.
@@ -267,11 +269,14 @@ def test_triangle_engines_vs_float64(mods, N, Np, step, Ncut, Nmax):
         nrm[a:a + B] = prod.pow(2).sum(dim=1).sqrt()
     for engine in ('fma', 'tc'):
         got = pipe.triangle_sums(fields, Nmax, Ncut, step, engine=engine)
-        if engine == 'tc' and fields.shape[1] % 256:
-            continue
-        err = ((got - ref).abs() / (nrm + ref.abs())).max().item()
-        # tc: mean bias -8.5e-7, median 7e-7; the maximum over the 34 021 triangles of the 70-shell case reaches 1.1e-5
-        assert err < (2e-6 if engine == 'fma' else (8e-6 if len(tri) < 10000 else 2e-5)), (engine, err)
+        rel = (got - ref) / (nrm + ref.abs())
+        err = rel.abs().max().item()
+        print('K6 %s N=%d shells=%d triangles=%d: max err %.2e, mean signed %.2e' % (engine, N, Nmax - s0 + 1, len(tri), err, rel.mean().item()))
+        assert err < (2e-6 if engine == 'fma' else 8e-6), (engine, err)
+        if engine == 'tc' and len(tri) > 1000:
+            big = ref.abs() > 0.2 * nrm                          # triangles with a real signal: the systematic bias would show here
+            if int(big.sum()) > 50:
+                assert abs(((got - ref) / ref.abs())[big].mean().item()) < 4e-7
     # scaling is an exact power of two and the tracked maxima are right
     sc = scales.cpu().numpy()
     assert np.all(np.log2(sc) == np.rint(np.log2(sc)))
@@ -348,3 +353,34 @@ def test_full_size_properties_c2(mods):
     sigma = np.sqrt(L ** 3 * p1 * p2 * p3 / bk1['counts'])
     d = np.abs((bk1['b123'] + bk1['b123_sn']) - (bk2['b123'] + bk2['b123_sn'])) / (scale + sigma)
     assert d.max() < 2e-5, d.max()
+
+
+# ------------------------------------------------------------------------------ code='python' (k,mu) estimator
+@pytest.mark.parametrize('tag', ['A', 'B', 'C'])
+def test_pk_rsd_code_python_matches_reference_numpy(mods, golden_dir, tag):
+    """_Pk_periodic_rsd(code='python') (py:545-626) against goldens made by the reference's own pure-numpy branch
+    (tests/golden/make_golden.py kmupy): no restated code on the reference side.  Counts bit exact."""
+    pySpec, _, _ = mods
+    g = _g(golden_dir, 'small_%s.npz' % tag)
+    k = _g(golden_dir, 'kmu_python.npz')
+    N, L = int(g['Ngrid']), float(g['Lbox'])
+    full = pySpec.reflect_delta(g['delta_half'], Ngrid=N)
+    for rsd, nmu, Lb in [(2, 5, L), (0, 5, L), (1, 4, None), (2, 10, None)]:
+        pre = '%s_rsd%d_mu%d_L%s_' % (tag, rsd, nmu, 'none' if Lb is None else 'box')
+        ks, p0k, p2k, p4k, nk, k_kmu, mu_kmu, p_kmu, n_kmu = pySpec._Pk_periodic_rsd(full, Lbox=Lb, rsd=rsd, Nmubin=nmu, code='python')
+        assert np.array_equal(nk, k[pre + 'nk']), pre
+        assert np.array_equal(n_kmu, k[pre + 'n_kmu']), pre
+        np.testing.assert_allclose(ks, k[pre + 'k'], rtol=1e-12)
+        np.testing.assert_allclose(k_kmu, k[pre + 'k_kmu'], rtol=1e-12)
+        np.testing.assert_allclose(mu_kmu, k[pre + 'mu_kmu'], rtol=1e-12, atol=1e-15)
+        np.testing.assert_allclose(p0k, k[pre + 'p0k'], rtol=RTOL)
+        np.testing.assert_allclose(p_kmu, k[pre + 'p_kmu'], rtol=RTOL)
+        assert np.all(np.abs(p2k - k[pre + 'p2k']) <= 5 * RTOL * np.abs(k[pre + 'p0k']))
+        assert np.all(np.abs(p4k - k[pre + 'p4k']) <= 9 * RTOL * np.abs(k[pre + 'p0k']))
+    # the public entry point: the reference passes the half field to this branch and fails; here the reflected field is used
+    pr = pySpec.Pk_periodic_rsd(g['xyz'], w=g.get('w'), Lbox=L, Ngrid=N, rsd=2, Nmubin=5, code='python')
+    pre = '%s_rsd2_mu5_Lbox_' % tag
+    assert np.array_equal(pr['counts'], k[pre + 'nk']) and np.array_equal(pr['counts_kmu'], k[pre + 'n_kmu'])
+    np.testing.assert_allclose(pr['p0k'] + pr['p_sn'], k[pre + 'p0k'], rtol=3 * RTOL)       # delta(k) itself is the GPU's here
+    with pytest.raises(ValueError):
+        pySpec._Pk_periodic_rsd(full, Lbox=L, code='c')
