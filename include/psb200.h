@@ -129,8 +129,12 @@ int psb_shell_mode_counts(int ngrid, const uint16_t* irk_of_m, int nshell, uint6
  *   fa,fb   out: I_sa(x), I_sb(x) on [z][y][x] (fb may be NULL when sb < 0)
  *   sumsq   device double[2]: += sum_x I_sa^2, sum_x I_sb^2   (py:404)
  *   t1,t2   scratch of (2R+1)^2*N and (2R+1)*N^2 complex elements (clamped to N per axis)
- *   half_c64 == NULL -> delta == 1 (triangle counts, py:977 / estimator.f:74-80) */
-int psb_bk_shell_pair_f32(const float* half_c64, const uint16_t* irk_of_m, int ngrid, int sa, int sb, int R,
+ *   half_c64 == NULL -> delta == 1 (triangle counts, py:977 / estimator.f:74-80)
+ *   ngrid_src  grid of half_c64 (0 or ngrid: the same).  ngrid_src > ngrid transforms the shells on a COARSER grid than delta(k)
+ *              lives on: a shell field is band limited to |k_i| <= R, so for 2R < ngrid the coarse transform is the same function
+ *              sampled at fewer points, and sum_x I_i I_j I_l / ngrid^3 is unchanged as long as R_i + R_j + R_l < ngrid (no
+ *              triangle can close through a wrap on either grid).  irk_of_m is the table of the TRANSFORM grid (it depends on m only). */
+int psb_bk_shell_pair_f32(const float* half_c64, const uint16_t* irk_of_m, int ngrid, int ngrid_src, int sa, int sb, int R,
                           float* t1_c64, float* t2_c64, float* fa, float* fb, double* sumsq,
                           const float* scale2, uint32_t* maxabs2, int pack_half, const float* tw_c64, void* stream);
 /* pack_half != 0: each aligned pair of cells (x, x+1) of fa/fb is stored as the two 32-bit words
@@ -145,7 +149,7 @@ int psb_bk_shell_pair_f32(const float* half_c64, const uint16_t* irk_of_m, int n
  * (last-bit order dependent) -- it only feeds the power-of-two scale, the shell power that is reported comes from K5; nshell <= 1024 */
 int psb_bk_shell_power(const float* half_c64, int ngrid, const uint16_t* irk_of_m, int nshell, double* psum, void* stream);
 int psb_bk_shell_scales(const double* psum, int nshell, float target_rms, float* scales, void* stream);
-int psb_bk_shell_pair_f64(const float* half_c64, const uint16_t* irk_of_m, int ngrid, int sa, int sb, int R,
+int psb_bk_shell_pair_f64(const float* half_c64, const uint16_t* irk_of_m, int ngrid, int ngrid_src, int sa, int sb, int R,
                           double* t1_c128, double* t2_c128, double* fa, double* fb, double* sumsq,
                           const double* tw_c128, void* stream);
 

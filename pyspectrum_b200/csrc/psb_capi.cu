@@ -222,19 +222,19 @@ int psb_shell_mode_counts(int N, const uint16_t* irk, int nshell, uint64_t* nk, 
     return shell_mode_counts(N, irk, nshell, reinterpret_cast<unsigned long long*>(nk), S(stream));
 }
 
-int psb_bk_shell_pair_f32(const float* half, const uint16_t* irk, int N, int sa, int sb, int R, float* t1, float* t2,
+int psb_bk_shell_pair_f32(const float* half, const uint16_t* irk, int N, int Ns, int sa, int sb, int R, float* t1, float* t2,
                           float* fa, float* fb, double* sumsq, const float* scale2, uint32_t* maxabs2, int pack_half, const float* tw, void* stream)
 {
     if (!irk || !t1 || !t2 || !fa || !sumsq || !tw || R < 0 || (sb >= 0 && !fb)) return PSB_ERR_ARG;
-    return fft_shell_pair<float>(reinterpret_cast<const Cx<float>*>(half), irk, N, sa, sb, R, reinterpret_cast<Cx<float>*>(t1),
+    return fft_shell_pair<float>(reinterpret_cast<const Cx<float>*>(half), irk, N, Ns, sa, sb, R, reinterpret_cast<Cx<float>*>(t1),
                                  reinterpret_cast<Cx<float>*>(t2), fa, fb, sumsq, scale2, maxabs2, pack_half, reinterpret_cast<const Cx<float>*>(tw), S(stream));
 }
 
-int psb_bk_shell_pair_f64(const float* half, const uint16_t* irk, int N, int sa, int sb, int R, double* t1, double* t2,
+int psb_bk_shell_pair_f64(const float* half, const uint16_t* irk, int N, int Ns, int sa, int sb, int R, double* t1, double* t2,
                           double* fa, double* fb, double* sumsq, const double* tw, void* stream)
 {
     if (!irk || !t1 || !t2 || !fa || !sumsq || !tw || R < 0 || (sb >= 0 && !fb)) return PSB_ERR_ARG;
-    return fft_shell_pair<double>(reinterpret_cast<const Cx<float>*>(half), irk, N, sa, sb, R, reinterpret_cast<Cx<double>*>(t1),
+    return fft_shell_pair<double>(reinterpret_cast<const Cx<float>*>(half), irk, N, Ns, sa, sb, R, reinterpret_cast<Cx<double>*>(t1),
                                   reinterpret_cast<Cx<double>*>(t2), fa, fb, sumsq, nullptr, nullptr, 0, reinterpret_cast<const Cx<double>*>(tw), S(stream));
 }
 
@@ -431,7 +431,7 @@ int psb_host_bk_counts(double* coun, int N, float step, int ncut, int nmax)
         const int Rp = (int)std::floor(((double)(sb >= 0 ? sb : sa) + 0.5) * (double)step) + 1;
         double* fa = dfields.as<double>() + ncell * (size_t)s;
         double* fb = dfields.as<double>() + ncell * (size_t)(s + 1);       // spare plane exists (nsh+1 allocated)
-        PSB_TRY(psb_bk_shell_pair_f64(nullptr, dirk.as<uint16_t>(), N, sa, sb, Rp, dt1.as<double>(), dt2.as<double>(), fa, fb,
+        PSB_TRY(psb_bk_shell_pair_f64(nullptr, dirk.as<uint16_t>(), N, N, sa, sb, Rp, dt1.as<double>(), dt2.as<double>(), fa, fb,
                                       dsq.as<double>(), dtw.as<double>(), nullptr));
     }
     PSB_TRY(psb_bk_triangle_sums_f64(dptr.as<const double*>(), nfield, (int64_t)ncell, dtiles.as<int32_t>(), ntiles, dsums.as<double>(), dws.p, wsb, nullptr));

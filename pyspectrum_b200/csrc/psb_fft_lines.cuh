@@ -455,16 +455,17 @@ struct IoZFcomb {
 
 // shell pass 1: line = compact (ky',kz'), idx = kx index; input built on the fly from the half field.
 template <typename T> struct IoShellX {
-    const Cx<float>* half;     // delta half field [kz][ky][kx]; null -> delta == 1 (triangle counts, py:977)
+    const Cx<float>* half;     // delta half field [kz][ky][kx] on the SOURCE grid Ns; null -> delta == 1 (triangle counts, py:977)
     const unsigned short* irk; // shell index of m = kx^2+ky^2+kz^2 (host table, pyspectrum.py:378)
     Cx<T>* out;                // T1 [kz'][ky'][x]
     int sa, sb;                // shell indices packed as real / imaginary part (sb < 0: none)
     int Rm, Rp, W;             // signed k range [-Rm,Rp], W = Rm+Rp+1
+    int Ns;                    // grid of the half field (>= N).  Ns > N: the shells are transformed on a COARSER grid N than the one
+                               // delta(k) was measured on -- the same band-limited field sampled at fewer points (needs R < N/2)
     template <int LPC_T> __device__ void load(Cx<T>* s, int LPCP, int LPC, int N) const {
-        const int h = N / 2;
+        const int hs = Ns / 2;
         const int kyp0 = blockIdx.x * LPC, kzp = blockIdx.y;
         const int kz = kzp - Rm;
-        const int kzi = kz < 0 ? kz + N : kz;
         for (int e = threadIdx.x; e < LPC * N; e += blockDim.x) {
             const int line = e / N, idx = e - line * N;
             Cx<T> v = mk<T>(0, 0);
@@ -475,15 +476,16 @@ template <typename T> struct IoShellX {
                 const int m = kx * kx + ky * ky + kz * kz;
                 const int sh = irk[m];
                 if (sh == sa || sh == sb) {
-                    const int kyi = ky < 0 ? ky + N : ky;
                     Cx<float> d = mk<float>(1.f, 0.f);
                     if (half) {
-                        if (idx <= h) {
-                            d = half[((long long)kzi * N + kyi) * (h + 1) + idx];
+                        if (kx >= 0) {
+                            const int kyi = ky < 0 ? ky + Ns : ky, kzi = kz < 0 ? kz + Ns : kz;
+                            d = half[((long long)kzi * Ns + kyi) * (hs + 1) + kx];
                             // reflect_delta (py:1149-1156): the self-conjugate points are made real
-                            if ((idx == 0 || idx == h) && (kyi == 0 || kyi == h) && (kzi == 0 || kzi == h)) d.y = 0.f;
+                            if ((kx == 0 || kx == hs) && (kyi == 0 || kyi == hs) && (kzi == 0 || kzi == hs)) d.y = 0.f;
                         } else {
-                            d = conj(half[((long long)kneg(kzi, N) * N + kneg(kyi, N)) * (h + 1) + (N - idx)]);
+                            const int kyn = ky > 0 ? Ns - ky : -ky, kzn = kz > 0 ? Ns - kz : -kz;      // indices of -ky, -kz
+                            d = conj(half[((long long)kzn * Ns + kyn) * (hs + 1) + (-kx)]);
                         }
                     }
                     v = (sh == sa) ? mk<T>((T)d.x, (T)d.y) : mk<T>(-(T)d.y, (T)d.x);

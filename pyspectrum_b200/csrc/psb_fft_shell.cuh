@@ -8,19 +8,21 @@
 namespace psb {
 
 template <typename T>
-int fft_shell_pair(const Cx<float>* half, const unsigned short* irk, int N, int sa, int sb, int R,
+int fft_shell_pair(const Cx<float>* half, const unsigned short* irk, int N, int Ns, int sa, int sb, int R,
                    Cx<T>* t1, Cx<T>* t2, T* fa, T* fb, double* sumsq, const float* scale2, unsigned int* maxabs2, int halfpack,
                    const Cx<T>* tw, cudaStream_t st)
 {
     FftPlan p;
     if (N % 2 || !make_plan(N, &p)) return PSB_ERR_UNSUPPORTED_N;
+    if (Ns <= 0) Ns = N;
+    if (Ns % 2 || Ns < N || (Ns > N && 2 * R >= N)) return PSB_ERR_ARG;      // a coarser transform grid must hold the shells without wrap
     const int Rp = R < N / 2 ? R : N / 2;
     const int Rm = R < (N - 1) / 2 ? R : (N - 1) / 2;
     const int W = Rm + Rp + 1;
     return dispatch_plan(N, [&](auto cfg) -> int {
         const int LPC = cfg_lpc(cfg, p);
         if (LPC < 1) return (int)PSB_ERR_UNSUPPORTED_N;
-        IoShellX<T> io1{ half, irk, t1, sa, sb, Rm, Rp, W };
+        IoShellX<T> io1{ half, irk, t1, sa, sb, Rm, Rp, W, Ns };
         int rc = launch_any<T, -1>(cfg, p, LPC, dim3((W + LPC - 1) / LPC, W), tw, io1, st);
         if (rc) return rc;
         // pass 2 (y): batch = kz', T1[kz'][ky'][x] -> T2[kz'][y][x]

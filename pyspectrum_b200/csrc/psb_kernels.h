@@ -30,7 +30,7 @@ int fft_c2c_3d(Cx<float>* data, int N, int dir, const Cx<float>* tw, cudaStream_
 int fcomb_standalone(const Cx<float>* full, Cx<float>* half, int N, const Cx<double>* rec, const float* Wk,
                      const double* sumw, int periodic, cudaStream_t st);
 template <typename T>
-int fft_shell_pair(const Cx<float>* half, const unsigned short* irk, int N, int sa, int sb, int R,
+int fft_shell_pair(const Cx<float>* half, const unsigned short* irk, int N, int Ns, int sa, int sb, int R,
                    Cx<T>* t1, Cx<T>* t2, T* fa, T* fb, double* sumsq, const float* scale2, unsigned int* maxabs2, int halfpack,
                    const Cx<T>* tw, cudaStream_t st);
 

@@ -383,7 +383,7 @@ class PeriodicPipeline(object):
               'psb_bk_shell_scales')
         return scales
 
-    def shell_fields(self, half, step, s0, Nmax, dtype=torch.float32, scaled=False, pairs=None, scales=None):
+    def shell_fields(self, half, step, s0, Nmax, dtype=torch.float32, scaled=False, pairs=None, scales=None, src=None):
         """K5: shells s0..Nmax as real fields [S_alloc, N^3] + sum_x I_j^2 per shell.
         half=None -> delta == 1 (counts).  Two shells ride on one complex transform.
         scaled=True stores I_j * scale_j with scale_j an exact power of two putting the rms near 2 (from the
@@ -392,8 +392,13 @@ class PeriodicPipeline(object):
         (still 4 bytes per cell; `unpack_fields` gives the float32 values back).
         returns (fields, sumsq, scales, maxabs) -- sumsq and maxabs refer to the scaled values before the split.
         pairs: optional list of pair indices p (shells s0+2p, s0+2p+1) to compute -- the multi-GPU path shards shells this way;
-        the returned fields then hold only those pairs, in the given order (2 rows per pair), sumsq/maxabs likewise."""
+        the returned fields then hold only those pairs, in the given order (2 rows per pair), sumsq/maxabs likewise.
+        src: the pipeline (finer grid) `half` was measured on, if not this one: the shells are then transformed on THIS coarser
+        grid -- the same band-limited fields at fewer points (needs 2*floor(step*(Nmax+1/2)) < N; see `coarse_levels`)."""
         N = self.N
+        Ns = N if src is None else src.N
+        if Ns != N and (Ns < N or 2 * int(np.floor(step * (Nmax + 0.5))) >= N):
+            raise ValueError('a coarser shell grid must hold every shell without wrap-around')
         ncell = N * N * N
         S = Nmax - s0 + 1
         S_alloc = S + (S % 2)
@@ -408,7 +413,7 @@ class PeriodicPipeline(object):
         if scaled:
             assert not f64 and half is not None
             if scales is None:
-                scales = self.shell_scales(half, step, s0, Nmax)
+                scales = (src or self).shell_scales(half, step, s0, Nmax)
             maxabs = torch.zeros(nrow, dtype=torch.int32, device=self.dev)
             if pairs is None:
                 sc_local = scales
@@ -431,14 +436,14 @@ class PeriodicPipeline(object):
             R = int(np.floor(step * (max(sa, sb) + 0.5)))
             sq = ctypes.c_void_p(sumsq.data_ptr() + 8 * 2 * r)
             if f64:
-                check(self.L.psb_bk_shell_pair_f64(_ptr(half), _ptr(irk), N, sa, sb, R, _ptr(t1), _ptr(t2), _ptr(fields[2 * r]),
+                check(self.L.psb_bk_shell_pair_f64(_ptr(half), _ptr(irk), N, Ns, sa, sb, R, _ptr(t1), _ptr(t2), _ptr(fields[2 * r]),
                                                    _ptr(fields[2 * r + 1]), sq, _ptr(tw), st), 'psb_bk_shell_pair_f64')
             else:
                 sc = mx = None
                 if scaled:
                     sc = ctypes.c_void_p(sc_local.data_ptr() + 4 * 2 * r)
                     mx = ctypes.c_void_p(maxabs.data_ptr() + 4 * 2 * r)
-                check(self.L.psb_bk_shell_pair_f32(_ptr(half), _ptr(irk), N, sa, sb, R, _ptr(t1), _ptr(t2), _ptr(fields[2 * r]),
+                check(self.L.psb_bk_shell_pair_f32(_ptr(half), _ptr(irk), N, Ns, sa, sb, R, _ptr(t1), _ptr(t2), _ptr(fields[2 * r]),
                                                    _ptr(fields[2 * r + 1]), sq, sc, mx, 1 if scaled else 0, _ptr(tw), st),
                       'psb_bk_shell_pair_f32')
         if scaled:

@@ -191,7 +191,7 @@ def test_pk_periodic_rsd_from_half_field(mods, golden_dir):
         assert np.all(np.abs(p4k - g[pre + 'p4k']) <= 9 * RTOL * scale)
         m = n_kmu > 0
         np.testing.assert_allclose(p_kmu[m], (g[pre + 'p_kmu'] + sn)[m], rtol=RTOL)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):                          # code='python' takes the FULL field (py:546)
         pySpec._Pk_periodic_rsd(g['delta_half'], Lbox=L, code='python')
     with pytest.raises(ValueError):
         pySpec._Pk_periodic_rsd(g['delta_half'][:, :, :-1], Lbox=L)
