@@ -172,20 +172,24 @@ def run_b200(args):
     S = Nmax - s0 + 1
 
     engine = args.engine
+    tri_all, levels = pipe.bk_levels(step, Ncut, Nmax)
+    level_desc = [{'grid': pc.N, 'triangles': int(len(idx)), 'shells': int(smax - s0 + 1)} for pc, idx, _, smax in levels]
 
-    def step_device():
+    def step_device(timers=None):
         mesh, sumw = pipe.assign(xyz_dev, 0, None, L)
+        e1 = torch.cuda.Event(enable_timing=True); e1.record()
         half = pipe.mesh_to_delta(mesh, sumw)
-        fields, sumsq, scales, maxabs = pipe.shell_fields(half, step, s0, Nmax, scaled=True)
-        sums = pipe.triangle_sums(fields, Nmax, Ncut, step, engine=engine)
-        return torch.cat([sums, sumsq, scales.double()]).to('cpu', non_blocking=False)
+        e2 = torch.cuda.Event(enable_timing=True); e2.record()
+        h = pipe.bispectrum_launch(half, step, Ncut, Nmax, engine=engine, sumw=sumw, timers=timers)
+        del mesh, half
+        return e1, e2, h
 
     barrier = D.barrier
 
     for _ in range(args.warmup):
-        step_device()
+        pipe.bispectrum_finish(step_device()[2])
     # per-stage device times (CUDA events on the launching stream), same timed loop
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
+    stage_acc = {'assign': 0., 'fft_fcomb': 0., 'shell_fields': 0., 'triangles': 0.}
     clocks = ClockSampler(local)
     barrier()
     clocks.start()
@@ -193,22 +197,18 @@ def run_b200(args):
     t_end = torch.cuda.Event(enable_timing=True)
     t_start.record()
     for it in range(args.steps):
-        e = ev[it]
-        e[0].record()
-        mesh, sumw = pipe.assign(xyz_dev, 0, None, L)
-        e[1].record()
-        half = pipe.mesh_to_delta(mesh, sumw)
-        e[2].record()
-        fields, sumsq, scales, maxabs = pipe.shell_fields(half, step, s0, Nmax, scaled=True)
-        e[3].record()
-        sums = pipe.triangle_sums(fields, Nmax, Ncut, step, engine=engine)
-        e[4].record()
-        res = torch.cat([sums, sumsq, scales.double()]).to('cpu')
-        del mesh, half, fields
+        e0 = torch.cuda.Event(enable_timing=True); e0.record()
+        timers = []
+        e1, e2, h = step_device(timers)
+        res = pipe.bispectrum_finish(h)                  # waits for the step's device->host copy of the sums
+        stage_acc['assign'] += e0.elapsed_time(e1)
+        stage_acc['fft_fcomb'] += e1.elapsed_time(e2)
+        for name, a_, b_ in timers:
+            stage_acc[name] += a_.elapsed_time(b_)
     t_end.record()
     barrier()
     dev_ms = t_start.elapsed_time(t_end)
-    stage_ms = np.array([[e[i].elapsed_time(e[i + 1]) for i in range(4)] for e in ev]).mean(axis=0)
+    stage_ms = np.array([stage_acc[k] / args.steps for k in ('assign', 'fft_fcomb', 'shell_fields', 'triangles')])
 
     # end to end through the public API, host catalogue in pinned memory
     for _ in range(max(1, args.warmup // 2)):
@@ -293,7 +293,9 @@ def run_b200(args):
                     'd2h_bytes_per_step': int(8 * (len(tri) + S + (S % 2))),
                     'api': 'pyspectrum_b200.pyspectrum.Bk_periodic_many over pinned host catalogues (float64 positions)',
                     'single_call_value': e2e1_ms * 1e-3 / ncat, 'single_call_api': 'Bk_periodic, one catalogue per call, no overlap'},
-            'gpu_launches': int(args.steps * (6 + 3 + 2 + 3 * ((S + 1) // 2) + 2)),      # K1 6, mesh FFT 3, shell power/scales 2, 3 per shell pair, K6 2
+            # K1 6, mesh FFT 3, shell power/scales 2, per level: 3 per shell pair + K6 (kernel + fold) per pass
+            'gpu_launches': int(args.steps * (6 + 3 + 2 + sum(3 * ((d['shells'] + 1) // 2) + 2 for d in level_desc))),
+            'shell_grids': level_desc,
             'stages_ms': {'assign': float(stage_ms[0]), 'fft_fcomb': float(stage_ms[1]), 'shell_fields': float(stage_ms[2]),
                           'triangles': tri_ms},
             'assign_mpart_per_s': Np / (float(stage_ms[0]) * 1e-3) / 1e6,

@@ -571,7 +571,9 @@ template <class F> static int dispatch_plan(int N, F&& f)
         PSB_PLAN_CASE(64, 16, 1, 8, 8)
         PSB_PLAN_CASE(128, 16, 1, 8, 4, 4)
         PSB_PLAN_CASE_OCC(256, 16, 1, 3, 16, 16)
+        PSB_PLAN_CASE_OCC(320, 16, 1, 3, 20, 16)         // 320, 400: coarse shell grids (pyspectrum.py coarse_levels)
         PSB_PLAN_CASE_OCC(360, 16, 1, 3, 20, 18)
+        PSB_PLAN_CASE_OCC(400, 16, 1, 3, 20, 20)
         PSB_PLAN_CASE_OCC(512, 16, 2, 2, 8, 8, 8)
         PSB_PLAN_CASE(1024, 8, 4, 8, 8, 4, 4)
         default: break;

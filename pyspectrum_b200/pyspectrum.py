@@ -122,6 +122,51 @@ def build_tc_plan(tri, s0, Nmax, layout=1):
     return NT, MT, layout, passes
 
 
+def shell_reach(shell, step):
+    """Largest |k_a| of any mode of a shell: irk = int(|k|/step + 0.5) == shell  =>  |k| < step*(shell + 1/2) (py:376-378)."""
+    return np.floor(step * (np.asarray(shell) + 0.5)).astype(np.int64)
+
+
+COARSE_GRIDS = (256, 320, 400)           # grids with compiled two-stage FFT plans that the shell stage may drop to
+
+
+def coarse_levels(N, step, tri, sizes):
+    """Split the triangle list over transform grids.  sum_x I_i I_j I_l / Ngrid^3 = sum over closed mode triples
+    (k1 + k2 + k3 = 0 mod Ngrid) of delta delta delta: as long as R_i + R_j + R_l < Nc no triple can close through a wrap on a
+    grid of Nc or more points per side, so the sum -- and the triangle count -- is the SAME number on every such grid, and the
+    band-limited shell fields (2 R < Nc) are the same functions sampled at fewer points.  A triangle goes to the coarsest of
+    `sizes` (ascending, all < N) that holds it; the rest (at Ngrid=360, Nmax=40 those whose aliases the reference includes) stay
+    on N.  Returns [(Nc, index array into tri, largest shell used)], empty levels dropped."""
+    tri = np.asarray(tri)
+    R = shell_reach(tri, step)
+    rs, rmax = R.sum(axis=1), R.max(axis=1)
+    left = np.ones(len(tri), dtype=bool)
+    out = []
+    for Nc in sorted(int(x) for x in sizes):
+        if Nc >= N:
+            continue
+        take = left & (rs < Nc) & (2 * rmax < Nc)
+        if take.any():
+            out.append((Nc, np.nonzero(take)[0], int(tri[take].max())))
+            left &= ~take
+    if left.any():
+        out.append((int(N), np.nonzero(left)[0], int(tri[left].max())))
+    return out
+
+
+def default_level_sizes(N, step, tri):
+    """Which coarse grids the shell stage uses by default (PSB_BK_LEVELS overrides: 'off', or a comma list of grid sizes).
+    Policy from the measurements in profiles/r2_summary.md: drop to coarse grids when they are at most ~0.8 N (below that the
+    extra shell transforms cost more than the triangle stage saves)."""
+    import os
+    spec = os.environ.get('PSB_BK_LEVELS', 'auto').strip().lower()
+    if spec in ('off', 'none', '0'):
+        return []
+    if spec != 'auto':
+        return [int(x) for x in spec.split(',') if x.strip()]
+    return [c for c in COARSE_GRIDS if c <= 0.8 * N]
+
+
 class PeriodicPipeline(object):
     """Device-resident pipeline for one (Ngrid) on the current CUDA device.  Holds the host-built tables
     (twiddles, fcomb phase/window tables, shell / bin index tables) and caches per-configuration data
@@ -459,25 +504,33 @@ class PeriodicPipeline(object):
         return (h[:, :, 0, :].float() + h[:, :, 1, :].float()).reshape(nrow, ncell)
 
     # ------------------------------------------------------------------ K6
-    def triangle_tiles(self, Nmax, Ncut, step):
-        key = (Nmax, Ncut, step)
+    @staticmethod
+    def _tri_key(tri):
+        return None if tri is None else (len(tri), hash(np.ascontiguousarray(tri, dtype=np.int32).tobytes()))
+
+    def triangle_tiles(self, Nmax, Ncut, step, tri=None):
+        """4x4x4 tile descriptors of the FFMA kernel for the loop-nest triangles (or the given subset), cached."""
+        key = (Nmax, Ncut, step, self._tri_key(tri))
         if key not in self._tiles:
-            tri = triangle_list(Nmax, Ncut, step)
+            if tri is None:
+                tri = triangle_list(Nmax, Ncut, step)
             s0 = Ncut // step
             nt = ctypes.c_int(0)
-            tri_c = np.ascontiguousarray(tri)
+            tri_c = np.ascontiguousarray(tri, dtype=np.int32)
             check(self.L.psb_bk_build_tiles(_np_ptr(tri_c), len(tri_c), s0, None, ctypes.byref(nt)), 'psb_bk_build_tiles')
             tiles = np.empty((nt.value, 68), np.int32)
             check(self.L.psb_bk_build_tiles(_np_ptr(tri_c), len(tri_c), s0, _np_ptr(tiles), ctypes.byref(nt)), 'psb_bk_build_tiles')
-            self._tiles[key] = (tri, torch.from_numpy(tiles).to(self.dev), nt.value)
+            self._tiles[key] = (tri_c, torch.from_numpy(tiles).to(self.dev), nt.value)
         return self._tiles[key]
 
-    def triangle_sums(self, fields, Nmax, Ncut, step, engine='auto', field_rows=None, packed=None):
+    def triangle_sums(self, fields, Nmax, Ncut, step, engine='auto', field_rows=None, packed=None, tri=None):
         """K6: sum_x I_i I_j I_l for every triangle of the loop nest (float64 tensor, loop order).
         engine: 'tc' = tcgen05 split-fp16 kernel (needs the scaled + packed fields of shell_fields(scaled=True)),
                 'fma' = FFMA/DFMA register-tile kernel (plain float32/float64 fields, or packed ones which it decodes),
                 'auto' = tc when the fields are packed and the shapes allow it.
-        packed: whether `fields` holds packed hi/lo halves (default: the tag shell_fields put on the tensor)."""
+        packed: whether `fields` holds packed hi/lo halves (default: the tag shell_fields put on the tensor).
+        tri: optional subset of triangles, int array [n,3] of shell indices (i,j,l) all <= Nmax (the largest shell held in
+             `fields`); the sums come back in the order of `tri`."""
         S = Nmax - Ncut // step + 1
         rows = list(range(S)) if field_rows is None else list(field_rows)                  # row of `fields` holding shell slot f
         if packed is None:
@@ -486,8 +539,8 @@ class PeriodicPipeline(object):
         if engine == 'tc' and not tc_ok:
             raise ValueError('tensor-core triangle kernel needs packed float32 fields, N^3 % 64 == 0 and <= 128 shells')
         if engine == 'tc' or (engine == 'auto' and tc_ok):
-            return self._triangle_sums_tc(fields, Nmax, Ncut, step, rows)
-        tri, tiles, ntiles = self.triangle_tiles(Nmax, Ncut, step)
+            return self._triangle_sums_tc(fields, Nmax, Ncut, step, rows, tri)
+        tri, tiles, ntiles = self.triangle_tiles(Nmax, Ncut, step, tri)
         nf = (S + 3) // 4 * 4
         ptrs = [fields[rows[min(f, S - 1)]].data_ptr() for f in range(nf)]
         dptr = torch.tensor(ptrs, dtype=torch.int64).to(self.dev)
@@ -502,20 +555,22 @@ class PeriodicPipeline(object):
         check(rc, 'psb_bk_triangle_sums')
         return sums
 
-    def tc_passes(self, Nmax, Ncut, step, layout=None):
-        """Device copy of the tensor-core plan (`build_tc_plan`), cached per configuration."""
+    def tc_passes(self, Nmax, Ncut, step, layout=None, tri=None):
+        """Device copy of the tensor-core plan (`build_tc_plan`) for the loop-nest triangles or a subset, cached."""
         if layout is None:
             layout = int(os.environ.get('PSB_TC_LAYOUT', '1'))       # 2x2 blocks: 17 % faster (profiles/r1_summary.md)
-        key = ('tc', Nmax, Ncut, step, layout)
+        key = ('tc', Nmax, Ncut, step, layout, self._tri_key(tri))
         if key not in self._tiles:
-            tri = triangle_list(Nmax, Ncut, step)
+            if tri is None:
+                tri = triangle_list(Nmax, Ncut, step)
+            tri = np.ascontiguousarray(tri, dtype=np.int32)
             NT, MT, layout_used, passes = build_tc_plan(tri, Ncut // step, Nmax, layout)
             dev_passes = [(torch.from_numpy(lij).to(self.dev), MT, torch.from_numpy(rc).to(self.dev)) for lij, rc in passes]
             self._tiles[key] = (tri, NT, dev_passes, layout_used)
         return self._tiles[key]
 
-    def _triangle_sums_tc(self, fields, Nmax, Ncut, step, rows):
-        tri, NT, passes, layout = self.tc_passes(Nmax, Ncut, step)
+    def _triangle_sums_tc(self, fields, Nmax, Ncut, step, rows, tri=None):
+        tri, NT, passes, layout = self.tc_passes(Nmax, Ncut, step, tri=tri)
         S = Nmax - Ncut // step + 1
         dptr = torch.tensor([fields[rows[f]].data_ptr() for f in range(S)], dtype=torch.int64).to(self.dev)
         sums = torch.zeros(len(tri), dtype=torch.float64, device=self.dev)
@@ -532,29 +587,75 @@ class PeriodicPipeline(object):
         free = self._pin_pool.setdefault(n, [])
         return free.pop() if free else torch.empty(n, dtype=torch.float64, pin_memory=True)
 
-    def bispectrum_launch(self, half, step, Ncut, Nmax, engine='auto', sumw=None):
+    def bk_levels(self, step, Ncut, Nmax):
+        """(triangle list, [(pipeline of the transform grid, triangle indices (numpy), the same on the device, largest shell)])
+        for this configuration: `coarse_levels` with the default / PSB_BK_LEVELS grid sizes, cached."""
+        key = ('levels', step, Ncut, Nmax, os.environ.get('PSB_BK_LEVELS', 'auto'))
+        if key not in self._tiles:
+            tri = triangle_list(Nmax, Ncut, step)
+            lev = []
+            for Nc, idx, smax in coarse_levels(self.N, step, tri, default_level_sizes(self.N, step, tri)):
+                pc = self if Nc == self.N else PeriodicPipeline.get(Nc)
+                lev.append((pc, idx, torch.from_numpy(idx).to(self.dev), smax))
+            self._tiles[key] = (tri, lev)
+        return self._tiles[key]
+
+    def bispectrum_launch(self, half, step, Ncut, Nmax, engine='auto', sumw=None, timers=None):
         """Enqueue K5 + K6 for one catalogue and the device->host copy of everything the host epilogue needs (triangle sums,
         shell powers, scales, max|I|, sum of weights) into pinned memory.  Returns a handle for `bispectrum_finish`; nothing
-        here waits for the GPU, so the caller can enqueue the next catalogue before collecting this one."""
+        here waits for the GPU, so the caller can enqueue the next catalogue before collecting this one.
+        The triangles are split over transform grids (`bk_levels`): each level transforms the shells it needs on its own grid
+        straight from `half` and sums its triangles there; sums and shell powers are brought to the units of this grid
+        (x (N/Nc)^3).  timers: optional list receiving (stage, start event, end event) for bench.py."""
         s0 = Ncut // step
         S = Nmax - s0 + 1
-        fields, sumsq, scales, maxabs = self.shell_fields(half, step, s0, Nmax, scaled=True)
-        use_tc = engine in ('auto', 'tc') and fields.shape[1] % 64 == 0 and S <= 128
-        sums = self.triangle_sums(fields, Nmax, Ncut, step, engine='tc' if use_tc else 'fma')
+        SA = S + (S % 2)
+        tri, levels = self.bk_levels(step, Ncut, Nmax)
+        scales = self.shell_scales(half, step, s0, Nmax)
+        sums = torch.zeros(len(tri), dtype=torch.float64, device=self.dev)
+        sumsq = torch.zeros(SA, dtype=torch.float64, device=self.dev)
+        maxabs = torch.zeros(SA, dtype=torch.float32, device=self.dev)
+        have, all_tc = 0, True
+
+        def mark():
+            if timers is None:
+                return None
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            return e
+        for pc, idx, idx_dev, smax in levels:
+            Sl = smax - s0 + 1
+            vol = (float(self.N) / pc.N) ** 3
+            t0 = mark()
+            fields, sq, _, mx = pc.shell_fields(half, step, s0, smax, scaled=True, scales=scales, src=None if pc is self else self)
+            t1 = mark()
+            use_tc = engine in ('auto', 'tc') and fields.shape[1] % 64 == 0 and Sl <= 128
+            all_tc = all_tc and use_tc
+            sl = pc.triangle_sums(fields, smax, Ncut, step, engine='tc' if use_tc else 'fma', tri=tri[idx])
+            t2 = mark()
+            if timers is not None:
+                timers.append(('shell_fields', t0, t1))
+                timers.append(('triangles', t1, t2))
+            del fields
+            sums.index_copy_(0, idx_dev, sl if vol == 1.0 else sl * vol)
+            if Sl > have:                                   # shell powers from the coarsest level that holds the shell (Parseval)
+                sumsq[have:Sl] = sq[have:Sl] if vol == 1.0 else sq[have:Sl] * vol
+                have = Sl
+            maxabs[:Sl] = torch.maximum(maxabs[:Sl], mx.view(torch.float32)[:Sl])
         sw = sumw.double().reshape(1) if sumw is not None else torch.zeros(1, dtype=torch.float64, device=self.dev)
-        dev = torch.cat([sums, sumsq, scales.double(), maxabs.view(torch.float32).double(), sw])
+        dev = torch.cat([sums, sumsq, scales.double(), maxabs.double(), sw])
         host = self._pinned(dev.numel())
         host.copy_(dev, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
-        return {'host': host, 'ev': ev, 'fields': fields, 'nt': sums.numel(), 'SA': sumsq.numel(), 'use_tc': use_tc,
+        return {'host': host, 'ev': ev, 'half': half, 'nt': sums.numel(), 'SA': SA, 'use_tc': all_tc and engine != 'fma',
                 'args': (Nmax, Ncut, step)}
 
     def bispectrum_finish(self, h):
         """Wait for a `bispectrum_launch` and return host arrays (sum_x I_i I_j I_l per triangle, sum_x I_j^2 per shell,
         sum of weights) in the reference's units.  The tensor-core path works on power-of-two scaled fields; if a pair
         product could leave the fp16 range (max|I_i| max|I_j| >= 4e4 after scaling -- only for pathologically concentrated
-        catalogues) the triangle sums are redone by the FFMA kernel."""
+        catalogues) the shell and triangle stage is redone with the FFMA kernel."""
         h['ev'].synchronize()
         host = h['host'].numpy().copy()
         self._pin_pool[h['host'].numel()].append(h['host'])
@@ -563,8 +664,10 @@ class PeriodicPipeline(object):
         nt, SA = h['nt'], h['SA']
         sums_h, sumsq_h, sc, mx = host[:nt], host[nt:nt + SA], host[nt + SA:nt + 2 * SA], host[nt + 2 * SA:nt + 3 * SA]
         if h['use_tc'] and mx.max() ** 2 >= 4.0e4:
-            sums_h = self.triangle_sums(h['fields'], Nmax, Ncut, step, engine='fma').cpu().numpy()
-        h['fields'] = None
+            redo = self.bispectrum_launch(h['half'], step, Ncut, Nmax, engine='fma')
+            h['half'] = None
+            return self.bispectrum_finish(redo)[:2] + (float(host[-1]),)
+        h['half'] = None
         tri = triangle_list(Nmax, Ncut, step)
         sums_h = sums_h / (sc[tri[:, 0] - s0] * sc[tri[:, 1] - s0] * sc[tri[:, 2] - s0])
         sumsq_h = sumsq_h / sc ** 2
@@ -600,18 +703,23 @@ class PeriodicPipeline(object):
         return counts
 
     def compute_counts(self, Nmax, Ncut, step):
+        """Exact triangle counts N^3 * #{closed mode triples} in float64 on the GPU (delta == 1 through K5 + K6, py:975-1023).
+        The number of closed triples of a triangle is the same on every grid that holds it without wrap, so each level of
+        `bk_levels` counts its triangles on its own (coarser) grid."""
         N = self.N
         s0 = Ncut // step
-        fields, _ = self.shell_fields(None, step, s0, Nmax, dtype=torch.float64)
-        sums = self.triangle_sums(fields, Nmax, Ncut, step).cpu().numpy()
-        del fields
-        tri, _, _ = self.triangle_tiles(Nmax, Ncut, step)
-        n3 = float(N) ** 3
-        nint = np.rint(sums / n3)
-        if np.abs(sums / n3 - nint).max() > 1e-3:
-            raise RuntimeError('triangle counts did not come out as integers (max dev %g)' % np.abs(sums / n3 - nint).max())
+        tri, levels = self.bk_levels(step, Ncut, Nmax)
         counts = np.zeros((Nmax, Nmax, Nmax), dtype=np.float64)
-        counts[tri[:, 0] - 1, tri[:, 1] - 1, tri[:, 2] - 1] = nint * n3
+        for pc, idx, _, smax in levels:
+            fields, _ = pc.shell_fields(None, step, s0, smax, dtype=torch.float64)
+            sums = pc.triangle_sums(fields, smax, Ncut, step, tri=tri[idx]).cpu().numpy()
+            del fields
+            n3 = float(pc.N) ** 3
+            nint = np.rint(sums / n3)
+            if np.abs(sums / n3 - nint).max() > 1e-3:
+                raise RuntimeError('triangle counts did not come out as integers (max dev %g)' % np.abs(sums / n3 - nint).max())
+            t = tri[idx]
+            counts[t[:, 0] - 1, t[:, 1] - 1, t[:, 2] - 1] = nint * float(N) ** 3
         return counts
 
 
