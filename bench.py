@@ -231,6 +231,12 @@ def run_b200(args):
     assert len(out['b123']) == len(tri) == 6350 and np.all(np.isfinite(out['b123']))
 
     dev_ms, e2e_ms, e2e1_ms = D.max_over_ranks([dev_ms, e2e_s * 1e3, e2e1_s * 1e3], device=dev)
+    sharded = None
+    if world > 1 and os.environ.get('PSB_BENCH_SHARDED', '1') != '0':
+        del out, out1
+        pipe._pin_pool.clear()
+        torch.cuda.empty_cache()
+        sharded = run_sharded_section(args, dev, rank, world, xyz_dev)
     ncat = args.steps * world
     if rank == 0:
         ncell = N ** 3
@@ -306,10 +312,114 @@ def run_b200(args):
                 'fft_fcomb': {'bound': 'hbm', 'alg_bytes': 44.0 * ncell, 'achieved_gbs': 44.0 * ncell / (float(stage_ms[1]) * 1e-3) / 1e9},
                 'shell_fields': {'bound': 'hbm', 'alg_bytes': 20.0 * ncell * S, 'achieved_gbs': 20.0 * ncell * S / (float(stage_ms[2]) * 1e-3) / 1e9}},
             'cpu_baseline': cpu, 'clocks': ck,
+            'sharded': sharded,
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------
+# ONE catalogue sharded over the GPUs (pyspectrum_b200.multigpu): strong scaling, reported next to the headline
+# --------------------------------------------------------------------------------------------
+def c5_shard(dev, rank, world, Np_total=10 ** 9, L=4000.):
+    """BASELINE configs[4] catalogue, generated per rank on the device (seed 5, L=4000, Np=1e9): uniform randoms with a
+    sinusoidal displacement (clustered along x); float32 positions, 1e9/world particles per rank."""
+    import torch
+    g = torch.Generator(device=dev)
+    g.manual_seed(5 + rank)
+    n = Np_total // world
+    xyz = torch.rand((3, n), generator=g, device=dev, dtype=torch.float32) * L
+    xyz[0] = (xyz[0] + 40.0 * torch.sin(2 * np.pi * xyz[1] / 500.0)) % L
+    return xyz
+
+
+def run_sharded_config(name, shard, cfg, dev, world, reps=3):
+    """Times multigpu.Bk_periodic_sharded(return_pk=True) on this rank's shard: device time (CUDA events) as max over ranks, the
+    per-stage device times of the slowest rank, bytes each collective puts on the wire per rank and the bandwidth it achieves."""
+    import torch
+    from pyspectrum_b200 import dist as D, multigpu as M, pyspectrum as pySpec
+    kw = dict(Lbox=cfg['L'], Ngrid=cfg['N'], step=cfg['step'], Ncut=cfg['Ncut'], Nmax=cfg['Nmax'])
+    Ng = M.carrier_grid(cfg['N'], cfg['step'], cfg['Nmax'], cfg['Ncut'])
+    t0 = time.perf_counter()
+    M.sharded_counts(pySpec.PeriodicPipeline.get(Ng), cfg['step'], cfg['Ncut'], cfg['Nmax'])      # once per configuration (cached)
+    D.barrier()
+    t_counts = time.perf_counter() - t0
+    M.Bk_periodic_sharded(shard, None, return_pk=True, **kw)                                       # warm-up
+    torch.cuda.reset_peak_memory_stats()
+    D.barrier()
+    tot, stages, nbytes = 0., {}, {}
+    for _ in range(reps):
+        st = M.Stats(timed=True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        D.barrier()
+        e0.record()
+        out, pk = M.Bk_periodic_sharded(shard, None, stats=st, return_pk=True, **kw)
+        e1.record()
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+        for k, v in st.times_ms().items():
+            stages[k] = stages.get(k, 0.) + v
+        nbytes = st.bytes
+    names = sorted(stages)
+    red = D.max_over_ranks([tot / reps] + [stages[k] / reps for k in names] + [torch.cuda.max_memory_allocated() / 1e9], device=dev)
+    stage_ms = dict(zip(names, red[1:1 + len(names)]))
+    coll = {}
+    for k, b in nbytes.items():
+        ms = stage_ms.get(k)
+        coll[k] = {'bytes_per_rank': int(b), 'ms': ms, 'gbs_per_rank': (b / (ms * 1e-3) / 1e9) if ms else None}
+    res = {'config': name, 'n_gpus': world, 'Ngrid': cfg['N'], 'particles': int(out['meta']['N']), 'triangles': int(len(out['b123'])),
+           'carrier_grid': Ng, 'shell_grids': [pc.N for pc, _, _, _ in pySpec.PeriodicPipeline.get(Ng).bk_levels(cfg['step'], cfg['Ncut'], cfg['Nmax'])[1]],
+           's_per_catalog': red[0] * 1e-3, 'stage_ms_max_over_ranks': stage_ms, 'collectives': coll,
+           'mem_gb_max_per_gpu': red[-1], 'counts_float64_once_s': t_counts,
+           'api': 'pyspectrum_b200.multigpu.Bk_periodic_sharded(return_pk=True): P(k) + B(k) of one catalogue, particles spread over the ranks',
+           'finite': bool(np.all(np.isfinite(out['b123'])) and np.all(np.isfinite(pk['p0k'])))}
+    # roofline view of the stages north_star names (per GPU, measured HBM peak): assignment and the shell / triangle stage
+    return res
+
+
+def run_sharded_section(args, dev, rank, world, xyz_dev_rank0):
+    """Strong scaling of ONE catalogue over the GPUs of the box: C2 (the headline catalogue, split over the ranks) and, when
+    PSB_BENCH_C5 != 0, BASELINE configs[4] (Ngrid=1024, 1e9 particles)."""
+    import torch
+    import torch.distributed as dist
+    out = {}
+    L, N = CFG['Lbox'], CFG['Ngrid']
+    n = torch.tensor([xyz_dev_rank0.shape[1] if rank == 0 else 0], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.broadcast(n, 0)
+    full = xyz_dev_rank0 if rank == 0 else torch.empty((3, int(n.item())), dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.broadcast(full, 0)
+    shard = full[:, rank::world].contiguous()
+    del full
+    try:
+        out['c2'] = run_sharded_config('BASELINE configs[1] sharded', shard, dict(N=N, L=L, step=CFG['step'], Ncut=CFG['Ncut'], Nmax=CFG['Nmax']),
+                                       dev, world)
+    except Exception as e:                                   # the headline line must still be printed
+        out['c2'] = {'error': repr(e)[:300]}
+    del shard
+    torch.cuda.empty_cache()
+    if os.environ.get('PSB_BENCH_C5', '1') != '0' and world >= 2:
+        try:
+            shard = c5_shard(dev, rank, world)
+            out['c5'] = run_sharded_config('BASELINE configs[4]: Ngrid=1024, 1e9 particles, P(k)+B(k)', shard,
+                                           dict(N=1024, L=4000., step=3, Ncut=3, Nmax=40), dev, world, reps=2)
+            Np5 = out['c5']['particles']
+            peak = None
+            try:
+                peak = float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'])
+            except Exception:
+                pass
+            sm = out['c5']['stage_ms_max_over_ranks']
+            if sm.get('assign_slab'):
+                b = (16.0 * Np5 + 8.0 * 1024 ** 3) / world                    # SURVEY 8d algorithmic bytes of K1, this rank's share
+                out['c5']['assign_roofline'] = {'alg_bytes_per_gpu': b, 'achieved_gbs_per_gpu': b / (sm['assign_slab'] * 1e-3) / 1e9,
+                                                'frac_of_measured_hbm_peak': (b / (sm['assign_slab'] * 1e-3) / 1e9 / peak) if peak else None,
+                                                'mpart_per_s_all_gpus': Np5 / (sm['assign_slab'] * 1e-3) / 1e6}
+        except Exception as e:
+            out['c5'] = {'error': repr(e)[:300]}
+    return out
 
 
 # --------------------------------------------------------------------------------------------

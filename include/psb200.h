@@ -68,6 +68,25 @@ int psb_assign_pcs_interlaced(const void* pos, int pos_f64, int pos_aos, const v
                               int64_t np, int ngrid, double lbox_clip, float kf_ks, float offset,
                               float* mesh, int zero_mesh, void* ws, size_t ws_bytes, double* sumw, void* stream);
 
+/* Slab-owned assignment for ONE catalogue sharded over G GPUs: rank q owns the mesh planes [q*nz, (q+1)*nz), nz = N/G.
+ * A particle in cell c touches planes c-1 .. c+3, so it goes to the owner of plane c-1 and, if different, to the owner of plane
+ * c+3 (ghost copy); no mesh collective is needed afterwards.
+ *   psb_slab_route_count    counts [G] (device uint64): particles (ghost copies included) this rank sends to every rank;
+ *                           sumw: sum of the weights of the rank's own particles (no copies) in float64
+ *   psb_slab_route_scatter  send_xyzw: destination-major buffer of float4 {x,y,z,w} (float32 after the float64 clip of
+ *                           py:938-941); base [G] = exclusive scan of counts (device), cursor [G] scratch
+ *   (caller: all-to-all of the counts, then of the float4 rows)
+ *   psb_assign_slab         K1 on the received particles onto the rank's planes: mesh_slab float32 [nzs][N][N][2]; contributions
+ *                           to planes outside [zbase, zbase+nzs) are dropped (the owner has its own copy of the particle);
+ *                           workspace psb_assign_workspace_bytes(np, ngrid); sumw_scratch receives the sum over the received copies */
+int psb_slab_route_count(const void* pos, int pos_f64, int pos_aos, const void* w, int w_f64, int64_t np, int ngrid, double lbox_clip,
+                         float kf_ks, float offset, int nz_per_rank, int nranks, uint64_t* counts, double* sumw, void* stream);
+int psb_slab_route_scatter(const void* pos, int pos_f64, int pos_aos, const void* w, int w_f64, int64_t np, int ngrid, double lbox_clip,
+                           float kf_ks, float offset, int nz_per_rank, int nranks, const uint64_t* base, uint64_t* cursor,
+                           float* send_xyzw, void* stream);
+int psb_assign_slab(const float* xyzw, int64_t np, int ngrid, float kf_ks, float offset, int zbase, int nzs, float* mesh_slab,
+                    int zero_mesh, void* ws, size_t ws_bytes, double* sumw_scratch, void* stream);
+
 /* Survey-geometry catalogue pre-step, one pass on the device (pyspectrum.py:776-806 + util.py:27-51):
  * (RA, Dec, z) -> comoving Cartesian float32 positions, FKP weights, normalisation sums, bounding box.
  *   radecz      device float64 [3][np]: RA [deg], Dec [deg], redshift
@@ -114,6 +133,16 @@ int psb_pk_monopole(const float* half_c64, int ngrid, const uint16_t* bin_of_m, 
                     double* out, void* stream);
 int psb_pk_multipoles(const float* half_c64, int ngrid, const uint16_t* bin_of_m, int nbin, int nmu,
                       float kf32, const float* trig4_host, double* out, void* stream);
+
+/* The same on a rank's ky-slab of the half field, [kz][ky0 .. ky0+ny-1][kx] (multi-GPU: partial sums, all-reduced by the caller). */
+int psb_pk_monopole_slab(const float* half_slab_c64, int ngrid, int ky0, int ny, const uint16_t* bin_of_m, int nbin, double kf,
+                         double* out, void* stream);
+int psb_pk_multipoles_slab(const float* half_slab_c64, int ngrid, int ky0, int ny, const uint16_t* bin_of_m, int nbin, int nmu,
+                           float kf32, const float* trig4_host, double* out, void* stream);
+/* Low-|k| modes of a ky-slab -> half field [ngrid_carrier][ngrid_carrier][ngrid_carrier/2+1] of a coarser (or equal) grid, zero
+ * elsewhere; |k_a| < ngrid_carrier/2 are kept (everything if the grids are equal).  The sum over the ranks is the carrier field
+ * the shell stage transforms from (see psb_bk_shell_pair_f32, ngrid_src). */
+int psb_half_extract(const float* half_slab_c64, int ngrid, int ky0, int ny, float* carrier_c64, int ngrid_carrier, void* stream);
 
 /* code='python' branch of _Pk_periodic_rsd (pyspectrum.py:545-626): float64 (k,mu) estimator over ALL modes of a FULL field
  * full_c64 [kx][ky][kz] (what reflect_delta returns, C order) with |k_a| = min(i, N-i), mu bin ceil(mu * nmu);

@@ -47,6 +47,9 @@ PROTOTYPES = {
     'psb_irk_table_f32': (_i, [_f, _i, _vp]),
     'psb_assign_workspace_bytes': (_sz, [_i64, _i]),
     'psb_assign_pcs_interlaced': (_i, [_vp, _i, _i, _vp, _i, _i64, _i, _d, _f, _f, _vp, _i, _vp, _sz, _vp, _vp]),
+    'psb_slab_route_count': (_i, [_vp, _i, _i, _vp, _i, _i64, _i, _d, _f, _f, _i, _i, _vp, _vp, _vp]),
+    'psb_slab_route_scatter': (_i, [_vp, _i, _i, _vp, _i, _i64, _i, _d, _f, _f, _i, _i, _vp, _vp, _vp, _vp]),
+    'psb_assign_slab': (_i, [_vp, _i64, _i, _f, _f, _i, _i, _vp, _i, _vp, _sz, _vp, _vp]),
     'psb_survey_prepare': (_i, [_vp, _vp, _vp, _i64, _vp, _i, _d, _d, _vp, _vp, _vp, _vp]),
     'psb_fft_mesh_to_delta': (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp]),
     'psb_fft_c2c_3d': (_i, [_vp, _i, _i, _vp, _vp]),
@@ -57,6 +60,9 @@ PROTOTYPES = {
     'psb_slab_fcomb': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp]),
     'psb_pk_monopole': (_i, [_vp, _i, _vp, _i, _d, _vp, _vp]),
     'psb_pk_multipoles': (_i, [_vp, _i, _vp, _i, _i, _f, _vp, _vp, _vp]),
+    'psb_pk_monopole_slab': (_i, [_vp, _i, _i, _i, _vp, _i, _d, _vp, _vp]),
+    'psb_pk_multipoles_slab': (_i, [_vp, _i, _i, _i, _vp, _i, _i, _f, _vp, _vp, _vp]),
+    'psb_half_extract': (_i, [_vp, _i, _i, _i, _vp, _i, _vp]),
     'psb_pk_kmu_python': (_i, [_vp, _i, _vp, _i, _i, _d, _vp, _vp, _vp]),
     'psb_shell_mode_counts': (_i, [_i, _vp, _i, _vp, _vp]),
     'psb_bk_shell_pair_f32': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),

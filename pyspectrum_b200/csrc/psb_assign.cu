@@ -16,6 +16,11 @@ namespace psb {
 
 __device__ __forceinline__ void load_particle(const AssignIn& a, long long i, float& x, float& y, float& z, float& w, double& wd)
 {
+    if (a.pos_aos == 2) {            // routed particles of the slab path: float4 {x, y, z, w}, already clipped and cast
+        const float4 p = static_cast<const float4*>(a.pos)[i];
+        x = p.x; y = p.y; z = p.z; w = p.w; wd = (double)p.w;
+        return;
+    }
     const long long s = a.pos_aos ? 1 : a.Np, b = a.pos_aos ? 3 * i : i;
     if (a.pos_f64) {
         const double* p = static_cast<const double*>(a.pos);
@@ -47,10 +52,15 @@ __device__ __forceinline__ float grid_coord(float kf_ks, float r, float offset)
 
 __device__ __forceinline__ int wrapN(int c, int N) { c %= N; return c < 0 ? c + N : c; }
 
+// Sort key = (z plane, y row) of the particle's cell.  Full grid: N*N keys.  Slab [zbase, zbase+nzs): planes are counted from
+// zbase - 4 (a particle in cell c touches planes c-1 .. c+3, so cells zbase-3 .. zbase+nzs reach the slab): (nzs+8)*N keys plus
+// one trailing bucket for particles that cannot touch the slab (they are sorted behind the valid ones and never assigned).
 __device__ __forceinline__ int row_key(const AssignIn& a, float y, float z)
 {
     const int cy = (int)grid_coord(a.kf_ks, y, a.offset) - 1, cz = (int)grid_coord(a.kf_ks, z, a.offset) - 1;
-    return wrapN(cz, a.N) * a.N + wrapN(cy, a.N);
+    if (a.nzs >= a.N) return wrapN(cz, a.N) * a.N + wrapN(cy, a.N);
+    const int zr = wrapN(cz - (a.zbase - 4), a.N);
+    return zr < a.nzs + 8 ? zr * a.N + wrapN(cy, a.N) : (a.nzs + 8) * a.N;
 }
 
 __global__ void k_hist(AssignIn a, unsigned int* hist, double* sumw)
@@ -259,13 +269,17 @@ __global__ void __launch_bounds__(256) k_assign_pairs(const float4* __restrict__
 // lane and particle, REDG only 1.7 % of them): periodic wraps by compare-and-subtract from one wrapped base cell instead of a
 // modulo per row, 32-bit element offsets (2 N^3 < 2^32), weights pre-multiplied per z row, and the four "product != 0" tests of
 // a reduction replaced by tests on its factors.
-__global__ void __launch_bounds__(256) k_assign_tri(const float4* __restrict__ sorted, long long Np, int N, float kf_ks, float offset, float* mesh)
+// Slab mode (nzs < N): `mesh` holds the planes zbase .. zbase+nzs-1 only, contributions to other planes are dropped (their owner
+// rank receives the same particle as a ghost), and only the first *nvalid sorted particles can touch the slab.
+__global__ void __launch_bounds__(256) k_assign_tri(const float4* __restrict__ sorted, long long Np, int N, float kf_ks, float offset, float* mesh,
+                                                    int zbase, int nzs, const unsigned int* __restrict__ nvalid)
 {
     const int lane = threadIdx.x & 31;
     const int g = lane / 3, pr = lane - 3 * g;
     const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     const long long i = warp * 10 + g;
     if (g >= 10 || i >= Np) return;
+    if (nvalid && i >= (long long)*nvalid) return;
     const float4 p = sorted[i];
     const AxisWin X = axis_window(kf_ks, p.x, offset), Y = axis_window(kf_ks, p.y, offset), Z = axis_window(kf_ks, p.z, offset);
     const int P0 = X.c0 >> 1, off = X.c0 - 2 * P0, Nh = N / 2;
@@ -292,6 +306,9 @@ __global__ void __launch_bounds__(256) k_assign_tri(const float4* __restrict__ s
         if (za[rz] == 0.f && zb[rz] == 0.f) continue;
         int zz = z0 + rz;
         zz = zz >= N ? zz - N : zz;
+        zz -= zbase;                                           // plane inside the slab (full grid: zbase = 0, nzs = N)
+        zz = zz < 0 ? zz + N : zz;
+        if (zz >= nzs) continue;
         const unsigned zoff = (unsigned)zz * (unsigned)N * rowlen;
 #pragma unroll
         for (int ry = 0; ry < 5; ++ry) {
@@ -302,9 +319,100 @@ __global__ void __launch_bounds__(256) k_assign_tri(const float4* __restrict__ s
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// Slab routing (multi-GPU): rank q owns the mesh planes [q*nzr, (q+1)*nzr).  A particle in cell c touches planes
+// c-1 .. c+3 (grid A: c-1..c+2, the half-cell shifted grid B up to c+3), so it is sent to the owner of plane c-1 and, if
+// different, to the owner of plane c+3 (ghost copy).  Positions leave as float32 after the float64 clip of py:938-941, exactly
+// what assign_quad receives, packed with the weight as float4.  Two kernels: counts per destination (+ sum of weights over the
+// un-duplicated particles), then a scatter into a destination-major send buffer; chunk-local shared-memory ranks keep the
+// global atomics at one per destination and 256-particle chunk.
+__device__ __forceinline__ void slab_dests(const AssignIn& a, float z, int nzr, int& d0, int& d1)
+{
+    const int c = (int)grid_coord(a.kf_ks, z, a.offset) - 1;
+    d0 = wrapN(c - 1, a.N) / nzr;
+    d1 = wrapN(c + 3, a.N) / nzr;
+}
+
+constexpr int ROUTE_MAXR = 64;
+
+__global__ void __launch_bounds__(256) k_route_count(AssignIn a, int nzr, int nranks, unsigned long long* counts, double* sumw)
+{
+    __shared__ unsigned int h[ROUTE_MAXR];
+    if (threadIdx.x < ROUTE_MAXR) h[threadIdx.x] = 0u;
+    __syncthreads();
+    double acc = 0.0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < a.Np; i += (long long)gridDim.x * blockDim.x) {
+        float x, y, z, w; double wd;
+        load_particle(a, i, x, y, z, w, wd);
+        acc += wd;
+        int d0, d1;
+        slab_dests(a, z, nzr, d0, d1);
+        atomicAdd(&h[d0], 1u);
+        if (d1 != d0) atomicAdd(&h[d1], 1u);
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    __shared__ double red[8];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < nranks && h[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)h[threadIdx.x]);
+    if (threadIdx.x == 0) { double t = 0.0; for (int k = 0; k < 8; ++k) t += red[k]; atomicAdd(sumw, t); }
+}
+
+__global__ void __launch_bounds__(256) k_route_scatter(AssignIn a, int nzr, int nranks, const unsigned long long* __restrict__ base,
+                                                       unsigned long long* cursor, float4* send)
+{
+    __shared__ unsigned int cnt[ROUTE_MAXR];
+    __shared__ unsigned long long off[ROUTE_MAXR];
+    const long long nchunk = (a.Np + blockDim.x - 1) / blockDim.x;
+    for (long long ch = blockIdx.x; ch < nchunk; ch += gridDim.x) {
+        if (threadIdx.x < ROUTE_MAXR) cnt[threadIdx.x] = 0u;
+        __syncthreads();
+        const long long i = ch * blockDim.x + threadIdx.x;
+        float x = 0.f, y = 0.f, z = 0.f, w = 0.f; double wd;
+        int d0 = -1, d1 = -1;
+        unsigned int r0 = 0, r1 = 0;
+        if (i < a.Np) {
+            load_particle(a, i, x, y, z, w, wd);
+            slab_dests(a, z, nzr, d0, d1);
+            r0 = atomicAdd(&cnt[d0], 1u);
+            if (d1 != d0) r1 = atomicAdd(&cnt[d1], 1u); else d1 = -1;
+        }
+        __syncthreads();
+        if (threadIdx.x < nranks) off[threadIdx.x] = base[threadIdx.x] + atomicAdd(&cursor[threadIdx.x], (unsigned long long)cnt[threadIdx.x]);
+        __syncthreads();
+        if (d0 >= 0) send[off[d0] + r0] = make_float4(x, y, z, w);
+        if (d1 >= 0) send[off[d1] + r1] = make_float4(x, y, z, w);
+        __syncthreads();
+    }
+}
+
+int slab_route_count(const AssignIn& in, int nzr, int nranks, unsigned long long* counts, double* sumw, cudaStream_t st)
+{
+    if (in.N < 4 || in.N % 2 || in.Np < 0 || nranks < 1 || nranks > ROUTE_MAXR || nzr < 8 || nzr * nranks != in.N) return PSB_ERR_ARG;
+    if (cudaMemsetAsync(counts, 0, nranks * sizeof(unsigned long long), st) != cudaSuccess) return PSB_ERR_CUDA;
+    if (cudaMemsetAsync(sumw, 0, sizeof(double), st) != cudaSuccess) return PSB_ERR_CUDA;
+    if (in.Np > 0) {
+        const long long nb = (in.Np + 255) / 256;
+        k_route_count<<<(unsigned)(nb < sm_count() * 16 ? nb : sm_count() * 16), 256, 0, st>>>(in, nzr, nranks, counts, sumw);
+    }
+    return cudaGetLastError() == cudaSuccess ? PSB_OK : PSB_ERR_CUDA;
+}
+
+int slab_route_scatter(const AssignIn& in, int nzr, int nranks, const unsigned long long* base, unsigned long long* cursor, float4* send,
+                       cudaStream_t st)
+{
+    if (in.N < 4 || in.N % 2 || in.Np < 0 || nranks < 1 || nranks > ROUTE_MAXR || nzr < 8 || nzr * nranks != in.N) return PSB_ERR_ARG;
+    if (cudaMemsetAsync(cursor, 0, nranks * sizeof(unsigned long long), st) != cudaSuccess) return PSB_ERR_CUDA;
+    if (in.Np > 0) {
+        const long long nb = (in.Np + 255) / 256;
+        k_route_scatter<<<(unsigned)(nb < sm_count() * 16 ? nb : sm_count() * 16), 256, 0, st>>>(in, nzr, nranks, base, cursor, send);
+    }
+    return cudaGetLastError() == cudaSuccess ? PSB_OK : PSB_ERR_CUDA;
+}
+
 size_t assign_workspace_bytes(long long Np, int N)
 {
-    size_t hist = (((size_t)N * N + 1) * sizeof(unsigned int) + 255) / 256 * 256;
+    size_t hist = (((size_t)N * N + 2) * sizeof(unsigned int) + 255) / 256 * 256;      // also covers any slab ((nzs+8)*N + 1 keys, nzs + 8 <= N)
     return 2 * hist + (size_t)Np * sizeof(float4) + 256;
 }
 
@@ -312,14 +420,18 @@ int assign_pcs_interlaced(const AssignIn& in, float* mesh, int zero_mesh, void* 
 {
     if (in.N < 4 || (in.N % 2) || in.Np < 0) return PSB_ERR_ARG;
     if (ws_bytes < assign_workspace_bytes(in.Np, in.N)) return PSB_ERR_WORKSPACE;
-    const size_t nrow = (size_t)in.N * in.N;
-    const size_t hist_b = ((nrow + 1) * sizeof(unsigned int) + 255) / 256 * 256;
+    const bool slab = in.nzs < in.N;
+    if (in.nzs < 1 || in.nzs > in.N || (slab && (in.nzs + 8 > in.N || in.zbase < 0 || in.zbase >= in.N))) return PSB_ERR_ARG;
+    if (slab && 2.0 * in.nzs * in.N * in.N >= 4294967296.0) return PSB_ERR_ARG;
+    const size_t nrow = slab ? (size_t)(in.nzs + 8) * in.N + 1 : (size_t)in.N * in.N;      // sort keys (slab: + the "cannot touch" bucket)
+    const size_t mesh_rows = (size_t)in.nzs * in.N;
+    const size_t hist_b = (((size_t)in.N * in.N + 2) * sizeof(unsigned int) + 255) / 256 * 256;
     unsigned int* hist = static_cast<unsigned int*>(ws);
     unsigned int* tile_sum = hist + hist_b / sizeof(unsigned int);      // second counter area: scan tile sums (<= 4096 entries)
     float4* sorted = reinterpret_cast<float4*>(static_cast<char*>(ws) + 2 * hist_b);
     if (cudaMemsetAsync(hist, 0, hist_b, st) != cudaSuccess) return PSB_ERR_CUDA;
     if (cudaMemsetAsync(sumw, 0, sizeof(double), st) != cudaSuccess) return PSB_ERR_CUDA;
-    if (zero_mesh && cudaMemsetAsync(mesh, 0, sizeof(float) * 2 * nrow * in.N, st) != cudaSuccess) return PSB_ERR_CUDA;
+    if (zero_mesh && cudaMemsetAsync(mesh, 0, sizeof(float) * 2 * mesh_rows * in.N, st) != cudaSuccess) return PSB_ERR_CUDA;
     if (in.Np > 0) {
         const int blk = 256;
         const int grid = (int)((in.Np + blk - 1) / blk < sm_count() * 16 ? (in.Np + blk - 1) / blk : sm_count() * 16);
@@ -331,7 +443,10 @@ int assign_pcs_interlaced(const AssignIn& in, float* mesh, int zero_mesh, void* 
         k_scan_apply<<<ntile, 256, 0, st>>>(hist, (int)nrow, tile_sum);
         k_sort_scatter<<<grid, blk, 0, st>>>(in, hist, sorted);
         static const int variant = [] { const char* e = getenv("PSB_ASSIGN_VARIANT"); return e ? atoi(e) : 2; }();
-        if (variant == 2 && in.N <= 1024) k_assign_tri<<<(unsigned)((in.Np + 79) / 80), 256, 0, st>>>(sorted, in.Np, in.N, in.kf_ks, in.offset, mesh);
+        // after the scatter cursor[k] = start of key k+1: cursor[nrow-2] = number of particles that can touch the slab
+        if (slab || (variant == 2 && in.N <= 1024))
+            k_assign_tri<<<(unsigned)((in.Np + 79) / 80), 256, 0, st>>>(sorted, in.Np, in.N, in.kf_ks, in.offset, mesh, slab ? in.zbase : 0,
+                                                                       slab ? in.nzs : in.N, slab ? hist + (nrow - 2) : nullptr);
         else if (variant == 1) k_assign_pairs<<<(unsigned)((4 * in.Np + 255) / 256), 256, 0, st>>>(sorted, in.Np, in.N, in.kf_ks, in.offset, mesh);
         else k_assign<<<(unsigned)((in.Np + 255) / 256), 256, 0, st>>>(sorted, in.Np, in.N, in.kf_ks, in.offset, mesh);
     }

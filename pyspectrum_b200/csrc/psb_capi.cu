@@ -143,7 +143,45 @@ int psb_assign_pcs_interlaced(const void* pos, int pos_f64, int pos_aos, const v
     AssignIn in;
     in.pos = pos; in.pos_f64 = pos_f64; in.pos_aos = pos_aos; in.w = w; in.w_f64 = w_f64; in.Np = np; in.N = ngrid;
     in.do_clip = lbox_clip > 0.0; in.clip_hi = lbox_clip * (1. - 1e-6); in.kf_ks = kf_ks; in.offset = offset;
+    in.zbase = 0; in.nzs = ngrid;
     return assign_pcs_interlaced(in, mesh, zero_mesh, ws, ws_bytes, sumw, S(stream));
+}
+
+static AssignIn route_in(const void* pos, int pos_f64, int pos_aos, const void* w, int w_f64, int64_t np, int ngrid, double lbox_clip,
+                         float kf_ks, float offset)
+{
+    AssignIn in;
+    in.pos = pos; in.pos_f64 = pos_f64; in.pos_aos = pos_aos; in.w = w; in.w_f64 = w_f64; in.Np = np; in.N = ngrid;
+    in.do_clip = lbox_clip > 0.0; in.clip_hi = lbox_clip * (1. - 1e-6); in.kf_ks = kf_ks; in.offset = offset;
+    in.zbase = 0; in.nzs = ngrid;
+    return in;
+}
+
+int psb_slab_route_count(const void* pos, int pos_f64, int pos_aos, const void* w, int w_f64, int64_t np, int ngrid, double lbox_clip,
+                         float kf_ks, float offset, int nz_per_rank, int nranks, uint64_t* counts, double* sumw, void* stream)
+{
+    if ((!pos && np > 0) || !counts || !sumw) return PSB_ERR_ARG;
+    return slab_route_count(route_in(pos, pos_f64, pos_aos, w, w_f64, np, ngrid, lbox_clip, kf_ks, offset), nz_per_rank, nranks,
+                            reinterpret_cast<unsigned long long*>(counts), sumw, S(stream));
+}
+
+int psb_slab_route_scatter(const void* pos, int pos_f64, int pos_aos, const void* w, int w_f64, int64_t np, int ngrid, double lbox_clip,
+                           float kf_ks, float offset, int nz_per_rank, int nranks, const uint64_t* base, uint64_t* cursor, float* send_xyzw,
+                           void* stream)
+{
+    if ((!pos && np > 0) || !base || !cursor || (!send_xyzw && np > 0)) return PSB_ERR_ARG;
+    return slab_route_scatter(route_in(pos, pos_f64, pos_aos, w, w_f64, np, ngrid, lbox_clip, kf_ks, offset), nz_per_rank, nranks,
+                              reinterpret_cast<const unsigned long long*>(base), reinterpret_cast<unsigned long long*>(cursor),
+                              reinterpret_cast<float4*>(send_xyzw), S(stream));
+}
+
+int psb_assign_slab(const float* xyzw, int64_t np, int ngrid, float kf_ks, float offset, int zbase, int nzs, float* mesh_slab, int zero_mesh,
+                    void* ws, size_t ws_bytes, double* sumw_scratch, void* stream)
+{
+    if ((!xyzw && np > 0) || !mesh_slab || !ws || !sumw_scratch) return PSB_ERR_ARG;
+    AssignIn in = route_in(xyzw, 0, 2, nullptr, 0, np, ngrid, 0.0, kf_ks, offset);
+    in.zbase = zbase; in.nzs = nzs;
+    return assign_pcs_interlaced(in, mesh_slab, zero_mesh, ws, ws_bytes, sumw_scratch, S(stream));
 }
 
 int psb_fft_mesh_to_delta(float* mesh, float* half, int N, const float* tw, const double* rec, const float* wk,
@@ -194,21 +232,39 @@ int psb_slab_fcomb(const float* p, const float* q, float* half, int N, int ky0, 
                       ny, hp, reinterpret_cast<const Cx<double>*>(rec), wk, sumw, periodic, S(stream));
 }
 
-int psb_pk_monopole(const float* half, int N, const uint16_t* bin, int nbin, double kf, double* out, void* stream)
+int psb_pk_monopole_slab(const float* half, int N, int ky0, int ny, const uint16_t* bin, int nbin, double kf, double* out, void* stream)
 {
     if (!half || !bin || !out) return PSB_ERR_ARG;
     SpectraIn in{};
     in.half = reinterpret_cast<const Cx<float>*>(half); in.N = N; in.bin = bin; in.Nbin = nbin; in.mode = 0; in.kf = kf; in.Nmu = 1;
+    in.ky0 = ky0; in.ny = ny;
     return binned_spectra(in, out, S(stream));
 }
 
-int psb_pk_multipoles(const float* half, int N, const uint16_t* bin, int nbin, int nmu, float kf32, const float* trig4, double* out, void* stream)
+int psb_pk_monopole(const float* half, int N, const uint16_t* bin, int nbin, double kf, double* out, void* stream)
+{
+    return psb_pk_monopole_slab(half, N, 0, N, bin, nbin, kf, out, stream);
+}
+
+int psb_pk_multipoles_slab(const float* half, int N, int ky0, int ny, const uint16_t* bin, int nbin, int nmu, float kf32, const float* trig4,
+                           double* out, void* stream)
 {
     if (!half || !bin || !out || !trig4 || nmu < 1) return PSB_ERR_ARG;
     SpectraIn in{};
     in.half = reinterpret_cast<const Cx<float>*>(half); in.N = N; in.bin = bin; in.Nbin = nbin; in.mode = 1; in.kf32 = kf32; in.Nmu = nmu;
     in.costh = trig4[0]; in.sinth = trig4[1]; in.cosph = trig4[2]; in.sinph = trig4[3];
+    in.ky0 = ky0; in.ny = ny;
     return binned_spectra(in, out, S(stream));
+}
+
+int psb_pk_multipoles(const float* half, int N, const uint16_t* bin, int nbin, int nmu, float kf32, const float* trig4, double* out, void* stream)
+{
+    return psb_pk_multipoles_slab(half, N, 0, N, bin, nbin, nmu, kf32, trig4, out, stream);
+}
+
+int psb_half_extract(const float* half_slab, int N, int ky0, int ny, float* carrier, int Ng, void* stream)
+{
+    return half_extract(reinterpret_cast<const Cx<float>*>(half_slab), N, ky0, ny, reinterpret_cast<Cx<float>*>(carrier), Ng, S(stream));
 }
 
 int psb_pk_kmu_python(const float* full, int N, const uint16_t* bin, int nbin, int nmu, double kf, const double* trig4, double* out, void* stream)

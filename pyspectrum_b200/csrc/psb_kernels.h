@@ -11,7 +11,7 @@ int sm_count();
 struct AssignIn {
     const void* pos;      // positions
     int pos_f64;          // 1: float64, 0: float32
-    int pos_aos;          // 1: [Np][3] (Fortran (3,Np)), 0: [3][Np] (numpy 3xN C order)
+    int pos_aos;          // 1: [Np][3] (Fortran (3,Np)), 0: [3][Np] (numpy 3xN C order), 2: float4 {x,y,z,w} (routed slab particles)
     const void* w;        // weights or null
     int w_f64;            // 1: float64, 0: float32
     long long Np;
@@ -19,10 +19,16 @@ struct AssignIn {
     int do_clip;          // pyspectrum.py:938-941
     double clip_hi;       // Lbox*(1-1e-6)
     float kf_ks, offset;
+    int zbase, nzs;       // planes [zbase, zbase+nzs) held by `mesh` (full grid: 0, N); see k_assign_tri
 };
 
 size_t assign_workspace_bytes(long long Np, int N);
 int assign_pcs_interlaced(const AssignIn& in, float* mesh, int zero_mesh, void* ws, size_t ws_bytes, double* sumw, cudaStream_t st);
+
+// slab routing of the multi-GPU path (psb_assign.cu): per-destination counts, then the destination-major float4 send buffer
+int slab_route_count(const AssignIn& in, int nz_per_rank, int nranks, unsigned long long* counts, double* sumw, cudaStream_t st);
+int slab_route_scatter(const AssignIn& in, int nz_per_rank, int nranks, const unsigned long long* base, unsigned long long* cursor,
+                       float4* send, cudaStream_t st);
 
 int fft_mesh_to_delta(Cx<float>* mesh, Cx<float>* half, int N, const Cx<float>* tw,
                       const Cx<double>* rec, const float* Wk, const double* sumw, int periodic, cudaStream_t st);
@@ -35,8 +41,9 @@ int fft_shell_pair(const Cx<float>* half, const unsigned short* irk, int N, int 
                    const Cx<T>* tw, cudaStream_t st);
 
 struct SpectraIn {
-    const Cx<float>* half;       // [kz][ky][kx]
+    const Cx<float>* half;       // [kz][ky][kx], ky = ky0 .. ky0+ny-1 (the whole half field: ky0 = 0, ny = N)
     int N;
+    int ky0, ny;
     const unsigned short* bin;   // bin index (1-based, 0 = none) of m = |k|^2, host table
     int Nbin;
     int mode;                    // 0: Pk_periodic (float64 |k|, realified self-conjugate points)
@@ -53,6 +60,7 @@ int binned_spectra(const SpectraIn& in, double* out, cudaStream_t st);
 int kmu_python(const Cx<float>* full, int N, const unsigned short* bin, int Nbin, int Nmu, double kf, const double* trig4, double* out,
                cudaStream_t st);
 int shell_power(const Cx<float>* half, int N, const unsigned short* irk, int nshell, double* psum, cudaStream_t st);
+int half_extract(const Cx<float>* src, int N, int ky0, int ny, Cx<float>* dst, int Ng, cudaStream_t st);
 int shell_scales(const double* psum, int nshell, float target_rms, float* scales, cudaStream_t st);
 int shell_mode_counts(int N, const unsigned short* irk, int nshell_max, unsigned long long* nk, cudaStream_t st);
 

@@ -62,9 +62,10 @@ __global__ void __launch_bounds__(256) k_spectra(SpectraIn in, double* out, int 
     for (int i = threadIdx.x; i < nsm; i += blockDim.x) sbin[i] = 0.0;
     __syncthreads();
     double* tab = (MODE == 1 && table_in_smem) ? sbin + NV * Nbin : out + 5 * (long long)Nbin;
-    const int nrow = N * N, nwarp = gridDim.x * (blockDim.x >> 5);
+    // rows of the array: all kz, ky in [ky0, ky0 + ny) (the whole half field: ky0 = 0, ny = N; a rank's ky-slab otherwise)
+    const int ny = in.ny, nrow = N * ny, nwarp = gridDim.x * (blockDim.x >> 5);
     for (int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < nrow; r += nwarp) {
-        const int iz = r / N, iy = r - iz * N;
+        const int iz = r / ny, iy = in.ky0 + (r - iz * ny);
         const int ky = kfreq(iy, N), kz = kfreq(iz, N);
         const int m0 = ky * ky + kz * kz;
         if (in.bin[m0] > Nbin) continue;                         // bins are non-decreasing in m
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(256) k_spectra(SpectraIn in, double* out, int 
 
 int binned_spectra(const SpectraIn& in, double* out, cudaStream_t st)
 {
-    if (in.N < 2 || in.N % 2 || in.Nbin < 1) return PSB_ERR_ARG;
+    if (in.N < 2 || in.N % 2 || in.Nbin < 1 || in.ny < 1 || in.ky0 < 0 || in.ky0 + in.ny > in.N) return PSB_ERR_ARG;
     const size_t nout = in.mode == 0 ? 3 * (size_t)in.Nbin : (5 + 4 * (size_t)in.Nmu) * in.Nbin;
     if (cudaMemsetAsync(out, 0, nout * sizeof(double), st) != cudaSuccess) return PSB_ERR_CUDA;
     if (in.mode == 0) {
@@ -320,6 +321,33 @@ __global__ void k_shell_scales(const double* psum, int nshell, float target, flo
     float s = 1.f;
     if (p > 0.0) s = exp2f(rintf(log2f(target / (float)sqrt(p))));
     scales[j] = s;
+}
+
+// Low-|k| modes of a ky-slab of the half field on grid N -> the half field of a (coarser or equal) carrier grid Ng, zero elsewhere.
+// Ng < N keeps |k_a| < Ng/2 (the carrier's Nyquist planes stay empty); Ng == N copies the slab's rows.  Every rank writes the
+// modes it owns into its own zeroed copy; the sum over ranks (disjoint supports) is the carrier field.
+__global__ void __launch_bounds__(256) k_half_extract(const Cx<float>* __restrict__ src, int N, int ky0, int ny, Cx<float>* __restrict__ dst, int Ng)
+{
+    const int h = N / 2, hg = Ng / 2;
+    const long long n = (long long)Ng * Ng * (hg + 1);
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const int kx = (int)(e % (hg + 1));
+        const long long r = e / (hg + 1);
+        const int jy = (int)(r % Ng), jz = (int)(r / Ng);
+        const int ky = kfreq(jy, Ng), kz = kfreq(jz, Ng);
+        if (Ng != N && (kx >= hg || jy == hg || jz == hg)) continue;
+        const int iy = ky < 0 ? ky + N : ky, iz = kz < 0 ? kz + N : kz;
+        if (iy < ky0 || iy >= ky0 + ny) continue;
+        dst[e] = src[((long long)iz * ny + (iy - ky0)) * (h + 1) + kx];
+    }
+}
+
+int half_extract(const Cx<float>* src, int N, int ky0, int ny, Cx<float>* dst, int Ng, cudaStream_t st)
+{
+    if (!src || !dst || N < 2 || N % 2 || Ng < 2 || Ng % 2 || Ng > N || ny < 1 || ky0 < 0 || ky0 + ny > N) return PSB_ERR_ARG;
+    if (cudaMemsetAsync(dst, 0, sizeof(Cx<float>) * (size_t)Ng * Ng * (Ng / 2 + 1), st) != cudaSuccess) return PSB_ERR_CUDA;
+    k_half_extract<<<sm_count() * 8, 256, 0, st>>>(src, N, ky0, ny, dst, Ng);
+    return cudaGetLastError() == cudaSuccess ? PSB_OK : PSB_ERR_CUDA;
 }
 
 int shell_scales(const double* psum, int nshell, float target_rms, float* scales, cudaStream_t st)

@@ -1,29 +1,30 @@
 """pyspectrum_b200.multigpu -- ONE catalogue sharded over the GPUs of a node (one process per GPU, torchrun + NCCL).
 
-Design ("alternative for grids that fit one GPU's memory", and what makes Ngrid=1024 fit at all):
+The slab design of SURVEY 8e; every exchange is a data-plane collective on NVLink, nothing is replicated at grid size:
 
-  1. particles are sharded arbitrarily over the ranks; every rank assigns its shard onto a FULL mesh (K1)
-     -> NCCL all-reduce (sum) of the mesh and of sum(w)                                   [exchange 1: 8 N^3 bytes]
-  2. every rank runs the FFT + fcomb (K2+K3) on the reduced mesh: identical delta(k) half field everywhere
-  3. the packed shell PAIRS are dealt round-robin to the ranks; each rank transforms only its pairs (K5)
-  4. NCCL all-to-all: every shell field is cut into G slabs of N^3/G cells, slab q goes to rank q
-     -> every rank holds all shells on its slab                                          [exchange 2: 4 S N^3 (G-1)/G bytes]
-  5. slab-local triangle sums (K6) and shell powers -> all-reduce of Ntri + S float64   [exchange 3: ~50-400 kB]
-  6. the float64 exact triangle counts use the same steps 3-5 with delta == 1
+  1. ROUTE      every rank holds an arbitrary shard of the particles.  Rank q owns the mesh planes [q nz, (q+1) nz), nz = N/G; a
+                particle in cell c touches planes c-1 .. c+3, so it is sent (float32 {x,y,z,w} after the float64 clip of py:938-941)
+                to the owner of plane c-1 and, if different, of plane c+3 (ghost copy)      [all-to-all: 16 B per particle (+ ghosts)]
+  2. ASSIGN     K1 on the received particles onto the rank's OWN planes only (psb_assign_slab): no mesh collective at all
+  3. FFT        x and y passes in the slab, separation of the two interlaced grids' spectra (the conjugate partner (-kx,-ky) is
+                in the same plane), z-slabs -> ky-slabs                                    [all-to-all: 2 x 4 (N/2+1) N^2 / G B per rank]
+                z pass + point-wise fcomb: the rank now owns the rows ky in [q ny, (q+1) ny) of delta(k)
+  4. P(k)       K4 on the ky-slab (psb_pk_*_slab) -> partial bins                          [all-reduce: Nbin (5 + 4 Nmu) float64]
+  5. CARRIER    the shells of B(k) only reach |k_a| <= R = floor(step (Nmax + 1/2)), and all their triangles close without a wrap
+                on any grid with more than R_i + R_j + R_l points per side (pyspectrum.coarse_levels): every rank copies the low-k
+                modes it owns into the half field of a small carrier grid Ng                [all-reduce: 4 (Ng/2+1) Ng^2 B]
+                (Ng = N when the reference's own grid lets triangles wrap, e.g. Ngrid=360 with Nmax=40.)
+  6. SHELLS     per transform grid (level) of the carrier: the packed shell PAIRS are dealt round-robin, each rank transforms its
+                pairs (K5), every field is cut into G slabs of cells, slab q -> rank q      [ONE all-to-all per level: 4 S Nc^3 (G-1)/G B]
+  7. TRIANGLES  slab-local K6 on every rank, partial sums                                  [all-reduce: Ntri + 3 S float64, once]
+  8. COUNTS     the float64 exact counts use steps 6-7 with delta == 1 (cached per configuration)
 
-Steps 1-2 have a slab-decomposed alternative (`sharded_delta(..., fft='slab')` or PSB_SHARDED_FFT=slab): the mesh is
-reduce-scattered into z-slabs instead of all-reduced, every rank transforms its slab along x and y, separates the two
-interlaced grids' spectra inside each plane (P = A^xy, Q = B^xy: the conjugate partner (-kx,-ky) is local), one all-to-all turns
-z-slabs into ky-slabs, the z pass and the point-wise fcomb follow, and an all-gather rebuilds the replicated half field that
-steps 3-5 use.  No conjugate-partner exchange; the FFT work is divided by G instead of replicated.  Validated on one GPU with
-emulated ranks (tests/test_gpu_slab.py: 2e-6 of max|delta| against the single-GPU K2+K3 for G = 1..8), the exchange bookkeeping
-on gloo (tests/test_multigpu_host.py), and under NCCL on 2 GPUs at C2 (tools/run_sharded.py: same outputs as the single-GPU
-path, 21.4 vs 20.9 ms -- at 360^3 on two GPUs the extra exchanges cost what the halved FFT saves).  It is meant for 1024^3 on 8
-GPUs, where the 8.6 GB mesh all-reduce and the replicated 25 ms FFT dominate P(k); the default stays 'replicated' until that
-configuration has been timed (profiles/r1_multigpu.jsonl).
+Every kernel is the single-GPU one (K1 with a plane window, K4 with a row window); the collectives are torch.distributed calls so
+the same code runs under NCCL (GPU) and gloo (the CPU tests of the host logic: tests/test_multigpu_host.py).  They are bulk
+exchanges between kernels, not fused with a compute tile.  `stats` dictionaries collect the bytes each collective puts on the wire
+and, with `timed=True`, its device time (bench.py reports them)."""
+import ctypes
 
-Every kernel is the single-GPU one; only the orchestration differs.  The collectives are torch.distributed calls so the
-same code runs under NCCL (GPU) and gloo (the CPU tests of the host logic: tests/test_multigpu_host.py)."""
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -31,6 +32,53 @@ import torch.distributed as dist
 from . import pyspectrum as P
 
 
+# ------------------------------------------------------------------------------------------ plumbing
+def _world():
+    return dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+
+
+def _rank():
+    return dist.get_rank() if _world() > 1 else 0
+
+
+def _allreduce(t, op=None):
+    if _world() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM if op is None else op)
+    return t
+
+
+class Stats(object):
+    """Bytes on the wire and (optionally) device time per named collective / stage of one sharded call."""
+
+    def __init__(self, timed=False):
+        self.timed, self.bytes, self.ev = timed, {}, []
+
+    def add_bytes(self, name, n):
+        self.bytes[name] = self.bytes.get(name, 0) + int(n)
+
+    def mark(self):
+        if not self.timed or not torch.cuda.is_available():
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def span(self, name, e0):
+        if e0 is not None:
+            self.ev.append((name, e0, self.mark()))
+
+    def times_ms(self):
+        out = {}
+        for name, a, b in self.ev:
+            out[name] = out.get(name, 0.) + a.elapsed_time(b)
+        return out
+
+
+def _stats(stats):
+    return stats if stats is not None else Stats()
+
+
+# ------------------------------------------------------------------------------------------ shell pairs and slabs of cells
 def pair_assignment(npairs, world):
     """Round-robin deal of packed shell pairs; every rank gets the same number (padding pairs = empty shells)."""
     per = (npairs + world - 1) // world
@@ -38,43 +86,120 @@ def pair_assignment(npairs, world):
 
 
 def slab_field_rows(S, world, per):
-    """After the all-to-all the slab buffer is laid out [k][owner rank][e] (k = local pair index, e = 0/1 within the pair);
+    """After the all-to-all the slab buffer is laid out [owner rank][k][e] (k = local pair index, e = 0/1 within the pair);
     returns for every shell slot f the row of that buffer which holds it."""
     rows = []
     for f in range(S):
         p, e = divmod(f, 2)
         owner, k = p % world, p // world
-        rows.append((k * world + owner) * 2 + e)
+        rows.append(owner * 2 * per + 2 * k + e)
     return rows
 
 
-def exchange_to_slabs(fields_local, world):
-    """fields_local: [2*per, ncell] on every rank (its shell pairs, full grid).  Returns [2*per*world, ncell/world]:
-    row ((k*world + owner)*2 + e) = slab of this rank of shell e of the k-th pair of rank `owner`."""
+def check_cell_slabs(ncell, world, packed=True):
+    """The cells of a field are cut into `world` equal slabs; packed fields hold aligned cell PAIRS and the tensor-core kernel
+    works on 64-cell chunks.  Raised on every rank before any collective."""
+    if ncell % world:
+        raise ValueError('the number of cells (%d) must be a multiple of the number of ranks (%d)' % (ncell, world))
+    if packed and (ncell // world) % 2:
+        raise ValueError('a slab of %d cells would split a packed cell pair' % (ncell // world))
+
+
+def exchange_to_slabs(fields_local, world, stats=None):
+    """fields_local: [2*per, ncell] on every rank (its shell pairs, full grid).  ONE all-to-all; returns [world*2*per, ncell/world]:
+    row (owner*2*per + 2*k + e) = this rank's slab of shell e of the k-th pair of rank `owner` (see slab_field_rows)."""
     nrow, ncell = fields_local.shape
+    check_cell_slabs(ncell, world, packed=False)
     slab = ncell // world
-    per = nrow // 2
-    out = torch.empty((per, world, 2, slab), dtype=fields_local.dtype, device=fields_local.device)
     if world == 1:
-        out.copy_(fields_local.view(per, 2, 1, slab).permute(0, 2, 1, 3))
-        return out.view(nrow, slab)
-    for k in range(per):
-        for e in range(2):
-            src = fields_local[2 * k + e].view(world, slab)                 # contiguous: slab q -> rank q
-            dst = torch.empty((world, slab), dtype=fields_local.dtype, device=fields_local.device)
-            dist.all_to_all_single(dst, src)
-            out[k, :, e, :] = dst                                            # dst[q'] = my slab of rank q''s row (k, e)
-    return out.view(nrow * world, slab)
+        return fields_local
+    send = fields_local.view(nrow, world, slab).permute(1, 0, 2).contiguous()          # [dest][row][cell]
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send)                                                   # recv[q] = rank q's rows of MY slab
+    _stats(stats).add_bytes('shell_fields_all_to_all', send.numel() * send.element_size() * (world - 1) // world)
+    return recv.view(world * nrow, slab)
 
 
-# ------------------------------------------------------------------------------------------ slab-decomposed mesh -> delta(k)
+# ------------------------------------------------------------------------------------------ 1-2: route + slab assignment
 def slab_geometry(N, world):
     """(planes per rank, padded half-row length): N must divide by the number of ranks; rows hold kx = 0..N/2 padded to even."""
     if N % world:
-        raise ValueError('Ngrid must be a multiple of the number of ranks for the slab FFT')
+        raise ValueError('Ngrid must be a multiple of the number of ranks for the slab path')
     return N // world, (N // 2 + 2) // 2 * 2
 
 
+def route_counts(pipe, pos, aos, wt, Lbox, world, offset=0., clip=True):
+    """Per-destination particle counts (ghost copies included) of this rank's shard + the float64 sum of its weights (device)."""
+    N = pipe.N
+    nz = N // world
+    Np = pos.shape[0] if aos else pos.shape[1]
+    counts = torch.zeros(world, dtype=torch.int64, device=pipe.dev)
+    sumw = torch.zeros(1, dtype=torch.float64, device=pipe.dev)
+    P.check(pipe.L.psb_slab_route_count(P._ptr(pos), int(pos.dtype == torch.float64), aos, P._ptr(wt),
+                                        int(wt is not None and wt.dtype == torch.float64), Np, N, float(Lbox) if clip else 0.0,
+                                        np.float32(float(N) / Lbox), np.float32(offset), nz, world, P._ptr(counts), P._ptr(sumw),
+                                        P._stream()), 'psb_slab_route_count')
+    return counts, sumw
+
+
+def route_scatter(pipe, pos, aos, wt, Lbox, world, counts, offset=0., clip=True):
+    """Destination-major send buffer [sum(counts), 4] float32 {x,y,z,w}."""
+    N = pipe.N
+    Np = pos.shape[0] if aos else pos.shape[1]
+    base = (torch.cumsum(counts, 0) - counts).contiguous()
+    cursor = torch.zeros(world, dtype=torch.int64, device=pipe.dev)
+    total = int(counts.sum().item())
+    send = torch.empty((max(total, 1), 4), dtype=torch.float32, device=pipe.dev)
+    P.check(pipe.L.psb_slab_route_scatter(P._ptr(pos), int(pos.dtype == torch.float64), aos, P._ptr(wt),
+                                          int(wt is not None and wt.dtype == torch.float64), Np, N, float(Lbox) if clip else 0.0,
+                                          np.float32(float(N) / Lbox), np.float32(offset), N // world, world, P._ptr(base), P._ptr(cursor),
+                                          P._ptr(send), P._stream()), 'psb_slab_route_scatter')
+    return send[:total]
+
+
+def route_particles(pipe, xyz_local, w_local, Lbox, offset=0., clip=True, stats=None):
+    """Step 1.  Returns (received particles [n,4] float32 on the device, global sum of weights (device, float64), global N)."""
+    st = _stats(stats)
+    world = _world()
+    slab_geometry(pipe.N, world)
+    if pipe.N // world < 8:
+        raise ValueError('need at least 8 mesh planes per rank')
+    pos, aos, wt = pipe.to_device(xyz_local, w_local)
+    Np = pos.shape[0] if aos else pos.shape[1]
+    e0 = st.mark()
+    counts, sumw = route_counts(pipe, pos, aos, wt, Lbox, world, offset, clip)
+    send = route_scatter(pipe, pos, aos, wt, Lbox, world, counts, offset, clip)
+    st.span('route_kernels', e0)
+    ntot = torch.tensor([float(Np)], dtype=torch.float64, device=pipe.dev)
+    if world == 1:
+        return send, sumw, Np
+    e0 = st.mark()
+    meta = torch.cat([sumw, ntot])
+    _allreduce(meta)
+    rc = torch.empty_like(counts)
+    dist.all_to_all_single(rc, counts)
+    sc_h, rc_h = counts.cpu().tolist(), rc.cpu().tolist()
+    recv = torch.empty((max(sum(rc_h), 1), 4), dtype=torch.float32, device=pipe.dev)[:sum(rc_h)]
+    dist.all_to_all_single(recv, send, output_split_sizes=rc_h, input_split_sizes=sc_h)
+    st.span('particles_all_to_all', e0)
+    st.add_bytes('particles_all_to_all', 16 * (sum(sc_h) - sc_h[_rank()]))
+    return recv, meta[:1].clone(), int(round(meta[1].item()))
+
+
+def assign_slab(pipe, xyzw, zbase, nzs, Lbox, offset=0.):
+    """Step 2: K1 on routed particles onto the planes [zbase, zbase+nzs) only.  Returns mesh_slab [nzs, N, N, 2] float32."""
+    N = pipe.N
+    n = int(xyzw.shape[0])
+    mesh = torch.empty((nzs, N, N, 2), dtype=torch.float32, device=pipe.dev)
+    wsb = pipe.L.psb_assign_workspace_bytes(n, N)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=pipe.dev)
+    scratch = torch.empty(1, dtype=torch.float64, device=pipe.dev)
+    P.check(pipe.L.psb_assign_slab(P._ptr(xyzw), n, N, np.float32(float(N) / Lbox), np.float32(offset), zbase, nzs,
+                                   P._ptr(mesh), 1, P._ptr(ws), wsb, P._ptr(scratch), P._stream()), 'psb_assign_slab')
+    return mesh
+
+
+# ------------------------------------------------------------------------------------------ 3: slab FFT
 def z_to_y_chunks(t, world):
     """t: [nz, N, hp, 2] (a rank's z-planes, all ky) -> send buffer [world, nz, ny, hp, 2]: chunk q = the ky range of rank q."""
     nz, N, hp, two = t.shape
@@ -82,7 +207,7 @@ def z_to_y_chunks(t, world):
     return t.view(nz, world, ny, hp, two).permute(1, 0, 2, 3, 4).contiguous()
 
 
-def z_to_y_slabs(t, world):
+def z_to_y_slabs(t, world, stats=None):
     """All-to-all of z-slabs into ky-slabs: [nz, N, hp, 2] on every rank -> [N, ny, hp, 2] (all z of this rank's ky range)."""
     nz, N, hp, two = t.shape
     send = z_to_y_chunks(t, world)
@@ -90,11 +215,12 @@ def z_to_y_slabs(t, world):
         return send.view(N, N, hp, two)
     recv = torch.empty_like(send)
     dist.all_to_all_single(recv, send)                   # recv[g] = rank g's planes (z = g*nz .. ) of my ky range
+    _stats(stats).add_bytes('fft_all_to_all', send.numel() * send.element_size() * (world - 1) // world)
     return recv.view(world * nz, N // world, hp, two)
 
 
 def slab_phase1(pipe, mesh_slab):
-    """x and y passes of a reduced z-slab [nz, N, N, 2] (destroyed) + separation -> (P, Q) each [nz, N, hp, 2]."""
+    """x and y passes of a z-slab [nz, N, N, 2] (destroyed) + separation -> (P, Q) each [nz, N, hp, 2]."""
     N = pipe.N
     nz = mesh_slab.shape[0]
     hp = (N // 2 + 2) // 2 * 2
@@ -120,7 +246,7 @@ def slab_phase2(pipe, py, qy, ky0, sumw, periodic=1):
 
 
 def slab_mesh_to_delta_emulated(pipe, mesh, sumw, world, periodic=1):
-    """The slab pipeline for `world` emulated ranks on ONE device (the exchanges are slices): mesh [N,N,N,2] -> half field
+    """The slab FFT for `world` emulated ranks on ONE device (the exchanges are slices): mesh [N,N,N,2] -> half field
     [N,N,N/2+1,2].  Used to validate the building blocks without a multi-GPU box."""
     N = pipe.N
     nz, hp = slab_geometry(N, world)
@@ -133,24 +259,22 @@ def slab_mesh_to_delta_emulated(pipe, mesh, sumw, world, periodic=1):
     return half
 
 
-def slab_mesh_to_delta(pipe, mesh, sumw, periodic=1):
-    """Distributed slab pipeline: every rank passes its UNREDUCED full mesh [N,N,N,2] (destroyed); returns the replicated half
-    field.  reduce-scatter (z-slabs) -> x,y passes + separation -> all-to-all -> z pass + fcomb -> all-gather."""
+def slab_delta(pipe, mesh_slab, sumw, periodic=1, stats=None):
+    """Step 3: a rank's mesh planes [nz,N,N,2] (destroyed) -> its rows ky in [rank*ny, (rank+1)*ny) of delta(k): [N, ny, N/2+1, 2]."""
+    st = _stats(stats)
     world = _world()
-    N = pipe.N
-    nz, hp = slab_geometry(N, world)
-    rank = dist.get_rank() if world > 1 else 0
-    if world > 1:
-        slab = torch.empty((nz, N, N, 2), dtype=torch.float32, device=pipe.dev)
-        dist.reduce_scatter_tensor(slab, mesh)
-    else:
-        slab = mesh
-    p, q = slab_phase1(pipe, slab)
-    del slab
-    py, qy = z_to_y_slabs(p, world), z_to_y_slabs(q, world)
+    nz, hp = slab_geometry(pipe.N, world)
+    e0 = st.mark()
+    p, q = slab_phase1(pipe, mesh_slab)
+    st.span('fft_xy', e0)
+    e0 = st.mark()
+    py, qy = z_to_y_slabs(p, world, st), z_to_y_slabs(q, world, st)
     del p, q
-    mine = slab_phase2(pipe, py, qy, rank * nz, sumw, periodic)
-    return gather_ky_slabs(mine, world)
+    st.span('fft_all_to_all', e0)
+    e0 = st.mark()
+    half = slab_phase2(pipe, py, qy, _rank() * nz, sumw, periodic)
+    st.span('fft_z_fcomb', e0)
+    return half
 
 
 def gather_ky_slabs(mine, world):
@@ -163,93 +287,162 @@ def gather_ky_slabs(mine, world):
     return gathered.view(world, N, ny, hx, two).permute(1, 0, 2, 3, 4).reshape(N, world * ny, hx, two)
 
 
-def _allreduce(t, op=dist.ReduceOp.SUM):
-    if dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(t, op=op)
-    return t
+def sharded_delta_slab(pipe, xyz_local, w_local, Lbox, offset=0., clip=True, periodic=1, stats=None):
+    """Steps 1-3.  Returns (this rank's ky-slab of delta(k) [N, ny, N/2+1, 2], ky0, global sum of weights (device), global N)."""
+    st = _stats(stats)
+    world, rank = _world(), _rank()
+    nz, _ = slab_geometry(pipe.N, world)
+    xyzw, sumw, ntot = route_particles(pipe, xyz_local, w_local, Lbox, offset, clip, st)
+    e0 = st.mark()
+    mesh = assign_slab(pipe, xyzw, rank * nz, nz, Lbox, offset)
+    st.span('assign_slab', e0)
+    del xyzw
+    half = slab_delta(pipe, mesh, sumw, periodic, st)
+    return half, rank * nz, sumw, ntot
 
 
-def _world():
-    return dist.get_world_size() if dist.is_initialized() else 1
+# ------------------------------------------------------------------------------------------ 4: spectra on ky-slabs
+def slab_pk_monopole(pipe, half_slab, ky0, Lbox, stats=None):
+    Nbins = pipe.N // 2
+    out = torch.empty(3 * Nbins, dtype=torch.float64, device=pipe.dev)
+    kf = 2 * np.pi / float(Lbox)
+    P.check(pipe.L.psb_pk_monopole_slab(P._ptr(half_slab), pipe.N, ky0, half_slab.shape[1], P._ptr(pipe.pk_bin_table(Lbox)), Nbins, kf,
+                                        P._ptr(out), P._stream()), 'psb_pk_monopole_slab')
+    _allreduce(out)
+    _stats(stats).add_bytes('pk_all_reduce', out.numel() * 8)
+    return out
 
 
-def sharded_delta(pipe, xyz_local, w_local, Lbox, fft=None):
-    """Steps 1-2: returns (half field, global sum of weights as a device tensor).  fft = 'replicated' (all-reduce of the mesh,
-    every rank transforms all of it) or 'slab' (see the module docstring); default from PSB_SHARDED_FFT, else 'replicated'."""
-    import os
-    fft = fft or os.environ.get('PSB_SHARDED_FFT', 'replicated')
-    if fft not in ('replicated', 'slab'):
-        raise ValueError("fft must be 'replicated' or 'slab'")
-    pos, aos, wt = pipe.to_device(xyz_local, w_local)
-    mesh, sumw = pipe.assign(pos, aos, wt, Lbox)
-    _allreduce(sumw)
-    if fft == 'slab' and pipe.N % _world() == 0:
-        return slab_mesh_to_delta(pipe, mesh, sumw), sumw
-    _allreduce(mesh)
-    half = pipe.mesh_to_delta(mesh, sumw)
-    return half, sumw
+def slab_pk_multipoles(pipe, half_slab, ky0, Lbox_int, rsd, Nmubin, stats=None):
+    Nbins = pipe.N // 2
+    out = torch.empty((5 + 4 * Nmubin) * Nbins, dtype=torch.float64, device=pipe.dev)
+    trig = np.empty(4, np.float32)
+    P.check(pipe.L.psb_rsd_trig(int(rsd), P._np_ptr(trig)), 'psb_rsd_trig')
+    kf32 = np.float32(np.float32(2.) * np.float32(3.141592654)) / np.float32(Lbox_int)
+    P.check(pipe.L.psb_pk_multipoles_slab(P._ptr(half_slab), pipe.N, ky0, half_slab.shape[1], P._ptr(pipe.rsd_bin_table(Nbins)), Nbins,
+                                          int(Nmubin), kf32, P._np_ptr(trig), P._ptr(out), P._stream()), 'psb_pk_multipoles_slab')
+    _allreduce(out)
+    _stats(stats).add_bytes('pk_all_reduce', out.numel() * 8)
+    return out, kf32
 
 
-def sharded_triangle_sums(pipe, half, step, Ncut, Nmax, dtype=torch.float32):
-    """Steps 3-5.  Returns host arrays (sums per triangle, sum_x I_j^2 per shell) in the reference's units, identical
-    on every rank."""
-    world = _world()
-    rank = dist.get_rank() if world > 1 else 0
+# ------------------------------------------------------------------------------------------ 5: carrier grid
+def carrier_grid(N, step, Nmax, Ncut):
+    """Smallest compiled grid on which EVERY triangle of the configuration closes without a wrap (and every shell fits), else N:
+    the grid the replicated low-k copy of delta(k) lives on."""
+    tri = P.triangle_list(Nmax, Ncut, step)
+    R = P.shell_reach(tri, step)
+    need = int(max(R.sum(axis=1).max(), 2 * R.max()))
+    for c in sorted(set(P.COARSE_GRIDS) | {360, 512}):
+        if need < c < N:
+            return int(c)
+    return int(N)
+
+
+def low_k_carrier(pipe, half_slab, ky0, Ng, stats=None):
+    """Step 5: replicated half field on the carrier grid Ng from the ranks' ky-slabs (zero outside |k_a| < Ng/2 when Ng < N)."""
+    N = pipe.N
+    car = torch.empty((Ng, Ng, Ng // 2 + 1, 2), dtype=torch.float32, device=pipe.dev)
+    P.check(pipe.L.psb_half_extract(P._ptr(half_slab), N, ky0, half_slab.shape[1], P._ptr(car), Ng, P._stream()), 'psb_half_extract')
+    st = _stats(stats)
+    e0 = st.mark()
+    _allreduce(car)
+    st.span('carrier_all_reduce', e0)
+    if _world() > 1:
+        st.add_bytes('carrier_all_reduce', car.numel() * 4)
+    return car
+
+
+# ------------------------------------------------------------------------------------------ 6-7: sharded shell / triangle stage
+def sharded_triangle_sums(pipe, half, step, Ncut, Nmax, dtype=torch.float32, stats=None):
+    """Steps 6-7 on a replicated half field `half` of `pipe`'s grid (the carrier).  Returns host arrays (sum_x I_i I_j I_l per
+    triangle, sum_x I_j^2 per shell) in the units of `pipe`'s grid, identical on every rank.  half=None with float64: the exact
+    counts (delta == 1)."""
+    st = _stats(stats)
+    world, rank = _world(), _rank()
     s0 = Ncut // step
     S = Nmax - s0 + 1
-    npairs = (S + 1) // 2
-    assign, per = pair_assignment(npairs, world)
-    mine = assign[rank]
+    SA = S + (S % 2)
     f64 = dtype == torch.float64
-    if f64:
-        fields, sumsq = pipe.shell_fields(half, step, s0, Nmax, dtype=torch.float64, pairs=mine)
-        sc_rows = None
-    else:
+    tri, levels = pipe.bk_levels(step, Ncut, Nmax)
+    for pc, _, _, _ in levels:                           # every rank checks every level before the first collective
+        check_cell_slabs(pc.N ** 3, world, packed=not f64)
+    scales = None
+    if not f64:
         scales = pipe.shell_scales(half, step, s0, Nmax)
         if world > 1:
-            dist.broadcast(scales, 0)                  # the sampled shell power uses unordered atomics: make ranks agree exactly
-        fields, sumsq, sc_rows, maxabs = pipe.shell_fields(half, step, s0, Nmax, scaled=True, pairs=mine, scales=scales)
-    slabs = exchange_to_slabs(fields, world)
-    del fields
-    rows = slab_field_rows(S, world, per)
-    engine = 'fma' if f64 else 'auto'
-    sums = pipe.triangle_sums(slabs, Nmax, Ncut, step, engine=engine, field_rows=rows, packed=not f64)
-    _allreduce(sums)
-    # per-shell quantities live on the owner rank: scatter them into global shell order, then sum over ranks
-    glob_sq = torch.zeros(2 * npairs, dtype=torch.float64, device=pipe.dev)
-    glob_sc = torch.zeros(2 * npairs, dtype=torch.float64, device=pipe.dev)
-    glob_mx = torch.zeros(2 * npairs, dtype=torch.float64, device=pipe.dev)
-    for k, pidx in enumerate(mine):
-        if pidx < npairs:
-            glob_sq[2 * pidx:2 * pidx + 2] = sumsq[2 * k:2 * k + 2]
-            if not f64:
-                glob_sc[2 * pidx:2 * pidx + 2] = sc_rows[2 * k:2 * k + 2].double()
-                glob_mx[2 * pidx:2 * pidx + 2] = maxabs[2 * k:2 * k + 2].view(torch.float32).double()
-    _allreduce(glob_sq)
+            dist.broadcast(scales, 0)                    # the sampled shell power uses unordered atomics: make ranks agree exactly
+    sums = torch.zeros(len(tri), dtype=torch.float64, device=pipe.dev)
+    glob = torch.zeros((3, SA), dtype=torch.float64, device=pipe.dev)       # sum_x I^2, scale, max|I| per shell (owner rank writes)
+    have = 0
+    keep = []
+    for pc, idx, idx_dev, smax in levels:
+        Sl = smax - s0 + 1
+        npairs = (Sl + 1) // 2
+        deal, per = pair_assignment(npairs, world)
+        mine = deal[rank]
+        vol = (float(pipe.N) / pc.N) ** 3
+        src = None if pc is pipe else pipe
+        e0 = st.mark()
+        if f64:
+            fields, sq = pc.shell_fields(half, step, s0, smax, dtype=torch.float64, pairs=mine, src=src)
+            sc_rows = mx = None
+        else:
+            fields, sq, sc_rows, mx = pc.shell_fields(half, step, s0, smax, scaled=True, pairs=mine, scales=scales, src=src)
+        st.span('shell_fields', e0)
+        e0 = st.mark()
+        slabs = exchange_to_slabs(fields, world, st)
+        del fields
+        st.span('shell_fields_all_to_all', e0)
+        rows = slab_field_rows(Sl, world, per)
+        use_tc = (not f64) and slabs.shape[1] % 64 == 0 and Sl <= 128
+        e0 = st.mark()
+        sl = pc.triangle_sums(slabs, smax, Ncut, step, engine='tc' if use_tc else 'fma', field_rows=rows, packed=not f64, tri=tri[idx])
+        st.span('triangles', e0)
+        keep.append((pc, slabs, rows, idx_dev, smax, vol, use_tc))
+        sums.index_copy_(0, idx_dev, sl if vol == 1.0 else sl * vol)
+        for k, pidx in enumerate(mine):                  # per-shell quantities live on the owner rank of the pair
+            for e in (0, 1):
+                f = 2 * pidx + e
+                if f >= Sl:
+                    continue
+                if f >= have:                            # shell power from the coarsest level that holds the shell (Parseval)
+                    glob[0, f] = sq[2 * k + e] * vol
+                if not f64:
+                    glob[1, f] = sc_rows[2 * k + e].double()
+                    glob[2, f] = torch.maximum(glob[2, f], mx[2 * k + e].view(torch.float32).double())
+        have = max(have, Sl)
+    e0 = st.mark()
+    flat = torch.cat([sums, glob[0], glob[2]])
+    _allreduce(flat)
+    st.span('sums_all_reduce', e0)
+    if world > 1:
+        st.add_bytes('sums_all_reduce', flat.numel() * 8)
+    host = flat.cpu().numpy()
+    nt = len(tri)
+    sums_h, sq_h, mx_h = host[:nt], host[nt:nt + SA], host[nt + SA:]
     if f64:
-        return sums.cpu().numpy(), glob_sq.cpu().numpy()[:S]
-    _allreduce(glob_sc)
-    _allreduce(glob_mx)
-    host = torch.cat([sums, glob_sq, glob_sc, glob_mx]).cpu().numpy()
-    nt = sums.numel()
-    n2 = 2 * npairs
-    sums_h, sq, sc, mx = host[:nt], host[nt:nt + n2], host[nt + n2:nt + 2 * n2], host[nt + 2 * n2:]
-    if mx.max() ** 2 >= 4.0e4:                                           # fp16 range guard: redo with the FFMA kernel
-        sums = pipe.triangle_sums(slabs, Nmax, Ncut, step, engine='fma', field_rows=rows, packed=True)
+        return sums_h, sq_h[:S]
+    sc = scales.double().cpu().numpy()[:SA]
+    if mx_h.max() ** 2 >= 4.0e4:                         # fp16 range guard (pathological catalogues): redo with the FFMA kernel
+        sums.zero_()
+        for pc, slabs, rows, idx_dev, smax, vol, _ in keep:
+            sl = pc.triangle_sums(slabs, smax, Ncut, step, engine='fma', field_rows=rows, packed=True, tri=tri[idx_dev.cpu().numpy()])
+            sums.index_copy_(0, idx_dev, sl * vol)
         _allreduce(sums)
         sums_h = sums.cpu().numpy()
-    tri = P.triangle_list(Nmax, Ncut, step)
+    del keep
     sums_h = sums_h / (sc[tri[:, 0] - s0] * sc[tri[:, 1] - s0] * sc[tri[:, 2] - s0])
-    return sums_h, (sq / sc ** 2)[:S]
+    return sums_h, (sq_h / sc ** 2)[:S]
 
 
 def sharded_counts(pipe, step, Ncut, Nmax):
-    """Exact triangle counts with the float64 fields sharded over the ranks (at Ngrid=1024 they do not fit one GPU)."""
+    """Exact triangle counts with the float64 fields sharded over the ranks, in the units of `pipe`'s grid (N^3 * closed triples)."""
     key = (Nmax, Ncut, step)
     if key in pipe._counts:
         return pipe._counts[key]
+    tri, levels = pipe.bk_levels(step, Ncut, Nmax)
     sums, _ = sharded_triangle_sums(pipe, None, step, Ncut, Nmax, dtype=torch.float64)
-    tri = P.triangle_list(Nmax, Ncut, step)
     n3 = float(pipe.N) ** 3
     nint = np.rint(sums / n3)
     if np.abs(sums / n3 - nint).max() > 1e-3:
@@ -260,24 +453,30 @@ def sharded_counts(pipe, step, Ncut, Nmax):
     return counts
 
 
-def Bk_periodic_sharded(xyz_local, w_local=None, Lbox=2600, Ngrid=360, step=3, Ncut=3, Nmax=40, silent=True):
-    """Bk_periodic (pyspectrum.py:285-356) for ONE catalogue whose particles are spread over the ranks; every rank
-    passes its own shard and receives the full result dictionary."""
+# ------------------------------------------------------------------------------------------ public API
+def Bk_periodic_sharded(xyz_local, w_local=None, Lbox=2600, Ngrid=360, step=3, Ncut=3, Nmax=40, silent=True, stats=None,
+                        return_pk=False):
+    """Bk_periodic (pyspectrum.py:285-356) for ONE catalogue whose particles are spread over the ranks; every rank passes its own
+    shard (any split) and receives the full result dictionary.  return_pk=True also returns Pk_periodic's dictionary from the same
+    delta(k) (BASELINE configs[4] asks for both)."""
     pipe = P.PeriodicPipeline.get(Ngrid)
     s0 = Ncut // step
     if s0 < 1:
         raise ValueError('Ncut//step must be >= 1')
-    Nloc = torch.tensor([float(xyz_local.shape[1])], dtype=torch.float64, device=pipe.dev)
-    _allreduce(Nloc)
-    N = int(Nloc.item())
-    half, sumw = sharded_delta(pipe, xyz_local, w_local, Lbox)
-    Nk = pipe.shell_mode_counts(step, Nmax)
-    counts = sharded_counts(pipe, step, Ncut, Nmax)
-    sums_h, sumsq_h = sharded_triangle_sums(pipe, half, step, Ncut, Nmax)
+    st = _stats(stats)
+    half, ky0, sumw, N = sharded_delta_slab(pipe, xyz_local, w_local, Lbox, stats=st)
+    pk = _pk_from_slab(pipe, half, ky0, Lbox, N, w_local, sumw, st) if return_pk else None
+    Ng = carrier_grid(Ngrid, step, Nmax, Ncut)
+    car = low_k_carrier(pipe, half, ky0, Ng, st)
+    del half
+    pg = P.PeriodicPipeline.get(Ng)
+    Nk = pg.shell_mode_counts(step, Nmax)                # shells lie inside the carrier: the same mode counts as on Ngrid
+    counts_g = sharded_counts(pg, step, Ncut, Nmax)      # N_g^3 * closed triples; the epilogue below works in the carrier's units
+    sums_h, sumsq_h = sharded_triangle_sums(pg, car, step, Ncut, Nmax, stats=st)
     tri = P.triangle_list(Nmax, Ncut, step)
     nbar = (float(N) if w_local is None else float(sumw.item())) / Lbox ** 3
     kf = 2 * np.pi / Lbox
-    bispec = P._bk_epilogue(Ngrid, tri, sums_h, sumsq_h, Nk, counts, step, Ncut, Nmax)
+    bispec = P._bk_epilogue(Ng, tri, sums_h, sumsq_h, Nk, counts_g, step, Ncut, Nmax)
     bispec['meta'] = {'Lbox': Lbox, 'Ngrid': Ngrid, 'step': step, 'Ncut': Ncut, 'Nmax': Nmax, 'N': N, 'nbar': nbar, 'kf': kf}
     for k in ('p0k1', 'p0k2', 'p0k3'):
         bispec[k] = bispec[k] * (2 * np.pi) ** 3 / kf ** 3 - 1. / nbar
@@ -287,21 +486,17 @@ def Bk_periodic_sharded(xyz_local, w_local=None, Lbox=2600, Ngrid=360, step=3, N
     bispec['b123_sn'] = b_sn
     with np.errstate(divide='ignore', invalid='ignore'):
         bispec['q123'] = bispec['b123'] / (bispec['p0k1'] * bispec['p0k2'] + bispec['p0k1'] * bispec['p0k3'] + bispec['p0k2'] * bispec['p0k3'])
-    return bispec
+    return (bispec, pk) if return_pk else bispec
 
 
-def Pk_periodic_sharded(xyz_local, w_local=None, Lbox=2600, Ngrid=360, silent=True):
-    """Pk_periodic (pyspectrum.py:644-728) for one catalogue sharded over the ranks (binning is done redundantly: it is
-    one pass over the half field)."""
-    pipe = P.PeriodicPipeline.get(Ngrid)
-    Nloc = torch.tensor([float(xyz_local.shape[1])], dtype=torch.float64, device=pipe.dev)
-    _allreduce(Nloc)
-    N = int(Nloc.item())
-    half, sumw = sharded_delta(pipe, xyz_local, w_local, Lbox)
-    out = pipe.pk_monopole(half, Lbox).cpu().numpy()
+def _pk_from_slab(pipe, half, ky0, Lbox, N, w_local, sumw, stats):
+    st = _stats(stats)
+    e0 = st.mark()
+    out = slab_pk_monopole(pipe, half, ky0, Lbox, st).cpu().numpy()
+    st.span('pk_binning', e0)
     nbar = (float(N) if w_local is None else float(sumw.item())) / Lbox ** 3
     kf = 2 * np.pi / float(Lbox)
-    Nbins = Ngrid // 2
+    Nbins = pipe.N // 2
     nk, ksum, psum = out[:Nbins], out[Nbins:2 * Nbins], out[2 * Nbins:]
     k = np.zeros(Nbins); p0k = np.zeros(Nbins); cnt = np.zeros(Nbins)
     ok = nk > 0
@@ -309,5 +504,27 @@ def Pk_periodic_sharded(xyz_local, w_local=None, Lbox=2600, Ngrid=360, silent=Tr
     p0k[ok] = psum[ok] / nk[ok] / kf ** 3
     cnt[ok] = nk[ok]
     p0k *= (2. * np.pi) ** 3
-    meta = {'Lbox': Lbox, 'Ngrid': Ngrid, 'N': N, 'nbar': nbar, 'kf': 2 * np.pi / Lbox}
+    meta = {'Lbox': Lbox, 'Ngrid': pipe.N, 'N': N, 'nbar': nbar, 'kf': 2 * np.pi / Lbox}
     return {'meta': meta, 'k': k, 'p0k': p0k - 1. / nbar, 'counts': cnt, 'p0k_sn': 1. / nbar}
+
+
+def Pk_periodic_sharded(xyz_local, w_local=None, Lbox=2600, Ngrid=360, silent=True, stats=None):
+    """Pk_periodic (pyspectrum.py:644-728) for one catalogue sharded over the ranks: slab assignment, slab FFT, binning on the
+    ky-slabs and an all-reduce of the bins."""
+    pipe = P.PeriodicPipeline.get(Ngrid)
+    st = _stats(stats)
+    half, ky0, sumw, N = sharded_delta_slab(pipe, xyz_local, w_local, Lbox, stats=st)
+    return _pk_from_slab(pipe, half, ky0, Lbox, N, w_local, sumw, st)
+
+
+def Pk_periodic_rsd_sharded(xyz_local, w_local=None, Lbox=2600, Ngrid=360, rsd=2, Nmubin=10, silent=True, stats=None):
+    """Pk_periodic_rsd (pyspectrum.py:460-538) for one catalogue sharded over the ranks."""
+    pipe = P.PeriodicPipeline.get(Ngrid)
+    st = _stats(stats)
+    half, ky0, sumw, N = sharded_delta_slab(pipe, xyz_local, w_local, Lbox, stats=st)
+    raw, kf32 = slab_pk_multipoles(pipe, half, ky0, int(Lbox), rsd, Nmubin, st)
+    ks, p0k, p2k, p4k, nk, k_kmu, mu_kmu, p_kmu, n_kmu = P._pk_rsd_normalise(raw.cpu().numpy(), kf32, pipe.N // 2, Nmubin)
+    nbar = float(N) / Lbox ** 3
+    meta = {'Lbox': Lbox, 'Ngrid': Ngrid, 'N': N, 'nbar': nbar, 'kf': 2 * np.pi / Lbox}
+    return {'meta': meta, 'k': ks, 'p0k': p0k - 1. / nbar, 'p2k': p2k, 'p4k': p4k, 'p_sn': np.repeat(1. / nbar, len(ks)), 'counts': nk,
+            'k_kmu': k_kmu, 'mu_kmu': mu_kmu, 'p_kmu': p_kmu - 1. / nbar, 'counts_kmu': n_kmu}

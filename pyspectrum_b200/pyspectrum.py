@@ -68,19 +68,35 @@ def triangle_list(Nmax, Ncut, step):
     return np.stack([I[m], J[m], L[m]], axis=1).astype(np.int32)      # C-order ravel == nested loop order
 
 
-def build_tc_plan(tri, s0, Nmax, layout=1):
+def build_tc_plan(tri, s0, Nmax, layout=1, MT=None):
     """Host plan of the tensor-core triangle kernel (pure numpy): which pair row (i,j) sits in which TMEM lane and M tile.
     layout 0: a lane holds one i and up to MT of its partners j (one per M tile): a thread loads I_i once for MT rows.
     layout 1 (MT == 4 only): a lane holds a 2x2 block (i0,i1) x (j0,j1), rows (i0,j0), (i0,j1), (i1,j0), (i1,j1) in tiles 0..3:
              four field vectors give four rows of products.
     Lanes are cut into passes of 128.  Returns (NT, MT, layout_used, [(lane_ij int32 [128][5], tri_rc int32 [ntri][2]), ...]):
     lane_ij holds field slots (shell - s0, -1 = unused), tri_rc the (row = tile*128 + lane, column = l - s0) of every triangle
-    owned by the pass, (-1,-1) otherwise."""
+    owned by the pass, (-1,-1) otherwise.
+    MT: M tiles per pass for layout 0 (default: the largest that fits TMEM, lowered as long as the number of passes stays the
+    same -- the kernel's cost per cell grows with the tiles it forms, whether their rows are used or not)."""
     S = Nmax - s0 + 1
     NT = (S + 15) // 16 * 16
-    MT = 4 if NT <= 64 else 256 // NT              # accumulator tiles that fit in 256 TMEM columns
-    if MT != 4:
+    MT_max = 4 if NT <= 64 else 256 // NT          # accumulator tiles that fit in 256 TMEM columns
+    nj = {}
+    for i, j in {(int(a), int(b)) for a, b, _ in tri}:
+        nj[i] = nj.get(i, 0) + 1
+    npass = lambda m: (sum((n + m - 1) // m for n in nj.values()) + 127) // 128
+    if layout == 1 and (MT_max != 4 or (MT is not None and MT != 4)):
         layout = 0
+    if layout == 1 and MT is None and npass(1) == 1:
+        layout = 0                                  # <= 128 pair rows: one tile of plain rows is cheaper than four tiles of 2x2 blocks
+    if layout == 0:
+        if MT is None:
+            MT = MT_max
+            while MT > 1 and npass(MT - 1) == npass(MT_max):
+                MT -= 1
+        MT = max(1, min(int(MT), MT_max))
+    else:
+        MT = 4
     partners = {}
     for i, j, _ in tri:
         partners.setdefault(int(i), set()).add(int(j))
@@ -154,17 +170,63 @@ def coarse_levels(N, step, tri, sizes):
     return out
 
 
-def default_level_sizes(N, step, tri):
-    """Which coarse grids the shell stage uses by default (PSB_BK_LEVELS overrides: 'off', or a comma list of grid sizes).
-    Policy from the measurements in profiles/r2_summary.md: drop to coarse grids when they are at most ~0.8 N (below that the
-    extra shell transforms cost more than the triangle stage saves)."""
+def tc_plan_shape(tri, s0, smax, layout=1):
+    """(layout, MT, NT, passes) `build_tc_plan` would choose for a triangle subset, without building the plan."""
+    S = smax - s0 + 1
+    NT = (S + 15) // 16 * 16
+    MT_max = 4 if NT <= 64 else 256 // NT
+    pairs = {(int(a), int(b)) for a, b, _ in np.asarray(tri)[:, :3]}
+    nj = {}
+    for i, j in pairs:
+        nj.setdefault(i, set()).add(j)
+    npass = lambda m: (sum((len(v) + m - 1) // m for v in nj.values()) + 127) // 128
+    if layout == 1 and MT_max == 4 and npass(1) > 1:
+        iv = sorted(nj)
+        lanes = sum((len(nj[iv[a]] | (nj[iv[a + 1]] if a + 1 < len(iv) else set())) + 1) // 2 for a in range(0, len(iv), 2))
+        return 1, 4, NT, (lanes + 127) // 128
+    MT = MT_max
+    while MT > 1 and npass(MT - 1) == npass(MT_max):
+        MT -= 1
+    return 0, MT, NT, npass(MT)
+
+
+def level_cost(N, step, s0, tri, sizes):
+    """Modelled device seconds of the shell + triangle stage for a set of coarse grids (constants measured on B200,
+    profiles/r2_summary.md): K5 ~ 6e-12 s per (shell pair x cell); K6 per pass and cell 2.1e-10 s in the 2x2 layout,
+    (1.6 + 0.29 MT) e-10 s with MT tiles of plain rows, +2 % per column beyond 48."""
+    cost = 0.
+    for Nc, idx, smax in coarse_levels(N, step, tri, sizes):
+        cells = float(Nc) ** 3
+        cost += 6e-12 * ((smax - s0 + 2) // 2) * cells
+        layout, MT, NT, npass = tc_plan_shape(tri[idx], s0, smax)
+        per_cell = 2.1e-10 if layout == 1 else (1.6e-10 + 0.29e-10 * MT)
+        cost += npass * cells * per_cell * (1. + 0.02 * max(NT - 48, 0))
+    return cost
+
+
+def default_level_sizes(N, step, tri, s0=None):
+    """Which coarse grids the shell stage uses by default (PSB_BK_LEVELS overrides: 'off', or a comma list of grid sizes):
+    the subset of COARSE_GRIDS below N with the smallest modelled cost (`level_cost`).  At the reference's Ngrid=360 that is none
+    (the extra shell transforms cost more than the triangle stage saves); at 512 with 80 shells it is {256, 400}; at 1024 with 40
+    shells {400} -- there the fine grid is not needed at all."""
+    import itertools
     import os
     spec = os.environ.get('PSB_BK_LEVELS', 'auto').strip().lower()
     if spec in ('off', 'none', '0'):
         return []
     if spec != 'auto':
         return [int(x) for x in spec.split(',') if x.strip()]
-    return [c for c in COARSE_GRIDS if c <= 0.8 * N]
+    tri = np.asarray(tri)
+    if s0 is None:
+        s0 = int(tri.min())
+    cand = [c for c in COARSE_GRIDS if c < N]
+    best, best_cost = [], level_cost(N, step, s0, tri, [])
+    for r in range(1, len(cand) + 1):
+        for sub in itertools.combinations(cand, r):
+            c = level_cost(N, step, s0, tri, sub)
+            if c < 0.97 * best_cost:
+                best, best_cost = list(sub), c
+    return best
 
 
 class PeriodicPipeline(object):
@@ -559,12 +621,13 @@ class PeriodicPipeline(object):
         """Device copy of the tensor-core plan (`build_tc_plan`) for the loop-nest triangles or a subset, cached."""
         if layout is None:
             layout = int(os.environ.get('PSB_TC_LAYOUT', '1'))       # 2x2 blocks: 17 % faster (profiles/r1_summary.md)
-        key = ('tc', Nmax, Ncut, step, layout, self._tri_key(tri))
+        MT = int(os.environ['PSB_TC_MT']) if os.environ.get('PSB_TC_MT') else None      # experiments only
+        key = ('tc', Nmax, Ncut, step, layout, MT, self._tri_key(tri))
         if key not in self._tiles:
             if tri is None:
                 tri = triangle_list(Nmax, Ncut, step)
             tri = np.ascontiguousarray(tri, dtype=np.int32)
-            NT, MT, layout_used, passes = build_tc_plan(tri, Ncut // step, Nmax, layout)
+            NT, MT, layout_used, passes = build_tc_plan(tri, Ncut // step, Nmax, layout, MT)
             dev_passes = [(torch.from_numpy(lij).to(self.dev), MT, torch.from_numpy(rc).to(self.dev)) for lij, rc in passes]
             self._tiles[key] = (tri, NT, dev_passes, layout_used)
         return self._tiles[key]
@@ -594,7 +657,7 @@ class PeriodicPipeline(object):
         if key not in self._tiles:
             tri = triangle_list(Nmax, Ncut, step)
             lev = []
-            for Nc, idx, smax in coarse_levels(self.N, step, tri, default_level_sizes(self.N, step, tri)):
+            for Nc, idx, smax in coarse_levels(self.N, step, tri, default_level_sizes(self.N, step, tri, Ncut // step)):
                 pc = self if Nc == self.N else PeriodicPipeline.get(Nc)
                 lev.append((pc, idx, torch.from_numpy(idx).to(self.dev), smax))
             self._tiles[key] = (tri, lev)
@@ -817,12 +880,8 @@ def Pk_periodic(xyz, w=None, Lbox=2600, Ngrid=360, fft='pyfftw', silent=True):
     return {'meta': meta, 'k': k, 'p0k': p0k - 1. / nbar, 'counts': counts, 'p0k_sn': 1. / nbar}
 
 
-def _pk_rsd_from_half(pipe, half, Lbox, rsd, Nmubin):
-    """K4 multipoles of a device half field + the normalisation of estimator.f:246-262 and pyspectrum.py:634-640.
-    Returns (ks, p0k, p2k, p4k, nk, k_kmu, mu_kmu, p_kmu, n_kmu) like the reference's _Pk_periodic_rsd."""
-    Nbins = pipe.N // 2
-    raw, kf32 = pipe.pk_multipoles(half, int(Lbox), rsd, Nmubin)      # Lbox is an INTEGER dummy: estimator.f:158
-    raw = raw.cpu().numpy()
+def _pk_rsd_normalise(raw, kf32, Nbins, Nmubin):
+    """The normalisation of estimator.f:246-262 and pyspectrum.py:634-640 applied to the raw K4 sums (host float64 array)."""
     nk = raw[:Nbins].copy()
     ks, p0k, p2k, p4k = [raw[(a + 1) * Nbins:(a + 2) * Nbins].copy() for a in range(4)]
     tb = Nbins * Nmubin
@@ -843,6 +902,13 @@ def _pk_rsd_from_half(pipe, half, Lbox, rsd, Nmubin):
     p4k *= pk_norm
     p_kmu *= pk_norm
     return ks, p0k, p2k, p4k, nk, k_kmu, mu_kmu, p_kmu, n_kmu
+
+
+def _pk_rsd_from_half(pipe, half, Lbox, rsd, Nmubin):
+    """K4 multipoles of a device half field + the normalisation of estimator.f:246-262 and pyspectrum.py:634-640.
+    Returns (ks, p0k, p2k, p4k, nk, k_kmu, mu_kmu, p_kmu, n_kmu) like the reference's _Pk_periodic_rsd."""
+    raw, kf32 = pipe.pk_multipoles(half, int(Lbox), rsd, Nmubin)      # Lbox is an INTEGER dummy: estimator.f:158
+    return _pk_rsd_normalise(raw.cpu().numpy(), kf32, pipe.N // 2, Nmubin)
 
 
 def _Pk_periodic_rsd(delta, Lbox=None, rsd=2, Nmubin=5, code='fortran'):

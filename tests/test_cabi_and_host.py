@@ -170,8 +170,14 @@ def test_tensor_core_plan_covers_every_triangle_once(Nmax, Ncut, step, layout):
     s0 = Ncut // step
     S = Nmax - s0 + 1
     NT, MT, used, passes = P.build_tc_plan(tri, s0, Nmax, layout)
-    assert NT % 16 == 0 and NT >= S and MT == (4 if NT <= 64 else 256 // NT) and MT * NT <= 256
-    assert used == (layout if MT == 4 else 0)
+    MT_max = 4 if NT <= 64 else 256 // NT
+    assert NT % 16 == 0 and NT >= S and 1 <= MT <= MT_max and MT * NT <= 256
+    assert used == (layout if MT_max == 4 else 0) and (MT == 4 or used == 0)
+    if used == 0:                                       # the fewest tiles that do not add a pass
+        _, _, _, full = P.build_tc_plan(tri, s0, Nmax, 0, MT_max)
+        assert len(passes) == len(full)
+        if MT > 1:
+            assert len(P.build_tc_plan(tri, s0, Nmax, 0, MT - 1)[3]) > len(full)
     owner = np.zeros(len(tri), int)
     for lij, rc in passes:
         assert lij.shape == (128, 5) and lij.dtype == np.int32 and rc.shape == (len(tri), 2) and rc.dtype == np.int32

@@ -28,7 +28,7 @@ def _cat(seed, Np, L):
 
 def test_level_split_is_a_partition():
     from pyspectrum_b200 import pyspectrum as P
-    for N, step, Nmax, sizes in [(360, 3, 40, [256]), (512, 2, 80, [256, 320, 400]), (1024, 3, 40, [256, 400]), (96, 1, 20, [48, 64])]:
+    for N, step, Nmax, sizes in [(360, 3, 40, [256]), (512, 2, 80, [256, 320, 400]), (1024, 3, 40, [256, 400]), (96, 1, 24, [48, 64])]:
         tri = P.triangle_list(Nmax, 3 if step > 1 else 1, step)
         lev = P.coarse_levels(N, step, tri, sizes)
         allidx = np.sort(np.concatenate([idx for _, idx, _ in lev]))
@@ -44,12 +44,12 @@ def test_level_split_is_a_partition():
 @pytest.mark.parametrize('levels', ['48,64', '64'])
 def test_small_grid_levels_match_oracle(mods, monkeypatch, levels):
     pySpec, O = mods
-    N, L, Np, step, Ncut, Nmax = 96, 400., 150000, 1, 1, 20
+    N, L, Np, step, Ncut, Nmax = 96, 400., 150000, 1, 1, 24
     xyz = _cat(96, Np, L)
     monkeypatch.setenv('PSB_BK_LEVELS', levels)
     pipe = pySpec.PeriodicPipeline.get(N)
     tri, lev = pipe.bk_levels(step, Ncut, Nmax)
-    assert len(lev) == len(levels.split(',')) + 1 and lev[-1][0].N == N      # some triangles stay on the fine grid (they alias there)
+    assert len(lev) == len(levels.split(',')) + 1 and lev[-1][0].N == N      # the largest triangles (R_i+R_j+R_l >= 64) stay on the fine grid
     pipe._counts.pop((Nmax, Ncut, step), None)
     monkeypatch.setattr(pySpec, '_DAT_DIR', '/tmp/psb_levels_test_%s' % levels.replace(',', '_'))
     bk = pySpec.Bk_periodic(xyz, Lbox=L, Ngrid=N, step=step, Ncut=Ncut, Nmax=Nmax)

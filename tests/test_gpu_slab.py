@@ -73,7 +73,123 @@ def test_slab_single_rank_distributed_entry_point(mods):
     pySpec, M = mods
     pipe, mesh, sumw = _mesh(pySpec, 32, 20000, 100., 5)
     ref = pipe.mesh_to_delta(mesh.clone(), sumw)
-    got = M.slab_mesh_to_delta(pipe, mesh.clone(), sumw)             # no process group: world = 1
+    got = M.slab_delta(pipe, mesh.clone(), sumw)                     # no process group: world = 1, the slab is the whole mesh
     assert (got - ref).abs().max().item() <= 2e-6 * ref.abs().max().item()
     with pytest.raises(ValueError):
         M.slab_geometry(32, 5)
+
+
+# ------------------------------------------------------------------------------------------ slab-owned assignment
+def _catalogue(N, Np, L, seed):
+    rng = np.random.default_rng(seed)
+    xyz = rng.uniform(0, L, (3, Np))
+    xyz[:, :Np // 2] = (xyz[:, :Np // 2] * 0.25 + 0.3 * L) % L
+    xyz[:, :6] = np.array([[0., L, -3., L * (1 - 1e-6), 0.5 * L, L + 2.],          # faces and outside the box: clip, wrap of the stencil
+                           [0., 0.5 * L, L, 0., L * (1 - 1e-6), -1.],
+                           [0., L * (1 - 1e-6), 0.25 * L, L + 5., -2., 0.5 * L]])
+    return np.ascontiguousarray(xyz), rng.uniform(0.5, 2., Np)
+
+
+@pytest.mark.parametrize('N,world,Np', [(32, 1, 20000), (32, 2, 20000), (32, 4, 30000), (64, 8, 100000), (360, 8, 1000000), (40, 5, 20000)])
+@pytest.mark.parametrize('weighted', [True, False])
+def test_routed_slab_assignment_equals_the_full_mesh(mods, N, world, Np, weighted):
+    """Every emulated rank routes the catalogue (it is the only sender here), takes its own segment of the destination-major
+    send buffer -- its planes' particles plus the ghost copies -- and assigns it onto its planes only: the slabs stacked are the
+    single-GPU mesh (same float32 contributions, another summation order), and nothing outside a rank's planes is written."""
+    import torch
+    pySpec, M = mods
+    if N == 360 and not weighted:
+        pytest.skip('one large case is enough')
+    L = 100.
+    xyz, w = _catalogue(N, Np, L, N + world)
+    w = w if weighted else None
+    pipe = pySpec.PeriodicPipeline.get(N)
+    pos, aos, wt = pipe.to_device(xyz, w)
+    mesh, sumw = pipe.assign(pos, aos, wt, L)
+    nz = N // world
+    counts, sw = M.route_counts(pipe, pos, aos, wt, L, world)
+    send = M.route_scatter(pipe, pos, aos, wt, L, world, counts)
+    c = counts.cpu().numpy()
+    assert Np <= c.sum() <= (2 * Np if world > 1 else Np) and abs(sw.item() - sumw.item()) <= 1e-9 * abs(sumw.item())
+    if world > 1:
+        assert c.sum() - Np <= 1.3 * Np * 4. / nz + 50          # ghost copies: the cells within reach of a slab boundary
+    base = np.concatenate([[0], np.cumsum(c)])
+    scale = mesh.abs().max().item()
+    for r in range(world):
+        seg = send[base[r]:base[r + 1]].contiguous()
+        slab = M.assign_slab(pipe, seg, r * nz, nz, L)
+        assert slab.shape == (nz, N, N, 2)
+        assert (slab - mesh[r * nz:(r + 1) * nz]).abs().max().item() <= 2e-6 * scale
+    # routed positions are the float32 values assign_quad receives (clip in float64, then the cast: py:938-941)
+    ref32 = np.clip(xyz, 0., L * (1 - 1e-6)).astype(np.float32)
+    got = send[:, :3].cpu().numpy()
+    assert set(map(bytes, np.unique(got, axis=0))) <= set(map(bytes, np.unique(ref32.T, axis=0)))
+
+
+@pytest.mark.parametrize('N,world', [(32, 2), (48, 4), (64, 8)])
+def test_slab_spectra_partial_bins_sum_to_the_full_binning(mods, N, world):
+    import torch
+    pySpec, M = mods
+    pipe, mesh, sumw = _mesh(pySpec, N, 30000, 100., 7 * N)
+    half = pipe.mesh_to_delta(mesh, sumw)
+    ny = N // world
+    full = pipe.pk_monopole(half, 100.)
+    fullm, _ = pipe.pk_multipoles(half, 100, 2, 5)
+    acc, accm = torch.zeros_like(full), torch.zeros_like(fullm)
+    for r in range(world):
+        sl = half[:, r * ny:(r + 1) * ny].contiguous()
+        acc += M.slab_pk_monopole(pipe, sl, r * ny, 100.)
+        accm += M.slab_pk_multipoles(pipe, sl, r * ny, 100, 2, 5)[0]
+    Nb = N // 2
+    assert torch.equal(acc[:Nb], full[:Nb]) and torch.equal(accm[:Nb], fullm[:Nb])                 # mode counts: exact
+    assert torch.equal(accm[5 * Nb:5 * Nb + 5 * Nb], fullm[5 * Nb:5 * Nb + 5 * Nb])                # (k,mu) counts: exact
+    assert torch.allclose(acc, full, rtol=1e-12, atol=0) and torch.allclose(accm, fullm, rtol=1e-11, atol=1e-9 * fullm.abs().max().item())
+
+
+@pytest.mark.parametrize('N,Ng,world', [(64, 32, 2), (64, 64, 4), (96, 48, 3), (128, 64, 8)])
+def test_carrier_extraction(mods, N, Ng, world):
+    import torch
+    pySpec, M = mods
+    pipe = pySpec.PeriodicPipeline.get(N)
+    h, hg = N // 2, Ng // 2
+    half = torch.randn((N, N, h + 1, 2), device='cuda', dtype=torch.float32)
+    ny = N // world
+    car = torch.zeros((Ng, Ng, hg + 1, 2), device='cuda', dtype=torch.float32)
+    for r in range(world):
+        car += M.low_k_carrier(pipe, half[:, r * ny:(r + 1) * ny].contiguous(), r * ny, Ng)
+    a = half.cpu().numpy()
+    ref = np.zeros((Ng, Ng, hg + 1, 2), np.float32)
+    if Ng == N:
+        ref[:] = a
+    else:
+        k = np.arange(-hg + 1, hg)
+        ref[np.ix_(k % Ng, k % Ng, np.arange(hg))] = a[np.ix_(k % N, k % N, np.arange(hg))]
+    assert np.array_equal(car.cpu().numpy(), ref)
+
+
+def test_sharded_entry_points_on_one_rank(mods, monkeypatch, tmp_path):
+    """World size 1 runs every step of the sharded path (route, slab assignment, slab FFT, slab binning, carrier, levels, dealt
+    pairs, cell slabs) without a process group: same results as the single-GPU API."""
+    pySpec, M = mods
+    monkeypatch.setattr(pySpec, '_DAT_DIR', str(tmp_path))
+    for N, L, Np, step, Ncut, Nmax in [(64, 500., 100000, 2, 3, 12), (512, 2600., 1000000, 3, 3, 20)]:
+        xyz, w = _catalogue(N, Np, L, N)
+        assert M.carrier_grid(N, step, Nmax, Ncut) == (N if N == 64 else 256)
+        ref = pySpec.Bk_periodic(xyz, w=w, Lbox=L, Ngrid=N, step=step, Ncut=Ncut, Nmax=Nmax)
+        st = M.Stats(timed=True)
+        got, pk = M.Bk_periodic_sharded(xyz, w, Lbox=L, Ngrid=N, step=step, Ncut=Ncut, Nmax=Nmax, stats=st, return_pk=True)
+        assert np.array_equal(got['i_k1'], ref['i_k1']) and np.array_equal(got['i_k3'], ref['i_k3'])
+        assert np.array_equal(got['counts'], ref['counts'])
+        assert got['meta']['N'] == Np and abs(got['meta']['nbar'] / ref['meta']['nbar'] - 1) < 1e-12
+        np.testing.assert_allclose(got['p0k1'] + got['p0k_sn'], ref['p0k1'] + ref['p0k_sn'], rtol=1e-5)
+        scale = np.abs(ref['b123'] + ref['b123_sn'])
+        assert np.all(np.abs(got['b123'] - ref['b123']) <= 1e-5 * scale + 1e-7 * scale.max())
+        rpk = pySpec.Pk_periodic(xyz, w=w, Lbox=L, Ngrid=N)
+        assert np.array_equal(pk['counts'], rpk['counts'])
+        np.testing.assert_allclose(pk['p0k'] + pk['p0k_sn'], rpk['p0k'] + rpk['p0k_sn'], rtol=1e-5)
+        assert 'assign_slab' in st.times_ms() and 'triangles' in st.times_ms()
+    xyz, w = _catalogue(64, 100000, 500., 3)
+    a = M.Pk_periodic_rsd_sharded(xyz, None, Lbox=500., Ngrid=64, rsd=2, Nmubin=5)
+    b = pySpec.Pk_periodic_rsd(xyz, Lbox=500., Ngrid=64, rsd=2, Nmubin=5)
+    assert np.array_equal(a['counts'], b['counts']) and np.array_equal(a['counts_kmu'], b['counts_kmu'])
+    np.testing.assert_allclose(a['p0k'] + a['p_sn'], b['p0k'] + b['p_sn'], rtol=1e-5)

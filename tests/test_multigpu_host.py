@@ -15,9 +15,9 @@ def test_pair_assignment_and_rows():
         assert got == list(range(npairs))
         rows = slab_field_rows(S, world, per)
         assert len(set(rows)) == S and max(rows) < 2 * per * world
-        for f, r in enumerate(rows):                       # row -> (k, owner, e) -> shell slot
-            k, rem = divmod(r, 2 * world)
-            owner, e = divmod(rem, 2)
+        for f, r in enumerate(rows):                       # row -> (owner, k, e) -> shell slot
+            owner, rem = divmod(r, 2 * per)
+            k, e = divmod(rem, 2)
             assert 2 * (owner + world * k) + e == f
 
 
@@ -116,3 +116,22 @@ def test_slab_geometry_and_single_rank_exchange():
     assert torch.equal(ch[0], t[:, :4]) and torch.equal(ch[1], t[:, 4:])
     full = torch.arange(8 * 8 * 6 * 2, dtype=torch.float32).view(8, 8, 6, 2)
     assert torch.equal(z_to_y_slabs(full, 1), full) and torch.equal(gather_ky_slabs(full, 1), full)
+
+
+def test_cell_slab_checks_raise_before_any_collective():
+    import pytest
+    from pyspectrum_b200.multigpu import check_cell_slabs
+    check_cell_slabs(360 ** 3, 8)
+    with pytest.raises(ValueError):
+        check_cell_slabs(360 ** 3, 7)                       # 360^3 is not a multiple of 7
+    with pytest.raises(ValueError):
+        check_cell_slabs(10 ** 3, 8)                        # 125 cells per slab would split a packed cell pair
+    check_cell_slabs(10 ** 3, 8, packed=False)
+
+
+def test_carrier_grid_choice():
+    from pyspectrum_b200.multigpu import carrier_grid
+    assert carrier_grid(1024, 3, 40, 3) == 400              # 3*(3*40+1) = 363 < 400: BASELINE configs[4] never needs the 1024^3 shell fields
+    assert carrier_grid(360, 3, 40, 3) == 360               # the reference's own grid lets the largest triangles wrap: stay on it
+    assert carrier_grid(512, 2, 80, 3) == 512               # 483 < 512 but no compiled grid in between
+    assert carrier_grid(512, 3, 20, 3) == 256
