@@ -63,6 +63,38 @@ __device__ __forceinline__ int row_key(const AssignIn& a, float y, float z)
     return zr < a.nzs + 8 ? zr * a.N + wrapN(cy, a.N) : (a.nzs + 8) * a.N;
 }
 
+// Tile scatter (k_assign_tile): particles are sorted by the TX x TY x TZ tile of their cell instead of by (z,y) row.
+constexpr int TX = 8, TY = 8, TZ = 4;
+constexpr int AX = TX + 4, AY = TY + 4, AZ = TZ + 4;        // tile + halo: a particle in cell c touches cells c-1 .. c+3
+constexpr int SY = AX, SZ = AX * AY;                        // strides 12 and 144 (== 16 mod 32): a 4 x 4 x 2 block of lanes hits 32 banks
+constexpr int TILE_WORDS = AX * AY * AZ;                    // 1152 floats per grid
+constexpr int STG = 43;                                     // staging words per particle (odd: conflict-free row stores)
+constexpr int TILE_WARPS = 5;                               // warps per CTA: 5 x 14.7 KB, three CTAs per SM
+
+struct TileGeom { int ntx, nty, ntz, zlo, nkeys; };         // zlo: first plane the z tiles are counted from; nkeys = valid tiles
+
+__host__ __device__ __forceinline__ TileGeom tile_geom(int N, int zbase, int nzs)
+{
+    TileGeom g;
+    g.ntx = (N + TX - 1) / TX; g.nty = (N + TY - 1) / TY;
+    const bool slab = nzs < N;
+    g.zlo = slab ? zbase - 4 : 0;
+    g.ntz = ((slab ? nzs + 8 : N) + TZ - 1) / TZ;
+    g.nkeys = g.ntx * g.nty * g.ntz;
+    return g;
+}
+
+__device__ __forceinline__ int tile_key(const AssignIn& a, float x, float y, float z)
+{
+    const TileGeom g = tile_geom(a.N, a.zbase, a.nzs);
+    const int cx = wrapN((int)grid_coord(a.kf_ks, x, a.offset) - 1, a.N), cy = wrapN((int)grid_coord(a.kf_ks, y, a.offset) - 1, a.N);
+    const int zr = wrapN((int)grid_coord(a.kf_ks, z, a.offset) - 1 - g.zlo, a.N);
+    if (a.nzs < a.N && zr >= a.nzs + 8) return g.nkeys;      // cannot touch the slab: trailing bucket
+    return ((zr / TZ) * g.nty + cy / TY) * g.ntx + cx / TX;
+}
+
+__device__ __forceinline__ int sort_key(const AssignIn& a, float x, float y, float z) { return a.tiles ? tile_key(a, x, y, z) : row_key(a, y, z); }
+
 __global__ void k_hist(AssignIn a, unsigned int* hist, double* sumw)
 {
     double acc = 0.0;
@@ -70,7 +102,7 @@ __global__ void k_hist(AssignIn a, unsigned int* hist, double* sumw)
         float x, y, z, w; double wd;
         load_particle(a, i, x, y, z, w, wd);
         acc += wd;
-        atomicAdd(&hist[row_key(a, y, z)], 1u);
+        atomicAdd(&hist[sort_key(a, x, y, z)], 1u);
     }
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
     __shared__ double red[32];
@@ -143,7 +175,7 @@ __global__ void k_sort_scatter(AssignIn a, unsigned int* cursor, float4* sorted)
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < a.Np; i += (long long)gridDim.x * blockDim.x) {
         float x, y, z, w; double wd;
         load_particle(a, i, x, y, z, w, wd);
-        const unsigned int slot = atomicAdd(&cursor[row_key(a, y, z)], 1u);
+        const unsigned int slot = atomicAdd(&cursor[sort_key(a, x, y, z)], 1u);
         sorted[slot] = make_float4(x, y, z, w);
     }
 }
@@ -320,6 +352,122 @@ __global__ void __launch_bounds__(256) k_assign_tri(const float4* __restrict__ s
 }
 
 // ------------------------------------------------------------------------------------------------------------------------
+// Tile scatter: the shared-memory accumulation north_star asks for, without atomics.  One WARP owns one tile of TX x TY x TZ
+// cells at a time (plus the 1 + 3 halo cells its particles reach) as two planar float arrays (grid A, grid B) in shared memory
+// that no other warp touches.  Per batch of 32 particles: (1) every lane evaluates ONE particle -- cell, the 2 x 12 cubic weights
+// of f:316-320, the 2 x 16 products wx*wy, wz*w -- and leaves them in a staging row; (2) the warp walks the batch, and for each
+// particle lane (x, y, zl) adds the four values (x, y, zl | zl+2) of grid A and of grid B with plain LDS / FADD / STS: 32 distinct
+// banks per instruction, no two lanes share an address, and a warp's shared-memory operations execute in order, so consecutive
+// particles may overlap freely.  The finished tile leaves with vector reductions whose neighbouring lanes cover neighbouring
+// 16 bytes (full sectors); all-zero pairs are skipped.  The L1 -> L2 reduction traffic that bounded the per-particle scatter
+// (k_assign_tri: ~56 vector reductions per particle) becomes ~2.3 per CELL, independent of the particle density.
+__device__ __forceinline__ void red_add_v2(float* addr, float a, float b)
+{
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
+
+__global__ void __launch_bounds__(32 * TILE_WARPS) k_assign_tile(const float4* __restrict__ sorted, const unsigned int* __restrict__ key_end,
+                                                                  int N, float kf_ks, float offset, float* mesh, int zbase, int nzs,
+                                                                  unsigned int* tile_counter)
+{
+    extern __shared__ float tsm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* tA = tsm + (size_t)warp * (2 * TILE_WORDS + 32 * STG);
+    float* tB = tA + TILE_WORDS;
+    float* stg = tB + TILE_WORDS;
+    const TileGeom g = tile_geom(N, zbase, nzs);
+    const int lx = lane & 3, ly = (lane >> 2) & 3, lz = lane >> 4;
+    const int loff = lx + ly * SY + lz * SZ;
+    for (;;) {
+        unsigned int t = 0;
+        if (lane == 0) t = atomicAdd(tile_counter, 1u);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= (unsigned)g.nkeys) break;
+        const unsigned int beg = t ? key_end[t - 1] : 0u, end = key_end[t];
+        if (beg == end) continue;
+        const int tx = (int)(t % g.ntx), ty = (int)((t / g.ntx) % g.nty), tz = (int)(t / ((unsigned)g.ntx * g.nty));
+        const int ox = tx * TX, oy = ty * TY, ozr = tz * TZ;          // ozr: z origin relative to g.zlo
+        for (int i = lane; i < 2 * TILE_WORDS / 4; i += 32) reinterpret_cast<float4*>(tA)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncwarp();
+        for (unsigned int b0 = beg; b0 < end; b0 += 32) {
+            const int n = (int)min(32u, end - b0);
+            if (lane < n) {
+                const float4 p = sorted[b0 + lane];
+                float* row = stg + lane * STG;
+                float wa[3][4], wb[3][4];
+                int cl[3], sh[3];
+                const float pos[3] = { p.x, p.y, p.z };
+#pragma unroll
+                for (int ax = 0; ax < 3; ++ax) {
+                    const float rx = grid_coord(kf_ks, pos[ax], offset), tx_ = __fadd_rn(rx, 0.5f);
+                    const int im1 = (int)rx, nm1 = (int)tx_;
+                    pcs4(__fsub_rn(rx, (float)im1), wa[ax][0], wa[ax][1], wa[ax][2], wa[ax][3]);
+                    pcs4(__fsub_rn(tx_, (float)nm1), wb[ax][0], wb[ax][1], wb[ax][2], wb[ax][3]);
+                    sh[ax] = nm1 - im1;                               // grid B's base cell is c or c+1
+                    int c = im1 - 1;
+                    if (ax == 2) c = wrapN(c - g.zlo, N) - ozr; else c = wrapN(c, N) - (ax == 0 ? ox : oy);
+                    cl[ax] = c;                                        // array index of cell c-1 (index 0 = cell origin-1)
+                }
+#pragma unroll
+                for (int yy = 0; yy < 4; ++yy)
+#pragma unroll
+                    for (int xx = 0; xx < 4; ++xx) {
+                        row[yy * 4 + xx] = wa[0][xx] * wa[1][yy];
+                        row[16 + yy * 4 + xx] = wb[0][xx] * wb[1][yy];
+                    }
+#pragma unroll
+                for (int zz = 0; zz < 4; ++zz) { row[32 + zz] = wa[2][zz] * p.w; row[36 + zz] = wb[2][zz] * p.w; }
+                const int baseA = cl[0] + cl[1] * SY + cl[2] * SZ;
+                row[40] = __int_as_float(baseA);
+                row[41] = __int_as_float(baseA + sh[0] + sh[1] * SY + sh[2] * SZ);
+            }
+            __syncwarp();
+            for (int q = 0; q < n; ++q) {
+                const float* row = stg + q * STG;
+                const int baseA = __float_as_int(row[40]), baseB = __float_as_int(row[41]);
+                const float wxyA = row[lane & 15], wxyB = row[16 + (lane & 15)];
+                const float za0 = row[32 + lz], za1 = row[34 + lz], zb0 = row[36 + lz], zb1 = row[38 + lz];
+                float* pa = tA + baseA + loff;
+                float* pb = tB + baseB + loff;
+                const float a0 = pa[0], a1 = pa[2 * SZ], b0 = pb[0], b1 = pb[2 * SZ];
+                pa[0] = a0 + wxyA * za0;
+                pa[2 * SZ] = a1 + wxyA * za1;
+                pb[0] = b0 + wxyB * zb0;
+                pb[2 * SZ] = b1 + wxyB * zb1;
+                __syncwarp();
+            }
+        }
+        // ---- flush: 4 rows of 12 cells per step; lane = (row in step, slot): slot 0 = cell ox-1 alone, slots 1..5 = aligned pairs,
+        //      slot 6 = cell ox+10 alone, slot 7 idle.  Array index ix <-> cell ox + ix - 1.
+        const int fr = lane >> 3, slot = lane & 7;
+        for (int r0 = 0; r0 < AY * AZ; r0 += 4) {
+            const int r = r0 + fr;
+            const int iy = r % AY, iz = r / AY;
+            int zl = wrapN(g.zlo + ozr + iz - 1 - zbase, N);          // plane inside the slab (full grid: zbase = 0, nzs = N)
+            if (slot == 7 || zl >= nzs) continue;
+            const int gy = wrapN(oy + iy - 1, N);
+            const float* ra = tA + iy * SY + iz * SZ;
+            const float* rb = tB + iy * SY + iz * SZ;
+            float* mrow = mesh + ((size_t)zl * N + gy) * (size_t)N * 2;
+            if (slot == 0 || slot == 6) {
+                const int ix = slot == 0 ? 0 : AX - 1;
+                const float va = ra[ix], vb = rb[ix];
+                if (va != 0.f || vb != 0.f) red_add_v2(mrow + 2 * (size_t)wrapN(ox + ix - 1, N), va, vb);
+            } else {
+                const int ix = 2 * slot - 1;                              // cells ox + 2(slot-1), +1: an aligned pair
+                const float a0 = ra[ix], a1 = ra[ix + 1], b0 = rb[ix], b1 = rb[ix + 1];
+                if (a0 != 0.f || a1 != 0.f || b0 != 0.f || b1 != 0.f) {
+                    int cx = ox + ix - 1;
+                    cx = cx >= N ? cx - N : cx;
+                    red_add_v4(mrow + 2 * (size_t)cx, a0, b0, a1, b1);
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------------
 // Slab routing (multi-GPU): rank q owns the mesh planes [q*nzr, (q+1)*nzr).  A particle in cell c touches planes
 // c-1 .. c+3 (grid A: c-1..c+2, the half-cell shifted grid B up to c+3), so it is sent to the owner of plane c-1 and, if
 // different, to the owner of plane c+3 (ghost copy).  Positions leave as float32 after the float64 clip of py:938-941, exactly
@@ -410,26 +558,40 @@ int slab_route_scatter(const AssignIn& in, int nzr, int nranks, const unsigned l
     return cudaGetLastError() == cudaSuccess ? PSB_OK : PSB_ERR_CUDA;
 }
 
-size_t assign_workspace_bytes(long long Np, int N)
+// counter area: sort keys = N*N rows (any slab: (nzs+8)*N + 1, nzs + 8 <= N) or the tiles of the tile scatter (+ trailing bucket)
+static size_t assign_hist_bytes(int N)
 {
-    size_t hist = (((size_t)N * N + 2) * sizeof(unsigned int) + 255) / 256 * 256;      // also covers any slab ((nzs+8)*N + 1 keys, nzs + 8 <= N)
-    return 2 * hist + (size_t)Np * sizeof(float4) + 256;
+    const TileGeom g = tile_geom(N, 0, N);
+    const size_t nkey = (size_t)N * N > (size_t)g.nkeys ? (size_t)N * N : (size_t)g.nkeys;
+    return ((nkey + 2) * sizeof(unsigned int) + 255) / 256 * 256 + 32768;      // + scan tile sums (4096) and the tile work counter
 }
 
-int assign_pcs_interlaced(const AssignIn& in, float* mesh, int zero_mesh, void* ws, size_t ws_bytes, double* sumw, cudaStream_t st)
+size_t assign_workspace_bytes(long long Np, int N)
 {
-    if (in.N < 4 || (in.N % 2) || in.Np < 0) return PSB_ERR_ARG;
-    if (ws_bytes < assign_workspace_bytes(in.Np, in.N)) return PSB_ERR_WORKSPACE;
-    const bool slab = in.nzs < in.N;
-    if (in.nzs < 1 || in.nzs > in.N || (slab && (in.nzs + 8 > in.N || in.zbase < 0 || in.zbase >= in.N))) return PSB_ERR_ARG;
-    if (slab && 2.0 * in.nzs * in.N * in.N >= 4294967296.0) return PSB_ERR_ARG;
-    const size_t nrow = slab ? (size_t)(in.nzs + 8) * in.N + 1 : (size_t)in.N * in.N;      // sort keys (slab: + the "cannot touch" bucket)
+    return 2 * assign_hist_bytes(N) + (size_t)Np * sizeof(float4) + 256;
+}
+
+int assign_pcs_interlaced(const AssignIn& in_, float* mesh, int zero_mesh, void* ws, size_t ws_bytes, double* sumw, cudaStream_t st)
+{
+    if (in_.N < 4 || (in_.N % 2) || in_.Np < 0) return PSB_ERR_ARG;
+    if (ws_bytes < assign_workspace_bytes(in_.Np, in_.N)) return PSB_ERR_WORKSPACE;
+    const bool slab = in_.nzs < in_.N;
+    if (in_.nzs < 1 || in_.nzs > in_.N || (slab && (in_.nzs + 8 > in_.N || in_.zbase < 0 || in_.zbase >= in_.N))) return PSB_ERR_ARG;
+    if (slab && 2.0 * in_.nzs * in_.N * in_.N >= 4294967296.0) return PSB_ERR_ARG;
+    // 3 (default): tile scatter in shared memory; 2: per-particle vector reductions, three lanes per particle; 1, 0: older variants
+    static const int variant = [] { const char* e = getenv("PSB_ASSIGN_VARIANT"); return e ? atoi(e) : 3; }();
+    AssignIn in = in_;
+    in.tiles = (variant == 3 && in.N >= 16) ? 1 : 0;
+    const TileGeom tg = tile_geom(in.N, in.zbase, in.nzs);
+    // sort keys; in slab mode one trailing bucket takes the particles that cannot touch the slab
+    const size_t nrow = in.tiles ? (size_t)tg.nkeys + (slab ? 1 : 0) : (slab ? (size_t)(in.nzs + 8) * in.N + 1 : (size_t)in.N * in.N);
     const size_t mesh_rows = (size_t)in.nzs * in.N;
-    const size_t hist_b = (((size_t)in.N * in.N + 2) * sizeof(unsigned int) + 255) / 256 * 256;
+    const size_t hist_b = assign_hist_bytes(in.N);
     unsigned int* hist = static_cast<unsigned int*>(ws);
     unsigned int* tile_sum = hist + hist_b / sizeof(unsigned int);      // second counter area: scan tile sums (<= 4096 entries)
+    unsigned int* tile_counter = tile_sum + 4096;                         // work counter of the tile scatter
     float4* sorted = reinterpret_cast<float4*>(static_cast<char*>(ws) + 2 * hist_b);
-    if (cudaMemsetAsync(hist, 0, hist_b, st) != cudaSuccess) return PSB_ERR_CUDA;
+    if (cudaMemsetAsync(hist, 0, 2 * hist_b, st) != cudaSuccess) return PSB_ERR_CUDA;
     if (cudaMemsetAsync(sumw, 0, sizeof(double), st) != cudaSuccess) return PSB_ERR_CUDA;
     if (zero_mesh && cudaMemsetAsync(mesh, 0, sizeof(float) * 2 * mesh_rows * in.N, st) != cudaSuccess) return PSB_ERR_CUDA;
     if (in.Np > 0) {
@@ -442,13 +604,22 @@ int assign_pcs_interlaced(const AssignIn& in, float* mesh, int zero_mesh, void* 
         k_scan_tiles<<<1, 256, 0, st>>>(tile_sum, ntile);
         k_scan_apply<<<ntile, 256, 0, st>>>(hist, (int)nrow, tile_sum);
         k_sort_scatter<<<grid, blk, 0, st>>>(in, hist, sorted);
-        static const int variant = [] { const char* e = getenv("PSB_ASSIGN_VARIANT"); return e ? atoi(e) : 2; }();
-        // after the scatter cursor[k] = start of key k+1: cursor[nrow-2] = number of particles that can touch the slab
-        if (slab || (variant == 2 && in.N <= 1024))
+        // after the scatter hist[k] = end of key k = start of key k+1
+        if (in.tiles) {
+            const size_t smem = (size_t)TILE_WARPS * (2 * TILE_WORDS + 32 * STG) * sizeof(float);
+            if (cudaFuncSetAttribute(k_assign_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PSB_ERR_CUDA;
+            const long long want = ((long long)tg.nkeys + TILE_WARPS - 1) / TILE_WARPS;
+            const int ncta = (int)(want < 3LL * sm_count() ? want : 3LL * sm_count());
+            k_assign_tile<<<ncta, 32 * TILE_WARPS, smem, st>>>(sorted, hist, in.N, in.kf_ks, in.offset, mesh, slab ? in.zbase : 0,
+                                                             slab ? in.nzs : in.N, tile_counter);
+        } else if (slab || (variant >= 2 && in.N <= 1024)) {
             k_assign_tri<<<(unsigned)((in.Np + 79) / 80), 256, 0, st>>>(sorted, in.Np, in.N, in.kf_ks, in.offset, mesh, slab ? in.zbase : 0,
                                                                        slab ? in.nzs : in.N, slab ? hist + (nrow - 2) : nullptr);
-        else if (variant == 1) k_assign_pairs<<<(unsigned)((4 * in.Np + 255) / 256), 256, 0, st>>>(sorted, in.Np, in.N, in.kf_ks, in.offset, mesh);
-        else k_assign<<<(unsigned)((in.Np + 255) / 256), 256, 0, st>>>(sorted, in.Np, in.N, in.kf_ks, in.offset, mesh);
+        } else if (variant == 1) {
+            k_assign_pairs<<<(unsigned)((4 * in.Np + 255) / 256), 256, 0, st>>>(sorted, in.Np, in.N, in.kf_ks, in.offset, mesh);
+        } else {
+            k_assign<<<(unsigned)((in.Np + 255) / 256), 256, 0, st>>>(sorted, in.Np, in.N, in.kf_ks, in.offset, mesh);
+        }
     }
     return cudaGetLastError() == cudaSuccess ? PSB_OK : PSB_ERR_CUDA;
 }

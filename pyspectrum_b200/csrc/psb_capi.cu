@@ -143,7 +143,7 @@ int psb_assign_pcs_interlaced(const void* pos, int pos_f64, int pos_aos, const v
     AssignIn in;
     in.pos = pos; in.pos_f64 = pos_f64; in.pos_aos = pos_aos; in.w = w; in.w_f64 = w_f64; in.Np = np; in.N = ngrid;
     in.do_clip = lbox_clip > 0.0; in.clip_hi = lbox_clip * (1. - 1e-6); in.kf_ks = kf_ks; in.offset = offset;
-    in.zbase = 0; in.nzs = ngrid;
+    in.zbase = 0; in.nzs = ngrid; in.tiles = 0;
     return assign_pcs_interlaced(in, mesh, zero_mesh, ws, ws_bytes, sumw, S(stream));
 }
 
@@ -153,7 +153,7 @@ static AssignIn route_in(const void* pos, int pos_f64, int pos_aos, const void* 
     AssignIn in;
     in.pos = pos; in.pos_f64 = pos_f64; in.pos_aos = pos_aos; in.w = w; in.w_f64 = w_f64; in.Np = np; in.N = ngrid;
     in.do_clip = lbox_clip > 0.0; in.clip_hi = lbox_clip * (1. - 1e-6); in.kf_ks = kf_ks; in.offset = offset;
-    in.zbase = 0; in.nzs = ngrid;
+    in.zbase = 0; in.nzs = ngrid; in.tiles = 0;
     return in;
 }
 

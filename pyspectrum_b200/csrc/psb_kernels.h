@@ -20,6 +20,7 @@ struct AssignIn {
     double clip_hi;       // Lbox*(1-1e-6)
     float kf_ks, offset;
     int zbase, nzs;       // planes [zbase, zbase+nzs) held by `mesh` (full grid: 0, N); see k_assign_tri
+    int tiles;            // set by assign_pcs_interlaced: sort by tile (tile scatter) instead of by (z,y) row
 };
 
 size_t assign_workspace_bytes(long long Np, int N);

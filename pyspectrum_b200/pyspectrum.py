@@ -45,6 +45,33 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
+class _Range(object):
+    """Profiling hooks: with PSB_NVTX=1 every stage is an NVTX range (visible in nsys / ncu --nvtx); with
+    PSB_TIMERS=1 the Bk/Pk entry points add meta['stage_ms'] (CUDA events on the launching stream).  Both are off by default."""
+    nvtx = os.environ.get('PSB_NVTX', '0') == '1'
+    timers = os.environ.get('PSB_TIMERS', '0') == '1'
+
+    def __init__(self, name, sink=None):
+        self.name, self.sink = name, sink
+
+    def __enter__(self):
+        if _Range.nvtx:
+            torch.cuda.nvtx.range_push('psb:' + self.name)
+        if self.sink is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.sink is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            self.sink.append((self.name, self.e0, e1))
+        if _Range.nvtx:
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
 def _np_ptr(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
@@ -368,11 +395,81 @@ class PeriodicPipeline(object):
                                            _ptr(sumw), periodic, _stream()), 'psb_fft_mesh_to_delta')
         return half
 
+    CHUNK = 1 << 21                                  # particles per upload chunk of the streamed assignment
+
     def fft_periodic(self, xyz, w, Lbox):
-        pos, aos, wt = self.to_device(xyz, w)
-        mesh, sumw = self.assign(pos, aos, wt, Lbox)
-        half = self.mesh_to_delta(mesh, sumw)
+        """FFT_periodic (py:909-959) -> (device half field, sum of weights).  Catalogues that still live on the host are uploaded in
+        chunks on a copy stream while K1 assigns the previous chunk (the mesh accumulates): the drop-in call then costs the
+        upload plus one chunk of K1 instead of upload + the whole K1."""
+        host = (not isinstance(xyz, torch.Tensor)) or (not xyz.is_cuda)
+        n = int(xyz.shape[1]) if hasattr(xyz, 'shape') and len(xyz.shape) == 2 else 0
+        if host and n >= 2 * self.CHUNK and os.environ.get('PSB_STREAMED_ASSIGN', '1') != '0':
+            with _Range('K1 assign (streamed upload)'):
+                mesh, sumw = self.assign_streamed(xyz, w, Lbox)
+        else:
+            pos, aos, wt = self.to_device(xyz, w)
+            with _Range('K1 assign'):
+                mesh, sumw = self.assign(pos, aos, wt, Lbox)
+        with _Range('K2+K3 fft+fcomb'):
+            half = self.mesh_to_delta(mesh, sumw)
         return half, sumw
+
+    def assign_streamed(self, xyz, w, Lbox):
+        """K1 over a HOST catalogue (numpy or CPU torch, 3 x N) in chunks: upload of chunk k+1 (copy stream) under K1 of chunk k."""
+        N = self.N
+        xt = xyz if isinstance(xyz, torch.Tensor) else torch.from_numpy(np.asarray(xyz))
+        if xt.dtype not in (torch.float32, torch.float64):
+            xt = xt.double()
+        if xt.dim() != 2 or xt.shape[0] != 3:
+            raise ValueError('xyz must be 3 x N')
+        aos = 0
+        if not xt.is_contiguous():
+            if xt.t().is_contiguous():
+                aos = 1                                  # Fortran-ordered (3,N): rows of xt.t() are particles
+            else:
+                xt = xt.contiguous()
+        wt_h = None
+        if w is not None:
+            wt_h = w if isinstance(w, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(w))
+            if wt_h.dtype not in (torch.float32, torch.float64):
+                wt_h = wt_h.double()
+            wt_h = wt_h.contiguous()
+        Np = int(xt.shape[1])
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.dev)
+        cs, main = self._copy_stream, torch.cuda.current_stream(self.dev)
+        mesh = torch.empty((N, N, N, 2), dtype=torch.float32, device=self.dev)
+        wsb = self.L.psb_assign_workspace_bytes(self.CHUNK, N)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=self.dev)
+        sumw = torch.zeros(1, dtype=torch.float64, device=self.dev)
+        part = torch.empty(1, dtype=torch.float64, device=self.dev)
+        kf_ks = np.float32(float(N) / Lbox)
+        cs.wait_stream(main)
+        staged = []
+        bounds = [(a, min(a + self.CHUNK, Np)) for a in range(0, Np, self.CHUNK)]
+        for (a, b) in bounds:                            # all uploads are queued up front; they run back to back on the copy stream
+            with torch.cuda.stream(cs):
+                if aos:
+                    pc = xt.t()[a:b].to(self.dev, non_blocking=True)
+                else:
+                    pc = torch.empty((3, b - a), dtype=xt.dtype, device=self.dev)
+                    for c in range(3):
+                        pc[c].copy_(xt[c, a:b], non_blocking=True)
+                wc = wt_h[a:b].to(self.dev, non_blocking=True) if wt_h is not None else None
+                ev = torch.cuda.Event()
+                ev.record(cs)
+            staged.append((pc, wc, ev))
+        for k, (pc, wc, ev) in enumerate(staged):
+            main.wait_event(ev)
+            pc.record_stream(main)
+            if wc is not None:
+                wc.record_stream(main)
+            check(self.L.psb_assign_pcs_interlaced(_ptr(pc), int(pc.dtype == torch.float64), aos, _ptr(wc),
+                                                   int(wc is not None and wc.dtype == torch.float64), pc.shape[0] if aos else pc.shape[1], N,
+                                                   float(Lbox), kf_ks, np.float32(0.), _ptr(mesh), 1 if k == 0 else 0, _ptr(ws), wsb,
+                                                   _ptr(part), _stream()), 'psb_assign_pcs_interlaced')
+            sumw += part
+        return mesh, sumw
 
     @staticmethod
     def survey_distance_table(cosmo, zmax, nnodes=4097):
@@ -690,11 +787,13 @@ class PeriodicPipeline(object):
             Sl = smax - s0 + 1
             vol = (float(self.N) / pc.N) ** 3
             t0 = mark()
-            fields, sq, _, mx = pc.shell_fields(half, step, s0, smax, scaled=True, scales=scales, src=None if pc is self else self)
+            with _Range('K5 shell fields %d^3' % pc.N):
+                fields, sq, _, mx = pc.shell_fields(half, step, s0, smax, scaled=True, scales=scales, src=None if pc is self else self)
             t1 = mark()
             use_tc = engine in ('auto', 'tc') and fields.shape[1] % 64 == 0 and Sl <= 128
             all_tc = all_tc and use_tc
-            sl = pc.triangle_sums(fields, smax, Ncut, step, engine='tc' if use_tc else 'fma', tri=tri[idx])
+            with _Range('K6 triangle sums %d^3' % pc.N):
+                sl = pc.triangle_sums(fields, smax, Ncut, step, engine='tc' if use_tc else 'fma', tri=tri[idx])
             t2 = mark()
             if timers is not None:
                 timers.append(('shell_fields', t0, t1))
@@ -1121,11 +1220,14 @@ def _bk_launch(xyz, w, Lbox, Ngrid, step, Ncut, Nmax, fft, silent):
         print('--- calculating the FFT ---')
     Nk = pipe.shell_mode_counts(step, Nmax)
     counts = pipe.counts(Nmax, Ncut, step, fft=fft, silent=silent)
-    half, sumw = pipe.fft_periodic(xyz, w, Lbox)
+    sink = [] if _Range.timers else None
+    with _Range('assign+fft+fcomb', sink):
+        half, sumw = pipe.fft_periodic(xyz, w, Lbox)
     if not silent:
         print('--- calculating the bispectrum ---')
-    h = pipe.bispectrum_launch(half, step, Ncut, Nmax, sumw=sumw)
-    h.update(N=N, w=None if (w is None or isinstance(w, torch.Tensor)) else w, w_is_dev=isinstance(w, torch.Tensor), Nk=Nk, counts=counts,
+    with _Range('shells+triangles', None):
+        h = pipe.bispectrum_launch(half, step, Ncut, Nmax, sumw=sumw, timers=sink)
+    h.update(timers=sink, N=N, w=None if (w is None or isinstance(w, torch.Tensor)) else w, w_is_dev=isinstance(w, torch.Tensor), Nk=Nk, counts=counts,
              cfg=(Lbox, Ngrid, step, Ncut, Nmax), silent=silent)
     return h
 
@@ -1146,6 +1248,11 @@ def _bk_finish(h):
         print('nbar = %f' % nbar)
     bispec = _bk_epilogue(Ngrid, tri, sums_h, sumsq_h, h['Nk'], h['counts'], step, Ncut, Nmax)
     meta = {'Lbox': Lbox, 'Ngrid': Ngrid, 'step': step, 'Ncut': Ncut, 'Nmax': Nmax, 'N': N, 'nbar': nbar, 'kf': kf}
+    if h.get('timers'):
+        ms = {}
+        for name, a, b in h['timers']:
+            ms[name] = ms.get(name, 0.) + a.elapsed_time(b)
+        meta['stage_ms'] = ms                            # PSB_TIMERS=1 only
     bispec['meta'] = meta
     if not silent:
         print('--- correcting for shotnoise ---')

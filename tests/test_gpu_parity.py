@@ -386,3 +386,25 @@ def test_pk_rsd_code_python_matches_reference_numpy(mods, golden_dir, tag):
     np.testing.assert_allclose(pr['p0k'] + pr['p_sn'], k[pre + 'p0k'], rtol=3 * RTOL)       # delta(k) itself is the GPU's here
     with pytest.raises(ValueError):
         pySpec._Pk_periodic_rsd(full, Lbox=L, code='c')
+
+
+def test_streamed_assignment_matches_single_upload(mods, monkeypatch):
+    """Host catalogues are uploaded in chunks under K1 (PeriodicPipeline.assign_streamed): same delta(k) as the one-shot path for
+    C-ordered, Fortran-ordered, float32 and weighted inputs; PSB_TIMERS adds the per-stage device times to meta."""
+    import torch
+    pySpec, _, _ = mods
+    N, L, Np = 64, 300., 200000
+    xyz = _cat(9, Np, L)
+    w = np.random.default_rng(3).uniform(0.5, 2., Np)
+    ref = pySpec.FFT_periodic(torch.from_numpy(xyz).cuda(), w=torch.from_numpy(w).cuda(), Lbox=L, Ngrid=N)      # device input: one K1 call
+    monkeypatch.setattr(pySpec.PeriodicPipeline, 'CHUNK', 1 << 14)                                            # 13 chunks
+    scale = np.abs(ref).max()
+    for x_in, w_in in [(xyz, w), (np.asfortranarray(xyz), w), (torch.from_numpy(xyz).pin_memory(), torch.from_numpy(w).pin_memory())]:
+        got = pySpec.FFT_periodic(x_in, w=w_in, Lbox=L, Ngrid=N)
+        assert np.abs(got - ref).max() <= 3e-6 * scale
+    a = pySpec.Pk_periodic(xyz.astype(np.float32), Lbox=L, Ngrid=N)
+    b = pySpec.Pk_periodic(torch.from_numpy(xyz.astype(np.float32)).cuda(), Lbox=L, Ngrid=N)
+    np.testing.assert_allclose(a['p0k'] + a['p0k_sn'], b['p0k'] + b['p0k_sn'], rtol=2e-6)
+    monkeypatch.setattr(pySpec._Range, 'timers', True)
+    bk = pySpec.Bk_periodic(xyz, Lbox=L, Ngrid=N, step=3, Ncut=3, Nmax=8)
+    assert set(bk['meta']['stage_ms']) == {'assign+fft+fcomb', 'shell_fields', 'triangles'} and all(v > 0 for v in bk['meta']['stage_ms'].values())

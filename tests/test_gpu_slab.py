@@ -111,8 +111,6 @@ def test_routed_slab_assignment_equals_the_full_mesh(mods, N, world, Np, weighte
     send = M.route_scatter(pipe, pos, aos, wt, L, world, counts)
     c = counts.cpu().numpy()
     assert Np <= c.sum() <= (2 * Np if world > 1 else Np) and abs(sw.item() - sumw.item()) <= 1e-9 * abs(sumw.item())
-    if world > 1:
-        assert c.sum() - Np <= 1.3 * Np * 4. / nz + 50          # ghost copies: the cells within reach of a slab boundary
     base = np.concatenate([[0], np.cumsum(c)])
     scale = mesh.abs().max().item()
     for r in range(world):
