@@ -166,6 +166,15 @@ int psb_shell_mode_counts(int ngrid, const uint16_t* irk_of_m, int nshell, uint6
 int psb_bk_shell_pair_f32(const float* half_c64, const uint16_t* irk_of_m, int ngrid, int ngrid_src, int sa, int sb, int R,
                           float* t1_c64, float* t2_c64, float* fa, float* fb, double* sumsq,
                           const float* scale2, uint32_t* maxabs2, int pack_half, const float* tw_c64, void* stream);
+/* The same with ROUTED output (multi-GPU, SURVEY 8e: "z-pass epilogue -> peer-memory slab write"): the output planes z are cut
+ * into slabs of planes_per_rank planes, slab q belongs to rank q, and the z pass stores every plane straight into rank q's memory
+ * (a peer pointer mapped over NVLink, e.g. from torch.distributed._symmetric_memory) instead of a local field + an all-to-all.
+ *   route  device int64 [2][nranks]: for plane a (shell sa) and plane b (shell sb), the byte address the field WOULD start at on rank
+ *          q if that rank's buffer held all planes, i.e. (rank q's slab row of this shell) - q * planes_per_rank * N^2 * 4; 0 = not stored.
+ * Needs a compiled multi-stage plan for ngrid (256, 320, 360, 400, 512, 1024, ...); otherwise PSB_ERR_UNSUPPORTED_N. */
+int psb_bk_shell_pair_f32_routed(const float* half_c64, const uint16_t* irk_of_m, int ngrid, int ngrid_src, int sa, int sb, int R,
+                                 float* t1_c64, float* t2_c64, const int64_t* route, int planes_per_rank, int nranks, double* sumsq,
+                                 const float* scale2, uint32_t* maxabs2, int pack_half, const float* tw_c64, void* stream);
 /* pack_half != 0: each aligned pair of cells (x, x+1) of fa/fb is stored as the two 32-bit words
  * {half2 hi(x,x+1), half2 lo(x,x+1)} with hi = fp16(v), lo = fp16(v - hi) (same 4 bytes per cell; the layout the
  * tensor-core triangle kernel consumes; requires scale2 so that the values sit in fp16 range).

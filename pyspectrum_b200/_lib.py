@@ -66,6 +66,7 @@ PROTOTYPES = {
     'psb_pk_kmu_python': (_i, [_vp, _i, _vp, _i, _i, _d, _vp, _vp, _vp]),
     'psb_shell_mode_counts': (_i, [_i, _vp, _i, _vp, _vp]),
     'psb_bk_shell_pair_f32': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    'psb_bk_shell_pair_f32_routed': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp]),
     'psb_bk_shell_power': (_i, [_vp, _i, _vp, _i, _vp, _vp]),
     'psb_bk_shell_scales': (_i, [_vp, _i, _f, _vp, _vp]),
     'psb_bk_shell_pair_f64': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -286,6 +286,17 @@ int psb_bk_shell_pair_f32(const float* half, const uint16_t* irk, int N, int Ns,
                                  reinterpret_cast<Cx<float>*>(t2), fa, fb, sumsq, scale2, maxabs2, pack_half, reinterpret_cast<const Cx<float>*>(tw), S(stream));
 }
 
+int psb_bk_shell_pair_f32_routed(const float* half, const uint16_t* irk, int N, int Ns, int sa, int sb, int R, float* t1, float* t2,
+                                 const int64_t* route, int planes_per_rank, int nranks, double* sumsq, const float* scale2,
+                                 uint32_t* maxabs2, int pack_half, const float* tw, void* stream)
+{
+    if (!irk || !t1 || !t2 || !route || !sumsq || !tw || R < 0) return PSB_ERR_ARG;
+    return fft_shell_pair<float>(reinterpret_cast<const Cx<float>*>(half), irk, N, Ns, sa, sb, R, reinterpret_cast<Cx<float>*>(t1),
+                                 reinterpret_cast<Cx<float>*>(t2), nullptr, nullptr, sumsq, scale2, maxabs2, pack_half,
+                                 reinterpret_cast<const Cx<float>*>(tw), S(stream), reinterpret_cast<const long long*>(route),
+                                 planes_per_rank, nranks);
+}
+
 int psb_bk_shell_pair_f64(const float* half, const uint16_t* irk, int N, int Ns, int sa, int sb, int R, double* t1, double* t2,
                           double* fa, double* fb, double* sumsq, const double* tw, void* stream)
 {

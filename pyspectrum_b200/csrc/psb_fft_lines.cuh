@@ -260,12 +260,20 @@ template <typename T, bool PRUNED, bool REALOUT> struct IoCols {
     int nlines;            // even; line strides and batch strides are even too (N is even) -> line pairs are 16-byte aligned
     long long in_bstride, in_istride, out_bstride, out_istride;
     int Rm, Rp;
+    // REALOUT, fused kernels only -- routed output (multi-GPU): the output planes (line index idx = z) are cut into slabs
+    // of `rplanes` planes, slab q belongs to rank q and is written straight into that rank's memory (peer pointer over NVLink):
+    // route[q] / route[rranks + q] = address that plane a / plane b of this pair would start at on rank q if the slab buffer held
+    // all planes (owner's row of the slab buffer minus q slabs), 0 = plane not stored.  null: everything goes to outa / outb.
+    const long long* route;
+    int rplanes, rranks;
+    unsigned rmagic;       // floor(2^32 / rplanes) + 1: idx / rplanes == __umulhi(idx, rmagic) for idx < 2^16
     // ---- fused edge stages (fft_lines_fused_kernel): element-wise access from registers
     static constexpr bool FUSED = true;
     struct Acc {
         T m, q;                                            // running max |value| and sum of squares of this thread's plane
         T sa, sb;                                          // plane scales (loaded once)
         T* outp;                                           // this thread's output plane (even line: a, odd line: b), offset to its cell pair
+                                                           // (routed output: the offset alone, as a pointer from null)
         const Cx<T>* inp;                                  // this thread's input column
         unsigned istr, ostr;                               // element strides between line indices (32-bit: every offset is < N^3 <= 2^30)
         int lo_max, hi_min, hi_sub;                        // pruned input: idx <= lo_max -> row idx + Rm; idx >= hi_min -> row idx - hi_sub
@@ -285,9 +293,14 @@ template <typename T, bool PRUNED, bool REALOUT> struct IoCols {
         if (REALOUT) {
             a.sa = scale2 ? (T)scale2[0] : (T)1;
             a.sb = scale2 ? (T)scale2[1] : (T)1;
-            T* pl = (line & 1) ? outb : outa;
-            a.st = a.live && pl != nullptr;
-            a.outp = (pl ? pl : outa) + (long long)blockIdx.y * out_bstride + (l & ~1);
+            if (route) {
+                a.st = a.live && route[(line & 1) ? rranks : 0] != 0;
+                a.outp = static_cast<T*>(nullptr) + ((long long)blockIdx.y * out_bstride + (l & ~1));
+            } else {
+                T* pl = (line & 1) ? outb : outa;
+                a.st = a.live && pl != nullptr;
+                a.outp = (pl ? pl : outa) + (long long)blockIdx.y * out_bstride + (l & ~1);
+            }
         } else {
             a.sa = a.sb = (T)1;
             a.st = a.live;
@@ -322,7 +335,12 @@ template <typename T, bool PRUNED, bool REALOUT> struct IoCols {
                 acc.q += r.a * r.a + r.b * r.b;
                 if (acc.st) {
                     if (halfpack) r = pack_hilo(r);
-                    *reinterpret_cast<Real2<T>*>(acc.outp + (unsigned)idx * acc.ostr) = r;
+                    T* dst = acc.outp + (unsigned)idx * acc.ostr;
+                    if (route) {                           // plane idx lives on rank idx / rplanes
+                        const unsigned q = __umulhi((unsigned)idx, rmagic);
+                        dst = reinterpret_cast<T*>(route[(acc.even ? 0u : (unsigned)rranks) + q] + reinterpret_cast<long long>(dst));
+                    }
+                    *reinterpret_cast<Real2<T>*>(dst) = r;
                 }
             }
         }
@@ -586,6 +604,11 @@ static int launch_any(CFG, const FftPlan& p, int lpc, dim3 grid, const Cx<T>* tw
 {
     if constexpr (CFG::Stages::IS_STATIC) return launch_static<T, DIR, CFG, IO>(grid, tw, io, st);
     else return launch_dyn<T, DIR, IO>(p, lpc, grid, tw, io, st);
+}
+// whether launch_static takes the fused-edge-stage kernel for this configuration (compiled plans with >= 2 stages)
+template <class CFG> static bool plan_is_fused(CFG)
+{
+    if constexpr (CFG::Stages::IS_STATIC) return CFG::Stages::NSTAGES >= 2; else return false;
 }
 template <class CFG> static int cfg_lpc(CFG, const FftPlan& p)
 {

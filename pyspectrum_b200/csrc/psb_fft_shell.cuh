@@ -10,12 +10,13 @@ namespace psb {
 template <typename T>
 int fft_shell_pair(const Cx<float>* half, const unsigned short* irk, int N, int Ns, int sa, int sb, int R,
                    Cx<T>* t1, Cx<T>* t2, T* fa, T* fb, double* sumsq, const float* scale2, unsigned int* maxabs2, int halfpack,
-                   const Cx<T>* tw, cudaStream_t st)
+                   const Cx<T>* tw, cudaStream_t st, const long long* route, int rplanes, int rranks)
 {
     FftPlan p;
     if (N % 2 || !make_plan(N, &p)) return PSB_ERR_UNSUPPORTED_N;
     if (Ns <= 0) Ns = N;
     if (Ns % 2 || Ns < N || (Ns > N && 2 * R >= N)) return PSB_ERR_ARG;      // a coarser transform grid must hold the shells without wrap
+    if (route && (rplanes < 1 || rranks < 1 || rplanes * rranks != N || N >= 65536)) return PSB_ERR_ARG;
     const int Rp = R < N / 2 ? R : N / 2;
     const int Rm = R < (N - 1) / 2 ? R : (N - 1) / 2;
     const int W = Rm + Rp + 1;
@@ -30,7 +31,9 @@ int fft_shell_pair(const Cx<float>* half, const unsigned short* irk, int N, int 
         rc = launch_any<T, -1>(cfg, p, LPC, dim3((N + LPC - 1) / LPC, W), tw, io2, st);
         if (rc) return rc;
         // pass 3 (z): batch = y, T2[kz'][y][x] -> real planes [z][y][x] (+ sums of squares)
-        IoCols<T, true, true> io3{ t2, nullptr, fa, fb, sumsq, scale2, maxabs2, halfpack, N, N, (long long)N * N, N, (long long)N * N, Rm, Rp };
+        IoCols<T, true, true> io3{ t2, nullptr, fa, fb, sumsq, scale2, maxabs2, halfpack, N, N, (long long)N * N, N, (long long)N * N, Rm, Rp,
+                                   route, rplanes, rranks, route ? (unsigned)(4294967296ULL / (unsigned)rplanes) + 1u : 0u };
+        if (route && !plan_is_fused(cfg)) return (int)PSB_ERR_UNSUPPORTED_N;      // routed stores exist in the fused epilogue only
         return launch_any<T, -1>(cfg, p, LPC, dim3((N + LPC - 1) / LPC, N), tw, io3, st);
     });
 }

@@ -39,7 +39,7 @@ int fcomb_standalone(const Cx<float>* full, Cx<float>* half, int N, const Cx<dou
 template <typename T>
 int fft_shell_pair(const Cx<float>* half, const unsigned short* irk, int N, int Ns, int sa, int sb, int R,
                    Cx<T>* t1, Cx<T>* t2, T* fa, T* fb, double* sumsq, const float* scale2, unsigned int* maxabs2, int halfpack,
-                   const Cx<T>* tw, cudaStream_t st);
+                   const Cx<T>* tw, cudaStream_t st, const long long* route = nullptr, int rplanes = 0, int rranks = 0);
 
 struct SpectraIn {
     const Cx<float>* half;       // [kz][ky][kx], ky = ky0 .. ky0+ny-1 (the whole half field: ky0 = 0, ny = N)
