@@ -404,6 +404,8 @@ def run_sharded_config(name, shard, cfg, dev, world, reps=3):
     res = {'config': name, 'n_gpus': world, 'Ngrid': cfg['N'], 'particles': int(out['meta']['N']), 'triangles': int(len(out['b123'])),
            'carrier_grid': Ng, 'shell_grids': [pc.N for pc, _, _, _ in pySpec.PeriodicPipeline.get(Ng).bk_levels(cfg['step'], cfg['Ncut'], cfg['Nmax'])[1]],
            's_per_catalog': red[0] * 1e-3, 'stage_ms_max_over_ranks': stage_ms, 'collectives': coll,
+           'shell_exchange': ('peer stores from inside the K5 z pass (symmetric memory over NVLink)' if 'shell_fields_peer_stores' in nbytes
+                              else 'all_to_all after K5'),
            'mem_gb_max_per_gpu': red[-1], 'counts_float64_once_s': t_counts,
            'api': 'pyspectrum_b200.multigpu.Bk_periodic_sharded(return_pk=True): P(k) + B(k) of one catalogue, particles spread over the ranks',
            'finite': bool(np.all(np.isfinite(out['b123'])) and np.all(np.isfinite(pk['p0k'])))}

@@ -362,11 +362,6 @@ __global__ void __launch_bounds__(256) k_assign_tri(const float4* __restrict__ s
 // particles may overlap freely.  The finished tile leaves with vector reductions whose neighbouring lanes cover neighbouring
 // 16 bytes (full sectors); all-zero pairs are skipped.  The L1 -> L2 reduction traffic that bounded the per-particle scatter
 // (k_assign_tri: ~56 vector reductions per particle) becomes ~2.3 per CELL, independent of the particle density.
-__device__ __forceinline__ void red_add_v2(float* addr, float a, float b)
-{
-    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
-}
-
 __global__ void __launch_bounds__(32 * TILE_WARPS) k_assign_tile(const float4* __restrict__ sorted, const unsigned int* __restrict__ key_end,
                                                                   int N, float kf_ks, float offset, float* mesh, int zbase, int nzs,
                                                                   unsigned int* tile_counter)
@@ -438,30 +433,31 @@ __global__ void __launch_bounds__(32 * TILE_WARPS) k_assign_tile(const float4* _
                 __syncwarp();
             }
         }
-        // ---- flush: 4 rows of 12 cells per step; lane = (row in step, slot): slot 0 = cell ox-1 alone, slots 1..5 = aligned pairs,
-        //      slot 6 = cell ox+10 alone, slot 7 idle.  Array index ix <-> cell ox + ix - 1.
+        // ---- flush: 4 rows of 12 cells per step; lane = (row in step, slot); slot s covers the ALIGNED cell pair ox + 2s - 2, + 1
+        //      = array indices 2s - 1, 2s (index ix <-> cell ox + ix - 1): slot 0 only has its right cell (ox - 1), slot 6 only its
+        //      left one (ox + 10), slot 7 is idle.  Every lane issues the same vector reduction (the missing half adds zero), and all
+        //      wrapping is one modulo per tile and axis plus compare-and-subtract inside the loops (the first version spent as many
+        //      instructions on % N here as the whole particle loop).
         const int fr = lane >> 3, slot = lane & 7;
-        for (int r0 = 0; r0 < AY * AZ; r0 += 4) {
-            const int r = r0 + fr;
-            const int iy = r % AY, iz = r / AY;
-            int zl = wrapN(g.zlo + ozr + iz - 1 - zbase, N);          // plane inside the slab (full grid: zbase = 0, nzs = N)
-            if (slot == 7 || zl >= nzs) continue;
-            const int gy = wrapN(oy + iy - 1, N);
-            const float* ra = tA + iy * SY + iz * SZ;
-            const float* rb = tB + iy * SY + iz * SZ;
-            float* mrow = mesh + ((size_t)zl * N + gy) * (size_t)N * 2;
-            if (slot == 0 || slot == 6) {
-                const int ix = slot == 0 ? 0 : AX - 1;
-                const float va = ra[ix], vb = rb[ix];
-                if (va != 0.f || vb != 0.f) red_add_v2(mrow + 2 * (size_t)wrapN(ox + ix - 1, N), va, vb);
-            } else {
-                const int ix = 2 * slot - 1;                              // cells ox + 2(slot-1), +1: an aligned pair
-                const float a0 = ra[ix], a1 = ra[ix + 1], b0 = rb[ix], b1 = rb[ix + 1];
-                if (a0 != 0.f || a1 != 0.f || b0 != 0.f || b1 != 0.f) {
-                    int cx = ox + ix - 1;
-                    cx = cx >= N ? cx - N : cx;
-                    red_add_v4(mrow + 2 * (size_t)cx, a0, b0, a1, b1);
-                }
+        const bool hasl = slot >= 1 && slot <= 6, hasr = slot <= 5;
+        const int ixl = 2 * slot - 1;
+        const int cxl = wrapN(ox + ixl - 1, N);                          // even: N and ox are
+        const int y0 = wrapN(oy - 1, N), z0 = wrapN(g.zlo + ozr - 1 - zbase, N);      // plane inside the slab (full grid: zbase = 0)
+        const size_t rowf = (size_t)N * 2;
+        for (int iz = 0; iz < AZ; ++iz) {
+            int zl = z0 + iz;
+            zl -= zl >= N ? N : 0;
+            if (zl >= nzs) continue;                                      // warp-uniform
+            float* mz = mesh + (size_t)zl * N * rowf + 2 * cxl;
+#pragma unroll
+            for (int j = 0; j < AY / 4; ++j) {
+                const int iy = 4 * j + fr;
+                int gy = y0 + iy;
+                gy -= gy >= N ? N : 0;
+                const float* ra = tA + iy * SY + iz * SZ + ixl;
+                const float* rb = tB + iy * SY + iz * SZ + ixl;
+                const float a0 = hasl ? ra[0] : 0.f, b0 = hasl ? rb[0] : 0.f, a1 = hasr ? ra[1] : 0.f, b1 = hasr ? rb[1] : 0.f;
+                if (a0 != 0.f || a1 != 0.f || b0 != 0.f || b1 != 0.f) red_add_v4(mz + gy * rowf, a0, b0, a1, b1);
             }
         }
         __syncwarp();

@@ -21,9 +21,12 @@ The slab design of SURVEY 8e; every exchange is a data-plane collective on NVLin
 
 Every kernel is the single-GPU one (K1 with a plane window, K4 with a row window); the collectives are torch.distributed calls so
 the same code runs under NCCL (GPU) and gloo (the CPU tests of the host logic: tests/test_multigpu_host.py).  They are bulk
-exchanges between kernels, not fused with a compute tile.  `stats` dictionaries collect the bytes each collective puts on the wire
+exchanges between kernels, except step 6 under NCCL: there the z pass of K5 stores every output plane straight into the slab
+buffer of the rank that owns it (peer pointers from symmetric memory, `SlabBuffers`), so the exchange rides inside the transform
+and the separate all-to-all disappears (it remains the path for float64 counts, gloo, and grids that do not divide into planes).  `stats` dictionaries collect the bytes each collective puts on the wire
 and, with `timed=True`, its device time (bench.py reports them)."""
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -118,6 +121,86 @@ def exchange_to_slabs(fields_local, world, stats=None):
     dist.all_to_all_single(recv, send)                                                   # recv[q] = rank q's rows of MY slab
     _stats(stats).add_bytes('shell_fields_all_to_all', send.numel() * send.element_size() * (world - 1) // world)
     return recv.view(world * nrow, slab)
+
+
+class SlabBuffers(object):
+    """The slab buffers of one level -- [world*2*per, slab] 32-bit words on every rank -- with every rank holding a device pointer
+    to every other rank's copy, so that K5's z-pass epilogue can store each output plane straight into the memory of the rank that
+    owns it (NVLink peer stores from inside the transform; SURVEY 8e "z-pass epilogue -> peer-memory slab write") instead of
+    writing a local field and exchanging it afterwards.  The buffers come from torch's symmetric memory (CUDA VMM allocations
+    mapped into every process of the group at rendezvous); `barrier()` is its stream-ordered device barrier.
+    `emulated(...)` builds the same object from plain tensors of ONE device (tests: the ranks take turns)."""
+    _cache = {}
+
+    def __init__(self, world, rank, nrow, slab, local, ptrs, handle=None, all_local=None):
+        self.world, self.rank, self.nrow, self.slab = world, rank, nrow, slab
+        self.local, self.ptrs, self.handle, self.all_local = local, [int(p) for p in ptrs], handle, all_local
+        self._tables = {}
+
+    @classmethod
+    def get(cls, dev, world, rank, nrow, slab):
+        """Cached per shape: the rendezvous is a host-synchronising collective.  Raises if symmetric memory is unavailable."""
+        key = (str(dev), world, nrow, slab)
+        if key not in cls._cache:
+            import torch.distributed._symmetric_memory as symm
+            buf = symm.empty((nrow, slab), dtype=torch.float32, device=dev)
+            hdl = symm.rendezvous(buf, dist.group.WORLD)
+            cls._cache[key] = cls(world, rank, nrow, slab, buf, hdl.buffer_ptrs, hdl)
+        return cls._cache[key]
+
+    @classmethod
+    def emulated(cls, dev, world, nrow, slab):
+        bufs = [torch.zeros((nrow, slab), dtype=torch.float32, device=dev) for _ in range(world)]
+        return [cls(world, r, nrow, slab, bufs[r], [b.data_ptr() for b in bufs], None, bufs) for r in range(world)]
+
+    def barrier(self):
+        if self.handle is not None:
+            self.handle.barrier()
+
+    def route(self, per, plist, S, dev):
+        """Route table [len(plist), 2, world] (int64, device) for this rank's pairs `plist` (local pair k = position in the list):
+        entry (k, e, q) = address at which shell e of the pair WOULD start in rank q's buffer if that buffer held the whole field,
+        i.e. row (rank*2*per + 2k + e) of the slab buffer (slab_field_rows) minus the q slabs in front; 0 = not stored."""
+        key = (per, tuple(plist), S)
+        if key not in self._tables:
+            t = np.zeros((len(plist), 2, self.world), np.int64)
+            for k, pidx in enumerate(plist):
+                for e in (0, 1):
+                    if 2 * pidx + e >= S:
+                        continue
+                    row = self.rank * 2 * per + 2 * k + e
+                    for q in range(self.world):
+                        t[k, e, q] = self.ptrs[q] + 4 * (row * self.slab - q * self.slab)
+            self._tables[key] = torch.from_numpy(t).to(dev)
+        return self._tables[key]
+
+
+ROUTED_GRIDS = (24, 32, 36, 48, 64, 128, 256, 320, 360, 400, 512, 1024)      # grids with a compiled multi-stage plan (psb_fft_lines.cuh)
+_ROUTED_BROKEN = []
+
+
+def routed_slabs(dev, world, rank, nrow, slab):
+    """SlabBuffers for the peer-store exchange, or None (PSB_SHARDED_ROUTED=0, or symmetric memory cannot be set up on this
+    system: reported once, the bulk all-to-all is used instead).  Every rank takes the same decision: the outcome of the
+    rendezvous is agreed with an all-reduce."""
+    if world == 1 or os.environ.get('PSB_SHARDED_ROUTED', '1') == '0' or _ROUTED_BROKEN:
+        return None
+    if (str(dev), world, nrow, slab) in SlabBuffers._cache:
+        return SlabBuffers._cache[(str(dev), world, nrow, slab)]
+    ok, bufs = 1, None
+    try:
+        bufs = SlabBuffers.get(dev, world, rank, nrow, slab)
+    except Exception as exc:                             # noqa: BLE001 -- any failure of the VMM / handle exchange
+        ok, err = 0, exc
+    flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) == 0:
+        if not _ROUTED_BROKEN and rank == 0:
+            print('pyspectrum_b200.multigpu: symmetric memory unavailable (%s); shell fields go through all_to_all'
+                  % (repr(err) if not ok else 'on another rank'))
+        _ROUTED_BROKEN.append(True)
+        return None
+    return bufs
 
 
 # ------------------------------------------------------------------------------------------ 1-2: route + slab assignment
@@ -383,17 +466,30 @@ def sharded_triangle_sums(pipe, half, step, Ncut, Nmax, dtype=torch.float32, sta
         mine = deal[rank]
         vol = (float(pipe.N) / pc.N) ** 3
         src = None if pc is pipe else pipe
+        slab = pc.N ** 3 // world
+        bufs = None
+        if not f64 and pc.N % world == 0 and pc.N in ROUTED_GRIDS:      # whole planes per rank: K5 stores into the owners' slab buffers
+            bufs = routed_slabs(pipe.dev, world, rank, world * 2 * per, slab)
         e0 = st.mark()
-        if f64:
-            fields, sq = pc.shell_fields(half, step, s0, smax, dtype=torch.float64, pairs=mine, src=src)
-            sc_rows = mx = None
+        if bufs is not None:
+            bufs.barrier()                               # every rank is done with the previous contents of the buffers
+            _, sq, sc_rows, mx = pc.shell_fields(half, step, s0, smax, scaled=True, pairs=mine, scales=scales, src=src,
+                                                 routed=(bufs.route(per, mine, Sl, pipe.dev), pc.N // world, world))
+            bufs.barrier()                               # every rank's planes have landed
+            slabs = bufs.local
+            st.span('shell_fields_peer_stores', e0)
+            st.add_bytes('shell_fields_peer_stores', 4 * sum(1 for q in mine for e in (0, 1) if 2 * q + e < Sl) * slab * (world - 1))
         else:
-            fields, sq, sc_rows, mx = pc.shell_fields(half, step, s0, smax, scaled=True, pairs=mine, scales=scales, src=src)
-        st.span('shell_fields', e0)
-        e0 = st.mark()
-        slabs = exchange_to_slabs(fields, world, st)
-        del fields
-        st.span('shell_fields_all_to_all', e0)
+            if f64:
+                fields, sq = pc.shell_fields(half, step, s0, smax, dtype=torch.float64, pairs=mine, src=src)
+                sc_rows = mx = None
+            else:
+                fields, sq, sc_rows, mx = pc.shell_fields(half, step, s0, smax, scaled=True, pairs=mine, scales=scales, src=src)
+            st.span('shell_fields', e0)
+            e0 = st.mark()
+            slabs = exchange_to_slabs(fields, world, st)
+            del fields
+            st.span('shell_fields_all_to_all', e0)
         rows = slab_field_rows(Sl, world, per)
         use_tc = (not f64) and slabs.shape[1] % 64 == 0 and Sl <= 128
         e0 = st.mark()

@@ -587,7 +587,7 @@ class PeriodicPipeline(object):
               'psb_bk_shell_scales')
         return scales
 
-    def shell_fields(self, half, step, s0, Nmax, dtype=torch.float32, scaled=False, pairs=None, scales=None, src=None):
+    def shell_fields(self, half, step, s0, Nmax, dtype=torch.float32, scaled=False, pairs=None, scales=None, src=None, routed=None):
         """K5: shells s0..Nmax as real fields [S_alloc, N^3] + sum_x I_j^2 per shell.
         half=None -> delta == 1 (counts).  Two shells ride on one complex transform.
         scaled=True stores I_j * scale_j with scale_j an exact power of two putting the rms near 2 (from the
@@ -598,7 +598,11 @@ class PeriodicPipeline(object):
         pairs: optional list of pair indices p (shells s0+2p, s0+2p+1) to compute -- the multi-GPU path shards shells this way;
         the returned fields then hold only those pairs, in the given order (2 rows per pair), sumsq/maxabs likewise.
         src: the pipeline (finer grid) `half` was measured on, if not this one: the shells are then transformed on THIS coarser
-        grid -- the same band-limited fields at fewer points (needs 2*floor(step*(Nmax+1/2)) < N; see `coarse_levels`)."""
+        grid -- the same band-limited fields at fewer points (needs 2*floor(step*(Nmax+1/2)) < N; see `coarse_levels`).
+        routed: (device int64 tensor [len(pairs), 2, nranks], planes per rank, nranks) -- multi-GPU: the z pass writes every output
+        plane straight into the slab buffer of the rank that owns it (psb_bk_shell_pair_f32_routed; the table holds, per local
+        pair, shell of the pair and rank, the address the field would start at in that rank's buffer, see
+        multigpu.SlabBuffers.route); no field tensor is allocated or returned (fields = None)."""
         N = self.N
         Ns = N if src is None else src.N
         if Ns != N and (Ns < N or 2 * int(np.floor(step * (Nmax + 0.5))) >= N):
@@ -609,7 +613,9 @@ class PeriodicPipeline(object):
         f64 = dtype == torch.float64
         plist = list(range(S_alloc // 2)) if pairs is None else list(pairs)
         nrow = 2 * len(plist)
-        fields = torch.empty((nrow, ncell), dtype=dtype, device=self.dev)
+        if routed is not None and (f64 or not scaled):
+            raise ValueError('routed output exists for the scaled float32 fields only')
+        fields = None if routed is not None else torch.empty((nrow, ncell), dtype=dtype, device=self.dev)
         sumsq = torch.zeros(nrow, dtype=torch.float64, device=self.dev)
         maxabs = None
         st = _stream()
@@ -633,7 +639,8 @@ class PeriodicPipeline(object):
         for r, pidx in enumerate(plist):
             s = 2 * pidx
             if s >= S:                                   # padding pair (shard equalisation): empty shells -> zero fields
-                fields[2 * r:2 * r + 2].zero_()
+                if fields is not None:
+                    fields[2 * r:2 * r + 2].zero_()
                 continue
             sa = s0 + s
             sb = sa + 1 if s + 1 < S else -1
@@ -642,6 +649,13 @@ class PeriodicPipeline(object):
             if f64:
                 check(self.L.psb_bk_shell_pair_f64(_ptr(half), _ptr(irk), N, Ns, sa, sb, R, _ptr(t1), _ptr(t2), _ptr(fields[2 * r]),
                                                    _ptr(fields[2 * r + 1]), sq, _ptr(tw), st), 'psb_bk_shell_pair_f64')
+            elif routed is not None:
+                table, rplanes, rranks = routed
+                check(self.L.psb_bk_shell_pair_f32_routed(_ptr(half), _ptr(irk), N, Ns, sa, sb, R, _ptr(t1), _ptr(t2),
+                                                          ctypes.c_void_p(table.data_ptr() + 8 * 2 * rranks * r), rplanes, rranks, sq,
+                                                          ctypes.c_void_p(sc_local.data_ptr() + 4 * 2 * r),
+                                                          ctypes.c_void_p(maxabs.data_ptr() + 4 * 2 * r), 1, _ptr(tw), st),
+                      'psb_bk_shell_pair_f32_routed')
             else:
                 sc = mx = None
                 if scaled:
@@ -651,7 +665,8 @@ class PeriodicPipeline(object):
                                                    _ptr(fields[2 * r + 1]), sq, sc, mx, 1 if scaled else 0, _ptr(tw), st),
                       'psb_bk_shell_pair_f32')
         if scaled:
-            fields.psb_packed = True                     # rows hold {half2 hi, half2 lo} per cell pair (see unpack_fields)
+            if fields is not None:
+                fields.psb_packed = True                 # rows hold {half2 hi, half2 lo} per cell pair (see unpack_fields)
             return fields, sumsq, sc_local, maxabs
         return fields, sumsq
 
@@ -850,9 +865,14 @@ class PeriodicPipeline(object):
         N = self.N
         fcnt = ''.join(['counts', '.Ngrid', str(N), '.Nmax', str(Nmax), '.Ncut', str(Ncut), '.step', str(step), '.', fft])
         f_counts = os.path.join(dat_dir(), fcnt)
+        counts = None
         if os.path.isfile(f_counts):
-            counts = _read_fortran_record(f_counts, Nmax)
-        else:
+            try:
+                counts = _read_fortran_record(f_counts, Nmax)
+            except ValueError as exc:                    # truncated / foreign file: recompute and replace it
+                if not silent:
+                    print('--- ignoring %s (%s) ---' % (f_counts, exc))
+        if counts is None:
             if not silent:
                 print('--- calculating %s ---' % f_counts)
             counts = self.compute_counts(Nmax, Ncut, step)
@@ -887,10 +907,11 @@ class PeriodicPipeline(object):
 
 def _read_fortran_record(fname, Nmax):
     """One Fortran sequential record of Nmax^3 float64 (scipy.io.FortranFile.read_reals, py:970-972)."""
-    raw = np.fromfile(fname, dtype=np.uint8)
-    n = int(np.frombuffer(raw[:4].tobytes(), '<i4')[0])
-    data = np.frombuffer(raw[4:4 + n].tobytes(), '<f8')
-    return data.reshape(Nmax, Nmax, Nmax).copy()
+    from .util import fortran_records
+    recs = fortran_records(fname)
+    if len(recs) != 1 or len(recs[0]) != 8 * Nmax ** 3:
+        raise ValueError('%s: expected one record of %d float64' % (fname, Nmax ** 3))
+    return np.frombuffer(recs[0], '<f8').reshape(Nmax, Nmax, Nmax).copy()
 
 
 def _write_fortran_record(fname, counts):

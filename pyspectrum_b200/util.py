@@ -132,15 +132,44 @@ def applyRSD(xyz, vxyz, redshift, h=0.7, omega0_m=0.3, LOS=None, Lbox=None):
     return xyz_rsd
 
 
+def fortran_records(path):
+    """Logical records of a Fortran sequential unformatted file with 4-byte markers (gfortran / ifort default) as a list of
+    byte strings.  Every (sub)record is `marker | payload | marker`; gfortran splits records of 2 GiB or more into subrecords:
+    a negative leading marker says another subrecord follows, the trailing marker repeats the length (negative if a subrecord
+    precedes).  Raises ValueError on a truncated file or markers that do not match."""
+    raw = np.fromfile(path, dtype=np.uint8)
+    out, parts, o = [], [], 0
+    while o < raw.size:
+        if o + 4 > raw.size:
+            raise ValueError('%s: truncated record marker at byte %d' % (path, o))
+        head = int(raw[o:o + 4].view('<i4')[0])
+        n = abs(head)
+        if o + 8 + n > raw.size:
+            raise ValueError('%s: record of %d bytes at byte %d runs past the end of the file' % (path, n, o))
+        tail = int(raw[o + 4 + n:o + 8 + n].view('<i4')[0])
+        if abs(tail) != n:
+            raise ValueError('%s: record markers disagree (%d vs %d) at byte %d' % (path, head, tail, o))
+        parts.append(raw[o + 4:o + 4 + n])
+        o += 8 + n
+        if head >= 0:                                    # last subrecord of this logical record
+            out.append(parts[0].tobytes() if len(parts) == 1 else np.concatenate(parts).tobytes())
+            parts = []
+    if parts:
+        raise ValueError('%s: file ends inside a split record' % path)
+    return out
+
+
 def read_fortFFT(file=None):
     """util.py:78-107: read `Ngrid` + the (Ngrid/2+1, Ngrid, Ngrid) complex64 half field from a Fortran-unformatted file
     and return the full Hermitian field (same completion as pyspectrum.reflect_delta)."""
     from .pyspectrum import reflect_delta
-    raw = np.fromfile(file, dtype=np.uint8)
-    n1 = int(np.frombuffer(raw[:4].tobytes(), '<i4')[0])
-    Ngrid = int(np.frombuffer(raw[4:4 + n1].tobytes(), '<i4')[0])
-    o = 4 + n1 + 4
-    n2 = int(np.frombuffer(raw[o:o + 4].tobytes(), '<i4')[0])
-    delt = np.frombuffer(raw[o + 4:o + 4 + n2].tobytes(), '<c8')
+    recs = fortran_records(file)
+    if len(recs) < 2 or len(recs[0]) < 4:
+        raise ValueError('%s: expected a record with Ngrid and a record with the half field' % file)
+    Ngrid = int(np.frombuffer(recs[0][:4], '<i4')[0])
+    want = 8 * (Ngrid // 2 + 1) * Ngrid * Ngrid
+    if len(recs[1]) != want:
+        raise ValueError('%s: the field record holds %d bytes, Ngrid=%d needs %d' % (file, len(recs[1]), Ngrid, want))
+    delt = np.frombuffer(recs[1], '<c8')
     delt = np.reshape(delt, (Ngrid // 2 + 1, Ngrid, Ngrid), order='F')
     return reflect_delta(delt, Ngrid=Ngrid)

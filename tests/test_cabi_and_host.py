@@ -101,6 +101,30 @@ def test_fortran_record_roundtrip_and_reflect_delta(tmp_path):
     assert np.array_equal(P.reflect_delta(d, Ngrid=N), O.reflect_delta(d, N))
 
 
+def test_fortran_records_are_validated(tmp_path):
+    """Record markers are checked (a truncated or foreign counts cache is refused, not reshaped), and gfortran's subrecords
+    (records of 2 GiB or more: negative leading marker = continued) are joined."""
+    from pyspectrum_b200 import pyspectrum as P, util as UT
+    c = np.arange(27, dtype='<f8').reshape(3, 3, 3)
+    f = str(tmp_path / 'counts.ok')
+    P._write_fortran_record(f, c)
+    raw = open(f, 'rb').read()
+    for bad in (raw[:-5], raw[:-4] + b'\x01\x00\x00\x00', raw[:40]):          # truncated, trailing marker differs, cut short
+        g = str(tmp_path / 'counts.bad')
+        open(g, 'wb').write(bad)
+        with pytest.raises(ValueError):
+            P._read_fortran_record(g, 3)
+    with pytest.raises(ValueError):
+        P._read_fortran_record(f, 4)                                             # a file for another Nmax
+    b = c.tobytes()
+    m = lambda v: np.array([v], '<i4').tobytes()
+    split = m(-104) + b[:104] + m(104) + m(112) + b[104:] + m(-112)            # two subrecords of one logical record
+    g = str(tmp_path / 'counts.split')
+    open(g, 'wb').write(split)
+    assert UT.fortran_records(g) == [b]
+    assert np.array_equal(P._read_fortran_record(g, 3), c)
+
+
 def test_api_signatures_match_reference():
     import inspect
     from pyspectrum_b200 import pyspectrum as P

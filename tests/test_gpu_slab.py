@@ -191,3 +191,46 @@ def test_sharded_entry_points_on_one_rank(mods, monkeypatch, tmp_path):
     b = pySpec.Pk_periodic_rsd(xyz, Lbox=500., Ngrid=64, rsd=2, Nmubin=5)
     assert np.array_equal(a['counts'], b['counts']) and np.array_equal(a['counts_kmu'], b['counts_kmu'])
     np.testing.assert_allclose(a['p0k'] + a['p_sn'], b['p0k'] + b['p_sn'], rtol=1e-5)
+
+
+@pytest.mark.parametrize('N,Ns,world,step,smax', [(64, 64, 2, 2, 13), (64, 64, 4, 2, 12), (48, 48, 3, 1, 9), (256, 360, 8, 3, 9), (360, 360, 4, 3, 6)])
+def test_routed_shell_planes_land_where_the_all_to_all_puts_them(mods, N, Ns, world, step, smax):
+    """K5 with routed output (psb_bk_shell_pair_f32_routed): every emulated rank transforms its dealt pairs and stores each plane
+    through the route table into the slab buffer of the plane's owner (here: `world` buffers of one device standing in for the
+    peers' symmetric memory).  The buffers must equal, bit for bit, what the local fields + the all-to-all deliver (same kernel,
+    only the store address differs), shell powers and max|I| included; rows of padding pairs / missing shells stay untouched."""
+    import torch
+    pySpec, M = mods
+    src = pySpec.PeriodicPipeline.get(Ns)
+    pc = pySpec.PeriodicPipeline.get(N)
+    h = Ns // 2
+    g = torch.Generator(device='cuda').manual_seed(N + world)
+    half = torch.randn((Ns, Ns, h + 1, 2), device='cuda', dtype=torch.float32, generator=g)
+    s0 = 1
+    Sl = smax - s0 + 1
+    scales = src.shell_scales(half, step, s0, smax)
+    deal, per = M.pair_assignment((Sl + 1) // 2, world)
+    slab = N ** 3 // world
+    M.check_cell_slabs(N ** 3, world)
+    ranks = M.SlabBuffers.emulated(pc.dev, world, world * 2 * per, slab)
+    for b in ranks:
+        b.local.fill_(-7.0)
+    other = None if Ns == N else src
+    for r in range(world):
+        table = ranks[r].route(per, deal[r], Sl, pc.dev)
+        none, sq, sc, mx = pc.shell_fields(half, step, s0, smax, scaled=True, pairs=deal[r], scales=scales, src=other,
+                                           routed=(table, N // world, world))
+        assert none is None
+        fields, sq_ref, sc_ref, mx_ref = pc.shell_fields(half, step, s0, smax, scaled=True, pairs=deal[r], scales=scales, src=other)
+        assert torch.equal(sq, sq_ref) and torch.equal(mx, mx_ref) and torch.equal(sc, sc_ref)
+        for k, pidx in enumerate(deal[r]):
+            for e in (0, 1):
+                row = r * 2 * per + 2 * k + e
+                for q in range(world):
+                    got = ranks[q].local[row].view(torch.int32)
+                    if 2 * pidx + e < Sl:
+                        assert torch.equal(got, fields[2 * k + e, q * slab:(q + 1) * slab].view(torch.int32)), (r, k, e, q)
+                    else:
+                        assert bool((ranks[q].local[row] == -7.0).all())
+    rows = M.slab_field_rows(Sl, world, per)
+    assert sorted(set(rows)) == sorted(rows) and max(rows) < world * 2 * per
