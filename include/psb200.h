@@ -218,13 +218,23 @@ int psb_bk_triangle_sums_tc(const float* const* fields, int nshell, int64_t ncel
 /* host helper: triangle list [ntri][3] (shell indices i,j,l) -> tile descriptors; tiles == NULL only sizes */
 int psb_bk_build_tiles(const int32_t* tri_ijl, int ntri, int s0, int32_t* tiles, int* ntiles);
 
+/* Quadrupole-field pieces on DEVICE arrays.
+ *   psb_quad_weights: we[i] of estimator.f:294-300 from r = Fortran (3,np) float32 and w; feed `we` to psb_assign_pcs_interlaced.
+ *   psb_quad_fields:  mode 1 FiveDelta2g_1 (out=dcgxx, a=dcgyy, b=dcgzz), mode 2 FiveDelta2g_2 (out=dcgxx, a=dcg, b=dcgxy, c=dcgyz,
+ *                     d=dcgzx), mode 3 build_quad (out=dclr2, a=dclr1, irsd 1..3); half arrays [kz][ky][kx<=N/2] complex64. */
+int psb_quad_weights(const float* r_aos, const float* w, int64_t np, int ia, int ib, int ic, int id, float* we, void* stream);
+int psb_quad_fields(int mode, const float* a_c64, const float* b_c64, const float* c_c64, const float* d_c64, float* out_c64,
+                    int ngrid, int irsd, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Host-buffer drop-ins: the f2py signatures of `estimator` (f2py -h, SURVEY 8b level 2).
  * All arrays are HOST memory in Fortran order exactly as f2py would hand them to the Fortran.
  * ---------------------------------------------------------------------------------------------- */
 /* assign_quad(r,w,dtl,kf_ks,offset,ia,ib,ic,id,[np,ngrid])   estimator.f:284
  *   r (3,np) float32, w (np) float32, dtl (2*ngrid,ngrid,ngrid) float32 intent(inout).
- *   Only ia=ib=ic=id=0 (the delta branch, the only one the periodic path uses) is implemented. */
+ *   ia=ib=ic=id=0: the delta branch (f:292-293); ia,ib in 1..3 with ic=id=0: Q_ij weights w r_ia r_ib / r^2 (f:294-296);
+ *   all four in 1..3: Q_ijkl weights w r_ia r_ib r_ic r_id / r^4 (f:297-299).  Any other combination indexes r(0,i) in the
+ *   Fortran (undefined) and returns PSB_ERR_ARG here. */
 int psb_host_assign_quad(const float* r, const float* w, float* dtl, int64_t np, int ngrid,
                          float kf_ks, float offset, int ia, int ib, int ic, int id);
 /* fcomb_periodic(dcl,n,[ngrid]) estimator.f:605; fcomb_survey(dcl,[ngrid]) estimator.f:677; in place,
@@ -238,6 +248,14 @@ int psb_host_ffting(float* dtl_c64, int ngrid);
 int psb_host_pk_pbox_rsd(const float* dtl_c64, double* k, double* p0, double* p2, double* p4, double* nk,
                          double* km, double* mk, double* pkm, double* nkm,
                          int irsd, int lbox, int nbin, int nmu, int ngrid);
+/* FiveDelta2g_1(dcgxx,dcgyy,dcgzz,ngrid) estimator.f:514, FiveDelta2g_2(dcg,dcgxx,dcgxy,dcgyz,dcgzx,ngrid) estimator.f:541,
+ * build_quad(dclr1,dclr2,irsd,ngrid) estimator.f:574: (ngrid/2+1,ngrid,ngrid) complex64 arrays; dcgxx / dclr2 are intent(inout).
+ * Reproduced as written, including the implicitly INTEGER unit-vector components of FiveDelta2g_* (see psb_quad.cu);
+ * irsd outside 1..3 (the Fortran stops) returns PSB_ERR_ARG. */
+int psb_host_fivedelta2g_1(float* dcgxx_c64, const float* dcgyy_c64, const float* dcgzz_c64, int ngrid);
+int psb_host_fivedelta2g_2(const float* dcg_c64, float* dcgxx_c64, const float* dcgxy_c64, const float* dcgyz_c64,
+                           const float* dcgzx_c64, int ngrid);
+int psb_host_build_quad(const float* dclr1_c64, float* dclr2_c64, int irsd, int ngrid);
 /* bk_counts(coun,nside,step,ncut,[nmax])  estimator.f:2: coun (nmax,nmax,nmax) float64 F-order, filled for
  * ncut/step <= i <= j <= l with sum_x N_i N_j N_l = nside^3 * (exact integer; computed in float64). */
 int psb_host_bk_counts(double* coun, int nside, float step, int ncut, int nmax);

@@ -310,3 +310,60 @@ double oracle_triple_sum_f32(const float *a, const float *b, const float *c, int
     for (; i < n; ++i) t += (double)a[i] * (double)b[i] * (double)c[i];
     return t;
 }
+
+
+/* ---------------------------------------------------------------------------------------------
+ * estimator.f:514-603: FiveDelta2g_1, FiveDelta2g_2, build_quad on (Ngrid/2+1,Ngrid,Ngrid) complex arrays (x fastest).
+ * The file has no `implicit none`: kxh, kyh, kzh are undeclared, start with `k`, and are therefore INTEGER -- the quotient
+ * float(ikx)/rk is truncated on assignment (f:531-533, 563-565).  `amu` in build_quad is declared real (f:578).
+ * mode 1: out = dcgxx, a = dcgyy, b = dcgzz;  mode 2: out = dcgxx, a = dcg, b = dcgxy, c = dcgyz, d = dcgzx;
+ * mode 3: out = dclr2, a = dclr1, irsd in 1..3 (anything else: the Fortran stops; here: nothing is written). */
+static inline int signed_k(int i0, int N) { return (i0 + N / 2 - 1) % N - N / 2 + 1; }      /* f:524 with i = i0 + 1 */
+
+void oracle_quad_fields(int mode, const float *a_, const float *b_, const float *c_, const float *d_, float *out_, int N, int irsd)
+{
+    const cf32 *a = (const cf32 *)a_, *b = (const cf32 *)b_, *c = (const cf32 *)c_, *d = (const cf32 *)d_;
+    cf32 *out = (cf32 *)out_;
+    const int hx = N / 2 + 1;
+    if (mode == 3 && (irsd < 1 || irsd > 3)) return;
+    for (int iz = 0; iz < N; ++iz)
+        for (int iy = 0; iy < N; ++iy)
+            for (int ix = 0; ix < hx; ++ix) {
+                const int64_t e = ((int64_t)iz * N + iy) * hx + ix;
+                const int ikx = signed_k(ix, N), iky = signed_k(iy, N), ikz = signed_k(iz, N);
+                const float rk = sqrtf((float)(ikx * ikx + iky * iky + ikz * ikz));
+                if (!(rk > 0.f)) continue;
+                if (mode == 3) {
+                    const float amu = (float)(irsd == 3 ? ikz : (irsd == 2 ? iky : ikx)) / rk;
+                    const float amu2 = amu * amu;
+                    const float t = 7.5f * amu2;
+                    const float fac = t - 2.5f;
+                    out[e].re = fac * a[e].re; out[e].im = fac * a[e].im;
+                    continue;
+                }
+                const int kxh = (int)((float)ikx / rk), kyh = (int)((float)iky / rk), kzh = (int)((float)ikz / rk);
+                if (mode == 1) {
+                    const float sx = (float)(kxh * kxh), sy = (float)(kyh * kyh), sz = (float)(kzh * kzh);
+                    cf32 s = { out[e].re * sx, out[e].im * sx };
+                    cf32 t = { a[e].re * sy, a[e].im * sy };
+                    s = caddf_(s, t);
+                    t.re = b[e].re * sz; t.im = b[e].im * sz;
+                    s = caddf_(s, t);
+                    out[e].re = 7.5f * s.re; out[e].im = 7.5f * s.im;
+                } else {
+                    const cf32 *src[3] = { b, c, d };
+                    const int f1[3] = { kxh, kyh, kzh }, f2[3] = { kyh, kzh, kxh };
+                    cf32 s = { 0.f, 0.f };
+                    for (int q = 0; q < 3; ++q) {
+                        cf32 t = { 2.f * src[q][e].re, 2.f * src[q][e].im };
+                        t.re = t.re * (float)f1[q]; t.im = t.im * (float)f1[q];
+                        t.re = t.re * (float)f2[q]; t.im = t.im * (float)f2[q];
+                        s = q == 0 ? t : caddf_(s, t);
+                    }
+                    cf32 u = { 7.5f * s.re, 7.5f * s.im };
+                    u = caddf_(out[e], u);
+                    cf32 v = { 2.5f * a[e].re, 2.5f * a[e].im };
+                    out[e] = csubf_(u, v);
+                }
+            }
+}

@@ -78,6 +78,8 @@ def lib():
         L.oracle_fcomb.restype = None
         L.oracle_pk_pbox_rsd.argtypes = [fp] + [dp] * 9 + [ctypes.c_int] * 5
         L.oracle_pk_pbox_rsd.restype = None
+        L.oracle_quad_fields.argtypes = [ctypes.c_int, fp, fp, fp, fp, fp, ctypes.c_int, ctypes.c_int]
+        L.oracle_quad_fields.restype = None
         L.oracle_triple_sum_f32.argtypes = [fp, fp, fp, ctypes.c_int64]
         L.oracle_triple_sum_f32.restype = ctypes.c_double
         _LIB = L
@@ -118,6 +120,31 @@ def fcomb_survey(dcl, ngrid=None):
     if not (dcl.dtype == np.complex64 and dcl.flags.f_contiguous):
         raise ValueError('dcl must be complex64 Fortran-contiguous (intent inout)')
     lib().oracle_fcomb(_fptr(dcl), np.float32(1.0), dcl.shape[0], 0)
+
+
+def _quad(mode, ins, out, irsd=0):
+    if not (out.dtype == np.complex64 and out.flags.f_contiguous):
+        raise ValueError('the intent(inout) array must be complex64 Fortran-contiguous')
+    N = out.shape[1]
+    ins = [np.asfortranarray(a, dtype=np.complex64) for a in ins]
+    assert all(a.shape == out.shape == (N // 2 + 1, N, N) for a in ins)
+    ptrs = [_fptr(a) for a in ins] + [None] * (4 - len(ins))
+    lib().oracle_quad_fields(mode, ptrs[0], ptrs[1], ptrs[2], ptrs[3], _fptr(out), N, int(irsd))
+
+
+def fivedelta2g_1(dcgxx, dcgyy, dcgzz, ngrid=None):
+    """estimator.f:514-539."""
+    _quad(1, [dcgyy, dcgzz], dcgxx)
+
+
+def fivedelta2g_2(dcg, dcgxx, dcgxy, dcgyz, dcgzx, ngrid=None):
+    """estimator.f:541-572."""
+    _quad(2, [dcg, dcgxy, dcgyz, dcgzx], dcgxx)
+
+
+def build_quad(dclr1, dclr2, irsd, ngrid=None):
+    """estimator.f:574-603."""
+    _quad(3, [dclr1], dclr2, irsd)
 
 
 def pk_pbox_rsd(dtl, irsd, lbox, nbin, nmu, ngrid=None):

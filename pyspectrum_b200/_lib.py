@@ -82,6 +82,11 @@ PROTOTYPES = {
     'psb_host_ffting': (_i, [_vp, _i]),
     'psb_host_pk_pbox_rsd': (_i, [_vp] * 10 + [_i] * 5),
     'psb_host_bk_counts': (_i, [_vp, _i, _f, _i, _i]),
+    'psb_host_fivedelta2g_1': (_i, [_vp, _vp, _vp, _i]),
+    'psb_host_fivedelta2g_2': (_i, [_vp, _vp, _vp, _vp, _vp, _i]),
+    'psb_host_build_quad': (_i, [_vp, _vp, _i, _i]),
+    'psb_quad_weights': (_i, [_vp, _vp, _i64, _i, _i, _i, _i, _vp, _vp]),
+    'psb_quad_fields': (_i, [_i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
 }
 
 

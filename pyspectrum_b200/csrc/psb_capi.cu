@@ -363,18 +363,74 @@ int psb_host_assign_quad(const float* r, const float* w, float* dtl, int64_t np,
                          int ia, int ib, int ic, int id)
 {
     if (!r || !w || !dtl || np < 0) return PSB_ERR_ARG;
-    if (ia || ib || ic || id) return PSB_ERR_ARG;       // Q_ij / Q_ijkl variants: survey-only, out of scope
+    const bool quad = ia || ib || ic || id;
     const size_t nmesh = 2 * (size_t)N * N * N;
-    DevBuf dr, dw, dm, dws, ds;
+    DevBuf dr, dw, dm, dws, ds, dq;
     const size_t wsb = assign_workspace_bytes(np, N);
     PSB_TRY(dr.alloc(sizeof(float) * 3 * np)); PSB_TRY(dw.alloc(sizeof(float) * np)); PSB_TRY(dm.alloc(sizeof(float) * nmesh));
     PSB_TRY(dws.alloc(wsb)); PSB_TRY(ds.alloc(sizeof(double)));
     PSB_CUDA(cudaMemcpy(dr.p, r, sizeof(float) * 3 * np, cudaMemcpyHostToDevice));
     PSB_CUDA(cudaMemcpy(dw.p, w, sizeof(float) * np, cudaMemcpyHostToDevice));
     PSB_CUDA(cudaMemcpy(dm.p, dtl, sizeof(float) * nmesh, cudaMemcpyHostToDevice));
-    PSB_TRY(psb_assign_pcs_interlaced(dr.p, 0, 1, dw.p, 0, np, N, 0.0, kf_ks, offset, dm.as<float>(), 0, dws.p, wsb, ds.as<double>(), nullptr));
+    const void* wdev = dw.p;
+    if (quad) {                                          // f:294-300: the weight becomes w r_ia r_ib / r^2 (or the four-index form)
+        PSB_TRY(dq.alloc(sizeof(float) * np));
+        PSB_TRY(quad_weights(dr.as<float>(), dw.as<float>(), np, ia, ib, ic, id, dq.as<float>(), nullptr));
+        wdev = dq.p;
+    }
+    PSB_TRY(psb_assign_pcs_interlaced(dr.p, 0, 1, wdev, 0, np, N, 0.0, kf_ks, offset, dm.as<float>(), 0, dws.p, wsb, ds.as<double>(), nullptr));
     PSB_CUDA(cudaMemcpy(dtl, dm.p, sizeof(float) * nmesh, cudaMemcpyDeviceToHost));
     return PSB_OK;
+}
+
+int psb_quad_weights(const float* r, const float* w, int64_t np, int ia, int ib, int ic, int id, float* we, void* stream)
+{
+    return quad_weights(r, w, np, ia, ib, ic, id, we, S(stream));
+}
+
+int psb_quad_fields(int mode, const float* a, const float* b, const float* c, const float* d, float* out, int N, int irsd, void* stream)
+{
+    return quad_fields(mode, reinterpret_cast<const Cx<float>*>(a), reinterpret_cast<const Cx<float>*>(b), reinterpret_cast<const Cx<float>*>(c),
+                       reinterpret_cast<const Cx<float>*>(d), reinterpret_cast<Cx<float>*>(out), N, irsd, S(stream));
+}
+
+// host arrays (ngrid/2+1,ngrid,ngrid) complex64 F-order: in[k] may be null; `out` is uploaded, combined in place and read back
+static int host_quad_fields(int mode, const float* const in[4], float* out, int N, int irsd)
+{
+    if (!out || N < 2 || N % 2) return PSB_ERR_ARG;
+    const size_t nb = 8 * (size_t)(N / 2 + 1) * N * N;
+    DevBuf din[4], dout;
+    PSB_TRY(dout.alloc(nb));
+    PSB_CUDA(cudaMemcpy(dout.p, out, nb, cudaMemcpyHostToDevice));
+    for (int k = 0; k < 4; ++k) {
+        if (!in[k]) continue;
+        PSB_TRY(din[k].alloc(nb));
+        PSB_CUDA(cudaMemcpy(din[k].p, in[k], nb, cudaMemcpyHostToDevice));
+    }
+    PSB_TRY(psb_quad_fields(mode, din[0].as<float>(), din[1].as<float>(), din[2].as<float>(), din[3].as<float>(), dout.as<float>(), N, irsd, nullptr));
+    PSB_CUDA(cudaMemcpy(out, dout.p, nb, cudaMemcpyDeviceToHost));
+    return PSB_OK;
+}
+
+int psb_host_fivedelta2g_1(float* xx, const float* yy, const float* zz, int N)
+{
+    if (!yy || !zz) return PSB_ERR_ARG;
+    const float* in[4] = { yy, zz, nullptr, nullptr };
+    return host_quad_fields(1, in, xx, N, 0);
+}
+
+int psb_host_fivedelta2g_2(const float* dcg, float* xx, const float* xy, const float* yz, const float* zx, int N)
+{
+    if (!dcg || !xy || !yz || !zx) return PSB_ERR_ARG;
+    const float* in[4] = { dcg, xy, yz, zx };
+    return host_quad_fields(2, in, xx, N, 0);
+}
+
+int psb_host_build_quad(const float* d1, float* d2, int irsd, int N)
+{
+    if (!d1) return PSB_ERR_ARG;
+    const float* in[4] = { d1, nullptr, nullptr, nullptr };
+    return host_quad_fields(3, in, d2, N, irsd);
 }
 
 static int host_fcomb(float* dcl, float n, int N, int periodic)

@@ -83,6 +83,11 @@ int slab_split_ab(const Cx<float>* d, Cx<float>* P, Cx<float>* Q, int N, int nz,
 int slab_fcomb(const Cx<float>* P, const Cx<float>* Q, Cx<float>* half, int N, int ky0, int ny, int hp, const Cx<double>* rec,
                const float* Wk, const double* sumw, int periodic, cudaStream_t st);
 
+// quadrupole-field pieces (psb_quad.cu): Q_ij / Q_ijkl particle weights (f:294-300), FiveDelta2g_1 / _2 / build_quad (f:514-603)
+int quad_weights(const float* r, const float* w, long long np, int ia, int ib, int ic, int id, float* we, cudaStream_t st);
+int quad_fields(int mode, const Cx<float>* a, const Cx<float>* b, const Cx<float>* c, const Cx<float>* d, Cx<float>* out, int N, int irsd,
+                cudaStream_t st);
+
 // survey-geometry catalogue pre-step (psb_survey.cu)
 int survey_prepare(const double* radecz, const double* nb, const double* w, long long np, const double* tab, int nn, double zmax,
                    double p0_fkp, float* xyz, float* wout, double* out12, cudaStream_t st);

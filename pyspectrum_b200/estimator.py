@@ -9,6 +9,9 @@ Fortran-order requirements and in-place semantics as the f2py wrappers (`f2py -h
     ffting(dtl,n,[ngrid])                                             estimator.f:266
     k,p0,p2,p4,nk,km,mk,pkm,nkm = pk_pbox_rsd(dtl,irsd,lbox,nbin,nmu,[ngrid])   estimator.f:155
     bk_counts(coun,nside,step,ncut,[nmax])                            estimator.f:2
+    fivedelta2g_1(dcgxx,dcgyy,dcgzz,[ngrid])                          estimator.f:514   (f2py lower-cases the names; the
+    fivedelta2g_2(dcg,dcgxx,dcgxy,dcgyz,dcgzx,[ngrid])                estimator.f:541    CamelCase spellings of py:1106, 1130
+    build_quad(dclr1,dclr2,irsd,[ngrid])                              estimator.f:574    are kept as aliases)
 """
 import ctypes
 
@@ -81,3 +84,44 @@ def bk_counts(coun, nside, step, ncut, nmax=None):
     if coun.shape != (nmax, nmax, nmax):
         raise ValueError('bk_counts: coun must be (nmax,nmax,nmax)')
     check(_lib.lib().psb_host_bk_counts(_p(coun), int(nside), np.float32(step), int(ncut), nmax), 'bk_counts')
+
+
+def _half(a, name, inout=False):
+    if inout:
+        _inout(a, np.complex64, name)
+    else:
+        a = np.asfortranarray(a, dtype=np.complex64)
+    n = a.shape[1] if a.ndim == 3 else 0
+    if a.ndim != 3 or a.shape != (n // 2 + 1, n, n):
+        raise ValueError('%s must be (ngrid/2+1,ngrid,ngrid) complex64' % name)
+    return a
+
+
+def fivedelta2g_1(dcgxx, dcgyy, dcgzz, ngrid=None):
+    """dcgxx <- 7.5 (dcgxx kxh^2 + dcgyy kyh^2 + dcgzz kzh^2) for k != 0, with the Fortran's implicitly INTEGER kxh, kyh, kzh."""
+    dcgxx = _half(dcgxx, 'dcgxx', True)
+    dcgyy, dcgzz = _half(dcgyy, 'dcgyy'), _half(dcgzz, 'dcgzz')
+    if dcgyy.shape != dcgxx.shape or dcgzz.shape != dcgxx.shape:
+        raise ValueError('fivedelta2g_1: shape mismatch')
+    check(_lib.lib().psb_host_fivedelta2g_1(_p(dcgxx), _p(dcgyy), _p(dcgzz), dcgxx.shape[1]), 'fivedelta2g_1')
+
+
+def fivedelta2g_2(dcg, dcgxx, dcgxy, dcgyz, dcgzx, ngrid=None):
+    """dcgxx <- dcgxx + 7.5 (2 dcgxy kxh kyh + 2 dcgyz kyh kzh + 2 dcgzx kzh kxh) - 2.5 dcg for k != 0 (integer kxh, kyh, kzh)."""
+    dcgxx = _half(dcgxx, 'dcgxx', True)
+    ins = [_half(a, n) for a, n in ((dcg, 'dcg'), (dcgxy, 'dcgxy'), (dcgyz, 'dcgyz'), (dcgzx, 'dcgzx'))]
+    if any(a.shape != dcgxx.shape for a in ins):
+        raise ValueError('fivedelta2g_2: shape mismatch')
+    check(_lib.lib().psb_host_fivedelta2g_2(_p(ins[0]), _p(dcgxx), _p(ins[1]), _p(ins[2]), _p(ins[3]), dcgxx.shape[1]), 'fivedelta2g_2')
+
+
+def build_quad(dclr1, dclr2, irsd, ngrid=None):
+    """dclr2 <- (7.5 mu^2 - 2.5) dclr1 for k != 0, mu along axis irsd (1 = x, 2 = y, 3 = z)."""
+    dclr2 = _half(dclr2, 'dclr2', True)
+    dclr1 = _half(dclr1, 'dclr1')
+    if dclr1.shape != dclr2.shape:
+        raise ValueError('build_quad: shape mismatch')
+    check(_lib.lib().psb_host_build_quad(_p(dclr1), _p(dclr2), int(irsd), dclr2.shape[1]), 'build_quad')
+
+
+FiveDelta2g_1, FiveDelta2g_2 = fivedelta2g_1, fivedelta2g_2

@@ -71,6 +71,46 @@ def test_assign_quad_matches_oracle(mods, N, Np):
     assert np.abs(a - 2 * b).max() <= 4e-6 * np.abs(b).max()
 
 
+@pytest.mark.parametrize('idx', [(1, 1, 0, 0), (2, 3, 0, 0), (3, 1, 0, 0), (1, 2, 3, 3), (2, 2, 2, 2)])
+def test_assign_quad_quadrupole_weights_match_oracle(mods, idx):
+    """Q_ij / Q_ijkl branches of assign_quad (f:294-300) through the f2py-shaped drop-in."""
+    _, est, O = mods
+    rng = np.random.default_rng(sum(idx))
+    N, L, Np = 36, 100., 20000
+    r = np.asfortranarray(rng.uniform(0.5, L * (1 - 1e-6), (3, Np)).astype(np.float32))
+    w = rng.uniform(0.5, 2., Np).astype(np.float32)
+    a = np.zeros((2 * N, N, N), np.float32, order='F')
+    b = np.zeros((2 * N, N, N), np.float32, order='F')
+    est.assign_quad(r, w, a, np.float32(N / L), 0, *idx)
+    O.assign_quad(r, w, b, np.float32(N / L), 0, *idx)
+    assert np.abs(b).max() > 0 and np.abs(a - b).max() <= 2e-6 * np.abs(b).max()
+    for bad in ((0, 1, 0, 0), (1, 4, 0, 0), (1, 1, 2, 0)):               # r(0,i) / r(4,i) in the Fortran: refused
+        with pytest.raises(RuntimeError):
+            est.assign_quad(r, w, a, np.float32(N / L), 0, *bad)
+
+
+@pytest.mark.parametrize('N', [12, 36, 64])
+def test_quadrupole_field_combinations_match_oracle(mods, N):
+    """FiveDelta2g_1, FiveDelta2g_2, build_quad (f:514-603): element-wise float32, bit-exact against the C restatement."""
+    _, est, O = mods
+    rng = np.random.default_rng(N)
+    f = [np.asfortranarray((rng.normal(size=(N // 2 + 1, N, N)) + 1j * rng.normal(size=(N // 2 + 1, N, N))).astype(np.complex64))
+         for _ in range(5)]
+    a, b = f[0].copy(order='F'), f[0].copy(order='F')
+    est.fivedelta2g_1(a, f[1], f[2]); O.fivedelta2g_1(b, f[1], f[2])
+    assert np.array_equal(a, b) and not np.array_equal(a, f[0])
+    est.FiveDelta2g_2(f[3], a, f[1], f[2], f[4]); O.fivedelta2g_2(f[3], b, f[1], f[2], f[4])
+    assert np.array_equal(a, b)
+    for irsd in (1, 2, 3):
+        a, b = f[0].copy(order='F'), f[0].copy(order='F')
+        est.build_quad(f[3], a, irsd); O.build_quad(f[3], b, irsd)
+        assert np.array_equal(a, b) and a[0, 0, 0] == f[0][0, 0, 0]
+    with pytest.raises(RuntimeError):
+        est.build_quad(f[3], a, 4)                                        # the Fortran stops
+    with pytest.raises(ValueError):
+        est.build_quad(f[3], np.ascontiguousarray(a), 1)                  # intent(inout) needs the Fortran-ordered array
+
+
 @pytest.mark.parametrize('N', [12, 24, 36])
 @pytest.mark.parametrize('periodic', [True, False])
 def test_fcomb_matches_oracle(mods, N, periodic):

@@ -147,3 +147,65 @@ def test_pk_pbox_rsd_single_mode_lands_in_its_bin():
     mu = kz / 3.
     assert np.isclose(p2[b] / p0[b], 5. * (-0.5 + 1.5 * mu * mu), rtol=1e-5)
     assert np.isclose(p4[b] / p0[b], 9. * (0.375 - 3.75 * mu ** 2 + 4.375 * mu ** 4), rtol=1e-4)
+
+
+# ------------------------------------------------------------------------------ quadrupole-field pieces (f:294-300, 514-603)
+def _half_fields(N, n, seed):
+    rng = np.random.default_rng(seed)
+    return [np.asfortranarray((rng.normal(size=(N // 2 + 1, N, N)) + 1j * rng.normal(size=(N // 2 + 1, N, N))).astype(np.complex64))
+            for _ in range(n)]
+
+
+def _kgrid(N):
+    s = lambda i: np.where(i <= N // 2, i, i - N)
+    kx, ky, kz = np.meshgrid(s(np.arange(N // 2 + 1)), s(np.arange(N)), s(np.arange(N)), indexing='ij')
+    rk = np.sqrt((kx ** 2 + ky ** 2 + kz ** 2).astype(np.float32))
+    return kx, ky, kz, rk
+
+
+@pytest.mark.parametrize('N', [8, 12])
+def test_quadrupole_field_combinations(N):
+    """FiveDelta2g_1/_2 and build_quad against an independent numpy evaluation.  The unit-vector components of FiveDelta2g_*
+    are implicitly INTEGER in estimator.f, so only on-axis modes pick up a Q_ii term and every cross term vanishes."""
+    kx, ky, kz, rk = _kgrid(N)
+    nz = rk > 0
+    with np.errstate(divide='ignore', invalid='ignore'):
+        ih = [np.where(nz, np.trunc(k.astype(np.float32) / rk), 0).astype(np.float32) for k in (kx, ky, kz)]
+    xx, yy, zz = _half_fields(N, 3, N)
+    want = np.where(nz, np.float32(7.5) * (xx * ih[0] ** 2 + yy * ih[1] ** 2 + zz * ih[2] ** 2), xx).astype(np.complex64)
+    got = xx.copy(order='F')
+    O.fivedelta2g_1(got, yy, zz)
+    assert np.array_equal(got, want)
+    on_axis = ((kx != 0).astype(int) + (ky != 0) + (kz != 0)) == 1
+    assert np.all(got[nz & ~on_axis] == 0) and np.all(got[on_axis] != 0) and got[0, 0, 0] == xx[0, 0, 0]
+    dcg, xy, yz, zx = _half_fields(N, 4, N + 1)
+    want = np.where(nz, xx - np.float32(2.5) * dcg, xx).astype(np.complex64)      # integer kxh kyh = 0 everywhere
+    got = xx.copy(order='F')
+    O.fivedelta2g_2(dcg, got, xy, yz, zx)
+    assert np.array_equal(got, want)
+    for irsd, k in ((1, kx), (2, ky), (3, kz)):
+        with np.errstate(divide='ignore', invalid='ignore'):
+            amu = (k.astype(np.float32) / rk).astype(np.float32)
+        fac = (np.float32(7.5) * (amu * amu) - np.float32(2.5)).astype(np.float32)
+        want = np.where(nz, np.stack([fac * dcg.real, fac * dcg.imag], -1).astype(np.float32).view(np.complex64)[..., 0], xx)
+        got = xx.copy(order='F')
+        O.build_quad(dcg, got, irsd)
+        assert np.array_equal(got, want.astype(np.complex64)), irsd
+
+
+def test_quadrupole_weights_of_assign_quad():
+    """f:294-300: the Q_ij mesh equals the delta mesh of the same particles with weights w r_ia r_ib / r^2 (float32, left to
+    right), likewise the four-index form; Q_xx + Q_yy + Q_zz gives back the delta mesh."""
+    rng = np.random.default_rng(3)
+    N, L, Np = 12, 30., 500
+    r = np.asfortranarray(rng.uniform(1., L, (3, Np)).astype(np.float32))
+    w = rng.uniform(0.5, 2., Np).astype(np.float32)
+    kf_ks = np.float32(N / L)
+    mesh = lambda wt, *idx: (lambda d: (O.assign_quad(r, wt, d, kf_ks, 0, *idx), d)[1])(np.zeros((2 * N, N, N), np.float32, order='F'))
+    rn = (r[0] * r[0] + r[1] * r[1]) + r[2] * r[2]
+    for ia, ib in ((1, 1), (2, 3), (3, 1)):
+        assert np.array_equal(mesh(w, ia, ib, 0, 0), mesh((w * r[ia - 1] * r[ib - 1] / rn).astype(np.float32), 0, 0, 0, 0))
+    assert np.array_equal(mesh(w, 1, 2, 3, 3), mesh((w * r[0] * r[1] * r[2] * r[2] / (rn * rn)).astype(np.float32), 0, 0, 0, 0))
+    tr = mesh(w, 1, 1, 0, 0) + mesh(w, 2, 2, 0, 0) + mesh(w, 3, 3, 0, 0)
+    d0 = mesh(w, 0, 0, 0, 0)
+    assert np.abs(tr - d0).max() < 1e-5 * np.abs(d0).max()
