@@ -287,12 +287,14 @@ def run_b200(args):
         fma_peak = 148 * 128 * 2 * sm_clk * 1e6 / 1e12
         tf_peak = float(peaks.get('bf16_tflops', 1590.0))
         ach_tf = alg_flops / (tri_ms * 1e-3) / 1e12
+        # MMAs actually issued: 3 split products on (pair rows padded to 128-row tiles) x (shells padded to 16) per cell
+        issued_tf = 2.0 * 3.0 * 512 * 48 * ncell / (tri_ms * 1e-3) / 1e12 if (S == 40 and len(tri) == 6350) else float('nan')
         if engine in ('auto', 'tc'):
             # the algorithm's arithmetic intensity (84.5 flop/B) is below the machine balance (bf16 peak / HBM peak = 256 flop/B):
             # the HBM roof is the one that applies; the tensor-pipe view is reported next to it
             traffic = None
             try:                                         # dram read+write of one k_tri_tc launch at this shape (ncu --set full, profiles/)
-                prof = json.load(open(os.path.join(ROOT, 'profiles', 'r1_k_tri_tc_ncu_full.json')))['metrics']
+                prof = json.load(open(os.path.join(ROOT, 'profiles', 'r2_k_tri_tc_ncu_full.json')))['metrics']
                 if S == 40 and N == 360:
                     traffic = (float(prof['dram__bytes_read.sum']['value']) * {'Gbyte': 1e9, 'Mbyte': 1e6}[prof['dram__bytes_read.sum']['unit']]
                                + float(prof['dram__bytes_write.sum']['value']) * {'Gbyte': 1e9, 'Mbyte': 1e6}[prof['dram__bytes_write.sum']['unit']])
@@ -302,12 +304,13 @@ def run_b200(args):
                     'bound': 'hbm', 'achieved': ach_gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach_gbs / hbm_peak,
                     'traffic': traffic, 'peak_source': peak_src,
                     'algorithmic_bytes': alg_bytes, 'algorithmic_flops': alg_flops,
-                    'tensor_view': {'achieved_tflops_algorithmic': ach_tf, 'issued_tflops': 9.4 * ach_tf, 'peak_tflops': tf_peak,
-                                    'frac_algorithmic': ach_tf / tf_peak, 'frac_issued': 9.4 * ach_tf / tf_peak},
+                    'tensor_view': {'achieved_tflops_algorithmic': ach_tf, 'issued_tflops': issued_tf, 'peak_tflops': tf_peak,
+                                    'frac_algorithmic': ach_tf / tf_peak, 'frac_issued': issued_tf / tf_peak},
                     'note': 'algorithmic bytes = 4 Nshell N^3 (every field read once), algorithmic flops = (Npair + 2 Ntri) N^3 '
-                            '(SURVEY 8d); as a GEMM the kernel issues 3 split MMAs on a dense 512 x 48 tile per 16 cells = 9.4x '
+                            '(SURVEY 8d); as a GEMM the kernel issues 3 split MMAs on a dense 512 x 48 tile per 16 cells = %.1fx '
                             'the algorithmic flops; it is limited by the SM load/store data path (shared-memory and TMEM wavefronts of '
-                            'forming the fp16 pair-product operand, DESIGN.md K6 / profiles/r1_summary.md), not by HBM or the tensor pipe'}
+                            'forming the fp16 pair-product operand, DESIGN.md K6 / profiles/r2_summary.md), not by HBM or the tensor pipe'
+                            % (issued_tf / ach_tf)}
         else:
             roof = {'kernel': 'k_tri (K6 triangle sums, FFMA path)', 'bound': 'hbm', 'achieved': ach_gbs, 'peak': hbm_peak,
                     'unit': 'GB/s', 'frac': ach_gbs / hbm_peak, 'traffic': None, 'peak_source': peak_src,
@@ -341,7 +344,10 @@ def run_b200(args):
             'roofline': roof,
             'roofline_stages': {
                 'assign': {'bound': 'hbm', 'alg_bytes': 16.0 * Np + 8.0 * ncell,
-                           'achieved_gbs': (16.0 * Np + 8.0 * ncell) / (float(stage_ms[0]) * 1e-3) / 1e9},
+                           'achieved_gbs': (16.0 * Np + 8.0 * ncell) / (float(stage_ms[0]) * 1e-3) / 1e9,
+                           'frac_of_measured_peak': (16.0 * Np + 8.0 * ncell) / (float(stage_ms[0]) * 1e-3) / 1e9 / hbm_peak,
+                           'note': 'not HBM bound: 128 read-modify-writes per particle; the tile scatter runs at the shared-memory '
+                                   'data pipe (ncu: l1tex data-pipe wavefronts 96.6 % of peak, profiles/r2_k1_assign_tile_ncu_full.json)'},
                 'fft_fcomb': {'bound': 'hbm', 'alg_bytes': 44.0 * ncell, 'achieved_gbs': 44.0 * ncell / (float(stage_ms[1]) * 1e-3) / 1e9},
                 'shell_fields': shell_fields_roofline(N, step, s0, Nmax, level_desc, float(stage_ms[2]), hbm_peak)},
             'cpu_baseline': cpu, 'clocks': ck,

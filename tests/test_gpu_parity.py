@@ -332,6 +332,21 @@ def test_triangle_engines_vs_float64(mods, N, Np, step, Ncut, Nmax):
     assert np.allclose(maxabs.view(torch.float32).cpu().numpy()[:S], pipe.unpack_fields(fields)[:S].abs().max(dim=1).values.cpu().numpy(), rtol=1e-6)
 
 
+def test_k6_tensor_core_sums_are_reproducible(mods):
+    """The tcgen05 kernel's hand-rolled pipeline (TMA -> formers -> MMA -> drain, ordered by mbarriers and tcgen05.commit, which
+    compute-sanitizer's racecheck cannot follow: profiles/r2_summary.md) leaves no run-to-run freedom: per-CTA partial sums in a
+    fixed order.  A lost or misordered hand-over between the roles would show up as differing bits here."""
+    import torch
+    pySpec, _, _ = mods
+    N, L, step, Ncut, Nmax = 64, 300., 1, 3, 30
+    pipe = pySpec.PeriodicPipeline.get(N)
+    half, _ = pipe.fft_periodic(_cat(5, 200000, L), None, L)
+    fields, _, _, _ = pipe.shell_fields(half, step, Ncut // step, Nmax, scaled=True)
+    ref = pipe.triangle_sums(fields, Nmax, Ncut, step, engine='tc')
+    for _ in range(5):
+        assert torch.equal(pipe.triangle_sums(fields, Nmax, Ncut, step, engine='tc'), ref)
+
+
 def test_many_generators_match_single_calls(mods):
     """Bk/Pk/Pk_rsd *_many (upload of catalogue n+1 overlapped with the kernels of n) give the single-call results, in order,
     for pinned torch tensors, numpy arrays (C and Fortran order) and (xyz, w) items."""
