@@ -458,6 +458,18 @@ def run_sharded_section(args, dev, rank, world, xyz_dev_rank0):
                 out['c5']['assign_roofline'] = {'alg_bytes_per_gpu': b, 'achieved_gbs_per_gpu': b / (sm['assign_slab'] * 1e-3) / 1e9,
                                                 'frac_of_measured_hbm_peak': (b / (sm['assign_slab'] * 1e-3) / 1e9 / peak) if peak else None,
                                                 'mpart_per_s_all_gpus': Np5 / (sm['assign_slab'] * 1e-3) / 1e6}
+            Ng5, S5 = out['c5']['carrier_grid'], 40
+            if sm.get('triangles'):
+                b6 = 4.0 * S5 * Ng5 ** 3 / world                           # K6: every packed field cell of the rank's slab read once
+                out['c5']['shell_sum_roofline'] = {
+                    'k6_alg_bytes_per_gpu': b6, 'k6_achieved_gbs_per_gpu': b6 / (sm['triangles'] * 1e-3) / 1e9,
+                    'k6_frac_of_measured_hbm_peak': (b6 / (sm['triangles'] * 1e-3) / 1e9 / peak) if peak else None,
+                    'note': 'K6 is bound by the SM load/store data path of forming the pair-product operand, not by HBM (DESIGN.md K6)'}
+            ps = out['c5']['collectives'].get('shell_fields_peer_stores')
+            if ps and ps.get('gbs_per_rank'):
+                out['c5']['shell_fields_nvlink'] = {'gbs_per_rank': ps['gbs_per_rank'], 'reference_gbs': 770.0,
+                                                    'frac_of_peer_copy_reference': ps['gbs_per_rank'] / 770.0,
+                                                    'note': 'fused K5 z pass + exchange; 770 GB/s = measured peer copy per direction (B200_PROFILING.md)'}
         except Exception as e:
             out['c5'] = {'error': repr(e)[:300]}
     return out

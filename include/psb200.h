@@ -122,6 +122,10 @@ int psb_fcomb(const float* full_c64, float* half_c64, int ngrid, const double* r
 int psb_fft_slab_xy(float* data_c64, int ngrid, int nz, int dir, const float* tw_c64, void* stream);
 int psb_fft_slab_z(float* data_c64, int ngrid, int ny, int nx, int dir, const float* tw_c64, void* stream);
 int psb_slab_split_ab(const float* d_c64, float* p_c64, float* q_c64, int ngrid, int nz, int hp, void* stream);
+/* The same with the exchange fused in (z-slabs -> ky-slabs through peer memory instead of an all-to-all): row ky of plane z is stored
+ * straight into rank ky/(N/nranks)'s arrays p, q [N][N/nranks][hp] at plane zbase + z.  route = device int64 [2][nranks]: the address of
+ * every rank's p array, then of every rank's q array (peer pointers, e.g. from torch.distributed._symmetric_memory). */
+int psb_slab_split_ab_routed(const float* d_c64, int ngrid, int nz, int hp, int zbase, int nranks, const int64_t* route, void* stream);
 int psb_slab_fcomb(const float* p_c64, const float* q_c64, float* half_c64, int ngrid, int ky0, int ny, int hp,
                    const double* rec_c128, const float* wk, const double* sumw, int periodic, void* stream);
 

@@ -57,6 +57,7 @@ PROTOTYPES = {
     'psb_fft_slab_xy': (_i, [_vp, _i, _i, _i, _vp, _vp]),
     'psb_fft_slab_z': (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     'psb_slab_split_ab': (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    'psb_slab_split_ab_routed': (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
     'psb_slab_fcomb': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp]),
     'psb_pk_monopole': (_i, [_vp, _i, _vp, _i, _d, _vp, _vp]),
     'psb_pk_multipoles': (_i, [_vp, _i, _vp, _i, _i, _f, _vp, _vp, _vp]),

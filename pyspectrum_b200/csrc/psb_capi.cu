@@ -224,6 +224,13 @@ int psb_slab_split_ab(const float* d, float* p, float* q, int N, int nz, int hp,
                          S(stream));
 }
 
+int psb_slab_split_ab_routed(const float* d, int N, int nz, int hp, int zbase, int nranks, const int64_t* route, void* stream)
+{
+    if (!d || !route) return PSB_ERR_ARG;
+    return slab_split_ab(reinterpret_cast<const Cx<float>*>(d), nullptr, nullptr, N, nz, hp, S(stream), reinterpret_cast<const long long*>(route),
+                         zbase, nranks);
+}
+
 int psb_slab_fcomb(const float* p, const float* q, float* half, int N, int ky0, int ny, int hp, const double* rec, const float* wk,
                    const double* sumw, int periodic, void* stream)
 {

@@ -126,7 +126,11 @@ int fft_slab_z(Cx<float>* data, int N, int ny, int nx, int dir, const Cx<float>*
     });
 }
 
-__global__ void k_slab_split_ab(const Cx<float>* __restrict__ d, Cx<float>* __restrict__ P, Cx<float>* __restrict__ Q, int N, int nz, int hp)
+// route != null (multi-GPU): P and Q leave as the z-slab -> ky-slab exchange of the slab FFT itself.  Row ky belongs to rank ky / ny;
+// route[q] / route[nranks + q] = address of rank q's P / Q array [N][ny][hp] (peer pointer over NVLink), plane z of this slab is plane
+// zbase + z there.  A (z, ky) row is hp contiguous complex numbers (4 KB at 1024^3): full-width NVLink runs.
+__global__ void k_slab_split_ab(const Cx<float>* __restrict__ d, Cx<float>* __restrict__ P, Cx<float>* __restrict__ Q, int N, int nz, int hp,
+                                const long long* __restrict__ route, int zbase, int ny, int nranks)
 {
     const int h = N / 2;
     const long long n = (long long)nz * N * hp;
@@ -142,15 +146,24 @@ __global__ void k_slab_split_ab(const Cx<float>* __restrict__ d, Cx<float>* __re
             p = mk<float>(0.5f * (Dk.x + Dm.x), 0.5f * (Dk.y - Dm.y));              // (Dk + conj Dm) / 2
             q = mk<float>(0.5f * (Dk.y + Dm.y), -0.5f * (Dk.x - Dm.x));             // (Dk - conj Dm) / (2i)
         }
-        P[e] = p;
-        Q[e] = q;
+        if (route) {
+            const int q_ = ky / ny;
+            const long long o = (((zbase + z) * ny + (ky - q_ * ny)) * hp + kx) * (long long)sizeof(Cx<float>);
+            *reinterpret_cast<Cx<float>*>(route[q_] + o) = p;
+            *reinterpret_cast<Cx<float>*>(route[nranks + q_] + o) = q;
+        } else {
+            P[e] = p;
+            Q[e] = q;
+        }
     }
 }
 
-int slab_split_ab(const Cx<float>* d, Cx<float>* P, Cx<float>* Q, int N, int nz, int hp, cudaStream_t st)
+int slab_split_ab(const Cx<float>* d, Cx<float>* P, Cx<float>* Q, int N, int nz, int hp, cudaStream_t st, const long long* route, int zbase,
+                  int nranks)
 {
     if (N < 2 || (N & 1) || nz < 1 || hp < N / 2 + 1) return PSB_ERR_ARG;
-    k_slab_split_ab<<<sm_count() * 8, 256, 0, st>>>(d, P, Q, N, nz, hp);
+    if (route ? (nranks < 1 || N % nranks || zbase < 0 || zbase + nz > N) : (!P || !Q)) return PSB_ERR_ARG;
+    k_slab_split_ab<<<sm_count() * 8, 256, 0, st>>>(d, P, Q, N, nz, hp, route, zbase, route ? N / nranks : N, nranks);
     return cudaGetLastError() == cudaSuccess ? PSB_OK : PSB_ERR_CUDA;
 }
 

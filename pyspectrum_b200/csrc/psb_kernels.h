@@ -79,7 +79,8 @@ int triangle_sums_tc_pass(const float* const* fields, int S, long long ncell, co
 // slab-decomposed mesh -> delta(k) building blocks of the sharded path (psb_fft_mesh.cu)
 int fft_slab_xy(Cx<float>* data, int N, int nz, int dir, const Cx<float>* tw, cudaStream_t st);
 int fft_slab_z(Cx<float>* data, int N, int ny, int nx, int dir, const Cx<float>* tw, cudaStream_t st);
-int slab_split_ab(const Cx<float>* d, Cx<float>* P, Cx<float>* Q, int N, int nz, int hp, cudaStream_t st);
+int slab_split_ab(const Cx<float>* d, Cx<float>* P, Cx<float>* Q, int N, int nz, int hp, cudaStream_t st, const long long* route = nullptr,
+                  int zbase = 0, int nranks = 0);
 int slab_fcomb(const Cx<float>* P, const Cx<float>* Q, Cx<float>* half, int N, int ky0, int ny, int hp, const Cx<double>* rec,
                const float* Wk, const double* sumw, int periodic, cudaStream_t st);
 

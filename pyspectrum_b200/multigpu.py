@@ -157,6 +157,13 @@ class SlabBuffers(object):
         if self.handle is not None:
             self.handle.barrier()
 
+    def row_table(self, dev):
+        """int64 [nrow, world] (device): address of row r of every rank's buffer (the slab-FFT exchange: rows = P, Q)."""
+        if 'rows' not in self._tables:
+            t = np.array([[p + 4 * r * self.slab for p in self.ptrs] for r in range(self.nrow)], np.int64)
+            self._tables['rows'] = torch.from_numpy(t).to(dev)
+        return self._tables['rows']
+
     def route(self, per, plist, S, dev):
         """Route table [len(plist), 2, world] (int64, device) for this rank's pairs `plist` (local pair k = position in the list):
         entry (k, e, q) = address at which shell e of the pair WOULD start in rank q's buffer if that buffer held the whole field,
@@ -342,11 +349,37 @@ def slab_mesh_to_delta_emulated(pipe, mesh, sumw, world, periodic=1):
     return half
 
 
+def slab_phase1_routed(pipe, mesh_slab, bufs, zbase):
+    """x and y passes of a z-slab (destroyed) + separation, with the z-slab -> ky-slab exchange fused in: every (z, ky) row of P and Q
+    is stored straight into the arrays [N, ny, hp] of the rank that owns ky (`bufs`: SlabBuffers with rows P, Q)."""
+    N = pipe.N
+    nz = mesh_slab.shape[0]
+    hp = (N // 2 + 2) // 2 * 2
+    st = P._stream()
+    P.check(pipe.L.psb_fft_slab_xy(P._ptr(mesh_slab), N, nz, 1, P._ptr(pipe.tw32), st), 'psb_fft_slab_xy')
+    P.check(pipe.L.psb_slab_split_ab_routed(P._ptr(mesh_slab), N, nz, hp, zbase, bufs.world, P._ptr(bufs.row_table(pipe.dev)), st),
+            'psb_slab_split_ab_routed')
+
+
 def slab_delta(pipe, mesh_slab, sumw, periodic=1, stats=None):
     """Step 3: a rank's mesh planes [nz,N,N,2] (destroyed) -> its rows ky in [rank*ny, (rank+1)*ny) of delta(k): [N, ny, N/2+1, 2]."""
     st = _stats(stats)
     world = _world()
     nz, hp = slab_geometry(pipe.N, world)
+    bufs = routed_slabs(pipe.dev, world, _rank(), 2, pipe.N * nz * hp * 2) if world > 1 else None
+    if bufs is not None:                                 # exchange fused into the separation kernel (peer stores)
+        e0 = st.mark()
+        bufs.barrier()                                   # every rank is done with the previous catalogue's P, Q
+        slab_phase1_routed(pipe, mesh_slab, bufs, _rank() * nz)
+        bufs.barrier()                                   # every rank's rows have landed
+        st.span('fft_xy_peer_stores', e0)
+        st.add_bytes('fft_xy_peer_stores', 2 * 8 * nz * pipe.N * hp * (world - 1) // world)
+        py = bufs.local[0].view(pipe.N, nz, hp, 2)
+        qy = bufs.local[1].view(pipe.N, nz, hp, 2)
+        e0 = st.mark()
+        half = slab_phase2(pipe, py, qy, _rank() * nz, sumw, periodic)
+        st.span('fft_z_fcomb', e0)
+        return half
     e0 = st.mark()
     p, q = slab_phase1(pipe, mesh_slab)
     st.span('fft_xy', e0)

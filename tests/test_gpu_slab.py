@@ -234,3 +234,25 @@ def test_routed_shell_planes_land_where_the_all_to_all_puts_them(mods, N, Ns, wo
                         assert bool((ranks[q].local[row] == -7.0).all())
     rows = M.slab_field_rows(Sl, world, per)
     assert sorted(set(rows)) == sorted(rows) and max(rows) < world * 2 * per
+
+
+@pytest.mark.parametrize('N,world', [(24, 2), (36, 3), (64, 4), (64, 8)])
+def test_routed_slab_fft_exchange_equals_the_all_to_all(mods, N, world):
+    """psb_slab_split_ab_routed: every emulated rank stores the (z, ky) rows of its separated spectra P, Q straight into the ky-slab
+    arrays of the owning rank; the arrays must equal, bit for bit, what split + all-to-all chunks deliver."""
+    import torch
+    pySpec, M = mods
+    pipe, mesh, sumw = _mesh(pySpec, N, 20000, 100., N + world)
+    nz, hp = M.slab_geometry(N, world)
+    ranks = M.SlabBuffers.emulated(pipe.dev, world, 2, N * nz * hp * 2)
+    for b in ranks:
+        b.local.fill_(float('nan'))
+    pq = []
+    for r in range(world):
+        M.slab_phase1_routed(pipe, mesh[r * nz:(r + 1) * nz].clone(), ranks[r], r * nz)
+        pq.append(M.slab_phase1(pipe, mesh[r * nz:(r + 1) * nz].clone()))
+    for q in range(world):
+        for k in (0, 1):
+            want = torch.cat([M.z_to_y_chunks(pq[g][k], world)[q] for g in range(world)], dim=0)        # [N, ny, hp, 2]
+            got = ranks[q].local[k].view(N, nz, hp, 2)
+            assert torch.equal(got.view(torch.int32), want.view(torch.int32)), (q, k)

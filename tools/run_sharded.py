@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""torchrun --nproc-per-node G tools/run_sharded.py [small|c2|c4|c5]: one catalogue sharded over G GPUs
+"""torchrun --nproc-per-node G tools/run_sharded.py [small|c2|c4|c5|c5check]: one catalogue sharded over G GPUs
 (pyspectrum_b200.multigpu: slab-owned assignment, slab FFT, slab binning, carrier grid, sharded shell/triangle stage)
 checked against the single-GPU API on rank 0 (when the problem fits one GPU)."""
 import json, os, sys, time
@@ -17,7 +17,8 @@ which = sys.argv[1] if len(sys.argv) > 1 else 'small'
 cfg = {'small': dict(N=64, L=500., Np=200000, step=2, Ncut=3, Nmax=12, check=True),
        'c2': dict(N=360, L=2600., Np=10 ** 7, step=3, Ncut=3, Nmax=40, check=True),
        'c4': dict(N=512, L=2600., Np=10 ** 7, step=2, Ncut=3, Nmax=80, check=True),
-       'c5': dict(N=1024, L=4000., Np=10 ** 9, step=3, Ncut=3, Nmax=40, check=False)}[which]
+       'c5': dict(N=1024, L=4000., Np=10 ** 9, step=3, Ncut=3, Nmax=40, check=False),
+       'c5check': dict(N=1024, L=4000., Np=10 ** 8, step=3, Ncut=3, Nmax=40, check=True)}[which]    # C5's grid at a size one GPU holds
 N, L = cfg['N'], cfg['L']
 if which == 'c5':
     shard, full = bench.c5_shard(dev, rank, world), None
