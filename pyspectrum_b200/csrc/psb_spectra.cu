@@ -14,7 +14,10 @@ namespace psb {
 
 // one mode of the estimator.f:196-244 loop body with signed integer wave numbers (rkx,rky,rkz): adds the five per-k-bin
 // contributions to acc[0..4] and the four (k,mu)-table contributions straight into `tab` (shared or global memory)
-__device__ __forceinline__ void rsd_mode(const SpectraIn& in, double* acc, double* tab, int b, float rkx, float rky, float rkz, double pk, double wgt)
+// tab == nullptr: the table contributions are handed back instead (tkey = b * 1024 + imu, 0 = none; tv[4]) for the caller's
+// segmented warp reduction.
+__device__ __forceinline__ void rsd_mode(const SpectraIn& in, double* acc, double* tab, int b, float rkx, float rky, float rkz, double pk, double wgt,
+                                         int* tkey = nullptr, double* tv = nullptr)
 {
     const int Nbin = in.Nbin;
     const float rk = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(rkx, rkx), __fmul_rn(rky, rky)), __fmul_rn(rkz, rkz)));
@@ -39,7 +42,10 @@ __device__ __forceinline__ void rsd_mode(const SpectraIn& in, double* acc, doubl
     acc[2] += wgt * pk;
     acc[3] += wgt * (pk * 5.0 * Le2);
     acc[4] += wgt * (pk * 9.0 * Le4);
-    if (imu <= in.Nmu && imu > 0) {
+    if (imu <= in.Nmu && imu > 0 && tab == nullptr) {
+        *tkey = b * 1024 + imu;
+        tv[0] = wgt; tv[1] = wgt * kk; tv[2] = wgt * amu; tv[3] = wgt * pk;
+    } else if (imu <= in.Nmu && imu > 0) {
         double* t = tab + (long long)(imu - 1) * Nbin + (b - 1);
         const long long tb = (long long)Nbin * in.Nmu;
         atomicAdd(t, wgt);
@@ -78,6 +84,8 @@ __global__ void __launch_bounds__(256) k_spectra(SpectraIn in, double* out, int 
             double v[NV];
 #pragma unroll
             for (int i = 0; i < NV; ++i) v[i] = 0.0;
+            int tkey = 0;                                        // mode 1: (k bin, mu bin) of this lane's table contribution
+            double tv[4] = { 0.0, 0.0, 0.0, 0.0 };
             if (b) {
                 Cx<float> d = row[ix];
                 const bool edge = ix == 0 || ix == h;
@@ -92,10 +100,11 @@ __global__ void __launch_bounds__(256) k_spectra(SpectraIn in, double* out, int 
                 } else {
                     const float ab = (float)sqrt((double)d.x * (double)d.x + (double)d.y * (double)d.y);    // cabs()
                     const double pk = (double)__fmul_rn(ab, ab);
+                    const bool warp_reduce = in.Nmu < 1024;          // table contributions leave through the segmented reduction below
                     if (edge) {
-                        rsd_mode(in, v, tab, b, (float)ix, (float)ky, (float)kz, pk, 1.0);
+                        rsd_mode(in, v, warp_reduce ? nullptr : tab, b, (float)ix, (float)ky, (float)kz, pk, 1.0, &tkey, tv);
                     } else if (iy != h && iz != h) {
-                        rsd_mode(in, v, tab, b, (float)ix, (float)ky, (float)kz, pk, 2.0);      // partner is exactly -k
+                        rsd_mode(in, v, warp_reduce ? nullptr : tab, b, (float)ix, (float)ky, (float)kz, pk, 2.0, &tkey, tv);      // partner is exactly -k
                     } else {
                         // the conjugate partner visited by the Fortran loop is (-kx, -ky, -kz) with a Nyquist
                         // component folded back to +N/2 (f:198-204), so it is not the exact negation: do both
@@ -119,6 +128,33 @@ __global__ void __launch_bounds__(256) k_spectra(SpectraIn in, double* out, int 
 #pragma unroll
                 for (int i = 0; i < NV; ++i) atomicAdd(&sbin[i * Nbin + b - 1], v[i]);
             }
+            if (MODE == 1) {
+                // (k,mu) table: |mu| is monotonic in kx along a row up to float32 rounding, so equal (bin, mu bin) keys form runs --
+                // but a one-ulp wiggle at a bin edge may split a key into two runs: the reduction is segmented by RUN (head flags),
+                // not by key equality, so every run is summed exactly once whatever the key order.  One atomic per run and quantity
+                // instead of one per mode (float64 shared-memory atomics are CAS loops, and the lanes of a run hit one address).
+                const int pk_ = __shfl_up_sync(0xffffffffu, tkey, 1);
+                const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || pk_ != tkey);
+                if (__any_sync(0xffffffffu, tkey != 0)) {
+                    const int rid = __popc(heads & (0xffffffffu >> (31 - lane)));
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int tr = __shfl_down_sync(0xffffffffu, rid, o);
+                        const bool take = lane + o < 32 && tr == rid;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const double t = __shfl_down_sync(0xffffffffu, tv[i], o);
+                            if (take) tv[i] += t;
+                        }
+                    }
+                    if (tkey != 0 && ((heads >> lane) & 1u)) {
+                        const int imu = tkey & 1023, bb = tkey >> 10;
+                        double* t = tab + (long long)(imu - 1) * Nbin + (bb - 1);
+                        const long long tb = (long long)Nbin * in.Nmu;
+                        atomicAdd(t, tv[0]); atomicAdd(t + tb, tv[1]); atomicAdd(t + 2 * tb, tv[2]); atomicAdd(t + 3 * tb, tv[3]);
+                    }
+                }
+            }
         }
     }
     __syncthreads();
@@ -139,10 +175,13 @@ int binned_spectra(const SpectraIn& in, double* out, cudaStream_t st)
     } else {
         size_t smem = nout * sizeof(double);
         int tab_smem = 1;
-        if (smem > 96 * 1024) { smem = 5 * (size_t)in.Nbin * sizeof(double); tab_smem = 0; }       // big (k,mu) tables stay in global memory
+        // the (k,mu) table stays in shared memory only while it leaves room for 8 CTAs per SM: the per-mode arithmetic (IEEE float32
+        // sqrt / div, float64 Legendre terms) is latency bound at low occupancy, and after the warp-level run reduction the table sees
+        // few atomics, which the L2 handles natively for float64
+        if (smem > 24 * 1024) { smem = 5 * (size_t)in.Nbin * sizeof(double); tab_smem = 0; }
         if (smem > 200 * 1024) return PSB_ERR_ARG;
         if (cudaFuncSetAttribute(k_spectra<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PSB_ERR_CUDA;
-        k_spectra<1><<<sm_count() * 2, 256, smem, st>>>(in, out, tab_smem);
+        k_spectra<1><<<sm_count() * 8, 256, smem, st>>>(in, out, tab_smem);
     }
     return cudaGetLastError() == cudaSuccess ? PSB_OK : PSB_ERR_CUDA;
 }
