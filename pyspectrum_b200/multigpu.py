@@ -232,13 +232,14 @@ def route_counts(pipe, pos, aos, wt, Lbox, world, offset=0., clip=True):
     return counts, sumw
 
 
-def route_scatter(pipe, pos, aos, wt, Lbox, world, counts, offset=0., clip=True):
-    """Destination-major send buffer [sum(counts), 4] float32 {x,y,z,w}."""
+def route_scatter(pipe, pos, aos, wt, Lbox, world, counts, offset=0., clip=True, total=None):
+    """Destination-major send buffer [sum(counts), 4] float32 {x,y,z,w} (total: sum(counts) if the caller already has it on the host)."""
     N = pipe.N
     Np = pos.shape[0] if aos else pos.shape[1]
     base = (torch.cumsum(counts, 0) - counts).contiguous()
     cursor = torch.zeros(world, dtype=torch.int64, device=pipe.dev)
-    total = int(counts.sum().item())
+    if total is None:
+        total = int(counts.sum().item())
     send = torch.empty((max(total, 1), 4), dtype=torch.float32, device=pipe.dev)
     P.check(pipe.L.psb_slab_route_scatter(P._ptr(pos), int(pos.dtype == torch.float64), aos, P._ptr(wt),
                                           int(wt is not None and wt.dtype == torch.float64), Np, N, float(Lbox) if clip else 0.0,
@@ -258,22 +259,25 @@ def route_particles(pipe, xyz_local, w_local, Lbox, offset=0., clip=True, stats=
     Np = pos.shape[0] if aos else pos.shape[1]
     e0 = st.mark()
     counts, sumw = route_counts(pipe, pos, aos, wt, Lbox, world, offset, clip)
-    send = route_scatter(pipe, pos, aos, wt, Lbox, world, counts, offset, clip)
-    st.span('route_kernels', e0)
-    ntot = torch.tensor([float(Np)], dtype=torch.float64, device=pipe.dev)
     if world == 1:
+        send = route_scatter(pipe, pos, aos, wt, Lbox, world, counts, offset, clip)
+        st.span('route_kernels', e0)
         return send, sumw, Np
-    e0 = st.mark()
-    meta = torch.cat([sumw, ntot])
+    # the small collectives first, then ONE device -> host copy with everything the host needs (split sizes both ways, N)
+    meta = torch.cat([sumw, torch.tensor([float(Np)], dtype=torch.float64, device=pipe.dev)])
     _allreduce(meta)
     rc = torch.empty_like(counts)
     dist.all_to_all_single(rc, counts)
-    sc_h, rc_h = counts.cpu().tolist(), rc.cpu().tolist()
+    host = torch.cat([counts.double(), rc.double(), meta[1:]]).cpu().tolist()
+    sc_h, rc_h, ntot = [int(v) for v in host[:world]], [int(v) for v in host[world:2 * world]], int(round(host[2 * world]))
+    send = route_scatter(pipe, pos, aos, wt, Lbox, world, counts, offset, clip, total=sum(sc_h))
+    st.span('route_kernels', e0)
+    e0 = st.mark()
     recv = torch.empty((max(sum(rc_h), 1), 4), dtype=torch.float32, device=pipe.dev)[:sum(rc_h)]
     dist.all_to_all_single(recv, send, output_split_sizes=rc_h, input_split_sizes=sc_h)
     st.span('particles_all_to_all', e0)
     st.add_bytes('particles_all_to_all', 16 * (sum(sc_h) - sc_h[_rank()]))
-    return recv, meta[:1].clone(), int(round(meta[1].item()))
+    return recv, meta[:1].clone(), ntot
 
 
 def assign_slab(pipe, xyzw, zbase, nzs, Lbox, offset=0.):
@@ -530,16 +534,17 @@ def sharded_triangle_sums(pipe, half, step, Ncut, Nmax, dtype=torch.float32, sta
         st.span('triangles', e0)
         keep.append((pc, slabs, rows, idx_dev, smax, vol, use_tc))
         sums.index_copy_(0, idx_dev, sl if vol == 1.0 else sl * vol)
-        for k, pidx in enumerate(mine):                  # per-shell quantities live on the owner rank of the pair
-            for e in (0, 1):
-                f = 2 * pidx + e
-                if f >= Sl:
-                    continue
-                if f >= have:                            # shell power from the coarsest level that holds the shell (Parseval)
-                    glob[0, f] = sq[2 * k + e] * vol
-                if not f64:
-                    glob[1, f] = sc_rows[2 * k + e].double()
-                    glob[2, f] = torch.maximum(glob[2, f], mx[2 * k + e].view(torch.float32).double())
+        # per-shell quantities live on the owner rank of the pair: three indexed updates per level instead of one tiny kernel per shell
+        loc = [(2 * k + e, 2 * pidx + e) for k, pidx in enumerate(mine) for e in (0, 1) if 2 * pidx + e < Sl]
+        if loc:
+            idx_t = lambda v: torch.tensor(v, dtype=torch.long, device=pipe.dev)
+            src_i, dst_i = idx_t([a for a, _ in loc]), idx_t([b for _, b in loc])
+            fresh = [(a, b) for a, b in loc if b >= have]    # shell power from the coarsest level that holds the shell (Parseval)
+            if fresh:
+                glob[0].index_copy_(0, idx_t([b for _, b in fresh]), sq[idx_t([a for a, _ in fresh])] * vol)
+            if not f64:
+                glob[1].index_copy_(0, dst_i, sc_rows[src_i].double())
+                glob[2].index_copy_(0, dst_i, torch.maximum(glob[2][dst_i], mx.view(torch.float32)[src_i].double()))
         have = max(have, Sl)
     e0 = st.mark()
     flat = torch.cat([sums, glob[0], glob[2]])
@@ -547,12 +552,12 @@ def sharded_triangle_sums(pipe, half, step, Ncut, Nmax, dtype=torch.float32, sta
     st.span('sums_all_reduce', e0)
     if world > 1:
         st.add_bytes('sums_all_reduce', flat.numel() * 8)
-    host = flat.cpu().numpy()
     nt = len(tri)
-    sums_h, sq_h, mx_h = host[:nt], host[nt:nt + SA], host[nt + SA:]
+    host = (flat if f64 else torch.cat([flat, scales.double()[:SA]])).cpu().numpy()      # one device -> host copy
+    sums_h, sq_h, mx_h = host[:nt], host[nt:nt + SA], host[nt + SA:nt + 2 * SA]
     if f64:
         return sums_h, sq_h[:S]
-    sc = scales.double().cpu().numpy()[:SA]
+    sc = host[nt + 2 * SA:]
     if mx_h.max() ** 2 >= 4.0e4:                         # fp16 range guard (pathological catalogues): redo with the FFMA kernel
         sums.zero_()
         for pc, slabs, rows, idx_dev, smax, vol, _ in keep:
@@ -594,7 +599,7 @@ def Bk_periodic_sharded(xyz_local, w_local=None, Lbox=2600, Ngrid=360, step=3, N
         raise ValueError('Ncut//step must be >= 1')
     st = _stats(stats)
     half, ky0, sumw, N = sharded_delta_slab(pipe, xyz_local, w_local, Lbox, stats=st)
-    pk = _pk_from_slab(pipe, half, ky0, Lbox, N, w_local, sumw, st) if return_pk else None
+    pk_dev = _pk_launch(pipe, half, ky0, Lbox, st) if return_pk else None       # collected after the B(k) stage is queued
     Ng = carrier_grid(Ngrid, step, Nmax, Ncut)
     car = low_k_carrier(pipe, half, ky0, Ng, st)
     del half
@@ -603,6 +608,7 @@ def Bk_periodic_sharded(xyz_local, w_local=None, Lbox=2600, Ngrid=360, step=3, N
     counts_g = sharded_counts(pg, step, Ncut, Nmax)      # N_g^3 * closed triples; the epilogue below works in the carrier's units
     sums_h, sumsq_h = sharded_triangle_sums(pg, car, step, Ncut, Nmax, stats=st)
     tri = P.triangle_list(Nmax, Ncut, step)
+    pk = _pk_finish(pipe, pk_dev, Lbox, N, w_local, sumw) if return_pk else None
     nbar = (float(N) if w_local is None else float(sumw.item())) / Lbox ** 3
     kf = 2 * np.pi / Lbox
     bispec = P._bk_epilogue(Ng, tri, sums_h, sumsq_h, Nk, counts_g, step, Ncut, Nmax)
@@ -619,10 +625,20 @@ def Bk_periodic_sharded(xyz_local, w_local=None, Lbox=2600, Ngrid=360, step=3, N
 
 
 def _pk_from_slab(pipe, half, ky0, Lbox, N, w_local, sumw, stats):
+    return _pk_finish(pipe, _pk_launch(pipe, half, ky0, Lbox, stats), Lbox, N, w_local, sumw)
+
+
+def _pk_launch(pipe, half, ky0, Lbox, stats):
+    """K4 on the ky-slab + the all-reduce of the bins; the result stays on the device (no host wait in the middle of the pipeline)."""
     st = _stats(stats)
     e0 = st.mark()
-    out = slab_pk_monopole(pipe, half, ky0, Lbox, st).cpu().numpy()
+    out = slab_pk_monopole(pipe, half, ky0, Lbox, st)
     st.span('pk_binning', e0)
+    return out
+
+
+def _pk_finish(pipe, out_dev, Lbox, N, w_local, sumw):
+    out = out_dev.cpu().numpy()
     nbar = (float(N) if w_local is None else float(sumw.item())) / Lbox ** 3
     kf = 2 * np.pi / float(Lbox)
     Nbins = pipe.N // 2
