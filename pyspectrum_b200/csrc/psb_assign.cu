@@ -96,14 +96,31 @@ __device__ __forceinline__ int tile_key(const AssignIn& a, float x, float y, flo
 
 __device__ __forceinline__ int sort_key(const AssignIn& a, float x, float y, float z) { return a.tiles ? tile_key(a, x, y, z) : row_key(a, y, z); }
 
-__global__ void k_hist(AssignIn a, unsigned int* hist, double* sumw)
+// `ordered` (optional): number of particles whose key is within 1 of their predecessor's in the input -- how spatially ordered
+// the catalogue already is, which decides between the one-pass and the two-pass sort ON THE DEVICE (k_sort_decide: no host sync)
+__global__ void k_hist(AssignIn a, unsigned int* hist, double* sumw, unsigned long long* ordered)
 {
     double acc = 0.0;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < a.Np; i += (long long)gridDim.x * blockDim.x) {
-        float x, y, z, w; double wd;
-        load_particle(a, i, x, y, z, w, wd);
-        acc += wd;
-        atomicAdd(&hist[sort_key(a, x, y, z)], 1u);
+    unsigned int near = 0;
+    const long long nround = (a.Np + (long long)gridDim.x * blockDim.x - 1) / ((long long)gridDim.x * blockDim.x);
+    for (long long it = 0; it < nround; ++it) {           // warp-uniform trip count: the shuffle below needs every lane
+        const long long i = (it * gridDim.x + blockIdx.x) * (long long)blockDim.x + threadIdx.x;
+        int key = -0x40000000;
+        if (i < a.Np) {
+            float x, y, z, w; double wd;
+            load_particle(a, i, x, y, z, w, wd);
+            acc += wd;
+            key = sort_key(a, x, y, z);
+            atomicAdd(&hist[key], 1u);
+        }
+        if (ordered) {
+            const int prev = __shfl_up_sync(0xffffffffu, key, 1);
+            if ((threadIdx.x & 31) && i < a.Np && (unsigned)(key - prev + 1) <= 2u) ++near;
+        }
+    }
+    if (ordered) {
+        for (int o = 16; o > 0; o >>= 1) near += __shfl_down_sync(0xffffffffu, near, o);
+        if ((threadIdx.x & 31) == 0 && near) atomicAdd(ordered, (unsigned long long)near);
     }
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
     __shared__ double red[32];
@@ -171,13 +188,145 @@ __global__ void __launch_bounds__(256) k_scan_apply(unsigned int* __restrict__ d
     for (int k = 0; k < 16; ++k) { if (t0 + k < n) data[t0 + k] = run; run += loc[k]; }
 }
 
-__global__ void k_sort_scatter(AssignIn a, unsigned int* cursor, float4* sorted)
+// flag[0] = 1: two-pass sort, 0: one pass.  Fewer than a quarter of the particles next to their predecessor = unordered input.
+__global__ void k_sort_decide(const unsigned long long* ordered, long long np, int* flag) { flag[0] = 4 * ordered[0] < (unsigned long long)np ? 1 : 0; }
+
+__global__ void k_sort_scatter(AssignIn a, unsigned int* cursor, float4* sorted, const int* flag = nullptr, int want = 0)
 {
+    if (flag && *flag != want) return;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < a.Np; i += (long long)gridDim.x * blockDim.x) {
         float x, y, z, w; double wd;
         load_particle(a, i, x, y, z, w, wd);
         const unsigned int slot = atomicAdd(&cursor[sort_key(a, x, y, z)], 1u);
         sorted[slot] = make_float4(x, y, z, w);
+    }
+}
+
+// Two-pass sort (randomly ordered catalogues on large grids).  The one-pass scatter above writes 16-byte particles to as many output
+// streams as there are keys.  When the input is not already spatially ordered and the keys number 5*10^5 or more, the half-written
+// 32-byte sectors of all streams do not survive in L2 until their other half arrives: ncu at 1024^3 / 5e8 particles shows 20.6 GB of
+// DRAM reads (sector fills) + 16.6 GB of writes for 6 GB in / 8 GB out, 50 ps per particle instead of 14 (33 ps at 5.6e5 keys).
+//   pass 0  k_partition_coarse: a CTA takes 4096 consecutive particles, ranks them per coarse bucket (2^gshift consecutive keys,
+//           <= 1024 buckets) with shared-memory counters, scans the counts, reserves the tile's range of every bucket with one global
+//           atomic, REORDERS the particles in shared memory and writes them out bucket by bucket: neighbouring lanes store
+//           neighbouring 16 bytes (runs of ~8-16 particles), full sectors, ~10^3 streams;
+//   pass 1  k_bucket_scatter: bucket by bucket (a few MB of output: L2 resident) in chunks of 8192 particles: count per key in shared
+//           memory (the returned count is the rank inside the chunk), reserve the chunk's range of every key with one atomic on the
+//           key cursor, store.  hist[] ends as after the one-pass scatter.
+constexpr int PC_THREADS = 512, PC_ITEMS = 8, PC_TILE = PC_THREADS * PC_ITEMS, PC_MAXB = 1024;
+constexpr int BS_THREADS = 512, BS_ITEMS = 16, BS_CHUNK = BS_THREADS * BS_ITEMS, BS_MAXD = 4352;
+
+__global__ void __launch_bounds__(256) k_bucket_starts(const unsigned int* __restrict__ key_start, long long nrow, int gshift, int nb,
+                                                       unsigned int np, unsigned int* __restrict__ bucket_start)
+{
+    const int b = blockIdx.x * 256 + threadIdx.x;
+    if (b <= nb) bucket_start[b] = ((long long)b << gshift) < nrow ? key_start[(size_t)b << gshift] : np;
+}
+
+__global__ void __launch_bounds__(PC_THREADS, 2) k_partition_coarse(AssignIn a, int gshift, int nb, const unsigned int* __restrict__ bucket_start,
+                                                                    unsigned int* coarse_cursor, float4* __restrict__ out, const int* flag)
+{
+    if (flag && *flag != 1) return;
+    extern __shared__ __align__(16) unsigned char pc_smem[];
+    float4* sp = reinterpret_cast<float4*>(pc_smem);                                  // [PC_TILE] particles in bucket order
+    unsigned short* sb = reinterpret_cast<unsigned short*>(sp + PC_TILE);            // [PC_TILE] bucket of every slot
+    unsigned int* cnt = reinterpret_cast<unsigned int*>(sb + PC_TILE);               // [PC_MAXB] count, then local start
+    unsigned int* gof = cnt + PC_MAXB;                                                // [PC_MAXB] global start - local start
+    __shared__ unsigned int wsum[PC_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long ntile = (a.Np + PC_TILE - 1) / PC_TILE;
+    for (long long tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+        const long long lo = tile * PC_TILE;
+        const int n = (int)(a.Np - lo < PC_TILE ? a.Np - lo : PC_TILE);
+        for (int b = threadIdx.x; b < PC_MAXB; b += PC_THREADS) cnt[b] = 0u;
+        __syncthreads();
+        float4 p[PC_ITEMS];
+        unsigned int br[PC_ITEMS];                        // bucket (low 10 bits) | rank inside the tile (high bits)
+#pragma unroll
+        for (int it = 0; it < PC_ITEMS; ++it) {
+            const int i = it * PC_THREADS + threadIdx.x;
+            if (i < n) {
+                float x, y, z, w; double wd;
+                load_particle(a, lo + i, x, y, z, w, wd);
+                p[it] = make_float4(x, y, z, w);
+                const unsigned int b = (unsigned)(sort_key(a, x, y, z) >> gshift);
+                br[it] = b | (atomicAdd(&cnt[b], 1u) << 10);
+            }
+        }
+        __syncthreads();
+        // exclusive scan of the PC_MAXB counts (two per thread) and the global reservation of every non-empty bucket
+        const unsigned int c0 = cnt[2 * threadIdx.x], c1 = cnt[2 * threadIdx.x + 1];
+        unsigned int x = c0 + c1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) wsum[warp] = x;
+        __syncthreads();
+        unsigned int base = 0;
+        for (int k = 0; k < warp; ++k) base += wsum[k];
+        const unsigned int s0 = base + x - (c0 + c1), s1 = s0 + c0;
+        __syncthreads();
+        cnt[2 * threadIdx.x] = s0; cnt[2 * threadIdx.x + 1] = s1;
+        if (c0) gof[2 * threadIdx.x] = bucket_start[2 * threadIdx.x] + atomicAdd(&coarse_cursor[2 * threadIdx.x], c0) - s0;
+        if (c1) gof[2 * threadIdx.x + 1] = bucket_start[2 * threadIdx.x + 1] + atomicAdd(&coarse_cursor[2 * threadIdx.x + 1], c1) - s1;
+        __syncthreads();
+#pragma unroll
+        for (int it = 0; it < PC_ITEMS; ++it) {
+            const int i = it * PC_THREADS + threadIdx.x;
+            if (i < n) {
+                const unsigned int b = br[it] & 1023u, slot = cnt[b] + (br[it] >> 10);
+                sp[slot] = p[it];
+                sb[slot] = (unsigned short)b;
+            }
+        }
+        __syncthreads();
+        for (int slot = threadIdx.x; slot < n; slot += PC_THREADS) out[gof[sb[slot]] + slot] = sp[slot];
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(BS_THREADS, 2) k_bucket_scatter(AssignIn a, int gshift, long long nrow, int pieces,
+                                                                  const unsigned int* __restrict__ bucket_start, unsigned int* key_cursor,
+                                                                  float4* out, const int* flag)
+{
+    if (flag && *flag != 1) return;
+    __shared__ unsigned int cnt[BS_MAXD];
+    __shared__ unsigned int off[BS_MAXD];
+    const int b = blockIdx.x / pieces, j = blockIdx.x % pieces;
+    const int kbase = b << gshift;
+    const long long rest = nrow - kbase;
+    const int nd = (int)(rest < (1LL << gshift) ? rest : (1LL << gshift));
+    const long long hi = bucket_start[b + 1], stride = (long long)pieces * BS_CHUNK;
+    for (long long lo = (long long)bucket_start[b] + (long long)j * BS_CHUNK; lo < hi; lo += stride) {
+        const long long end = lo + BS_CHUNK < hi ? lo + BS_CHUNK : hi;
+        for (int d = threadIdx.x; d < nd; d += BS_THREADS) cnt[d] = 0u;
+        __syncthreads();
+        unsigned int dr[BS_ITEMS];                       // key inside the bucket (low 16 bits) and rank inside the chunk (high 16 bits)
+#pragma unroll
+        for (int it = 0; it < BS_ITEMS; ++it) {
+            const long long i = lo + it * BS_THREADS + threadIdx.x;
+            if (i < end) {
+                float x, y, z, w; double wd;
+                load_particle(a, i, x, y, z, w, wd);
+                const unsigned int d = (unsigned)(sort_key(a, x, y, z) - kbase);
+                dr[it] = d | (atomicAdd(&cnt[d], 1u) << 16);
+            }
+        }
+        __syncthreads();
+        for (int d = threadIdx.x; d < nd; d += BS_THREADS) {
+            const unsigned int c = cnt[d];
+            if (c) off[d] = atomicAdd(&key_cursor[kbase + d], c);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int it = 0; it < BS_ITEMS; ++it) {           // the chunk is re-read (L2 resident) rather than held in registers
+            const long long i = lo + it * BS_THREADS + threadIdx.x;
+            if (i < end) {
+                float x, y, z, w; double wd;
+                load_particle(a, i, x, y, z, w, wd);
+                out[off[dr[it] & 0xffffu] + (dr[it] >> 16)] = make_float4(x, y, z, w);
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -560,12 +709,31 @@ static size_t assign_hist_bytes(int N)
 {
     const TileGeom g = tile_geom(N, 0, N);
     const size_t nkey = (size_t)N * N > (size_t)g.nkeys ? (size_t)N * N : (size_t)g.nkeys;
-    return ((nkey + 2) * sizeof(unsigned int) + 255) / 256 * 256 + 32768;      // + scan tile sums (4096) and the tile work counter
+    return ((nkey + 2) * sizeof(unsigned int) + 255) / 256 * 256 + 131072;     // + scan tile sums (4096), the tile work counter, coarse cursors (8192), bucket starts (16384)
+}
+
+// PSB_ASSIGN_TWOPASS (tests / A-B runs): 0 = never, 1 = always, n >= 2 = always with coarse buckets of 2^n keys; unset = by size
+static int two_pass_knob()
+{
+    static const int v = [] { const char* e = getenv("PSB_ASSIGN_TWOPASS"); return e ? atoi(e) : -1; }();
+    return v;
+}
+
+// whether the two-pass sort is a candidate (many keys AND a particle array far beyond L2); whether it RUNS is then decided on the
+// device from how ordered the input already is (measured: cell-ordered 1e8 particles at 512^3 sort 12 % faster in one pass,
+// shuffled ones 7 % faster in two; 1024^3 / 5e8 random particles 62.5 -> 49.9 ms in two)
+static bool sort_two_pass(long long Np, size_t nkeys)
+{
+    const int force = two_pass_knob();
+    if (force >= 0) return force != 0 && Np > 0;
+    return nkeys >= ((size_t)1 << 19) && (size_t)Np * sizeof(float4) >= ((size_t)512 << 20);
 }
 
 size_t assign_workspace_bytes(long long Np, int N)
 {
-    return 2 * assign_hist_bytes(N) + (size_t)Np * sizeof(float4) + 256;
+    const TileGeom g = tile_geom(N, 0, N);
+    const size_t copies = sort_two_pass(Np, (size_t)g.nkeys) ? 2 : 1;      // + the bucket-ordered copy
+    return 2 * assign_hist_bytes(N) + copies * ((size_t)Np * sizeof(float4) + 256) + 256;
 }
 
 int assign_pcs_interlaced(const AssignIn& in_, float* mesh, int zero_mesh, void* ws, size_t ws_bytes, double* sumw, cudaStream_t st)
@@ -597,13 +765,45 @@ int assign_pcs_interlaced(const AssignIn& in_, float* mesh, int zero_mesh, void*
     if (in.Np > 0) {
         const int blk = 256;
         const int grid = (int)((in.Np + blk - 1) / blk < sm_count() * 16 ? (in.Np + blk - 1) / blk : sm_count() * 16);
-        k_hist<<<grid, blk, 0, st>>>(in, hist, sumw);
+        // candidate for the two-pass sort by size: k_hist also measures how ordered the input is and k_sort_decide picks the path
+        // on the device (both paths are enqueued, the kernels of the other one return at once); the knob forces either path
+        const bool adaptive = in.tiles && two_pass_knob() < 0 && sort_two_pass(in.Np, nrow);
+        unsigned long long* ordered = reinterpret_cast<unsigned long long*>(tile_sum + 24576);      // zeroed with the counter areas
+        int* path_flag = reinterpret_cast<int*>(tile_sum + 24580);
+        k_hist<<<grid, blk, 0, st>>>(in, hist, sumw, adaptive ? ordered : nullptr);
+        if (adaptive) k_sort_decide<<<1, 1, 0, st>>>(ordered, in.Np, path_flag);
+        const int* flag = adaptive ? path_flag : nullptr;
         const int ntile = (int)((nrow + SCAN_TILE - 1) / SCAN_TILE);
         if (ntile > 4096) return PSB_ERR_UNSUPPORTED_N;
         k_scan_tile_sums<<<ntile, 256, 0, st>>>(hist, (int)nrow, tile_sum);
         k_scan_tiles<<<1, 256, 0, st>>>(tile_sum, ntile);
         k_scan_apply<<<ntile, 256, 0, st>>>(hist, (int)nrow, tile_sum);
-        k_sort_scatter<<<grid, blk, 0, st>>>(in, hist, sorted);
+        int gshift = two_pass_knob() >= 2 ? two_pass_knob() : 10;        // coarse buckets of >= 1024 keys, at most PC_MAXB of them
+        while ((((long long)nrow + (1LL << gshift) - 1) >> gshift) > PC_MAXB) ++gshift;
+        const size_t copy_b = ((size_t)in.Np * sizeof(float4) + 255) / 256 * 256;
+        const bool two_pass = in.tiles && sort_two_pass(in.Np, nrow) && (1 << gshift) <= BS_MAXD && in.Np < 4294967295LL &&
+                              ws_bytes >= 2 * hist_b + 2 * copy_b;
+        if (two_pass) {
+            const int nb = (int)(((long long)nrow + (1LL << gshift) - 1) >> gshift);
+            float4* bucketed = reinterpret_cast<float4*>(reinterpret_cast<char*>(sorted) + copy_b);
+            unsigned int* coarse_cursor = tile_sum + 8192;                 // zeroed with the counter areas
+            unsigned int* bucket_start = tile_sum + 16384;
+            k_bucket_starts<<<(PC_MAXB + 256) / 256, 256, 0, st>>>(hist, (long long)nrow, gshift, PC_MAXB, (unsigned)in.Np, bucket_start);
+            const size_t pc_smem = (size_t)PC_TILE * (sizeof(float4) + sizeof(unsigned short)) + 2 * PC_MAXB * sizeof(unsigned int);
+            if (cudaFuncSetAttribute(k_partition_coarse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pc_smem) != cudaSuccess) return PSB_ERR_CUDA;
+            const long long ntile = (in.Np + PC_TILE - 1) / PC_TILE;
+            k_partition_coarse<<<(unsigned)(ntile < 2LL * sm_count() ? ntile : 2LL * sm_count()), PC_THREADS, pc_smem, st>>>(
+                in, gshift, nb, bucket_start, coarse_cursor, bucketed, flag);
+            AssignIn in2 = in;                                            // second pass: float4 {x,y,z,w}, already clipped and cast
+            in2.pos = bucketed; in2.pos_aos = 2; in2.pos_f64 = 0; in2.w = nullptr; in2.do_clip = 0;
+            long long pieces = (in.Np / nb + BS_CHUNK - 1) / BS_CHUNK;   // CTAs per bucket: one chunk each at uniform density
+            pieces = pieces < 1 ? 1 : (pieces > 64 ? 64 : pieces);
+            k_bucket_scatter<<<(unsigned)(nb * pieces), BS_THREADS, 0, st>>>(in2, gshift, (long long)nrow, (int)pieces, bucket_start, hist, sorted,
+                                                                          flag);
+            if (adaptive) k_sort_scatter<<<grid, blk, 0, st>>>(in, hist, sorted, flag, 0);
+        } else {
+            k_sort_scatter<<<grid, blk, 0, st>>>(in, hist, sorted);
+        }
         // after the scatter hist[k] = end of key k = start of key k+1
         if (in.tiles) {
             const size_t smem = (size_t)TILE_WARPS * (2 * TILE_WORDS + 32 * STG) * sizeof(float);

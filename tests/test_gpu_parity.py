@@ -71,6 +71,43 @@ def test_assign_quad_matches_oracle(mods, N, Np):
     assert np.abs(a - 2 * b).max() <= 4e-6 * np.abs(b).max()
 
 
+_TWOPASS_CHILD = """
+import sys, numpy as np
+sys.path.insert(0, %r)
+from pyspectrum_b200 import pyspectrum as P, multigpu as M
+rng = np.random.default_rng(11)
+N, L, Np = 64, 100., 300000
+xyz = rng.uniform(0, L, (3, Np)); w = rng.uniform(0.5, 2., Np)
+pipe = P.PeriodicPipeline.get(N)
+pos, aos, wt = pipe.to_device(xyz, w)
+mesh, sumw = pipe.assign(pos, aos, wt, L)
+counts, sw = M.route_counts(pipe, pos, aos, wt, L, 2)
+send = M.route_scatter(pipe, pos, aos, wt, L, 2, counts)
+c = np.concatenate([[0], np.cumsum(counts.cpu().numpy())])
+slab = M.assign_slab(pipe, send[c[1]:c[2]].contiguous(), N // 2, N // 2, L)
+np.savez(sys.argv[1], mesh=mesh.cpu().numpy(), slab=slab.cpu().numpy(), sumw=sumw.cpu().numpy())
+"""
+
+
+def test_two_pass_sort_gives_the_same_mesh(mods, tmp_path):
+    """K1's two-pass sort (coarse partition with a shared-memory reorder, then bucket-local scatter; taken for randomly ordered
+    catalogues on grids with >= 5e5 tiles) forced on a small grid in a child process (PSB_ASSIGN_TWOPASS is read once): full-grid
+    and slab meshes equal the one-pass meshes up to the float32 order of the adds inside a tile, same mesh mass."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = {}
+    for flag in ('0', '1', '5'):                                          # one pass; 2 coarse buckets; 33 buckets of 32 keys
+        f = str(tmp_path / ('mesh%s.npz' % flag))
+        subprocess.check_call([sys.executable, '-c', _TWOPASS_CHILD % root, f], env=dict(os.environ, PSB_ASSIGN_TWOPASS=flag))
+        out[flag] = dict(np.load(f))
+    for flag in ('1', '5'):
+        for k in ('mesh', 'slab'):
+            a, b = out['0'][k], out[flag][k]
+            assert np.abs(a).max() > 0 and np.abs(a - b).max() <= 2e-6 * np.abs(a).max(), (flag, k)
+            assert abs(a.sum(dtype=np.float64) / b.sum(dtype=np.float64) - 1) < 1e-9
+        assert abs(out['0']['sumw'][0] / out[flag]['sumw'][0] - 1) < 1e-12       # float64 atomics: the order varies
+
+
 @pytest.mark.parametrize('idx', [(1, 1, 0, 0), (2, 3, 0, 0), (3, 1, 0, 0), (1, 2, 3, 3), (2, 2, 2, 2)])
 def test_assign_quad_quadrupole_weights_match_oracle(mods, idx):
     """Q_ij / Q_ijkl branches of assign_quad (f:294-300) through the f2py-shaped drop-in."""

@@ -117,7 +117,8 @@ def test_routed_slab_assignment_equals_the_full_mesh(mods, N, world, Np, weighte
         seg = send[base[r]:base[r + 1]].contiguous()
         slab = M.assign_slab(pipe, seg, r * nz, nz, L)
         assert slab.shape == (nz, N, N, 2)
-        assert (slab - mesh[r * nz:(r + 1) * nz]).abs().max().item() <= 2e-6 * scale
+        # the same adds in another float32 order (the sort places equal-key particles by atomic arrival): a few ulp of the largest cell
+        assert (slab - mesh[r * nz:(r + 1) * nz]).abs().max().item() <= 4e-6 * scale
     # routed positions are the float32 values assign_quad receives (clip in float64, then the cast: py:938-941)
     ref32 = np.clip(xyz, 0., L * (1 - 1e-6)).astype(np.float32)
     got = send[:, :3].cpu().numpy()

@@ -15,6 +15,8 @@ for item in spec.split(','):
         xyz = bench.lognormal_catalogue_torch(3, dev, Np, 2600., min(N, 512))
     else:
         xyz = bench.c5_shard(dev, 0, 1, Np, 2600.)
+    if os.environ.get('K1_SHUFFLE'):                       # the generators emit cell-ordered particles: destroy the order
+        xyz = xyz[:, torch.randperm(xyz.shape[1], device=dev)].contiguous()
     pipe = pySpec.PeriodicPipeline.get(N)
     for _ in range(2):
         mesh, sumw = pipe.assign(xyz, 0, None, 2600.)
