@@ -290,6 +290,7 @@ class PeriodicPipeline(object):
         self._irk, self._bins, self._nk, self._tiles, self._counts = {}, {}, {}, {}, {}
         self._pin_pool = {}                               # free pinned result buffers by size (bispectrum_launch/finish)
         self._copy_stream = None                          # upload stream of the *_many generators
+        self._side_stream = None                          # second stream of the routed shell stage (multi-GPU)
 
     # ------------------------------------------------------------------ tables
     @property
@@ -636,6 +637,19 @@ class PeriodicPipeline(object):
         t1 = torch.empty(W * W * N * 2, dtype=cdt, device=self.dev)
         t2 = torch.empty(W * N * N * 2, dtype=cdt, device=self.dev)
         tw = self.tw64 if f64 else self.tw32
+        # routed output: the z pass of a pair is bound by its NVLink stores, so consecutive pairs alternate between two streams (own
+        # scratch each) and the x / y passes of pair k+1 run under the z pass of pair k
+        nstream = int(os.environ.get('PSB_ROUTED_STREAMS', '2')) if (routed is not None and len(plist) > 1) else 1
+        main = torch.cuda.current_stream(self.dev)
+        lanes = [(main, t1, t2)]
+        if nstream > 1:
+            if self._side_stream is None:
+                self._side_stream = torch.cuda.Stream(device=self.dev)
+            side = self._side_stream
+            side.wait_stream(main)
+            lanes.append((side, torch.empty_like(t1), torch.empty_like(t2)))
+            for t in lanes[1][1:]:
+                t.record_stream(side)
         for r, pidx in enumerate(plist):
             s = 2 * pidx
             if s >= S:                                   # padding pair (shard equalisation): empty shells -> zero fields
@@ -651,10 +665,12 @@ class PeriodicPipeline(object):
                                                    _ptr(fields[2 * r + 1]), sq, _ptr(tw), st), 'psb_bk_shell_pair_f64')
             elif routed is not None:
                 table, rplanes, rranks = routed
-                check(self.L.psb_bk_shell_pair_f32_routed(_ptr(half), _ptr(irk), N, Ns, sa, sb, R, _ptr(t1), _ptr(t2),
+                ln_stream, ln_t1, ln_t2 = lanes[r % len(lanes)]
+                check(self.L.psb_bk_shell_pair_f32_routed(_ptr(half), _ptr(irk), N, Ns, sa, sb, R, _ptr(ln_t1), _ptr(ln_t2),
                                                           ctypes.c_void_p(table.data_ptr() + 8 * 2 * rranks * r), rplanes, rranks, sq,
                                                           ctypes.c_void_p(sc_local.data_ptr() + 4 * 2 * r),
-                                                          ctypes.c_void_p(maxabs.data_ptr() + 4 * 2 * r), 1, _ptr(tw), st),
+                                                          ctypes.c_void_p(maxabs.data_ptr() + 4 * 2 * r), 1, _ptr(tw),
+                                                          ctypes.c_void_p(ln_stream.cuda_stream)),
                       'psb_bk_shell_pair_f32_routed')
             else:
                 sc = mx = None
@@ -664,6 +680,8 @@ class PeriodicPipeline(object):
                 check(self.L.psb_bk_shell_pair_f32(_ptr(half), _ptr(irk), N, Ns, sa, sb, R, _ptr(t1), _ptr(t2), _ptr(fields[2 * r]),
                                                    _ptr(fields[2 * r + 1]), sq, sc, mx, 1 if scaled else 0, _ptr(tw), st),
                       'psb_bk_shell_pair_f32')
+        if len(lanes) > 1:
+            main.wait_stream(lanes[1][0])
         if scaled:
             if fields is not None:
                 fields.psb_packed = True                 # rows hold {half2 hi, half2 lo} per cell pair (see unpack_fields)
