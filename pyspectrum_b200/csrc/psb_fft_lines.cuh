@@ -249,7 +249,7 @@ __device__ __forceinline__ Real2<float> pack_hilo(Real2<float> v)
 }
 __device__ __forceinline__ Real2<double> pack_hilo(Real2<double> v) { return v; }       // float64 path is never packed
 
-template <typename T, bool PRUNED, bool REALOUT> struct IoCols {
+template <typename T, bool PRUNED, bool REALOUT, bool ROUTED = false> struct IoCols {
     const Cx<T>* in;
     Cx<T>* out;            // complex output (REALOUT == false)
     T* outa; T* outb;      // planar real outputs (REALOUT == true): re -> outa, im -> outb (outb may be null)
@@ -293,7 +293,7 @@ template <typename T, bool PRUNED, bool REALOUT> struct IoCols {
         if (REALOUT) {
             a.sa = scale2 ? (T)scale2[0] : (T)1;
             a.sb = scale2 ? (T)scale2[1] : (T)1;
-            if (route) {
+            if (ROUTED) {
                 a.st = a.live && route[(line & 1) ? rranks : 0] != 0;
                 a.outp = static_cast<T*>(nullptr) + ((long long)blockIdx.y * out_bstride + (l & ~1));
             } else {
@@ -336,7 +336,7 @@ template <typename T, bool PRUNED, bool REALOUT> struct IoCols {
                 if (acc.st) {
                     if (halfpack) r = pack_hilo(r);
                     T* dst = acc.outp + (unsigned)idx * acc.ostr;
-                    if (route) {                           // plane idx lives on rank idx / rplanes
+                    if (ROUTED) {                          // plane idx lives on rank idx / rplanes (compile-time: the local kernel pays nothing)
                         const unsigned q = __umulhi((unsigned)idx, rmagic);
                         dst = reinterpret_cast<T*>(route[(acc.even ? 0u : (unsigned)rranks) + q] + reinterpret_cast<long long>(dst));
                     }

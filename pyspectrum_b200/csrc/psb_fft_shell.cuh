@@ -32,18 +32,24 @@ int fft_shell_pair(const Cx<float>* half, const unsigned short* irk, int N, int 
         rc = launch_any<T, -1>(cfg, p, LPC, dim3((N + LPC - 1) / LPC, W), tw, io2, st);
         if (rc) return rc;
         // pass 3 (z): batch = y, T2[kz'][y][x] -> real planes [z][y][x] (+ sums of squares)
-        IoCols<T, true, true> io3{ t2, nullptr, fa, fb, sumsq, scale2, maxabs2, halfpack, N, N, (long long)N * N, N, (long long)N * N, Rm, Rp,
-                                   route, rplanes, rranks, route ? (unsigned)(4294967296ULL / (unsigned)rplanes) + 1u : 0u };
-        if (route && !plan_is_fused(cfg)) return (int)PSB_ERR_UNSUPPORTED_N;      // routed stores exist in the fused epilogue only
+        if (!route) {
+            IoCols<T, true, true> io3{ t2, nullptr, fa, fb, sumsq, scale2, maxabs2, halfpack, N, N, (long long)N * N, N, (long long)N * N, Rm, Rp,
+                                       nullptr, 0, 0, 0u };
+            return launch_any<T, -1>(cfg, p, LPC, dim3((N + LPC - 1) / LPC, N), tw, io3, st);
+        }
+        // routed output (multi-GPU): its own instantiation of the epilogue; stores exist in the fused kernels only
+        if (!plan_is_fused(cfg)) return (int)PSB_ERR_UNSUPPORTED_N;
+        IoCols<T, true, true, true> io3{ t2, nullptr, fa, fb, sumsq, scale2, maxabs2, halfpack, N, N, (long long)N * N, N, (long long)N * N, Rm, Rp,
+                                         route, rplanes, rranks, (unsigned)(4294967296ULL / (unsigned)rplanes) + 1u };
         // the routed z pass runs with 32 lines per CTA: a CTA's (plane, z) run is 128 bytes instead of 64, which NVLink stores need
         // (2 GPUs, C2: shell stage 5.78 -> 4.97 ms; locally the 16-line kernel is the faster one).  PSB_ROUTED_LPC=16 restores it.
         using CFG = decltype(cfg);
         if constexpr (CFG::Stages::IS_STATIC && sizeof(T) == 4) {
             if constexpr (CFG::Stages::NSTAGES >= 2 && CFG::LPC == 16 && 32 * CFG::TPL <= 1024) {
                 static const int wide = [] { const char* e = getenv("PSB_ROUTED_LPC"); return e ? atoi(e) : 32; }();
-                if (route && wide == 32) {
+                if (wide == 32) {
                     using C32 = Cfg<typename CFG::Stages, 32, CFG::MAXB, 1>;
-                    return launch_static<T, -1, C32, IoCols<T, true, true>>(dim3((N + 31) / 32, N), tw, io3, st);
+                    return launch_static<T, -1, C32, IoCols<T, true, true, true>>(dim3((N + 31) / 32, N), tw, io3, st);
                 }
             }
         }
