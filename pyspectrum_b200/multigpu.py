@@ -13,7 +13,7 @@ The slab design of SURVEY 8e; every exchange is a data-plane collective on NVLin
   5. CARRIER    the shells of B(k) only reach |k_a| <= R = floor(step (Nmax + 1/2)), and all their triangles close without a wrap
                 on any grid with more than R_i + R_j + R_l points per side (pyspectrum.coarse_levels): every rank copies the low-k
                 modes it owns into the half field of a small carrier grid Ng                [all-reduce: 4 (Ng/2+1) Ng^2 B]
-                (Ng = N when the reference's own grid lets triangles wrap, e.g. Ngrid=360 with Nmax=40.)
+                (Ng = N when the reference's own grid lets triangles wrap, e.g. Ngrid=360 with Nmax=40: then an all-gather of the ky-slabs.)
   6. SHELLS     per transform grid (level) of the carrier: the packed shell PAIRS are dealt round-robin, each rank transforms its
                 pairs (K5), every field is cut into G slabs of cells, slab q -> rank q      [ONE all-to-all per level: 4 S Nc^3 (G-1)/G B]
   7. TRIANGLES  slab-local K6 on every rank, partial sums                                  [all-reduce: Ntri + 3 S float64, once]
@@ -462,9 +462,15 @@ def carrier_grid(N, step, Nmax, Ncut):
 def low_k_carrier(pipe, half_slab, ky0, Ng, stats=None):
     """Step 5: replicated half field on the carrier grid Ng from the ranks' ky-slabs (zero outside |k_a| < Ng/2 when Ng < N)."""
     N = pipe.N
+    st = _stats(stats)
+    if Ng == N and _world() > 1:                         # the carrier IS delta(k): an all-gather of the ky-slabs moves 1/G of the bytes
+        e0 = st.mark()
+        car = gather_ky_slabs(half_slab, _world()).contiguous()
+        st.span('carrier_all_gather', e0)
+        st.add_bytes('carrier_all_gather', half_slab.numel() * 4 * (_world() - 1))
+        return car
     car = torch.empty((Ng, Ng, Ng // 2 + 1, 2), dtype=torch.float32, device=pipe.dev)
     P.check(pipe.L.psb_half_extract(P._ptr(half_slab), N, ky0, half_slab.shape[1], P._ptr(car), Ng, P._stream()), 'psb_half_extract')
-    st = _stats(stats)
     e0 = st.mark()
     _allreduce(car)
     st.span('carrier_all_reduce', e0)
