@@ -84,6 +84,14 @@ int psb_slab_route_count(const void* pos, int pos_f64, int pos_aos, const void* 
 int psb_slab_route_scatter(const void* pos, int pos_f64, int pos_aos, const void* w, int w_f64, int64_t np, int ngrid, double lbox_clip,
                            float kf_ks, float offset, int nz_per_rank, int nranks, const uint64_t* base, uint64_t* cursor,
                            float* send_xyzw, void* stream);
+/* The same with the exchange fused in: every copy is stored straight into the receive buffer of its destination rank (NVLink peer
+ * stores; the copies of a 2048-particle tile leave destination by destination in 16-byte-contiguous runs).  dest_addr = device
+ * int64 [G]: the address at which THIS rank's segment starts in rank d's receive buffer (peer pointer + 16 B x the particles the
+ * ranks in front of this one send to d: needs the all-gathered counts); cursor [G] scratch.  The caller brackets the call with a
+ * barrier over the ranks (the buffers must be free before, complete after). */
+int psb_slab_route_scatter_peer(const void* pos, int pos_f64, int pos_aos, const void* w, int w_f64, int64_t np, int ngrid, double lbox_clip,
+                                float kf_ks, float offset, int nz_per_rank, int nranks, const int64_t* dest_addr, uint64_t* cursor,
+                                void* stream);
 int psb_assign_slab(const float* xyzw, int64_t np, int ngrid, float kf_ks, float offset, int zbase, int nzs, float* mesh_slab,
                     int zero_mesh, void* ws, size_t ws_bytes, double* sumw_scratch, void* stream);
 

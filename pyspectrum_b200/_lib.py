@@ -49,6 +49,7 @@ PROTOTYPES = {
     'psb_assign_pcs_interlaced': (_i, [_vp, _i, _i, _vp, _i, _i64, _i, _d, _f, _f, _vp, _i, _vp, _sz, _vp, _vp]),
     'psb_slab_route_count': (_i, [_vp, _i, _i, _vp, _i, _i64, _i, _d, _f, _f, _i, _i, _vp, _vp, _vp]),
     'psb_slab_route_scatter': (_i, [_vp, _i, _i, _vp, _i, _i64, _i, _d, _f, _f, _i, _i, _vp, _vp, _vp, _vp]),
+    'psb_slab_route_scatter_peer': (_i, [_vp, _i, _i, _vp, _i, _i64, _i, _d, _f, _f, _i, _i, _vp, _vp, _vp]),
     'psb_assign_slab': (_i, [_vp, _i64, _i, _f, _f, _i, _i, _vp, _i, _vp, _sz, _vp, _vp]),
     'psb_survey_prepare': (_i, [_vp, _vp, _vp, _i64, _vp, _i, _d, _d, _vp, _vp, _vp, _vp]),
     'psb_fft_mesh_to_delta': (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp]),

@@ -680,6 +680,85 @@ __global__ void __launch_bounds__(256) k_route_scatter(AssignIn a, int nzr, int 
     }
 }
 
+// The same scatter with the particle exchange fused in (NVLink peer stores instead of a send buffer + all-to-all): dest[d] is the
+// address at which THIS rank's segment starts in rank d's receive buffer (peer pointer + the particles of the ranks in front, from
+// the all-gathered counts).  A CTA takes 2048 consecutive particles, ranks their <= 4096 copies per destination in shared memory,
+// reserves the tile's range of every destination with one atomic on the local cursor, REORDERS the copies in shared memory and
+// writes them out destination by destination: neighbouring lanes store neighbouring 16 bytes, runs of ~2048/G particles.
+constexpr int RP_THREADS = 512, RP_ITEMS = 4, RP_TILE = RP_THREADS * RP_ITEMS;
+
+__global__ void __launch_bounds__(RP_THREADS, 2) k_route_scatter_peer(AssignIn a, int nzr, int nranks, const long long* __restrict__ dest,
+                                                                      unsigned long long* cursor)
+{
+    extern __shared__ __align__(16) unsigned char rp_smem[];
+    float4* sp = reinterpret_cast<float4*>(rp_smem);                                  // [2 * RP_TILE] copies in destination order
+    unsigned char* sd = reinterpret_cast<unsigned char*>(sp + 2 * RP_TILE);          // [2 * RP_TILE] destination of every slot
+    __shared__ unsigned int cnt[ROUTE_MAXR], lstart[ROUTE_MAXR];
+    __shared__ long long gaddr[ROUTE_MAXR];                                          // address of slot lstart[d] in rank d's buffer
+    __shared__ unsigned int total;
+    const long long ntile = (a.Np + RP_TILE - 1) / RP_TILE;
+    for (long long tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+        const long long lo = tile * RP_TILE;
+        const int n = (int)(a.Np - lo < RP_TILE ? a.Np - lo : RP_TILE);
+        if (threadIdx.x < ROUTE_MAXR) cnt[threadIdx.x] = 0u;
+        __syncthreads();
+        float4 p[RP_ITEMS];
+        int d0[RP_ITEMS], d1[RP_ITEMS];
+        unsigned int r0[RP_ITEMS], r1[RP_ITEMS];
+#pragma unroll
+        for (int it = 0; it < RP_ITEMS; ++it) {
+            const int i = it * RP_THREADS + threadIdx.x;
+            d0[it] = d1[it] = -1;
+            if (i < n) {
+                float x, y, z, w; double wd;
+                load_particle(a, lo + i, x, y, z, w, wd);
+                p[it] = make_float4(x, y, z, w);
+                slab_dests(a, z, nzr, d0[it], d1[it]);
+                r0[it] = atomicAdd(&cnt[d0[it]], 1u);
+                if (d1[it] != d0[it]) r1[it] = atomicAdd(&cnt[d1[it]], 1u); else d1[it] = -1;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {                            // exclusive scan over the destinations (<= 64: two per lane) + reservation
+            const int e0 = 2 * threadIdx.x, e1 = e0 + 1;
+            const unsigned int c0 = e0 < nranks ? cnt[e0] : 0u, c1 = e1 < nranks ? cnt[e1] : 0u;
+            unsigned int x = c0 + c1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned int y = __shfl_up_sync(0xffffffffu, x, o); if (threadIdx.x >= o) x += y; }
+            const unsigned int s0 = x - (c0 + c1), s1 = s0 + c0;
+            if (e0 < nranks) { lstart[e0] = s0; if (c0) gaddr[e0] = dest[e0] + 16LL * (long long)atomicAdd(&cursor[e0], (unsigned long long)c0); }
+            if (e1 < nranks) { lstart[e1] = s1; if (c1) gaddr[e1] = dest[e1] + 16LL * (long long)atomicAdd(&cursor[e1], (unsigned long long)c1); }
+            if (threadIdx.x == 31) total = x;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int it = 0; it < RP_ITEMS; ++it) {
+            if (d0[it] >= 0) { const unsigned int s = lstart[d0[it]] + r0[it]; sp[s] = p[it]; sd[s] = (unsigned char)d0[it]; }
+            if (d1[it] >= 0) { const unsigned int s = lstart[d1[it]] + r1[it]; sp[s] = p[it]; sd[s] = (unsigned char)d1[it]; }
+        }
+        __syncthreads();
+        const unsigned int ne = total;
+        for (unsigned int s = threadIdx.x; s < ne; s += RP_THREADS) {
+            const int d = sd[s];
+            *reinterpret_cast<float4*>(gaddr[d] + 16LL * (long long)(s - lstart[d])) = sp[s];
+        }
+        __syncthreads();
+    }
+}
+
+int slab_route_scatter_peer(const AssignIn& in, int nzr, int nranks, const long long* dest, unsigned long long* cursor, cudaStream_t st)
+{
+    if (in.N < 4 || in.N % 2 || in.Np < 0 || nranks < 1 || nranks > ROUTE_MAXR || nzr < 8 || nzr * nranks != in.N || !dest || !cursor) return PSB_ERR_ARG;
+    if (cudaMemsetAsync(cursor, 0, nranks * sizeof(unsigned long long), st) != cudaSuccess) return PSB_ERR_CUDA;
+    if (in.Np > 0) {
+        const size_t smem = (size_t)2 * RP_TILE * (sizeof(float4) + 1);
+        if (cudaFuncSetAttribute(k_route_scatter_peer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PSB_ERR_CUDA;
+        const long long nt = (in.Np + RP_TILE - 1) / RP_TILE;
+        k_route_scatter_peer<<<(unsigned)(nt < 2LL * sm_count() ? nt : 2LL * sm_count()), RP_THREADS, smem, st>>>(in, nzr, nranks, dest, cursor);
+    }
+    return cudaGetLastError() == cudaSuccess ? PSB_OK : PSB_ERR_CUDA;
+}
+
 int slab_route_count(const AssignIn& in, int nzr, int nranks, unsigned long long* counts, double* sumw, cudaStream_t st)
 {
     if (in.N < 4 || in.N % 2 || in.Np < 0 || nranks < 1 || nranks > ROUTE_MAXR || nzr < 8 || nzr * nranks != in.N) return PSB_ERR_ARG;

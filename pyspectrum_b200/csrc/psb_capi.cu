@@ -175,6 +175,14 @@ int psb_slab_route_scatter(const void* pos, int pos_f64, int pos_aos, const void
                               reinterpret_cast<float4*>(send_xyzw), S(stream));
 }
 
+int psb_slab_route_scatter_peer(const void* pos, int pos_f64, int pos_aos, const void* w, int w_f64, int64_t np, int ngrid, double lbox_clip,
+                                float kf_ks, float offset, int nz_per_rank, int nranks, const int64_t* dest_addr, uint64_t* cursor, void* stream)
+{
+    if ((!pos && np > 0) || !dest_addr || !cursor) return PSB_ERR_ARG;
+    return slab_route_scatter_peer(route_in(pos, pos_f64, pos_aos, w, w_f64, np, ngrid, lbox_clip, kf_ks, offset), nz_per_rank, nranks,
+                                   reinterpret_cast<const long long*>(dest_addr), reinterpret_cast<unsigned long long*>(cursor), S(stream));
+}
+
 int psb_assign_slab(const float* xyzw, int64_t np, int ngrid, float kf_ks, float offset, int zbase, int nzs, float* mesh_slab, int zero_mesh,
                     void* ws, size_t ws_bytes, double* sumw_scratch, void* stream)
 {

@@ -30,6 +30,8 @@ int assign_pcs_interlaced(const AssignIn& in, float* mesh, int zero_mesh, void* 
 int slab_route_count(const AssignIn& in, int nz_per_rank, int nranks, unsigned long long* counts, double* sumw, cudaStream_t st);
 int slab_route_scatter(const AssignIn& in, int nz_per_rank, int nranks, const unsigned long long* base, unsigned long long* cursor,
                        float4* send, cudaStream_t st);
+int slab_route_scatter_peer(const AssignIn& in, int nz_per_rank, int nranks, const long long* dest_addr, unsigned long long* cursor,
+                            cudaStream_t st);
 
 int fft_mesh_to_delta(Cx<float>* mesh, Cx<float>* half, int N, const Cx<float>* tw,
                       const Cx<double>* rec, const float* Wk, const double* sumw, int periodic, cudaStream_t st);

@@ -4,7 +4,8 @@ The slab design of SURVEY 8e; every exchange is a data-plane collective on NVLin
 
   1. ROUTE      every rank holds an arbitrary shard of the particles.  Rank q owns the mesh planes [q nz, (q+1) nz), nz = N/G; a
                 particle in cell c touches planes c-1 .. c+3, so it is sent (float32 {x,y,z,w} after the float64 clip of py:938-941)
-                to the owner of plane c-1 and, if different, of plane c+3 (ghost copy)      [all-to-all: 16 B per particle (+ ghosts)]
+                to the owner of plane c-1 and, if different, of plane c+3 (ghost copy)      [16 B per particle (+ ghosts): peer stores
+                from inside the route kernel under NCCL, else an all-to-all]
   2. ASSIGN     K1 on the received particles onto the rank's OWN planes only (psb_assign_slab): no mesh collective at all
   3. FFT        x and y passes in the slab, separation of the two interlaced grids' spectra (the conjugate partner (-kx,-ky) is
                 in the same plane), z-slabs -> ky-slabs                                    [all-to-all: 2 x 4 (N/2+1) N^2 / G B per rank]
@@ -266,6 +267,10 @@ def route_particles(pipe, xyz_local, w_local, Lbox, offset=0., clip=True, stats=
     # the small collectives first, then ONE device -> host copy with everything the host needs (split sizes both ways, N)
     meta = torch.cat([sumw, torch.tensor([float(Np)], dtype=torch.float64, device=pipe.dev)])
     _allreduce(meta)
+    if _peer_exchange_enabled():
+        got = _route_particles_peer(pipe, pos, aos, wt, Lbox, world, counts, meta, offset, clip, st, e0)
+        if got is not None:
+            return got
     rc = torch.empty_like(counts)
     dist.all_to_all_single(rc, counts)
     host = torch.cat([counts.double(), rc.double(), meta[1:]]).cpu().tolist()
@@ -277,6 +282,56 @@ def route_particles(pipe, xyz_local, w_local, Lbox, offset=0., clip=True, stats=
     dist.all_to_all_single(recv, send, output_split_sizes=rc_h, input_split_sizes=sc_h)
     st.span('particles_all_to_all', e0)
     st.add_bytes('particles_all_to_all', 16 * (sum(sc_h) - sc_h[_rank()]))
+    return recv, meta[:1].clone(), ntot
+
+
+_RECV_CAP = {}
+
+
+def _peer_exchange_enabled():
+    return os.environ.get('PSB_SHARDED_ROUTED', '1') != '0' and not _ROUTED_BROKEN
+
+
+def _route_particles_peer(pipe, pos, aos, wt, Lbox, world, counts, meta, offset, clip, st, e0):
+    """The particle exchange as NVLink peer stores from inside the route kernel (psb_slab_route_scatter_peer) instead of a send
+    buffer + all-to-all: the counts of all ranks are all-gathered, so every rank knows where its segment starts in every receive
+    buffer; the buffers are one symmetric allocation per process group, grown when a catalogue needs more.  Returns None when
+    symmetric memory is unavailable (the caller then takes the bulk path)."""
+    rank = _rank()
+    N = pipe.N
+    Np = pos.shape[0] if aos else pos.shape[1]
+    mat = torch.empty(world * world, dtype=counts.dtype, device=pipe.dev)
+    dist.all_gather_into_tensor(mat, counts.contiguous())                     # mat[s * world + d] = copies rank s sends to rank d
+    host = torch.cat([mat.double(), meta[1:]]).cpu().numpy()
+    M_ = np.rint(host[:world * world]).astype(np.int64).reshape(world, world)
+    ntot = int(round(host[world * world]))
+    recv_tot = M_.sum(axis=0)
+    need = int(recv_tot.max())
+    key = (str(pipe.dev), world)
+    cap = _RECV_CAP.get(key, 0)
+    if cap < need:                                       # same decision on every rank (same matrix): grow the symmetric buffer
+        if cap:
+            SlabBuffers._cache.pop((str(pipe.dev), world, 1, 4 * cap), None)
+        cap = int(1.25 * need) + 4096
+        _RECV_CAP[key] = cap
+    bufs = routed_slabs(pipe.dev, world, rank, 1, 4 * cap)
+    if bufs is None:
+        _RECV_CAP.pop(key, None)
+        return None
+    seg = M_[:rank].sum(axis=0)                          # particles the ranks in front of this one send to every destination
+    dest = torch.from_numpy(np.array([bufs.ptrs[d] + 16 * int(seg[d]) for d in range(world)], np.int64)).to(pipe.dev)
+    cursor = torch.zeros(world, dtype=torch.int64, device=pipe.dev)
+    st.span('route_kernels', e0)
+    e1 = st.mark()
+    bufs.barrier()                                       # every rank has consumed its previous catalogue
+    P.check(pipe.L.psb_slab_route_scatter_peer(P._ptr(pos), int(pos.dtype == torch.float64), aos, P._ptr(wt),
+                                               int(wt is not None and wt.dtype == torch.float64), Np, N, float(Lbox) if clip else 0.0,
+                                               np.float32(float(N) / Lbox), np.float32(offset), N // world, world, P._ptr(dest),
+                                               P._ptr(cursor), P._stream()), 'psb_slab_route_scatter_peer')
+    bufs.barrier()                                       # every rank's copies have landed
+    st.span('particles_peer_stores', e1)
+    st.add_bytes('particles_peer_stores', 16 * int(M_[rank].sum() - M_[rank, rank]))
+    recv = bufs.local.view(-1, 4)[:int(recv_tot[rank])]
     return recv, meta[:1].clone(), ntot
 
 

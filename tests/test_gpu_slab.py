@@ -257,3 +257,42 @@ def test_routed_slab_fft_exchange_equals_the_all_to_all(mods, N, world):
             want = torch.cat([M.z_to_y_chunks(pq[g][k], world)[q] for g in range(world)], dim=0)        # [N, ny, hp, 2]
             got = ranks[q].local[k].view(N, nz, hp, 2)
             assert torch.equal(got.view(torch.int32), want.view(torch.int32)), (q, k)
+
+
+@pytest.mark.parametrize('N,world,Np', [(32, 2, 20000), (64, 4, 100000), (64, 8, 300000), (360, 8, 1000000)])
+def test_peer_store_route_scatter_delivers_the_all_to_all_segments(mods, N, world, Np):
+    """psb_slab_route_scatter_peer with emulated ranks: every rank routes ITS shard of the catalogue and stores the copies straight
+    into the receive buffers of their destinations (buffers of this device standing in for peer memory), at the segment offsets that
+    follow from the all-gathered counts.  Every (source, destination) segment must hold exactly the particles the send-buffer
+    scatter + all-to-all delivers (the order inside a segment is not defined in either path: compared as sorted byte rows)."""
+    import torch
+    pySpec, M = mods
+    L = 100.
+    xyz, w = _catalogue(N, Np, L, 3 * N + world)
+    pipe = pySpec.PeriodicPipeline.get(N)
+    shards = [(np.ascontiguousarray(xyz[:, r::world]), np.ascontiguousarray(w[r::world])) for r in range(world)]
+    dev = [pipe.to_device(x, ww) for x, ww in shards]
+    counts = [M.route_counts(pipe, pos, aos, wt, L, world)[0] for pos, aos, wt in dev]
+    Mh = np.stack([c.cpu().numpy() for c in counts])                          # [source][destination]
+    recv_tot = Mh.sum(axis=0)
+    bufs = [torch.full((int(recv_tot[d]) + 8, 4), float('nan'), dtype=torch.float32, device=pipe.dev) for d in range(world)]
+    for r, (pos, aos, wt) in enumerate(dev):
+        seg = Mh[:r].sum(axis=0)
+        dest = torch.tensor([bufs[d].data_ptr() + 16 * int(seg[d]) for d in range(world)], dtype=torch.int64, device=pipe.dev)
+        cursor = torch.zeros(world, dtype=torch.int64, device=pipe.dev)
+        npart = pos.shape[0] if aos else pos.shape[1]
+        pySpec.check(pipe.L.psb_slab_route_scatter_peer(pySpec._ptr(pos), int(pos.dtype == torch.float64), aos, pySpec._ptr(wt),
+                                                        int(wt.dtype == torch.float64), npart, N, float(L), np.float32(N / L), np.float32(0.),
+                                                        N // world, world, pySpec._ptr(dest), pySpec._ptr(cursor), pySpec._stream()),
+                     'psb_slab_route_scatter_peer')
+        assert np.array_equal(cursor.cpu().numpy(), Mh[r])
+    rows = lambda t: np.sort(np.ascontiguousarray(t.cpu().numpy()).view([('', np.float32)] * 4).ravel())
+    for r, (pos, aos, wt) in enumerate(dev):
+        send = M.route_scatter(pipe, pos, aos, wt, L, world, counts[r])
+        base = np.concatenate([[0], np.cumsum(Mh[r])])
+        seg = Mh[:r].sum(axis=0)
+        for d in range(world):
+            got = bufs[d][int(seg[d]):int(seg[d]) + int(Mh[r, d])]
+            assert np.array_equal(rows(got), rows(send[base[d]:base[d + 1]])), (r, d)
+    for d in range(world):                                                    # nothing written past the end
+        assert bool(torch.isnan(bufs[d][int(recv_tot[d]):]).all())
