@@ -288,6 +288,14 @@ def route_particles(pipe, xyz_local, w_local, Lbox, offset=0., clip=True, stats=
 _RECV_CAP = {}
 
 
+def peer_segments(counts_matrix, rank):
+    """Host bookkeeping of the peer-store particle exchange.  counts_matrix[s][d] = copies rank s sends to rank d (all-gathered, the
+    same on every rank).  Returns (recv_tot[d] = particles rank d receives, seg[d] = offset in particles of THIS rank's segment in
+    rank d's receive buffer: the ranks in front of it write first)."""
+    m = np.asarray(counts_matrix, dtype=np.int64)
+    return m.sum(axis=0), m[:rank].sum(axis=0)
+
+
 def _peer_exchange_enabled():
     return os.environ.get('PSB_SHARDED_ROUTED', '1') != '0' and not _ROUTED_BROKEN
 
@@ -305,7 +313,7 @@ def _route_particles_peer(pipe, pos, aos, wt, Lbox, world, counts, meta, offset,
     host = torch.cat([mat.double(), meta[1:]]).cpu().numpy()
     M_ = np.rint(host[:world * world]).astype(np.int64).reshape(world, world)
     ntot = int(round(host[world * world]))
-    recv_tot = M_.sum(axis=0)
+    recv_tot, seg = peer_segments(M_, rank)
     need = int(recv_tot.max())
     key = (str(pipe.dev), world)
     cap = _RECV_CAP.get(key, 0)
@@ -318,7 +326,6 @@ def _route_particles_peer(pipe, pos, aos, wt, Lbox, world, counts, meta, offset,
     if bufs is None:
         _RECV_CAP.pop(key, None)
         return None
-    seg = M_[:rank].sum(axis=0)                          # particles the ranks in front of this one send to every destination
     dest = torch.from_numpy(np.array([bufs.ptrs[d] + 16 * int(seg[d]) for d in range(world)], np.int64)).to(pipe.dev)
     cursor = torch.zeros(world, dtype=torch.int64, device=pipe.dev)
     st.span('route_kernels', e0)

@@ -135,3 +135,38 @@ def test_carrier_grid_choice():
     assert carrier_grid(360, 3, 40, 3) == 360               # the reference's own grid lets the largest triangles wrap: stay on it
     assert carrier_grid(512, 2, 80, 3) == 512               # 483 < 512 but no compiled grid in between
     assert carrier_grid(512, 3, 20, 3) == 256
+
+
+def _worker_segments(rank, world, port, out):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    import numpy as np
+    import torch.distributed as dist
+    dist.init_process_group('gloo')
+    from pyspectrum_b200.multigpu import peer_segments
+    counts = torch.tensor([[5, 2, 0], [1, 7, 3], [4, 0, 6]][rank][:world], dtype=torch.int64)        # copies this rank sends to every rank
+    gathered = [torch.empty_like(counts) for _ in range(world)]
+    dist.all_gather(gathered, counts)
+    m = np.stack([g.numpy() for g in gathered])
+    recv_tot, seg = peer_segments(m, rank)
+    # every rank "stores" its segment ids into every destination buffer through an all-to-all of (offset, length) pairs
+    out.put((rank, recv_tot.tolist(), seg.tolist(), counts.tolist()))
+    dist.destroy_process_group()
+
+
+def test_peer_segments_tile_the_receive_buffers_gloo():
+    """The segments of all sources tile every destination's receive buffer exactly (no gap, no overlap), in rank order."""
+    import torch.multiprocessing as mp
+    world = 3
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_segments, args=(r, world, 29631, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+    for d in range(world):
+        spans = sorted((res[s][2][d], res[s][2][d] + res[s][3][d]) for s in range(world))
+        assert spans[0][0] == 0 and all(a[1] == b[0] for a, b in zip(spans, spans[1:])) and spans[-1][1] == res[0][1][d]
+        assert [sp[0] for sp in spans] == [res[s][2][d] for s in range(world)]           # rank order
+    assert all(r[1] == res[0][1] for r in res)
