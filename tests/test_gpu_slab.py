@@ -296,3 +296,25 @@ def test_peer_store_route_scatter_delivers_the_all_to_all_segments(mods, N, worl
             assert np.array_equal(rows(got), rows(send[base[d]:base[d + 1]])), (r, d)
     for d in range(world):                                                    # nothing written past the end
         assert bool(torch.isnan(bufs[d][int(recv_tot[d]):]).all())
+
+
+def test_c5_grid_through_every_step_of_the_sharded_path(mods, monkeypatch, tmp_path):
+    """BASELINE configs[4]'s grid and shells (Ngrid = 1024, step 3, Ncut 3, Nmax 40: 6350 triangles, 400^3 carrier) at a particle
+    count one GPU holds, through every step of the sharded path on one rank (route, slab assignment incl. the two-pass sort candidate,
+    slab FFT, slab binning, carrier, dealt pairs, cell slabs) against the single-GPU API.  (The multi-rank run of the same
+    comparison is tools/run_sharded.py c5check: profiles/r2_summary.md.)"""
+    pySpec, M = mods
+    monkeypatch.setattr(pySpec, '_DAT_DIR', str(tmp_path))
+    N, L, Np, step, Ncut, Nmax = 1024, 4000., 3000000, 3, 3, 40
+    xyz, w = _catalogue(N, Np, L, 5)
+    assert M.carrier_grid(N, step, Nmax, Ncut) == 400
+    ref = pySpec.Bk_periodic(xyz, w=w, Lbox=L, Ngrid=N, step=step, Ncut=Ncut, Nmax=Nmax)
+    got, pk = M.Bk_periodic_sharded(xyz, w, Lbox=L, Ngrid=N, step=step, Ncut=Ncut, Nmax=Nmax, return_pk=True)
+    assert len(ref['b123']) == 6350 and np.array_equal(got['i_k1'], ref['i_k1']) and np.array_equal(got['i_k3'], ref['i_k3'])
+    assert np.array_equal(got['counts'], ref['counts'])
+    np.testing.assert_allclose(got['p0k1'] + got['p0k_sn'], ref['p0k1'] + ref['p0k_sn'], rtol=1e-5)
+    scale = np.abs(ref['b123'] + ref['b123_sn'])
+    assert np.all(np.abs(got['b123'] - ref['b123']) <= 1e-5 * scale + 1e-7 * scale.max())
+    rpk = pySpec.Pk_periodic(xyz, w=w, Lbox=L, Ngrid=N)
+    assert np.array_equal(pk['counts'], rpk['counts'])
+    np.testing.assert_allclose(pk['p0k'] + pk['p0k_sn'], rpk['p0k'] + rpk['p0k_sn'], rtol=1e-5)
