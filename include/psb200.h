@@ -106,6 +106,10 @@ int psb_assign_slab(const float* xyzw, int64_t np, int ngrid, float kf_ks, float
  *   out12       out, device float64 [12]: Ntot = sum w, I12, I13, I22, I23, I33 (py:794, 802-806), min x,y,z, max x,y,z */
 int psb_survey_prepare(const double* radecz, const double* nbar, const double* w, int64_t np, const double* dist_table, int nnodes,
                        double zmax, double p0_fkp, float* xyz_f32, float* w_f32, double* out12, void* stream);
+/* util.applyRSD (util.py:54-75) on device arrays: out [3][np] float64 = xyz [3][np] with row i_los replaced by
+ * (x + (rsd_factor * v_los + lbox)) mod lbox, numpy's float64 arithmetic and np.remainder bit for bit; v_los [np] = the velocity row
+ * along the line of sight (km/s), rsd_factor = (1+z)/(100 E(z)) from the caller's cosmology. */
+int psb_apply_rsd(const double* xyz, const double* v_los, int64_t np, int i_los, double rsd_factor, double lbox, double* out, void* stream);
 
 /* K2+K3  pyspectrum.py:1060-1080 + estimator.f:605-675 + the [:N/2+1] slice (py:959).
  *   mesh_c64  in: (A + iB) on [z][y][x]; destroyed (x and y passes run in place)

@@ -52,6 +52,7 @@ PROTOTYPES = {
     'psb_slab_route_scatter_peer': (_i, [_vp, _i, _i, _vp, _i, _i64, _i, _d, _f, _f, _i, _i, _vp, _vp, _vp]),
     'psb_assign_slab': (_i, [_vp, _i64, _i, _f, _f, _i, _i, _vp, _i, _vp, _sz, _vp, _vp]),
     'psb_survey_prepare': (_i, [_vp, _vp, _vp, _i64, _vp, _i, _d, _d, _vp, _vp, _vp, _vp]),
+    'psb_apply_rsd': (_i, [_vp, _vp, _i64, _i, _d, _d, _vp, _vp]),
     'psb_fft_mesh_to_delta': (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp]),
     'psb_fft_c2c_3d': (_i, [_vp, _i, _i, _vp, _vp]),
     'psb_fcomb': (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _vp]),

@@ -365,6 +365,11 @@ int psb_bk_build_tiles(const int32_t* tri, int ntri, int s0, int32_t* tiles, int
     return PSB_OK;
 }
 
+int psb_apply_rsd(const double* xyz, const double* v_los, int64_t np, int i_los, double rsd_factor, double lbox, double* out, void* stream)
+{
+    return apply_rsd(xyz, v_los, np, i_los, rsd_factor, lbox, out, S(stream));
+}
+
 int psb_survey_prepare(const double* radecz, const double* nbar, const double* w, int64_t np, const double* dist_table, int nnodes,
                        double zmax, double p0_fkp, float* xyz_f32, float* w_f32, double* out12, void* stream)
 {

@@ -95,4 +95,6 @@ int quad_fields(int mode, const Cx<float>* a, const Cx<float>* b, const Cx<float
 int survey_prepare(const double* radecz, const double* nb, const double* w, long long np, const double* tab, int nn, double zmax,
                    double p0_fkp, float* xyz, float* wout, double* out12, cudaStream_t st);
 
+int apply_rsd(const double* xyz, const double* v_los, long long np, int i_los, double fac, double L, double* out, cudaStream_t st);
+
 }  // namespace psb

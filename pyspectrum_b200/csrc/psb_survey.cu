@@ -113,4 +113,33 @@ int survey_prepare(const double* radecz, const double* nb, const double* w, long
     return cudaGetLastError() == cudaSuccess ? PSB_OK : PSB_ERR_CUDA;
 }
 
+// util.py:54-75 (applyRSD) on device arrays: out = xyz with the line-of-sight row replaced by (x + (f v + L)) mod L.  Every step is
+// numpy's: f*v and the sums rounded separately (no FMA), np.remainder = fmod with the sign fix-up of npy_divmod -- bit-exact.
+__global__ void __launch_bounds__(256) k_apply_rsd(const double* __restrict__ xyz, const double* __restrict__ v_los, long long np, int i_los,
+                                                   double fac, double L, double* __restrict__ out)
+{
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < 3 * np; e += (long long)gridDim.x * blockDim.x) {
+        const int row = (int)(e / np);
+        double x = xyz[e];
+        if (row == i_los) {
+            const double t = __dadd_rn(__dmul_rn(fac, v_los[e - row * np]), L);
+            x = __dadd_rn(x, t);
+            double m = fmod(x, L);
+            if (m != 0.0) { if ((L < 0.0) != (m < 0.0)) m = __dadd_rn(m, L); } else m = copysign(0.0, L);
+            x = m;
+        }
+        out[e] = x;
+    }
+}
+
+int apply_rsd(const double* xyz, const double* v_los, long long np, int i_los, double fac, double L, double* out, cudaStream_t st)
+{
+    if (!xyz || !v_los || !out || np < 0 || i_los < 0 || i_los > 2 || !(L > 0.0)) return PSB_ERR_ARG;
+    if (np == 0) return PSB_OK;
+    long long nblk = (3 * np + 255) / 256;
+    if (nblk > sm_count() * 16) nblk = sm_count() * 16;
+    k_apply_rsd<<<(unsigned)nblk, 256, 0, st>>>(xyz, v_los, np, i_los, fac, L, out);
+    return cudaGetLastError() == cudaSuccess ? PSB_OK : PSB_ERR_CUDA;
+}
+
 }  // namespace psb

@@ -115,8 +115,11 @@ def radecz_to_cartesian(radecz, cosmo=None):
 
 
 def applyRSD(xyz, vxyz, redshift, h=0.7, omega0_m=0.3, LOS=None, Lbox=None):
-    """util.py:54-75: x_s = (x + v (1+z)/(100 E(z)) + L) mod L along the line of sight, velocities in km/s."""
-    xyz, vxyz = np.asarray(xyz), np.asarray(vxyz)
+    """util.py:54-75: x_s = (x + v (1+z)/(100 E(z)) + L) mod L along the line of sight, velocities in km/s.
+    numpy arrays in -> numpy out (host, as the reference); torch CUDA tensors in -> the same arithmetic on the device (psb_apply_rsd)."""
+    dev_in = _is_cuda_tensor(xyz)                        # catalogue already on the GPU: psb_apply_rsd, result stays there
+    if not dev_in:
+        xyz, vxyz = np.asarray(xyz), np.asarray(vxyz)
     assert xyz.shape[0] == 3
     assert vxyz.shape[0] == 3
     if LOS is None:
@@ -126,10 +129,35 @@ def applyRSD(xyz, vxyz, redshift, h=0.7, omega0_m=0.3, LOS=None, Lbox=None):
     i_los = {'x': 0, 'y': 1, 'z': 2}[LOS]
     cosmo = FlatLambdaCDM(H0=100. * h, Om0=omega0_m)
     rsd_factor = (1 + redshift) / (100 * cosmo.efunc(redshift))
+    if dev_in:
+        return _apply_rsd_device(xyz, vxyz, i_los, float(rsd_factor), float(Lbox))
     xyz_rsd = xyz.copy()
     xyz_rsd[i_los] += rsd_factor * vxyz[i_los] + Lbox
     xyz_rsd[i_los] = (xyz_rsd[i_los] % Lbox)
     return xyz_rsd
+
+
+def _is_cuda_tensor(a):
+    try:
+        import torch
+        return isinstance(a, torch.Tensor) and a.is_cuda
+    except ImportError:
+        return False
+
+
+def _apply_rsd_device(xyz, vxyz, i_los, rsd_factor, Lbox):
+    """applyRSD for torch CUDA tensors (3 x N): float64 arithmetic of the numpy path bit for bit, no host round trip."""
+    import ctypes
+    import torch
+    from . import _lib
+    x = xyz.double().contiguous()
+    v = vxyz.to(x.device)[i_los].double().contiguous()
+    out = torch.empty_like(x)
+    st = ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().psb_apply_rsd(ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(v.data_ptr()), int(x.shape[1]), int(i_los),
+                                            rsd_factor, Lbox, ctypes.c_void_p(out.data_ptr()), st), 'psb_apply_rsd')
+    return out
 
 
 def fortran_records(path):

@@ -235,3 +235,24 @@ def test_survey_prepare_kernel(mods, Np, weighted):
     np.testing.assert_allclose(out[9:12], ref.max(axis=1), rtol=1e-10, atol=1e-8)
     with pytest.raises(ValueError):
         pySpec.PeriodicPipeline.get(24).survey_prepare(-radecz, nb, w, 1e4, cosmo)               # negative redshift
+
+
+@pytest.mark.parametrize('LOS', ['x', 'y', 'z'])
+def test_apply_rsd_on_device_equals_numpy_bit_for_bit(mods, LOS):
+    """util.applyRSD (util.py:54-75) with torch CUDA tensors runs psb_apply_rsd: float64 products, sums and np.remainder reproduced
+    exactly (the numpy path itself is pinned to the reference's output in tests/golden/util.npz on CPU)."""
+    import torch
+    from pyspectrum_b200 import util as UT
+    rng = np.random.default_rng(ord(LOS))
+    L, n = 2600., 200001
+    xyz = rng.uniform(0, L, (3, n))
+    v = rng.normal(0, 600., (3, n))
+    v[:, :4] = [[-5e5, 5e5, 0., -1e-300]] * 3                       # several box lengths either way, zero, denormal shift
+    xyz[:, 4] = 0.
+    v[:, 4] = 0.                                                     # lands exactly on L -> remainder 0
+    want = UT.applyRSD(xyz, v, 0.5, h=0.7, omega0_m=0.3, LOS=LOS, Lbox=L)
+    got = UT.applyRSD(torch.from_numpy(xyz).cuda(), torch.from_numpy(v).cuda(), 0.5, h=0.7, omega0_m=0.3, LOS=LOS, Lbox=L)
+    assert got.is_cuda and got.dtype == torch.float64
+    g = got.cpu().numpy()
+    assert np.array_equal(g.view(np.int64), want.view(np.int64))
+    assert g.min() >= 0. and g['xyz'.index(LOS)].max() < L
