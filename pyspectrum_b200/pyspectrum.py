@@ -291,6 +291,7 @@ class PeriodicPipeline(object):
         self._pin_pool = {}                               # free pinned result buffers by size (bispectrum_launch/finish)
         self._copy_stream = None                          # upload stream of the *_many generators
         self._side_stream = None                          # second stream of the routed shell stage (multi-GPU)
+        self._stage = {}                                  # pinned staging buffers + copy threads of the streamed upload
 
     # ------------------------------------------------------------------ tables
     @property
@@ -446,31 +447,79 @@ class PeriodicPipeline(object):
         part = torch.empty(1, dtype=torch.float64, device=self.dev)
         kf_ks = np.float32(float(N) / Lbox)
         cs.wait_stream(main)
-        staged = []
         bounds = [(a, min(a + self.CHUNK, Np)) for a in range(0, Np, self.CHUNK)]
-        for (a, b) in bounds:                            # all uploads are queued up front; they run back to back on the copy stream
+        # pageable host memory (what a numpy caller passes): the driver's own staged copy runs at ~9 GB/s (C2: 42 ms per call against
+        # 22 ms from pinned memory).  Worker threads copy each chunk into pinned staging buffers instead (numpy releases the GIL), the
+        # DMA of chunk k and K1 of chunk k-1 run under the host copy of chunk k+1.
+        staged_copy = not xt.is_pinned() and os.environ.get('PSB_HOST_STAGING', '1') != '0'
+        stage = self._staging(xt.dtype, aos, None if wt_h is None else wt_h.dtype) if staged_copy else None
+        src_np = xt.numpy() if staged_copy else None
+        w_np = wt_h.numpy() if (staged_copy and wt_h is not None) else None
+        for k, (a, b) in enumerate(bounds):
+            n = b - a
+            if staged_copy:
+                slot = stage['slots'][k % len(stage['slots'])]
+                if slot['ev'] is not None:
+                    slot['ev'].synchronize()             # the DMA that last read this staging buffer is done
+                jobs = []
+                nsp = stage['nsplit']
+                cuts = [n * i // nsp for i in range(nsp + 1)]
+                if aos:
+                    dst = slot['pos_np'][:n]
+                    src = src_np.T[a:b]
+                    jobs += [(dst[lo:hi], src[lo:hi]) for lo, hi in zip(cuts, cuts[1:])]
+                else:
+                    for c in range(3):
+                        jobs += [(slot['pos_np'][c, lo:hi], src_np[c, a + lo:a + hi]) for lo, hi in zip(cuts, cuts[1:])]
+                if w_np is not None:
+                    jobs.append((slot['w_np'][:n], w_np[a:b]))
+                list(stage['pool'].map(lambda j: np.copyto(j[0], j[1]), jobs))
+                hp = slot['pos'][:n] if aos else slot['pos'][:, :n]
+                hw = slot['w'][:n] if w_np is not None else None
+            else:
+                hp = xt.t()[a:b] if aos else xt[:, a:b]
+                hw = wt_h[a:b] if wt_h is not None else None
             with torch.cuda.stream(cs):
                 if aos:
-                    pc = xt.t()[a:b].to(self.dev, non_blocking=True)
+                    pc = hp.to(self.dev, non_blocking=True)
                 else:
-                    pc = torch.empty((3, b - a), dtype=xt.dtype, device=self.dev)
-                    for c in range(3):
-                        pc[c].copy_(xt[c, a:b], non_blocking=True)
-                wc = wt_h[a:b].to(self.dev, non_blocking=True) if wt_h is not None else None
+                    pc = torch.empty((3, n), dtype=xt.dtype, device=self.dev)
+                    if hp.is_contiguous():
+                        pc.copy_(hp, non_blocking=True)
+                    else:                                # a column range of a wider array: one copy per coordinate row
+                        for c in range(3):
+                            pc[c].copy_(hp[c], non_blocking=True)
+                wc = hw.to(self.dev, non_blocking=True) if hw is not None else None
                 ev = torch.cuda.Event()
                 ev.record(cs)
-            staged.append((pc, wc, ev))
-        for k, (pc, wc, ev) in enumerate(staged):
+            if staged_copy:
+                slot['ev'] = ev
             main.wait_event(ev)
             pc.record_stream(main)
             if wc is not None:
                 wc.record_stream(main)
             check(self.L.psb_assign_pcs_interlaced(_ptr(pc), int(pc.dtype == torch.float64), aos, _ptr(wc),
-                                                   int(wc is not None and wc.dtype == torch.float64), pc.shape[0] if aos else pc.shape[1], N,
+                                                   int(wc is not None and wc.dtype == torch.float64), n, N,
                                                    float(Lbox), kf_ks, np.float32(0.), _ptr(mesh), 1 if k == 0 else 0, _ptr(ws), wsb,
                                                    _ptr(part), _stream()), 'psb_assign_pcs_interlaced')
             sumw += part
         return mesh, sumw
+
+    def _staging(self, dtype, aos, wdtype):
+        """Pinned staging buffers (three chunks deep) + the copy thread pool of the streamed upload, created once per layout."""
+        key = (dtype, aos, wdtype)
+        st = self._stage.get(key)
+        if st is None:
+            from concurrent.futures import ThreadPoolExecutor
+            nthr = max(1, min(8, (os.cpu_count() or 2) - 1))
+            slots = []
+            for _ in range(3):
+                pos = torch.empty((self.CHUNK, 3) if aos else (3, self.CHUNK), dtype=dtype, pin_memory=True)
+                w = torch.empty(self.CHUNK, dtype=wdtype, pin_memory=True) if wdtype is not None else None
+                slots.append({'pos': pos, 'pos_np': pos.numpy(), 'w': w, 'w_np': None if w is None else w.numpy(), 'ev': None})
+            st = {'slots': slots, 'pool': ThreadPoolExecutor(max_workers=nthr), 'nsplit': max(1, nthr // (1 if aos else 3) or 1)}
+            self._stage[key] = st
+        return st
 
     @staticmethod
     def survey_distance_table(cosmo, zmax, nnodes=4097):
