@@ -333,6 +333,52 @@ class PeriodicPipeline(object):
         return self._bins[key]
 
     # ------------------------------------------------------------------ K1..K3
+    STAGE_BYTES = 48 << 20                           # pinned staging buffer size of `upload`
+
+    def upload(self, t):
+        """Host tensor -> device.  Large PAGEABLE arrays (numpy callers) go through pinned staging buffers filled by worker threads
+        under the DMA of the previous piece (the driver's own staged copy runs at ~9 GB/s); everything else is a plain async copy."""
+        if t.is_cuda:
+            return t
+        nbytes = t.numel() * t.element_size()
+        if t.is_pinned() or nbytes < 2 * self.STAGE_BYTES or not t.is_contiguous() or os.environ.get('PSB_HOST_STAGING', '1') == '0':
+            return t.to(self.dev, non_blocking=True)
+        st = self._staging_flat()
+        out = torch.empty(t.shape, dtype=t.dtype, device=self.dev)
+        src = t.view(-1).view(torch.uint8).numpy()
+        dst = out.view(-1).view(torch.uint8)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.dev)
+        cs, main = self._copy_stream, torch.cuda.current_stream(self.dev)
+        cs.wait_stream(main)
+        nthr = st['nthr']
+        for k, a in enumerate(range(0, nbytes, self.STAGE_BYTES)):
+            b = min(a + self.STAGE_BYTES, nbytes)
+            slot = st['slots'][k % len(st['slots'])]
+            if slot['ev'] is not None:
+                slot['ev'].synchronize()
+            cuts = [a + (b - a) * i // nthr for i in range(nthr + 1)]
+            list(st['pool'].map(lambda c: np.copyto(slot['np'][c[0] - a:c[1] - a], src[c[0]:c[1]]), zip(cuts, cuts[1:])))
+            with torch.cuda.stream(cs):
+                dst[a:b].copy_(slot['t'][:b - a], non_blocking=True)
+                slot['ev'] = torch.cuda.Event()
+                slot['ev'].record(cs)
+        main.wait_stream(cs)
+        return out
+
+    def _staging_flat(self):
+        st = self._stage.get('flat')
+        if st is None:
+            from concurrent.futures import ThreadPoolExecutor
+            nthr = max(1, min(8, (os.cpu_count() or 2) - 1))
+            slots = []
+            for _ in range(3):
+                t = torch.empty(self.STAGE_BYTES, dtype=torch.uint8, pin_memory=True)
+                slots.append({'t': t, 'np': t.numpy(), 'ev': None})
+            st = {'slots': slots, 'pool': ThreadPoolExecutor(max_workers=nthr), 'nthr': nthr}
+            self._stage['flat'] = st
+        return st
+
     def to_device(self, xyz, w=None):
         """Positions (3xN, numpy or torch, float32/float64) and weights -> device tensors + layout flags."""
         if isinstance(xyz, torch.Tensor):
@@ -348,7 +394,7 @@ class PeriodicPipeline(object):
                     pos = pos.t()                        # (N,3) contiguous, like the numpy branch
                 else:
                     pos = pos.contiguous()
-            pos = pos.to(self.dev, non_blocking=True)
+            pos = self.upload(pos)
         else:
             xyz = np.asarray(xyz)
             if xyz.ndim != 2 or xyz.shape[0] != 3:
@@ -358,19 +404,19 @@ class PeriodicPipeline(object):
             aos = 0
             if xyz.flags.f_contiguous and not xyz.flags.c_contiguous:
                 aos = 1
-                pos = torch.from_numpy(xyz.T).to(self.dev, non_blocking=True)       # (N,3) contiguous
+                pos = self.upload(torch.from_numpy(xyz.T))                           # (N,3) contiguous
             else:
-                pos = torch.from_numpy(np.ascontiguousarray(xyz)).to(self.dev, non_blocking=True)
+                pos = self.upload(torch.from_numpy(np.ascontiguousarray(xyz)))
         wt = None
         if w is not None:
             if isinstance(w, torch.Tensor):
                 wt = w if w.dtype in (torch.float32, torch.float64) else w.double()
-                wt = wt.contiguous().to(self.dev, non_blocking=True)
+                wt = self.upload(wt.contiguous())
             else:
                 w = np.asarray(w)
                 if w.dtype not in (np.float32, np.float64):
                     w = w.astype(np.float64)
-                wt = torch.from_numpy(np.ascontiguousarray(w)).to(self.dev, non_blocking=True)
+                wt = self.upload(torch.from_numpy(np.ascontiguousarray(w)))
         return pos, aos, wt
 
     def assign(self, pos, aos, wt, Lbox, offset=0., clip=True):
@@ -545,13 +591,13 @@ class PeriodicPipeline(object):
             raise ValueError('redshifts must be finite and >= 0')
         zmax = max(zmax, 1e-6)
         tab = torch.from_numpy(self.survey_distance_table(cosmo, zmax)).to(self.dev)
-        rdz = torch.from_numpy(radecz).to(self.dev, non_blocking=True)
-        nbd = torch.from_numpy(np.ascontiguousarray(nb, dtype=np.float64)).to(self.dev, non_blocking=True)
+        rdz = self.upload(torch.from_numpy(radecz))
+        nbd = self.upload(torch.from_numpy(np.ascontiguousarray(nb, dtype=np.float64)))
         if nbd.numel() != Np:
             raise ValueError('nbar must have one entry per object')
         wd = None
         if w is not None:
-            wd = torch.from_numpy(np.ascontiguousarray(w, dtype=np.float64)).to(self.dev, non_blocking=True)
+            wd = self.upload(torch.from_numpy(np.ascontiguousarray(w, dtype=np.float64)))
             if wd.numel() != Np:
                 raise ValueError('w must have one entry per object')
         xyz = torch.empty((3, Np), dtype=torch.float32, device=self.dev)

@@ -25,3 +25,12 @@ if os.environ.get('E2E_C3'):
     k3 = dict(Lbox=2600., Ngrid=512, rsd=2, Nmubin=10)
     print('C3 Pk_periodic_rsd  pageable numpy float64: %.1f ms   pinned: %.1f ms' % (
         timed(lambda: pySpec.Pk_periodic_rsd(x3, **k3), 3), timed(lambda: pySpec.Pk_periodic_rsd(p3, **k3), 3)), flush=True)
+# one-piece uploads (to_device -> upload): a 1e8-particle shard as the sharded path / survey path would pass it
+pipe = pySpec.PeriodicPipeline.get(360)
+big = np.random.default_rng(0).uniform(0, 2600., (3, 5 * 10 ** 7))
+for flag in ('1', '0'):
+    os.environ['PSB_HOST_STAGING'] = flag
+    pipe.to_device(big); torch.cuda.synchronize()
+    t0 = time.perf_counter(); pos, aos, wt = pipe.to_device(big); torch.cuda.synchronize()
+    print('to_device 1.2 GB pageable, staging %s: %.1f ms (%.1f GB/s)  equal %s' % (flag, (time.perf_counter() - t0) * 1e3, 1.2 / (time.perf_counter() - t0),
+          bool(torch.equal(pos.cpu(), torch.from_numpy(big)))), flush=True)
