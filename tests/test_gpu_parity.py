@@ -384,6 +384,25 @@ def test_k6_tensor_core_sums_are_reproducible(mods):
         assert torch.equal(pipe.triangle_sums(fields, Nmax, Ncut, step, engine='tc'), ref)
 
 
+def test_staged_upload_of_pageable_arrays(mods):
+    """PeriodicPipeline.upload: large pageable arrays travel through pinned staging buffers filled by worker threads; the bytes that
+    arrive are the bytes that left (odd sizes, several staging rounds, float64 and float32), pinned and small inputs take the plain copy."""
+    import torch
+    pySpec, _, _ = mods
+    pipe = pySpec.PeriodicPipeline.get(32)
+    rng = np.random.default_rng(9)
+    for dtype, n in ((np.float64, 3 * 7000003), (np.float32, 40000001), (np.float64, 1000)):
+        a = rng.standard_normal(n).astype(dtype)
+        t = torch.from_numpy(a)
+        d = pipe.upload(t)
+        assert d.is_cuda and d.dtype == t.dtype and torch.equal(d.cpu(), t)
+    p = torch.from_numpy(rng.standard_normal(3 * 5000000)).pin_memory()
+    assert torch.equal(pipe.upload(p).cpu(), p)
+    xyz = rng.uniform(0, 100., (3, 6000000))                                  # above the staging threshold through to_device
+    pos, aos, wt = pipe.to_device(xyz, rng.uniform(0.5, 2., 6000000))
+    assert aos == 0 and torch.equal(pos.cpu(), torch.from_numpy(xyz)) and wt.numel() == 6000000
+
+
 def test_many_generators_match_single_calls(mods):
     """Bk/Pk/Pk_rsd *_many (upload of catalogue n+1 overlapped with the kernels of n) give the single-call results, in order,
     for pinned torch tensors, numpy arrays (C and Fortran order) and (xyz, w) items."""
