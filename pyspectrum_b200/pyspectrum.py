@@ -72,6 +72,16 @@ class _Range(object):
         return False
 
 
+def _copy_threads():
+    """Worker threads of the host staging copies: up to 8, sharing the cores with the other ranks of the node."""
+    ranks = max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1') or 1))
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        cores = os.cpu_count() or 2
+    return max(1, min(8, (cores - 1) // ranks))
+
+
 def _np_ptr(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
@@ -370,7 +380,7 @@ class PeriodicPipeline(object):
         st = self._stage.get('flat')
         if st is None:
             from concurrent.futures import ThreadPoolExecutor
-            nthr = max(1, min(8, (os.cpu_count() or 2) - 1))
+            nthr = _copy_threads()
             slots = []
             for _ in range(3):
                 t = torch.empty(self.STAGE_BYTES, dtype=torch.uint8, pin_memory=True)
@@ -557,7 +567,7 @@ class PeriodicPipeline(object):
         st = self._stage.get(key)
         if st is None:
             from concurrent.futures import ThreadPoolExecutor
-            nthr = max(1, min(8, (os.cpu_count() or 2) - 1))
+            nthr = _copy_threads()
             slots = []
             for _ in range(3):
                 pos = torch.empty((self.CHUNK, 3) if aos else (3, self.CHUNK), dtype=dtype, pin_memory=True)
