@@ -42,7 +42,8 @@ int fft_shell_pair(const Cx<float>* half, const unsigned short* irk, int N, int 
         IoCols<T, true, true, true> io3{ t2, nullptr, fa, fb, sumsq, scale2, maxabs2, halfpack, N, N, (long long)N * N, N, (long long)N * N, Rm, Rp,
                                          route, rplanes, rranks, (unsigned)(4294967296ULL / (unsigned)rplanes) + 1u };
         // the routed z pass runs with 32 lines per CTA: a CTA's (plane, z) run is 128 bytes instead of 64, which NVLink stores need
-        // (2 GPUs, C2: shell stage 5.78 -> 4.97 ms; locally the 16-line kernel is the faster one).  PSB_ROUTED_LPC=16 restores it.
+        // (2 GPUs, C2: shell stage 5.78 -> 4.97 ms; with local stores the 16-line kernel wins, 5.3 vs 6.0 ms for the 20 pairs of C2:
+        // one CTA of 640 threads per SM instead of three of 320).  PSB_ROUTED_LPC=16 restores it.
         using CFG = decltype(cfg);
         if constexpr (CFG::Stages::IS_STATIC && sizeof(T) == 4) {
             if constexpr (CFG::Stages::NSTAGES >= 2 && CFG::LPC == 16 && 32 * CFG::TPL <= 1024) {
