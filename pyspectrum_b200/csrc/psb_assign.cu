@@ -1,13 +1,17 @@
 // psb_assign.cu -- K1: PCS (4th-order) mass assignment onto two half-cell interlaced grids.
 // Replaces estimator.f:284-512 (assign_quad, delta branch) and the clip/cast of pyspectrum.py:938-941.
 //
-// Design (sm_100a): shared-memory float atomics are CAS spin loops on this part (ATOMS.CAST.SPIN),
-// so the scatter goes straight to L2 with 16-byte vector reductions
-//     red.global.add.v4.f32  ->  SASS REDG.E.ADD.F32x4
-// one per aligned pair of interlaced cells {A(c),B(c),A(c+1),B(c+1)}: <= 75 (typically ~56) reductions
-// per particle instead of 128 scalar read-modify-writes.  Particles are first counting-sorted by
-// (z,y) row so that concurrently running warps hit a few-MB window of the mesh that stays L2 resident;
-// HBM then sees the mesh once (zero fill + final write-back) plus 16 B per sorted particle.
+// Design (sm_100a): shared-memory float atomics are CAS spin loops on this part (ATOMS.CAST.SPIN), so nothing here uses them.
+//   dense catalogues (>= 0.1 particles per cell): counting sort by 8 x 8 x 4 TILE of the particle's cell, then k_assign_tile -- one
+//       warp owns one tile (plus halo) in its own shared memory, lanes own distinct stencil points, plain LDS / FFMA / STS, and the
+//       finished tile leaves with coalesced red.global.add.v4.f32 (REDG.E.ADD.F32x4); runs at the shared-memory data pipe;
+//   sparse catalogues / chunks of a streamed upload: counting sort by (z,y) row, then k_assign_tri -- one vector reduction per
+//       aligned pair of interlaced cells {A(c),B(c),A(c+1),B(c+1)} and row, three lanes per particle (<= 75, typically ~56
+//       reductions per particle instead of 128 scalar read-modify-writes);
+//   the sort is one pass (k_sort_scatter) or, for unordered input on large grids, two (k_partition_coarse + k_bucket_scatter),
+//       chosen on the device from how ordered the input is (k_hist / k_sort_decide);
+//   slab mode (multi-GPU): the same kernels on a window of planes; k_route_count / k_route_scatter(_peer) deal the particles (with
+//       ghost copies) to the ranks that own the planes they touch, the peer variant by NVLink stores into the receive buffers.
 #include <cuda_runtime.h>
 #include <cstdlib>
 #include "psb_kernels.h"

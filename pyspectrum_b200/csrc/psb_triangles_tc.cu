@@ -228,8 +228,9 @@ __device__ __forceinline__ void drain_accumulators(const Params& p, uint64_t* ac
     const float bg = p.bias_gain;
     if (live && !(p.debug & 8)) {
         double* dst = p.partial + (size_t)blockIdx.x * MR * NT + (size_t)row;     // [col][row]: coalesced
-        // one 16-column TMEM load per round trip: keeping two or three in flight needs 32-48 more live registers and spills at the
-        // 80-register cap of this 704-thread CTA (measured: 11.7 -> 15.6 ms)
+        // one 16-column TMEM load per round trip: keeping two or three in flight needs 32-48 more live registers (measured on the
+        // 704-thread / 80-register predecessor of this kernel: spills, 11.7 -> 15.6 ms; at 640 threads / 96 registers the forming
+        // loop already holds 64 of them)
         for (int c0 = 0; c0 < NT; c0 += 16) {
             uint32_t r[16];
             tmem_ld16_issue(t_acc + (uint32_t)c0, r);
