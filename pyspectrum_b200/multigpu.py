@@ -26,7 +26,6 @@ exchanges between kernels, except step 6 under NCCL: there the z pass of K5 stor
 buffer of the rank that owns it (peer pointers from symmetric memory, `SlabBuffers`), so the exchange rides inside the transform
 and the separate all-to-all disappears (it remains the path for float64 counts, gloo, and grids that do not divide into planes).  `stats` dictionaries collect the bytes each collective puts on the wire
 and, with `timed=True`, its device time (bench.py reports them)."""
-import ctypes
 import os
 
 import numpy as np
