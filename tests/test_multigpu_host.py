@@ -170,3 +170,33 @@ def test_peer_segments_tile_the_receive_buffers_gloo():
         assert spans[0][0] == 0 and all(a[1] == b[0] for a, b in zip(spans, spans[1:])) and spans[-1][1] == res[0][1][d]
         assert [sp[0] for sp in spans] == [res[s][2][d] for s in range(world)]           # rank order
     assert all(r[1] == res[0][1] for r in res)
+
+
+def test_route_tables_address_the_rows_the_all_to_all_would_fill():
+    """SlabBuffers.route / row_table (host bookkeeping of the peer-store exchanges) with made-up base addresses: entry (k, e, q) of a
+    rank's route table + the byte offset of a cell in slab q must be the address of that cell in row slab_field_rows()[shell] of rank
+    q's buffer; shells that do not exist get 0."""
+    import numpy as np
+    from pyspectrum_b200.multigpu import SlabBuffers, pair_assignment, slab_field_rows
+    world, S, slab = 4, 13, 1000                                        # 13 shells -> 7 pairs -> 2 per rank, one padding pair
+    deal, per = pair_assignment((S + 1) // 2, world)
+    ptrs = [10 ** 9 * (q + 1) for q in range(world)]
+    rows = slab_field_rows(S, world, per)
+    seen = set()
+    for rank in range(world):
+        b = SlabBuffers(world, rank, world * 2 * per, slab, None, ptrs)
+        t = b.route(per, deal[rank], S, 'cpu').numpy()
+        assert t.shape == (per, 2, world)
+        for k, pidx in enumerate(deal[rank]):
+            for e in (0, 1):
+                f = 2 * pidx + e
+                for q in range(world):
+                    if f >= S:
+                        assert t[k, e, q] == 0
+                        continue
+                    cell = q * slab + 17                                  # a cell of slab q, addressed as if the buffer held the whole field
+                    assert t[k, e, q] + 4 * cell == ptrs[q] + 4 * (rows[f] * slab + 17)
+                    seen.add((f, q))
+        rt = b.row_table('cpu').numpy()
+        assert rt.shape == (world * 2 * per, world) and rt[3, 2] == ptrs[2] + 4 * 3 * slab
+    assert len(seen) == S * world
