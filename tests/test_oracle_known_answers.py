@@ -230,3 +230,23 @@ def test_pk_pbox_rsd_against_an_independent_numpy_restatement(N, irsd, Nmu):
         else:
             np.testing.assert_allclose(x, y, rtol=1e-12, atol=0, err_msg=name)
     assert a[4].sum() > 0 and a[8].sum() > 0
+
+
+@pytest.mark.parametrize('N', [8, 12])
+@pytest.mark.parametrize('periodic', [True, False])
+def test_fcomb_against_an_independent_python_restatement(N, periodic):
+    """estimator.f:605-745 restated a second time (tests/fcomb_numpy.py: a sequential Python loop written from the Fortran text, with its
+    implicit typing and in-place update order) against the C restatement: every element of the combined field, self-conjugate planes
+    included, bit for bit."""
+    import fcomb_numpy as FN
+    rng = np.random.default_rng(N)
+    F = np.asfortranarray((rng.normal(size=(N, N, N)) + 1j * rng.normal(size=(N, N, N))).astype(np.complex64))
+    a = F.copy(order='F')
+    b = F.copy(order='F')
+    if periodic:
+        O.fcomb_periodic(a, 1234.5)
+        FN.fcomb(b, 1234.5)
+    else:
+        O.fcomb_survey(a)
+        FN.fcomb(b, None)
+    assert np.abs(a).max() > 0 and np.array_equal(a.view(np.uint32), b.view(np.uint32))      # bit for bit, all 8 mirror images
