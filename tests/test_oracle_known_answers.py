@@ -249,4 +249,4 @@ def test_fcomb_against_an_independent_python_restatement(N, periodic):
     else:
         O.fcomb_survey(a)
         FN.fcomb(b, None)
-    assert np.abs(a).max() > 0 and np.array_equal(a.view(np.uint32), b.view(np.uint32))      # bit for bit, all 8 mirror images
+    assert np.abs(a).max() > 0 and a.tobytes(order='F') == b.tobytes(order='F')                 # bit for bit, all 8 mirror images
