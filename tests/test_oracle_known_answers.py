@@ -250,3 +250,23 @@ def test_fcomb_against_an_independent_python_restatement(N, periodic):
         O.fcomb_survey(a)
         FN.fcomb(b, None)
     assert np.abs(a).max() > 0 and a.tobytes(order='F') == b.tobytes(order='F')                 # bit for bit, all 8 mirror images
+
+
+@pytest.mark.parametrize('N,offset,idx', [(8, 0., (0, 0, 0, 0)), (12, 0., (0, 0, 0, 0)), (8, 4., (0, 0, 0, 0)), (8, 0., (1, 2, 0, 0)), (8, 0., (3, 3, 1, 2))])
+def test_assign_quad_against_an_independent_python_restatement(N, offset, idx):
+    """estimator.f:284-512 restated a second time (tests/assign_quad_numpy.py: a sequential Python loop over float32 scalars written from
+    the Fortran text) against the C restatement: the interlaced mesh bit for bit -- face particles (stencil wrap), the unwrapped base
+    cell of grid A, the wrapped one of grid B, the survey offset, the Q_ij / Q_ijkl weights."""
+    import assign_quad_numpy as AN
+    rng = np.random.default_rng(N + int(offset) + sum(idx))
+    L, Np = 50., 300
+    r = np.asfortranarray(rng.uniform(0.5 if offset == 0. else -0.45 * L, L * (1 - 1e-6) if offset == 0. else 0.45 * L, (3, Np)).astype(np.float32))
+    if offset == 0.:
+        r[:, 0] = [0.5, L * (1 - 1e-6), 0.5 * L]
+        r[:, 1] = [L * (1 - 1e-6), L * (1 - 1e-6), L * (1 - 1e-6)]
+    w = rng.uniform(0.5, 2., Np).astype(np.float32)
+    a = np.zeros((2 * N, N, N), np.float32, order='F')
+    b = np.zeros((2 * N, N, N), np.float32, order='F')
+    O.assign_quad(r, w, a, np.float32(N / L), offset, *idx)
+    AN.assign_quad(r, w, b, np.float32(N / L), offset, *idx)
+    assert np.abs(a).max() > 0 and a.tobytes(order='F') == b.tobytes(order='F')
