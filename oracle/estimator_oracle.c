@@ -8,6 +8,7 @@
  *   oracle_fcomb            <-  pyspectrum/estimator.f:605-675  (fcomb_periodic)
  *                               pyspectrum/estimator.f:677-745  (fcomb_survey, periodic=0)
  *   oracle_pk_pbox_rsd      <-  pyspectrum/estimator.f:155-264  (pk_pbox_rsd)
+ *   oracle_quad_fields      <-  pyspectrum/estimator.f:514-603  (FiveDelta2g_1, FiveDelta2g_2, build_quad)
  *
  * The restatement follows the Fortran's *implicit typing* to the letter (every
  * undeclared a-h/o-z name is a 4-byte real, i-n a 4-byte integer) and its
@@ -23,8 +24,12 @@
  * could not be diffed against a compiled estimator.f.  It is pinned instead by the
  * known-answer tests in tests/test_oracle_*.py (mesh mass = 216*sum(w) per grid,
  * single-particle plane wave, delta(k=0)=1, Hermitian pairing on self-conjugate
- * planes) and, through the Python layer, by the reference's shipped triangle-count
- * files.  See DESIGN.md "Oracle".
+ * planes), by a closed-form direct-summation delta(k) (tests/direct_sum.py), by SECOND
+ * restatements written independently from the Fortran text that agree with this file
+ * bit for bit (tests/assign_quad_numpy.py, tests/fcomb_numpy.py) or to 1e-12
+ * (tests/pk_pbox_rsd_numpy.py) and, through the Python layer, by the reference's shipped
+ * triangle-count files.  "Parity unpinned" against a compiled estimator.f still holds.
+ * See DESIGN.md "Oracle".
  *
  * Array conventions: all arrays are Fortran (column-major) as f2py passes them.
  *   r   : float  (3,Np)              -> r[3*i + a]
