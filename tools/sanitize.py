@@ -2,7 +2,7 @@
     compute-sanitizer --tool memcheck  python tools/sanitize.py
     compute-sanitizer --tool racecheck python tools/sanitize.py
 CI-size grids: K1 (tile scatter and per-particle scatter, full grid and slab), route kernels, K2+K3, slab FFT, K4 (all modes),
-K5 (one grid, a coarser transform grid, routed output), K6 (tcgen05 kernel, both lane layouts, and the FFMA kernel), routed slab-FFT
+K5 (one grid, a coarser transform grid, routed output), the peer-store particle scatter, K6 (tcgen05 kernel, both lane layouts, and the FFMA kernel), routed slab-FFT
 separation, survey pre-step.  PSB_ASSIGN_TWOPASS=5 in the environment also runs K1's two-pass sort kernels."""
 import os
 import sys
@@ -62,7 +62,15 @@ nz, hp = M.slab_geometry(64, world)
 fr = M.SlabBuffers.emulated(pipe.dev, world, 2, 64 * nz * hp * 2)
 for r in range(world):
     M.slab_phase1_routed(pipe, mesh[r * nz:(r + 1) * nz].clone(), fr[r], r * nz)
-print('routed', float(ranks[0].local.abs().sum()), float(fr[1].local.abs().sum()))
+# peer-store particle scatter: this device's buffers stand in for the receive buffers of two ranks
+cnts, _ = M.route_counts(pipe, pos, aos, wt, L, world)
+rb = [torch.zeros((int(cnts[d].item()) + 8, 4), dtype=torch.float32, device=pipe.dev) for d in range(world)]
+dest = torch.tensor([b.data_ptr() for b in rb], dtype=torch.int64, device=pipe.dev)
+cur = torch.zeros(world, dtype=torch.int64, device=pipe.dev)
+P.check(pipe.L.psb_slab_route_scatter_peer(P._ptr(pos), int(pos.dtype == torch.float64), aos, None, 0, pos.shape[1], 64, float(L),
+                                           np.float32(64 / L), np.float32(0.), 64 // world, world, P._ptr(dest), P._ptr(cur), P._stream()),
+        'psb_slab_route_scatter_peer')
+print('routed', float(ranks[0].local.abs().sum()), float(fr[1].local.abs().sum()), cur.cpu().tolist() == cnts.cpu().tolist())
 radecz = np.stack([rng.uniform(100, 140, 20000), rng.uniform(-5, 30, 20000), rng.uniform(0.2, 0.5, 20000)])
 d, Ntot, I12, I13, I22, I23, I33 = P.FFT_survey_mono(radecz, np.full(20000, 3e-4), Lbox=3000., Ngrid=48)
 print('survey', Ntot, I22)
